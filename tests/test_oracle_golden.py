@@ -1,0 +1,400 @@
+"""Pins the CPU oracle against the reference's own numeric known-answer tests
+(SURVEY.md section 8c).  Every test cites the reference test it restates."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import fvm_oracle as O
+
+
+def isapprox(x, y, rtol=None, atol=0.0):
+    """Julia's isapprox for arrays: norm(x-y) <= max(atol, rtol*max(norm(x),norm(y)))."""
+    x = np.asarray(x, dtype=float)
+    y = np.asarray(y, dtype=float)
+    if rtol is None:
+        rtol = math.sqrt(np.finfo(float).eps) if atol == 0 else 0.0
+    return np.linalg.norm(x - y) <= max(atol, rtol * max(np.linalg.norm(x), np.linalg.norm(y)))
+
+
+# ---- problems of /root/reference/test/test_functions.jl:304-374 ------------------------
+def example_diffusion_problem():
+    tri = O.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, 25, 25, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: 0.0 * u, O.Dirichlet)
+    ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
+    D = lambda x, y, t, u, p: 1 / 9
+    return O.FVMProblem(mesh, BCs, diffusion_function=D, initial_condition=ic, final_time=0.5)
+
+
+def example_heat_convection_problem(n=200):
+    L, k, T0, Tinf, alpha, q, h = 1.0, 237.0, 10.0, 10.0, 80.0e-6, 10.0, 25.0
+    tri = O.triangulate_rectangle(0, L, 0, L, n, n, single_boundary=False)
+    mesh = O.FVMGeometry(tri)
+    bot = lambda x, y, t, T, p: -p["a"] * p["q"] / p["k"]
+    right = lambda x, y, t, T, p: 0.0 * T
+    top = lambda x, y, t, T, p: -p["a"] * p["h"] / p["k"] * (p["Tinf"] - T)
+    left = lambda x, y, t, T, p: 0.0 * T
+    params = (dict(a=alpha, q=q, k=k), None, dict(a=alpha, h=h, k=k, Tinf=Tinf), None)
+    BCs = O.BoundaryConditions(mesh, (bot, right, top, left), (O.Neumann,) * 4, parameters=params)
+    flux = lambda x, y, t, a, b, g, p: (-p["a"] * a, -p["a"] * b)
+    ic = np.full(tri.num_points, T0)
+    return O.FVMProblem(mesh, BCs, flux_function=flux, flux_parameters=dict(a=alpha),
+                        initial_condition=ic, final_time=2000.0)
+
+
+# ---- independent control-volume integral, test_functions.jl:1-34 and :601-657 ----------
+def get_control_volume(tri, i):
+    """Polygon of the control volume of node i, with the triangle each piece lies in."""
+    P = tri.points
+    p = P[i]
+    pieces = []  # (point_a, point_b, triangle (i,j,k))
+    # find a starting neighbour: boundary nodes start at the right boundary node
+    start = None
+    for (u, v), (s, e) in tri.boundary_edge_map.items():
+        if u == i:
+            start = v
+    if start is None:
+        start = next(v for (u, v) in tri.adjacent if u == i and tri.adjacent[(u, v)] >= 0)
+    j = start
+    first = True
+    while True:
+        k = tri.adjacent.get((i, j), -1)
+        if k < 0:
+            break
+        q, r = P[j], P[k]
+        c = (p + q + r) / 3
+        pieces.append(((p + q) / 2, c, (i, j, k)))
+        pieces.append((c, (p + r) / 2, (i, j, k)))
+        j = k
+        if j == start:
+            break
+    return pieces
+
+
+def _on_same_side(a, b, L):
+    if np.isclose(a[1], 0.0) and np.isclose(b[1], 0.0):
+        return 1
+    if np.isclose(a[0], L) and np.isclose(b[0], L):
+        return 2
+    if np.isclose(a[1], L) and np.isclose(b[1], L):
+        return 3
+    if np.isclose(a[0], 0.0) and np.isclose(b[0], 0.0):
+        return 4
+    return 0
+
+
+def get_dudt_val(prob, u, t, i, is_diff=True):
+    if i in prob.conditions.dirichlet_nodes:
+        return 0.0
+    mesh = prob.mesh
+    tri = mesh.triangulation
+    P = tri.points
+    p = P[i]
+    integ = 0.0
+    pieces = get_control_volume(tri, i)
+
+    def tri_abg(T):
+        _, t_idx = mesh.safe_get_triangle_props(T)
+        Ts = tuple(int(v) for v in tri.triangles[t_idx])
+        s = mesh.s[t_idx]
+        a = s[0] * u[Ts[0]] + s[1] * u[Ts[1]] + s[2] * u[Ts[2]]
+        b = s[3] * u[Ts[0]] + s[4] * u[Ts[1]] + s[5] * u[Ts[2]]
+        g = s[6] * u[Ts[0]] + s[7] * u[Ts[1]] + s[8] * u[Ts[2]]
+        return a, b, g
+
+    for (pa, pb, T) in pieces:
+        Lseg = np.linalg.norm(pa - pb)
+        nx, ny = (pb[1] - pa[1]) / Lseg, (pa[0] - pb[0]) / Lseg
+        a, b, g = tri_abg(T)
+        if is_diff:
+            integ += Lseg * ((-a / 9) * nx + (-b / 9) * ny)
+        else:
+            integ += Lseg * ((-80.0e-6 * a) * nx + (-80.0e-6 * b) * ny)
+    if not is_diff:
+        # boundary pieces p -> midpoint on either boundary edge at i (test_functions.jl:627-643)
+        for (uu, vv) in tri.boundary_edge_map:
+            if uu != i and vv != i:
+                continue
+            other = vv if uu == i else uu
+            m = (p + P[other]) / 2
+            k = tri.adjacent[(uu, vv)]
+            a, b, g = tri_abg((uu, vv, k))
+            mx, my = (p + m) / 2
+            side = _on_same_side(p, m, 1.0)
+            if side == 1:
+                q = -80.0e-6 * 10.0 / 237.0
+            elif side == 3:
+                q = -80.0e-6 * 25.0 / 237.0 * (10.0 - (a * mx + b * my + g))
+            else:
+                q = 0.0
+            integ += np.linalg.norm(p - m) * q
+    S = prob.source_function(p[0], p[1], t, u[i], prob.source_parameters)
+    return S - integ / mesh.cv_volumes[i]
+
+
+def test_dudt_val_diffusion():
+    """test/equations.jl:13-23 -> test_dudt_val (test_functions.jl:645-657)."""
+    prob = example_diffusion_problem()
+    u = prob.initial_condition
+    ref = np.array([get_dudt_val(prob, u, 0.0, i) for i in range(len(u))])
+    du = O.fvm_eqs(np.zeros_like(u), u, prob, 0.0)
+    assert isapprox(ref, du)
+    rng = np.random.default_rng(1)
+    u = 50 * rng.random(len(u))
+    ref = np.array([get_dudt_val(prob, u, 0.0, i) for i in range(len(u))])
+    du = O.fvm_eqs(np.zeros_like(u), u, prob, 0.0)
+    assert isapprox(ref, du, rtol=1e-12)
+
+
+def test_dudt_val_convection_and_corner():
+    """test/equations.jl:25-92: all-Neumann convection problem on 200x200, and the exact
+    corner-node hand calculation with (alpha,beta,gamma) == (0,0,10)."""
+    prob = example_heat_convection_problem(200)
+    mesh = prob.mesh
+    tri = mesh.triangulation
+    u = prob.initial_condition
+    t = 0.0
+    # (1,2,201) is a stored triangle (0-based (0,1,200)), equations.jl:42
+    T = (0, 1, 200)
+    assert T in mesh.triangle_props
+    t_idx = mesh.triangle_props[T]
+    assert O.get_shape_function_coefficients(mesh, t_idx, T, u) == (0.0, 0.0, 10.0)
+    x1, y1 = tri.points[1, 0], tri.points[200, 1]
+    poly = np.array([(0.0, 0.0), (x1 / 2, 0.0), (x1 / 3, y1 / 3), (0.0, y1 / 2)])
+    area = 0.5 * abs(np.dot(poly[:, 0], np.roll(poly[:, 1], -1)) - np.dot(poly[:, 1], np.roll(poly[:, 0], -1)))
+    assert math.isclose(mesh.cv_volumes[0], area, rel_tol=1e-12)
+    # hand flux balance at node 1 (equations.jl:57-80)
+    c1, c2, c3, c4 = poly
+    m1, m2, m3, m4 = (c1 + c2) / 2, (c2 + c3) / 2, (c3 + c4) / 2, (c4 + c1) / 2
+    l1, l4 = np.linalg.norm(c2 - c1), np.linalg.norm(c1 - c4)
+    n2 = np.array([(c3 - c2)[1], -(c3 - c2)[0]])
+    n3 = np.array([(c4 - c3)[1], -(c4 - c3)[0]])
+    a, b, g = 0.0, 0.0, 10.0
+    f1 = prob.conditions.functions[0](m1[0], m1[1], t, a * m1[0] + b * m1[1] + g) * l1
+    f2 = np.dot(prob.flux_function(m2[0], m2[1], 0.0, a, b, g, prob.flux_parameters), n2)
+    f3 = np.dot(prob.flux_function(m3[0], m3[1], 0.0, a, b, g, prob.flux_parameters), n3)
+    f4 = prob.conditions.functions[3](m4[0], m4[1], t, a * m4[0] + b * m4[1] + g) * l4
+    fl = -(1 / area) * (f1 + f2 + f3 + f4)
+    du = O.fvm_eqs(np.zeros_like(u), u, prob, t)
+    assert math.isclose(fl, du[0], rel_tol=1e-9)
+    assert math.isclose(fl, get_dudt_val(prob, u, t, 0, False), rel_tol=1e-9)
+    # whole-field check on a non-trivial u (sampled nodes keep the CPU suite short)
+    rng = np.random.default_rng(2)
+    u2 = 10 + rng.random(len(u))
+    du2 = O.fvm_eqs(np.zeros_like(u2), u2, prob, t)
+    nodes = np.r_[0:400, 39600:40000, rng.integers(0, 40000, 600), np.arange(0, 40000, 200), np.arange(199, 40000, 200)]
+    ref = np.array([get_dudt_val(prob, u2, t, int(i), False) for i in nodes])
+    assert isapprox(ref, du2[nodes], rtol=1e-10)
+    # vectorised oracle == loop oracle bitwise
+    assert np.array_equal(du2, O.fvm_eqs_vec(np.zeros_like(u2), u2, prob, t))
+
+
+def test_shape_function_identities():
+    """test/test_functions.jl:385-393 and test/geometry.jl:10-76."""
+    prob = example_diffusion_problem()
+    mesh = prob.mesh
+    P, Tr = mesh.triangulation.points, mesh.triangulation.triangles
+    rng = np.random.default_rng(3)
+    u = rng.random(len(P))
+    for t, (i, j, k) in enumerate(Tr.tolist()):
+        s = mesh.s[t]
+        M = np.array([[P[i, 0], P[i, 1], 1], [P[j, 0], P[j, 1], 1], [P[k, 0], P[k, 1], 1]])
+        abg = np.linalg.solve(M, u[[i, j, k]])
+        a, b, g = O.get_shape_function_coefficients(mesh, t, (i, j, k), u)
+        assert np.allclose([a, b, g], abg, atol=1e-9)
+        c = (P[i] + P[j] + P[k]) / 3
+        assert math.isclose(s[0] * c[0] + s[3] * c[1] + s[6] + s[1] * c[0] + s[4] * c[1] + s[7]
+                            + s[2] * c[0] + s[5] * c[1] + s[8], 1.0, rel_tol=1e-12)
+        assert mesh.delta[t] > 0
+    assert math.isclose(mesh.cv_volumes.sum(), 4.0, rel_tol=1e-13)
+    h = 2.0 / 24
+    assert math.isclose(mesh.cv_volumes[0], h * h / 6, rel_tol=1e-12)
+    assert math.isclose(mesh.cv_volumes[24], h * h / 3, rel_tol=1e-12)
+    assert math.isclose(mesh.cv_volumes[26], h * h, rel_tol=1e-12)
+
+
+def test_cv_edge_geometry_direct():
+    """test/test_functions.jl:404-436: cv-edge midpoints/normals/lengths vs direct formulas."""
+    prob = example_heat_convection_problem(12)
+    mesh = prob.mesh
+    P, Tr = mesh.triangulation.points, mesh.triangulation.triangles
+    for t, T in enumerate(Tr.tolist()):
+        p, q, r = P[T[0]], P[T[1]], P[T[2]]
+        c = (p + q + r) / 3
+        for e, (i, j) in enumerate(((T[0], T[1]), (T[1], T[2]), (T[2], T[0]))):
+            m = (P[i] + P[j]) / 2
+            x, y = (c + m) / 2
+            ex, ey = c - m
+            l = math.hypot(ex, ey)
+            got = mesh.get_cv_components(t, e)
+            assert np.allclose(got, (x, y, ey / l, -ex / l, l), rtol=1e-13, atol=1e-15)
+
+
+def test_single_triangle_sign_pattern():
+    """test/test_functions.jl:527-556."""
+    prob = example_diffusion_problem()
+    u = 50 * np.random.default_rng(4).random(len(prob.initial_condition))
+    mesh = prob.mesh
+    for t_idx in range(0, len(mesh.triangulation.triangles), 7):
+        T = tuple(int(v) for v in mesh.triangulation.triangles[t_idx])
+        a, b, g = O.get_shape_function_coefficients(mesh, t_idx, T, u)
+        q1, q2, q3 = (O.get_flux(prob, t_idx, a, b, g, 0.0, e) for e in range(3))
+        du = np.zeros_like(u)
+        O.fvm_eqs_single_triangle(du, u, prob, 0.0, t_idx)
+        assert math.isclose(du[T[0]], -(q1 - q3), abs_tol=1e-9)
+        assert math.isclose(du[T[1]], -(-q1 + q2), abs_tol=1e-9)
+        assert math.isclose(du[T[2]], -(-q2 + q3), abs_tol=1e-9)
+
+
+def test_eval_flux_function_exact():
+    """test/problem.jl:30-35."""
+    tri = O.triangulate_rectangle(0, 1, 0, 1, 3, 3, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: 0.0, O.Dirichlet)
+
+    def flux(x, y, t, a, b, g, p):
+        u = a * x + b * y + g
+        return (-a * u * p[0] + t, x + t - b * u * p[1])
+
+    prob = O.FVMProblem(mesh, BCs, flux_function=flux, flux_parameters=(-0.5, 1.3),
+                        initial_condition=np.zeros(9), final_time=1.0)
+    x, y, t, a, b, g = 0.5, -1.0, 2.3, 0.371, -5.37, 17.5
+    u = a * x + b * y + g
+    qx, qy = prob.eval_flux_function(x, y, t, a, b, g)
+    assert qx == -a * u * (-0.5) + t
+    assert qy == x + t - b * u * 1.3
+    # construct_flux_function identity q = -D (alpha, beta), test/problem.jl:152-160
+    D = lambda x, y, t, u, p: x + y + t + u + p
+    q = O.construct_flux_function(None, D, 0.7)
+    qx, qy = q(x, y, t, a, b, g, None)
+    Dv = D(x, y, t, u, 0.7)
+    assert (qx, qy) == (-Dv * a, -Dv * b)
+
+
+def test_conditions_merge():
+    """test/conditions.jl: section -> edge/node dictionaries, fidx offset nif, precedence."""
+    tri = O.triangulate_rectangle(0, 1, 0, 1, 5, 4, single_boundary=False)
+    mesh = O.FVMGeometry(tri)
+    f = lambda x, y, t, u, p: 0.0
+    BCs = O.BoundaryConditions(mesh, (f, f, f, f), (O.Neumann, O.Dirichlet, O.Dudt, O.Constrained))
+    ICs = O.InternalConditions((f,), dirichlet_nodes={6: 0}, dudt_nodes={7: 0})
+    c = O.Conditions(mesh, BCs, ICs)
+    assert c.neumann_edges == {(i, i + 1): 1 for i in range(4)}
+    assert set(c.dirichlet_nodes) == {6, 4, 9, 14, 19} and c.dirichlet_nodes[4] == 2 and c.dirichlet_nodes[6] == 0
+    assert c.dudt_nodes[7] == 0 and all(c.dudt_nodes[n] == 3 for n in (19, 18, 17, 16, 15))
+    assert c.constrained_edges == {(15, 10): 4, (10, 5): 4, (5, 0): 4}
+    assert len(c.functions) == 5
+    # node 19 is both Dirichlet (right) and Dudt (top): Dirichlet wins in the node pass
+    assert c.is_dirichlet_node(19) and c.is_dudt_node(19)
+
+
+def test_readme_interior_row_and_template_consistency():
+    """SURVEY 8c (ix),(x): interior row = D/h^2 [1,1,-4,1,1]; A u + b == fvm_eqs(u) away from
+    conditioned nodes; MET b = -1 / identity rows."""
+    tri = O.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet)  # templates pass t=u=nothing
+    ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
+    tpl = O.DiffusionEquation(mesh, BCs, diffusion_function=lambda x, y, p: 1 / 9, initial_condition=ic, final_time=0.5)
+    h = 2 / 49
+    row = tpl.A[51 + 50].toarray().ravel()
+    i = 101
+    assert math.isclose(row[i], -4 / 9 / h**2, rel_tol=1e-12)
+    for nb in (i - 1, i + 1, i - 50, i + 50):
+        assert math.isclose(row[nb], 1 / 9 / h**2, rel_tol=1e-12)
+    assert abs(row[i + 49]) < 1e-10 and abs(row[i - 49]) < 1e-10
+    prob = O.FVMProblem(mesh, BCs, diffusion_function=lambda x, y, t, u, p: 1 / 9, initial_condition=ic, final_time=0.5)
+    u = 50 * np.random.default_rng(5).random(len(ic))
+    du = O.fvm_eqs(np.zeros_like(u), u, prob, 0.0)
+    assert isapprox(tpl.A @ u + tpl.b, du, rtol=1e-12)
+    assert np.all(tpl.u0[list(tpl.conditions.dirichlet_nodes)] == 0.0)
+    met = O.MeanExitTimeProblem(mesh, BCs, diffusion_function=lambda x, y, p: 1 / 9)
+    dn = np.array(sorted(met.conditions.dirichlet_nodes))
+    assert np.all(met.b[dn] == 0) and np.all(np.delete(met.b, dn) == -1)
+    assert np.all(met.A.diagonal()[dn] == 1.0)
+
+
+def test_poisson_closed_form():
+    """docs/src/literate_wyos/poissons_equation.jl:92-116,159-162: rtol 1e-4 on 100x100."""
+    tri = O.triangulate_rectangle(0, 1, 0, 1, 100, 100, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet)
+    src = lambda x, y, p: -math.sin(math.pi * x) * math.sin(math.pi * y)
+    tpl = O.PoissonsEquation(mesh, BCs, source_function=src)
+    sol = O.solve_steady(tpl)
+    P = tri.points
+    exact = 1 / (2 * math.pi**2) * np.sin(math.pi * P[:, 0]) * np.sin(math.pi * P[:, 1])
+    assert isapprox(sol, exact, rtol=1e-4)
+
+
+def test_laplace_closed_form():
+    """docs/src/literate_wyos/laplaces_equation.jl:160-193: u = 5 log6(1+x), rtol 1e-3."""
+    tri = O.triangulate_rectangle(0, 5, 0, 5, 100, 100, single_boundary=False)
+    mesh = O.FVMGeometry(tri)
+    zero_f = lambda x, y, t, u, p: 0.0
+    five_f = lambda x, y, t, u, p: 5.0
+    BCs = O.BoundaryConditions(mesh, (zero_f, five_f, zero_f, zero_f), (O.Neumann, O.Dirichlet, O.Neumann, O.Dirichlet))
+    tpl = O.LaplacesEquation(mesh, BCs, diffusion_function=lambda x, y, p: (x + 1) * (y + 2))
+    sol = O.solve_steady(tpl)
+    exact = 5 * np.log(1 + tri.points[:, 0]) / math.log(6)
+    assert isapprox(sol, exact, rtol=1e-3)
+
+
+def test_tsit5_tableau_order_conditions_and_convergence():
+    """row sums = c, order conditions 1..4, 5th-order convergence."""
+    A, C = O.TSIT5_A, O.TSIT5_C
+    for s in range(1, 7):
+        assert math.isclose(sum(A[s]), C[s], abs_tol=1e-14)
+    b = np.array(A[6] + (0.0,))
+    c = np.array(C)
+    Am = np.zeros((7, 7))
+    for s in range(1, 7):
+        Am[s, :s] = A[s]
+    assert math.isclose(b.sum(), 1, abs_tol=1e-14)
+    assert math.isclose(b @ c, 1 / 2, abs_tol=1e-14)
+    assert math.isclose(b @ c**2, 1 / 3, abs_tol=1e-14)
+    assert math.isclose(b @ (Am @ c), 1 / 6, abs_tol=1e-14)
+    assert math.isclose(b @ c**3, 1 / 4, abs_tol=1e-14)
+    assert math.isclose(b @ (c * (Am @ c)), 1 / 8, abs_tol=1e-14)
+    assert math.isclose(b @ (Am @ c**2), 1 / 12, abs_tol=1e-14)
+    assert math.isclose(b @ (Am @ (Am @ c)), 1 / 24, abs_tol=1e-14)
+    assert math.isclose(b @ c**4, 1 / 5, abs_tol=1e-14)
+
+    def f(du, u, t):
+        du[...] = -u + np.sin(t)
+
+    exact = lambda t: 1.5 * math.exp(-t) + 0.5 * (math.sin(t) - math.cos(t))
+    errs = []
+    for n in (10, 20, 40):
+        u = O.tsit5_fixed(f, np.array([1.0]), 0.0, 1.0, 1.0 / n)
+        errs.append(abs(u[0] - exact(1.0)))
+    assert 4.5 < math.log2(errs[0] / errs[1]) < 6.5 and 4.5 < math.log2(errs[1] / errs[2]) < 6.5
+
+
+def test_system_equals_scalar():
+    """test/equations.jl:106-121: a 2-species system of identical diffusion problems
+    reproduces the scalar RHS in both species."""
+    prob = example_diffusion_problem()
+    mesh = prob.mesh
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: 0.0, O.Dirichlet)
+    ic = prob.initial_condition
+    q1 = lambda x, y, t, a, b, g, p: (-a[0] / 9, -b[0] / 9)
+    q2 = lambda x, y, t, a, b, g, p: (-a[1] / 9, -b[1] / 9)
+    p1 = O.FVMProblem(mesh, BCs, flux_function=q1, initial_condition=ic, final_time=0.5)
+    p2 = O.FVMProblem(mesh, BCs, flux_function=q2, initial_condition=ic, final_time=0.5)
+    sys_ = O.FVMSystem(p1, p2)
+    rng = np.random.default_rng(6)
+    u = 50 * rng.random(len(ic))
+    U = np.stack([u, u], axis=1)
+    dU = O.fvm_eqs(np.zeros_like(U), U, sys_, 0.0)
+    du = O.fvm_eqs(np.zeros_like(u), u, prob, 0.0)
+    assert isapprox(dU[:, 0], du, rtol=1e-13) and isapprox(dU[:, 1], du, rtol=1e-13)
+    assert np.array_equal(dU, O.fvm_eqs_vec(np.zeros_like(U), U, sys_, 0.0))
+
+
+def test_jacobian_sparsity_counts():
+    """solve.jl:56-77: nnz = N + 2E with E = N + T - 1 on a lattice."""
+    tri = O.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True)
+    r, c = O.jacobian_sparsity(tri)
+    assert len(r) == 17102
