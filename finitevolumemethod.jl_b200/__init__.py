@@ -1,0 +1,10 @@
+"""finitevolumemethod.jl_b200 — host-side mirror of FiniteVolumeMethod.jl's public API for the
+B200-native `fvm_eqs!` / linear-template hot path (libfvmcuda.so).  Import it as `fvm_b200`
+(see fvm_b200.py at the repository root; the directory name is not a valid Python identifier)."""
+from ._lib import FVMCudaError, UnsupportedClosureError, LIB_PATH, exported_symbols  # noqa: F401
+from .conditions import (BoundaryConditions, Conditions, Constrained, Dirichlet, Dudt,  # noqa: F401
+                         InternalConditions, Neumann)
+from .functors import *  # noqa: F401,F403
+from .mesh import Triangulation, triangulate_rectangle  # noqa: F401
+from .problem import (CudaParameters, Engine, FVMGeometry, FVMProblem, FVMSystem,  # noqa: F401
+                      SteadyFVMProblem, fvm_eqs, get_cuda_parameters, update_dirichlet_nodes)

@@ -1,0 +1,206 @@
+// Device-side building blocks shared by the RHS, geometry and assembly kernels.
+#pragma once
+#include "fvm_internal.h"
+
+// ---- arithmetic policy: EXACT = every operation individually rounded (no FMA contraction),
+// so the geometry is bit-identical to the reference's Julia arithmetic; FAST lets nvcc contract.
+template <bool EXACT>
+struct Ar {
+    static __device__ __forceinline__ double mul(double a, double b) {
+        if constexpr (EXACT) return __dmul_rn(a, b);
+        else return a * b;
+    }
+    static __device__ __forceinline__ double add(double a, double b) {
+        if constexpr (EXACT) return __dadd_rn(a, b);
+        else return a + b;
+    }
+    static __device__ __forceinline__ double sub(double a, double b) {
+        if constexpr (EXACT) return __dsub_rn(a, b);
+        else return a - b;
+    }
+    static __device__ __forceinline__ double div(double a, double b) {
+        if constexpr (EXACT) return __ddiv_rn(a, b);
+        else return a / b;
+    }
+};
+
+struct TriGeom {
+    double s[9];          // shape-function coefficients s1..s9
+    double mx[3], my[3];  // cv-edge midpoints
+    double ex[3], ey[3];  // centroid - edge midpoint; length-scaled normal is (ey, -ex)
+};
+
+// /root/reference/src/geometry.jl:107-161, same operation order.
+template <bool EXACT>
+__device__ __forceinline__ void tri_geometry(double px, double py, double qx, double qy, double rx, double ry,
+                                             TriGeom& G, double* S /* 3 sub-cv areas or nullptr */) {
+    using A = Ar<EXACT>;
+    const double cx = A::div(A::add(A::add(px, qx), rx), 3.0), cy = A::div(A::add(A::add(py, qy), ry), 3.0);
+    const double m1x = A::mul(A::add(px, qx), 0.5), m1y = A::mul(A::add(py, qy), 0.5);
+    const double m2x = A::mul(A::add(qx, rx), 0.5), m2y = A::mul(A::add(qy, ry), 0.5);
+    const double m3x = A::mul(A::add(rx, px), 0.5), m3y = A::mul(A::add(ry, py), 0.5);
+    if (S) {
+        const double pcx = A::sub(cx, px), pcy = A::sub(cy, py);
+        const double qcx = A::sub(cx, qx), qcy = A::sub(cy, qy);
+        const double rcx = A::sub(cx, rx), rcy = A::sub(cy, ry);
+        const double m13x = A::sub(m1x, m3x), m13y = A::sub(m1y, m3y);
+        const double m21x = A::sub(m2x, m1x), m21y = A::sub(m2y, m1y);
+        const double m32x = A::sub(m3x, m2x), m32y = A::sub(m3y, m2y);
+        S[0] = 0.5 * fabs(A::sub(A::mul(pcx, m13y), A::mul(pcy, m13x)));
+        S[1] = 0.5 * fabs(A::sub(A::mul(qcx, m21y), A::mul(qcy, m21x)));
+        S[2] = 0.5 * fabs(A::sub(A::mul(rcx, m32y), A::mul(rcy, m32x)));
+    }
+    // Delta = qx*ry - qy*rx - px*ry + rx*py + px*qy - qx*py   (left to right)
+    double D = A::sub(A::mul(qx, ry), A::mul(qy, rx));
+    D = A::sub(D, A::mul(px, ry));
+    D = A::add(D, A::mul(rx, py));
+    D = A::add(D, A::mul(px, qy));
+    D = A::sub(D, A::mul(qx, py));
+    if constexpr (EXACT) {
+        G.s[0] = A::div(A::sub(qy, ry), D);
+        G.s[1] = A::div(A::sub(ry, py), D);
+        G.s[2] = A::div(A::sub(py, qy), D);
+        G.s[3] = A::div(A::sub(rx, qx), D);
+        G.s[4] = A::div(A::sub(px, rx), D);
+        G.s[5] = A::div(A::sub(qx, px), D);
+        G.s[6] = A::div(A::sub(A::mul(qx, ry), A::mul(rx, qy)), D);
+        G.s[7] = A::div(A::sub(A::mul(rx, py), A::mul(px, ry)), D);
+        G.s[8] = A::div(A::sub(A::mul(px, qy), A::mul(qx, py)), D);
+    } else {
+        const double iD = 1.0 / D;
+        G.s[0] = (qy - ry) * iD;
+        G.s[1] = (ry - py) * iD;
+        G.s[2] = (py - qy) * iD;
+        G.s[3] = (rx - qx) * iD;
+        G.s[4] = (px - rx) * iD;
+        G.s[5] = (qx - px) * iD;
+        G.s[6] = (qx * ry - rx * qy) * iD;
+        G.s[7] = (rx * py - px * ry) * iD;
+        G.s[8] = (px * qy - qx * py) * iD;
+    }
+    G.mx[0] = A::mul(A::add(m1x, cx), 0.5);
+    G.my[0] = A::mul(A::add(m1y, cy), 0.5);
+    G.mx[1] = A::mul(A::add(m2x, cx), 0.5);
+    G.my[1] = A::mul(A::add(m2y, cy), 0.5);
+    G.mx[2] = A::mul(A::add(m3x, cx), 0.5);
+    G.my[2] = A::mul(A::add(m3y, cy), 0.5);
+    G.ex[0] = A::sub(cx, m1x);
+    G.ey[0] = A::sub(cy, m1y);
+    G.ex[1] = A::sub(cx, m2x);
+    G.ey[1] = A::sub(cy, m2y);
+    G.ex[2] = A::sub(cx, m3x);
+    G.ey[2] = A::sub(cy, m3y);
+}
+
+// ---- flux registry: q(x, y, t, alpha, beta, gamma, p), src/problem.jl:113-116, 425-440 ----
+template <int MODEL, int NEQ>
+__device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double y, double t, const double* a,
+                                          const double* b, const double* g, double dtab, double* qx, double* qy) {
+    if constexpr (MODEL == FVM_FLUX_DIFF_CONST) {
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) {
+            qx[v] = -fp.p[v] * a[v];
+            qy[v] = -fp.p[v] * b[v];
+        }
+    } else if constexpr (MODEL == FVM_FLUX_DIFF_TABLE) {
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) {
+            qx[v] = -dtab * a[v];
+            qy[v] = -dtab * b[v];
+        }
+    } else if constexpr (MODEL == FVM_FLUX_DIFF_POWER) {
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) {
+            const double u = a[v] * x + b[v] * y + g[v];
+            const double D0 = fp.p[3 * v], mm = fp.p[3 * v + 1];
+            const double base = fp.p[3 * v + 2] != 0.0 ? fabs(u) : u;
+            double D;
+            if (mm == 1.0) D = D0;
+            else if (mm == 2.0) D = D0 * base;
+            else if (mm == 3.0) D = D0 * base * base;
+            else D = D0 * pow(base, mm - 1.0);
+            qx[v] = -D * a[v];
+            qy[v] = -D * b[v];
+        }
+    } else if constexpr (MODEL == FVM_FLUX_ADVDIFF) {
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) {
+            const double u = a[v] * x + b[v] * y + g[v];
+            const double D = fp.p[3 * v];
+            qx[v] = fp.p[3 * v + 1] * u - D * a[v];
+            qy[v] = fp.p[3 * v + 2] * u - D * b[v];
+        }
+    } else if constexpr (MODEL == FVM_FLUX_KELLER_SEGEL) {
+        // src/FiniteVolumeMethod.jl:98-110 : q_u = chi(u) grad v - grad u ; q_v = -D grad v
+        static_assert(NEQ == 2 || MODEL != FVM_FLUX_KELLER_SEGEL, "Keller-Segel is a 2-species model");
+        const double u = a[0] * x + b[0] * y + g[0];
+        const double chi = fp.p[0] * u / (1.0 + u * u);
+        qx[0] = chi * a[1] - a[0];
+        qy[0] = chi * b[1] - b[0];
+        qx[1] = -fp.p[1] * a[1];
+        qy[1] = -fp.p[1] * b[1];
+    }
+}
+
+template <int MODEL>
+struct FluxTraits {
+    // does the flux read (x, y, gamma)?  If not, only s1..s6 and the scaled normals are streamed.
+    static constexpr bool full = (MODEL == FVM_FLUX_DIFF_POWER || MODEL == FVM_FLUX_ADVDIFF || MODEL == FVM_FLUX_KELLER_SEGEL);
+    static constexpr bool table = (MODEL == FVM_FLUX_DIFF_TABLE);
+};
+
+// ---- sources S(x, y, t, u, p), src/problem.jl:10-13, 342-345 -------------------------------
+template <int NEQ>
+__device__ __forceinline__ double source_eval(const SourceParams& sp, int v, const double* u, const double* tab) {
+    switch (sp.model) {
+        case FVM_SRC_LINEAR: return sp.p[2 * v] * u[v] + sp.p[2 * v + 1];
+        case FVM_SRC_LOGISTIC: return sp.p[v] * u[v] * (1.0 - u[v]);
+        case FVM_SRC_TABLE: return tab[v];
+        case FVM_SRC_GRAY_SCOTT:
+            if constexpr (NEQ >= 2) return v == 0 ? sp.p[0] * (1.0 - u[0]) - u[0] * (u[1] * u[1]) : -sp.p[1] * u[1] + u[0] * (u[1] * u[1]);
+            return 0.0;
+        case FVM_SRC_BRUSSELATOR:
+            if constexpr (NEQ >= 2) return v == 0 ? (u[0] * u[0]) * u[1] - 2.0 * u[0] : -(u[0] * u[0]) * u[1] + u[0];
+            return 0.0;
+        case FVM_SRC_KELLER_SEGEL:
+            if constexpr (NEQ >= 2) return v == 0 ? u[0] * (1.0 - u[0]) : u[0] - sp.p[0] * u[1];
+            return 0.0;
+        default: return 0.0;  // zero(eltype(u)), src/problem.jl:123
+    }
+}
+
+// ---- condition functions a(x, y, t, u, p), src/conditions.jl:16-20 -------------------------
+__device__ __forceinline__ double cond_eval(const CondFn& c, double x, double y, double t, double u) {
+    switch (c.id) {
+        case FVM_COND_AFFINE_U: return c.p[0] + c.p[1] * u;
+        case FVM_COND_EXP_SAT: return c.p[0] * (1.0 - exp(-t / c.p[1]));
+        case FVM_COND_LINEAR_XY: return c.p[0] + c.p[1] * x + c.p[2] * y;
+        default: return c.p[0];
+    }
+}
+
+// ---- node pass, src/equations/source_contributions.jl:33-68 --------------------------------
+template <int NEQ>
+__device__ __forceinline__ void node_finish(const DevMesh& m, const SourceParams& sp, double t, int g, const double* acc,
+                                            const double* uv, double* __restrict__ du) {
+    const double V = m.vol[g];
+    double tab[NEQ];
+    if (sp.model == FVM_SRC_TABLE) {
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) tab[v] = m.src_tab[(size_t)g * NEQ + v];
+    }
+#pragma unroll
+    for (int v = 0; v < NEQ; ++v) {
+        const uint8_t kind = m.kind[(size_t)v * m.n_nodes + g];
+        double out;
+        if (kind == FVM_NODE_FREE) {
+            out = acc[v] / V + source_eval<NEQ>(sp, v, uv, tab);
+        } else if (kind == FVM_NODE_DUDT) {
+            const CondFn c = m.cond[v * FVM_MAX_COND_FN + m.fidx[(size_t)v * m.n_nodes + g]];
+            out = cond_eval(c, m.xy[2 * (size_t)g], m.xy[2 * (size_t)g + 1], t, uv[v]);
+        } else {
+            out = 0.0;  // Dirichlet node, or a point that is not a vertex
+        }
+        du[(size_t)g * NEQ + v] = out;
+    }
+}

@@ -1,0 +1,187 @@
+// Internal context of libfvmcuda.so.  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/fvmcuda.h"
+
+#define FVM_MAX_NEQ 4
+#define FVM_MAX_PARAMS 16
+#define FVM_MAX_COND_FN 64
+#define FVM_NGEO 21  // s1..s9, 3 cv-edge midpoints (x,y), 3 length-scaled normals (x,y)
+
+struct CondFn {
+    int32_t id;
+    double p[4];
+};
+
+// Device-side view of everything the kernels need; passed by value (kernel parameter space).
+struct DevMesh {
+    int32_t neq;
+    int32_t n_nodes;       // all points
+    int32_t n_vertices;    // points that are triangle vertices; native ids [0, n_vertices)
+    int32_t n_tris;
+    int32_t n_tiles;
+    int32_t tile_tris;     // TT
+    int64_t tpad;          // n_tiles * TT : stride between geometry components
+    // per triangle (native order, padded to tpad)
+    const ushort4* tri_loc;  // 3 tile-local vertex ids (+ spare)
+    const double* geo;       // [FVM_NGEO][tpad]
+    const double* dtab;      // [3][tpad] tabulated D at cv-edge midpoints (or null)
+    // per tile
+    const int32_t* tile_node0;   // first own node (native id)
+    const int32_t* tile_nint;    // interior nodes
+    const int32_t* tile_nown;    // interior + owned interface nodes
+    const int32_t* tile_nloc;    // own + external interface nodes
+    const int32_t* tile_ext0;    // offset into ext_ids
+    const int32_t* tile_loc0;    // offset into inc_ptr (per local node, +1 sentinel per tile)
+    const int32_t* tile_pp0;     // offset into ppos (per interface local)
+    const int32_t* ext_ids;      // native ids of external interface nodes
+    const uint16_t* inc_ptr;     // per local node offset into the tile's incidence list
+    const uint16_t* inc;         // [n_tiles][3*TT] entries (local_tri << 2 | slot)
+    const int32_t* ppos;         // partial-buffer slot of each interface local
+    // per node (native order)
+    const double* xy;            // interleaved
+    const double* vol;           // control-volume areas
+    const uint8_t* kind;         // [neq][n_nodes]
+    const int32_t* fidx;         // [neq][n_nodes]
+    const double* src_tab;       // [n_nodes][neq] or null
+    // interface nodes
+    int32_t n_ifc;
+    const int32_t* ifc_node;     // native id
+    const int32_t* ifc_pptr;     // [n_ifc+1] offsets into partial (units of neq doubles)
+    double* partial;             // [n_partial][neq]
+    int64_t n_partial;
+    // condition function table
+    const CondFn* cond;          // [neq][FVM_MAX_COND_FN]
+};
+
+struct BndEdge {  // one live boundary edge (native ids); tiny count, AoS is fine
+    int32_t v[3];      // stored vertex triple of the adjacent triangle
+    int32_t pi, pj;    // positions of i and j inside v
+    int32_t slot_i, slot_j;  // partial-buffer slots
+    int32_t orig;      // caller's edge index
+    double px, py, qx, qy;
+    uint8_t kind[FVM_MAX_NEQ];
+    int32_t fidx[FVM_MAX_NEQ];
+};
+
+struct FluxParams {
+    int32_t model;
+    int32_t nparams;
+    double p[FVM_MAX_PARAMS];
+};
+
+struct SourceParams {
+    int32_t model;
+    int32_t nparams;
+    double p[FVM_MAX_PARAMS];
+};
+
+struct Csr {
+    int64_t nnz = 0;
+    int32_t n = 0;
+    int32_t* rowptr = nullptr;  // native numbering
+    int32_t* col = nullptr;
+    double* val = nullptr;
+    double* b = nullptr;
+    double* rowscale = nullptr;  // -V (free rows) / 1 (identity rows), for the symmetrised PCG
+    bool assembled = false;
+    int32_t template_id = -1;
+};
+
+struct fvm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool finalized = false;
+    int32_t neq = 1;
+    int32_t h_index_base = 0;
+    void* graph_exec = nullptr;
+    int32_t* d_tri_native = nullptr;  // [T][3] native node ids per native triangle
+    int64_t N = 0, T = 0, Eb = 0;
+    int32_t geometry_mode = 0;
+    // host copies of the caller's mesh (caller order, 0-based)
+    std::vector<double> h_xy;
+    std::vector<int32_t> h_tri;
+    std::vector<int32_t> h_bedge;
+    std::vector<uint8_t> h_ekind[FVM_MAX_NEQ];
+    std::vector<int32_t> h_efidx[FVM_MAX_NEQ];
+    std::vector<uint8_t> h_nkind[FVM_MAX_NEQ];
+    std::vector<int32_t> h_nfidx[FVM_MAX_NEQ];
+    std::vector<double> h_dtab, h_dbnd, h_srctab;
+    std::vector<CondFn> h_cond;  // [neq][FVM_MAX_COND_FN]
+    FluxParams flux{};
+    SourceParams source{};
+    // permutations
+    std::vector<int32_t> node_new_of_old, node_old_of_new, tri_old_of_new;
+    int32_t* d_node_old_of_new = nullptr;
+    int32_t* d_node_new_of_old = nullptr;
+    // device mesh
+    DevMesh dm{};
+    std::vector<void*> allocs;  // every cudaMalloc, freed in destroy
+    BndEdge* d_bnd = nullptr;
+    int32_t n_bnd_live = 0;
+    double* d_dbnd = nullptr;  // [n_bnd_live][2] tabulated D at the quarter points
+    int32_t n_dir = 0;         // Dirichlet (node,species) pairs for the callback kernel
+    int32_t* d_dir_nodes = nullptr;
+    int32_t smem_rhs = 0;
+    std::map<const void*, int32_t> smem_configured;  // kernel -> opted-in dynamic smem bytes
+    int32_t max_nloc = 0;
+    // scratch state vectors (native order), lazily sized
+    double *d_u = nullptr, *d_du = nullptr, *d_io = nullptr;
+    // linear path
+    Csr csr;
+    double* d_work[12] = {nullptr};
+    double* d_red = nullptr;  // reduction scratch
+    int64_t stats[16] = {0};
+    // sharding
+    void* nccl_comm = nullptr;
+    int32_t rank = 0, nranks = 1;
+};
+
+// ---- helpers -----------------------------------------------------------------
+int32_t fvm_fail(fvm_ctx* h, int32_t code, const std::string& msg);
+#define FVM_CUDA(h, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t e__ = (call);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fvm_fail((h), FVM_ERR_CUDA,                                                    \
+                            std::string(#call) + ": " + cudaGetErrorString(e__));                \
+    } while (0)
+#define FVM_REQUIRE(h, cond, msg)                                 \
+    do {                                                          \
+        if (!(cond)) return fvm_fail((h), FVM_ERR_ARG, (msg));    \
+    } while (0)
+
+template <class Tp>
+int32_t fvm_dev_alloc(fvm_ctx* h, Tp** p, size_t count) {
+    void* q = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(Tp);
+    FVM_CUDA(h, cudaMalloc(&q, bytes));
+    h->allocs.push_back(q);
+    *p = (Tp*)q;
+    return FVM_OK;
+}
+template <class Tp>
+int32_t fvm_dev_upload(fvm_ctx* h, Tp** p, const std::vector<Tp>& v) {
+    int32_t rc = fvm_dev_alloc(h, p, v.size());
+    if (rc) return rc;
+    if (!v.empty())
+        FVM_CUDA(h, cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice, h->stream));
+    return FVM_OK;
+}
+
+// implemented in fvm_rhs.cu
+int32_t fvm_launch_geometry(fvm_ctx* h, const int32_t* d_tri_native /*[T][3] native node ids*/);
+int32_t fvm_launch_volumes(fvm_ctx* h);
+int32_t fvm_launch_rhs(fvm_ctx* h, double t, const double* u, double* du);
+int32_t fvm_launch_dirichlet(fvm_ctx* h, double t, double* u);
+int32_t fvm_launch_permute(fvm_ctx* h, const double* src, double* dst, bool to_native);
+int32_t fvm_export_geometry(fvm_ctx* h, double* s9, double* mid6, double* nrm6, double* len3);  // device, native tri order
+int32_t fvm_ensure_state(fvm_ctx* h);
+void fvm_shard_release(fvm_ctx* h);

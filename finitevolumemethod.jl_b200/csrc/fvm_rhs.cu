@@ -1,0 +1,596 @@
+// libfvmcuda: the semi-discrete right-hand side  du = fvm_eqs!(du, u, p, t)
+// (/root/reference/src/equations/main_equations.jl:38-44) as three kernels:
+//
+//   rhs_tile_kernel      one CTA per tile of TT Hilbert-sorted triangles: stages the tile's node
+//                        values in shared memory, streams the triangle geometry SoA once with
+//                        coalesced loads, evaluates the three control-volume-edge fluxes per
+//                        triangle (triangle_contributions.jl:28-35), then gathers them per node in
+//                        a fixed order from shared memory.  Interior nodes are finished in place
+//                        (node pass, source_contributions.jl:33-68) and `du` is written once;
+//                        interface nodes emit one partial sum per tile.
+//   rhs_boundary_kernel  live boundary edges (boundary_edge_contributions.jl:2-86) -> partials.
+//   rhs_interface_kernel sums the partials of interface/boundary nodes in slot order, node pass.
+//
+// No atomics anywhere: every output word has exactly one writer and a fixed summation order.
+#include "fvm_device.cuh"
+
+#define RHS_BLOCK 256
+#define MODEL_VOLUME 100
+
+// ------------------------------------------------------------------------------------------
+template <int MODEL, int NEQ, int GEOM>
+__global__ void __launch_bounds__(RHS_BLOCK)
+    rhs_tile_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t,
+                    const double* __restrict__ u, double* __restrict__ du, const int smem_nloc) {
+    extern __shared__ double smem[];
+    constexpr bool VOL = (MODEL == MODEL_VOLUME);
+    constexpr bool NEED_XY = VOL || GEOM == 1;
+    const int TT = m.tile_tris;
+    double* u_s = smem;                                            // [smem_nloc][NEQ]
+    double* xy_s = u_s + (VOL ? 0 : (size_t)smem_nloc * NEQ);      // [smem_nloc][2]
+    double* c_s = xy_s + (NEED_XY ? 2 * (size_t)smem_nloc : 0);    // [3][TT][NEQ]
+
+    const int tile = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int node0 = m.tile_node0[tile];
+    const int nint = m.tile_nint[tile];
+    const int nown = m.tile_nown[tile];
+    const int nloc = m.tile_nloc[tile];
+    const int ext0 = m.tile_ext0[tile];
+    const int64_t t0 = (int64_t)tile * TT;
+    const int ntri = (int)min((int64_t)TT, (int64_t)m.n_tris - t0);
+
+    // ---- stage node data: own range is contiguous, external interface nodes are gathered ----
+    if constexpr (!VOL) {
+        for (int idx = tid; idx < nown * NEQ; idx += RHS_BLOCK) u_s[idx] = u[(size_t)node0 * NEQ + idx];
+        for (int k = tid; k < nloc - nown; k += RHS_BLOCK) {
+            const int g = m.ext_ids[ext0 + k];
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) u_s[(nown + k) * NEQ + v] = u[(size_t)g * NEQ + v];
+        }
+    }
+    if constexpr (NEED_XY) {
+        for (int idx = tid; idx < nown * 2; idx += RHS_BLOCK) xy_s[idx] = m.xy[(size_t)node0 * 2 + idx];
+        for (int k = tid; k < nloc - nown; k += RHS_BLOCK) {
+            const int g = m.ext_ids[ext0 + k];
+            xy_s[(nown + k) * 2] = m.xy[2 * (size_t)g];
+            xy_s[(nown + k) * 2 + 1] = m.xy[2 * (size_t)g + 1];
+        }
+    }
+    __syncthreads();
+
+    // ---- triangle pass ------------------------------------------------------------------------
+    for (int lt = tid; lt < ntri; lt += RHS_BLOCK) {
+        const int64_t gt = t0 + lt;
+        const ushort4 vv = m.tri_loc[gt];
+        if constexpr (VOL) {
+            TriGeom G;
+            double S[3];
+            tri_geometry<true>(xy_s[2 * vv.x], xy_s[2 * vv.x + 1], xy_s[2 * vv.y], xy_s[2 * vv.y + 1], xy_s[2 * vv.z],
+                               xy_s[2 * vv.z + 1], G, S);
+            c_s[0 * TT + lt] = S[0];
+            c_s[1 * TT + lt] = S[1];
+            c_s[2 * TT + lt] = S[2];
+        } else {
+            constexpr bool FULL = FluxTraits<MODEL>::full;
+            double s[9], mx[3], my[3], nlx[3], nly[3], dt3[3] = {0, 0, 0};
+            if constexpr (GEOM == 0) {
+                const double* __restrict__ geo = m.geo + gt;
+                const int64_t st = m.tpad;
+#pragma unroll
+                for (int c = 0; c < (FULL ? 9 : 6); ++c) s[c] = __ldg(geo + c * st);
+                if constexpr (FULL) {
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        mx[e] = __ldg(geo + (9 + 2 * e) * st);
+                        my[e] = __ldg(geo + (10 + 2 * e) * st);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    nlx[e] = __ldg(geo + (15 + 2 * e) * st);
+                    nly[e] = __ldg(geo + (16 + 2 * e) * st);
+                }
+            } else {
+                TriGeom G;
+                tri_geometry<false>(xy_s[2 * vv.x], xy_s[2 * vv.x + 1], xy_s[2 * vv.y], xy_s[2 * vv.y + 1],
+                                    xy_s[2 * vv.z], xy_s[2 * vv.z + 1], G, nullptr);
+#pragma unroll
+                for (int c = 0; c < 9; ++c) s[c] = G.s[c];
+#pragma unroll
+                for (int e = 0; e < 3; ++e) {
+                    mx[e] = G.mx[e];
+                    my[e] = G.my[e];
+                    nlx[e] = G.ey[e];
+                    nly[e] = -G.ex[e];
+                }
+            }
+            if constexpr (FluxTraits<MODEL>::table) {
+#pragma unroll
+                for (int e = 0; e < 3; ++e) dt3[e] = __ldg(m.dtab + e * m.tpad + gt);
+            }
+            // shape-function coefficients, shape_functions.jl:2-19
+            double a[NEQ], b[NEQ], g[NEQ];
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) {
+                const double ui = u_s[vv.x * NEQ + v], uj = u_s[vv.y * NEQ + v], uk = u_s[vv.z * NEQ + v];
+                a[v] = s[0] * ui + s[1] * uj + s[2] * uk;
+                b[v] = s[3] * ui + s[4] * uj + s[5] * uk;
+                if constexpr (FULL) g[v] = s[6] * ui + s[7] * uj + s[8] * uk;
+                else g[v] = 0.0;
+            }
+            double Q[3][NEQ];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                double qx[NEQ], qy[NEQ];
+                flux_eval<MODEL, NEQ>(fp, FULL ? mx[e] : 0.0, FULL ? my[e] : 0.0, t, a, b, g, dt3[e], qx, qy);
+#pragma unroll
+                for (int v = 0; v < NEQ; ++v) Q[e][v] = qx[v] * nlx[e] + qy[v] * nly[e];
+            }
+            // vertex contributions, triangle_contributions.jl:10-25
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) {
+                c_s[(0 * TT + lt) * NEQ + v] = Q[2][v] - Q[0][v];
+                c_s[(1 * TT + lt) * NEQ + v] = Q[0][v] - Q[1][v];
+                c_s[(2 * TT + lt) * NEQ + v] = Q[1][v] - Q[2][v];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- per-node gather in ascending triangle order, then node pass --------------------------
+    const uint16_t* __restrict__ iptr = m.inc_ptr + m.tile_loc0[tile];
+    const uint16_t* __restrict__ inc = m.inc + (size_t)3 * TT * tile;
+    const int pp0 = m.tile_pp0[tile];
+    for (int l = tid; l < nloc; l += RHS_BLOCK) {
+        const int beg = iptr[l], end = iptr[l + 1];
+        double acc[NEQ];
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) acc[v] = 0.0;
+        for (int e = beg; e < end; ++e) {
+            const int code = inc[e];
+            const int off = ((code & 3) * TT + (code >> 2)) * NEQ;
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) acc[v] += c_s[off + v];
+        }
+        if (l < nint) {
+            if constexpr (VOL) du[node0 + l] = acc[0];
+            else node_finish<NEQ>(m, sp, t, node0 + l, acc, u_s + l * NEQ, du);
+        } else {
+            const size_t p = (size_t)m.ppos[pp0 + (l - nint)] * NEQ;
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) m.partial[p + v] = acc[v];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int NEQ, bool VOL>
+__global__ void __launch_bounds__(256)
+    rhs_interface_kernel(const DevMesh m, const SourceParams sp, const double t, const double* __restrict__ u,
+                         double* __restrict__ du) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < m.n_ifc) {
+        const int g = m.ifc_node[k];
+        const int beg = m.ifc_pptr[k], end = m.ifc_pptr[k + 1];
+        double acc[NEQ];
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) acc[v] = 0.0;
+        for (int p = beg; p < end; ++p) {
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) acc[v] += m.partial[(size_t)p * NEQ + v];
+        }
+        if constexpr (VOL) {
+            du[g] = acc[0];
+        } else {
+            double uv[NEQ];
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) uv[v] = u[(size_t)g * NEQ + v];
+            node_finish<NEQ>(m, sp, t, g, acc, uv, du);
+        }
+    } else {
+        // points that are not vertices of any triangle: du = 0 (source_contributions.jl:36-37)
+        const int g = m.n_vertices + (k - m.n_ifc);
+        if (g < m.n_nodes) {
+            if constexpr (VOL) du[g] = 0.0;
+            else {
+#pragma unroll
+                for (int v = 0; v < NEQ; ++v) du[(size_t)g * NEQ + v] = 0.0;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int NEQ>
+__device__ __forceinline__ void flux_dispatch(const FluxParams& fp, double x, double y, double t, const double* a,
+                                              const double* b, const double* g, double dtab, double* qx, double* qy) {
+    switch (fp.model) {
+        case FVM_FLUX_DIFF_TABLE: flux_eval<FVM_FLUX_DIFF_TABLE, NEQ>(fp, x, y, t, a, b, g, dtab, qx, qy); break;
+        case FVM_FLUX_DIFF_POWER: flux_eval<FVM_FLUX_DIFF_POWER, NEQ>(fp, x, y, t, a, b, g, dtab, qx, qy); break;
+        case FVM_FLUX_ADVDIFF: flux_eval<FVM_FLUX_ADVDIFF, NEQ>(fp, x, y, t, a, b, g, dtab, qx, qy); break;
+        case FVM_FLUX_KELLER_SEGEL:
+            if constexpr (NEQ == 2) flux_eval<FVM_FLUX_KELLER_SEGEL, NEQ>(fp, x, y, t, a, b, g, dtab, qx, qy);
+            break;
+        default: flux_eval<FVM_FLUX_DIFF_CONST, NEQ>(fp, x, y, t, a, b, g, dtab, qx, qy); break;
+    }
+}
+
+// boundary_edge_contributions.jl:41-86 and control_volumes.jl:41-56
+template <int NEQ>
+__global__ void __launch_bounds__(128)
+    rhs_boundary_kernel(const DevMesh m, const FluxParams fp, const double t, const BndEdge* __restrict__ edges,
+                        const double* __restrict__ dbnd, const int n_edges, const double* __restrict__ u) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_edges) return;
+    const BndEdge E = edges[k];
+    TriGeom G;
+    tri_geometry<true>(m.xy[2 * (size_t)E.v[0]], m.xy[2 * (size_t)E.v[0] + 1], m.xy[2 * (size_t)E.v[1]],
+                       m.xy[2 * (size_t)E.v[1] + 1], m.xy[2 * (size_t)E.v[2]], m.xy[2 * (size_t)E.v[2] + 1], G, nullptr);
+    double a[NEQ], b[NEQ], g[NEQ];
+#pragma unroll
+    for (int v = 0; v < NEQ; ++v) {
+        const double ui = u[(size_t)E.v[0] * NEQ + v], uj = u[(size_t)E.v[1] * NEQ + v], uk = u[(size_t)E.v[2] * NEQ + v];
+        a[v] = G.s[0] * ui + G.s[1] * uj + G.s[2] * uk;
+        b[v] = G.s[3] * ui + G.s[4] * uj + G.s[5] * uk;
+        g[v] = G.s[6] * ui + G.s[7] * uj + G.s[8] * uk;
+    }
+    const double dx = E.qx - E.px, dy = E.qy - E.py;
+    const double lij = sqrt(dx * dx + dy * dy);
+    const double nx = dy / lij, ny = -dx / lij;
+    const double mijx = (E.px + E.qx) / 2, mijy = (E.py + E.qy) / 2;
+    const double ptx[2] = {(E.px + mijx) / 2, (E.qx + mijx) / 2};
+    const double pty[2] = {(E.py + mijy) / 2, (E.qy + mijy) / 2};
+    const double hx = mijx - E.px, hy = mijy - E.py;
+    const double l = sqrt(hx * hx + hy * hy);
+    const int slot[2] = {E.slot_i, E.slot_j};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        double qx[NEQ], qy[NEQ];
+        flux_dispatch<NEQ>(fp, ptx[q], pty[q], t, a, b, g, dbnd ? dbnd[2 * k + q] : 0.0, qx, qy);
+#pragma unroll
+        for (int v = 0; v < NEQ; ++v) {
+            double Q;
+            if (E.kind[v] == FVM_EDGE_NEUMANN) {
+                const CondFn c = m.cond[v * FVM_MAX_COND_FN + E.fidx[v]];
+                const double ushape = a[v] * ptx[q] + b[v] * pty[q] + g[v];
+                Q = cond_eval(c, ptx[q], pty[q], t, ushape) * l;
+            } else {
+                Q = (qx[v] * nx + qy[v] * ny) * l;
+            }
+            m.partial[(size_t)slot[q] * NEQ + v] = -Q;  // du[i] -= Q_i
+        }
+    }
+}
+
+// update_dirichlet_nodes!, dirichlet.jl:2-86
+__global__ void dirichlet_kernel(const DevMesh m, const int32_t* __restrict__ pairs, const int n_pairs, const double t,
+                                 double* __restrict__ u) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const int g = pairs[2 * k], v = pairs[2 * k + 1];
+    const CondFn c = m.cond[v * FVM_MAX_COND_FN + m.fidx[(size_t)v * m.n_nodes + g]];
+    const size_t idx = (size_t)g * m.neq + v;
+    u[idx] = cond_eval(c, m.xy[2 * (size_t)g], m.xy[2 * (size_t)g + 1], t, u[idx]);
+}
+
+// caller order <-> native order
+__global__ void permute_kernel(const int32_t* __restrict__ old_of_new, const double* __restrict__ src,
+                               double* __restrict__ dst, const int64_t n, const int neq, const int to_native) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * neq) return;
+    const int64_t g = idx / neq;
+    const int v = (int)(idx - g * neq);
+    const int64_t o = (int64_t)old_of_new[g] * neq + v;
+    if (to_native) dst[idx] = src[o];
+    else dst[o] = src[idx];
+}
+
+// stored geometry SoA: one thread per native triangle, exact (reference-order) arithmetic
+__global__ void geometry_kernel(const DevMesh m, const int32_t* __restrict__ tri_native, double* __restrict__ geo) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= m.n_tris) return;
+    const int i = tri_native[3 * gt], j = tri_native[3 * gt + 1], k = tri_native[3 * gt + 2];
+    TriGeom G;
+    tri_geometry<true>(m.xy[2 * (size_t)i], m.xy[2 * (size_t)i + 1], m.xy[2 * (size_t)j], m.xy[2 * (size_t)j + 1],
+                       m.xy[2 * (size_t)k], m.xy[2 * (size_t)k + 1], G, nullptr);
+    const int64_t st = m.tpad;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) geo[c * st + gt] = G.s[c];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+        geo[(9 + 2 * e) * st + gt] = G.mx[e];
+        geo[(10 + 2 * e) * st + gt] = G.my[e];
+        geo[(15 + 2 * e) * st + gt] = G.ey[e];
+        geo[(16 + 2 * e) * st + gt] = -G.ex[e];
+    }
+}
+
+// read-back of TriangleProperties (geometry.jl:21-26) in the caller's triangle order
+__global__ void export_geometry_kernel(const DevMesh m, const int32_t* __restrict__ tri_native,
+                                       const int32_t* __restrict__ tri_old_of_new, double* s9, double* mid6, double* nrm6,
+                                       double* len3) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= m.n_tris) return;
+    const int i = tri_native[3 * gt], j = tri_native[3 * gt + 1], k = tri_native[3 * gt + 2];
+    TriGeom G;
+    tri_geometry<true>(m.xy[2 * (size_t)i], m.xy[2 * (size_t)i + 1], m.xy[2 * (size_t)j], m.xy[2 * (size_t)j + 1],
+                       m.xy[2 * (size_t)k], m.xy[2 * (size_t)k + 1], G, nullptr);
+    const int64_t o = tri_old_of_new[gt];
+    if (s9)
+        for (int c = 0; c < 9; ++c) s9[9 * o + c] = G.s[c];
+    for (int e = 0; e < 3; ++e) {
+        if (mid6) {
+            mid6[6 * o + 2 * e] = G.mx[e];
+            mid6[6 * o + 2 * e + 1] = G.my[e];
+        }
+        // geometry.jl:153-161: l = norm(e); n = (e_y / l, -e_x / l)
+        const double l = __dsqrt_rn(__dadd_rn(__dmul_rn(G.ex[e], G.ex[e]), __dmul_rn(G.ey[e], G.ey[e])));
+        if (len3) len3[3 * o + e] = l;
+        if (nrm6) {
+            nrm6[6 * o + 2 * e] = __ddiv_rn(G.ey[e], l);
+            nrm6[6 * o + 2 * e + 1] = __ddiv_rn(-G.ex[e], l);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static int32_t rhs_smem_bytes(const fvm_ctx* h, int neq, bool vol, bool need_xy) {
+    size_t d = 0;
+    if (!vol) d += (size_t)h->max_nloc * neq;
+    if (need_xy) d += 2 * (size_t)h->max_nloc;
+    d += (size_t)3 * h->dm.tile_tris * (vol ? 1 : neq);
+    return (int32_t)(d * sizeof(double));
+}
+
+template <int MODEL, int NEQ, int GEOM>
+static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du) {
+    constexpr bool VOL = (MODEL == MODEL_VOLUME);
+    const int32_t smem = rhs_smem_bytes(h, NEQ, VOL, VOL || GEOM == 1);
+    auto kern = rhs_tile_kernel<MODEL, NEQ, GEOM>;
+    if (smem > 200 * 1024) return fvm_fail(h, FVM_ERR_ARG, "tile needs more than 200 KB of shared memory; lower tile_triangles");
+    int32_t& configured = h->smem_configured[(const void*)kern];
+    if (configured < smem) {
+        FVM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    h->smem_rhs = smem;
+    kern<<<h->dm.n_tiles, RHS_BLOCK, smem, h->stream>>>(h->dm, h->flux, h->source, t, u, du, h->max_nloc);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+template <int NEQ>
+static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du) {
+    int32_t rc = FVM_OK;
+    if (h->n_bnd_live > 0) {
+        rhs_boundary_kernel<NEQ><<<(h->n_bnd_live + 127) / 128, 128, 0, h->stream>>>(h->dm, h->flux, t, h->d_bnd, h->d_dbnd,
+                                                                                     h->n_bnd_live, u);
+        FVM_CUDA(h, cudaGetLastError());
+    }
+    const int model = h->flux.model;
+    const int geom = h->geometry_mode;
+#define TILE_CASE(M)                                                        \
+    case M:                                                                 \
+        rc = geom ? launch_tile<M, NEQ, 1>(h, t, u, du) : launch_tile<M, NEQ, 0>(h, t, u, du); \
+        break;
+    switch (model) {
+        TILE_CASE(FVM_FLUX_DIFF_CONST)
+        TILE_CASE(FVM_FLUX_DIFF_TABLE)
+        TILE_CASE(FVM_FLUX_DIFF_POWER)
+        TILE_CASE(FVM_FLUX_ADVDIFF)
+        case FVM_FLUX_KELLER_SEGEL:
+            if constexpr (NEQ == 2) {
+                rc = geom ? launch_tile<FVM_FLUX_KELLER_SEGEL, 2, 1>(h, t, u, du)
+                          : launch_tile<FVM_FLUX_KELLER_SEGEL, 2, 0>(h, t, u, du);
+            } else {
+                rc = fvm_fail(h, FVM_ERR_ARG, "Keller-Segel flux needs neq == 2");
+            }
+            break;
+        default: rc = fvm_fail(h, FVM_ERR_UNSUPPORTED, "flux model is not in the compiled registry");
+    }
+#undef TILE_CASE
+    if (rc) return rc;
+    const int n_tail = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
+    if (n_tail > 0) {
+        rhs_interface_kernel<NEQ, false><<<(n_tail + 255) / 256, 256, 0, h->stream>>>(h->dm, h->source, t, u, du);
+        FVM_CUDA(h, cudaGetLastError());
+    }
+    return FVM_OK;
+}
+
+int32_t fvm_launch_rhs(fvm_ctx* h, double t, const double* u, double* du) {
+    switch (h->neq) {
+        case 1: return launch_rhs_neq<1>(h, t, u, du);
+        case 2: return launch_rhs_neq<2>(h, t, u, du);
+        case 3: return launch_rhs_neq<3>(h, t, u, du);
+        case 4: return launch_rhs_neq<4>(h, t, u, du);
+    }
+    return fvm_fail(h, FVM_ERR_ARG, "unsupported neq");
+}
+
+int32_t fvm_launch_geometry(fvm_ctx* h, const int32_t* d_tri_native) {
+    if (h->geometry_mode == 1) {
+        h->dm.geo = nullptr;
+        return FVM_OK;
+    }
+    double* geo = nullptr;
+    int32_t rc = fvm_dev_alloc(h, &geo, (size_t)FVM_NGEO * h->dm.tpad);
+    if (rc) return rc;
+    FVM_CUDA(h, cudaMemsetAsync(geo, 0, sizeof(double) * FVM_NGEO * h->dm.tpad, h->stream));
+    h->dm.geo = geo;
+    geometry_kernel<<<(unsigned)((h->dm.n_tris + 255) / 256), 256, 0, h->stream>>>(h->dm, d_tri_native, geo);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+int32_t fvm_launch_volumes(fvm_ctx* h) {
+    // cv_volumes (geometry.jl:119-135) through the same tile gather: deterministic summation
+    double* vol = const_cast<double*>(h->dm.vol);
+    FVM_CUDA(h, cudaMemsetAsync(h->dm.partial, 0, sizeof(double) * h->dm.n_partial * h->neq, h->stream));
+    int32_t rc = launch_tile<MODEL_VOLUME, 1, 1>(h, 0.0, nullptr, vol);
+    if (rc) return rc;
+    const int n_tail = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
+    if (n_tail > 0) {
+        rhs_interface_kernel<1, true><<<(n_tail + 255) / 256, 256, 0, h->stream>>>(h->dm, h->source, 0.0, nullptr, vol);
+        FVM_CUDA(h, cudaGetLastError());
+    }
+    return FVM_OK;
+}
+
+int32_t fvm_launch_dirichlet(fvm_ctx* h, double t, double* u) {
+    if (h->n_dir == 0) return FVM_OK;
+    dirichlet_kernel<<<(h->n_dir + 255) / 256, 256, 0, h->stream>>>(h->dm, h->d_dir_nodes, h->n_dir, t, u);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+int32_t fvm_launch_permute(fvm_ctx* h, const double* src, double* dst, bool to_native) {
+    const int64_t n = h->N * h->neq;
+    permute_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_node_old_of_new, src, dst, h->N, h->neq,
+                                                                        to_native ? 1 : 0);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+int32_t fvm_ensure_state(fvm_ctx* h) {
+    if (h->d_u) return FVM_OK;
+    const size_t n = (size_t)h->N * h->neq;
+    int32_t rc;
+    if ((rc = fvm_dev_alloc(h, &h->d_u, n))) return rc;
+    if ((rc = fvm_dev_alloc(h, &h->d_du, n))) return rc;
+    if ((rc = fvm_dev_alloc(h, &h->d_io, n))) return rc;
+    return FVM_OK;
+}
+
+#define NEED_FINAL(h)                                                                       \
+    do {                                                                                    \
+        if (!(h)) return FVM_ERR_ARG;                                                       \
+        if (!(h)->finalized) return fvm_fail((h), FVM_ERR_STATE, "call fvm_finalize first"); \
+        FVM_CUDA(h, cudaSetDevice((h)->device));                                            \
+    } while (0)
+
+extern "C" int32_t fvm_rhs_native(fvm_handle h, double t, const double* u, double* du) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, u && du, "fvm_rhs_native: null argument");
+    return fvm_launch_rhs(h, t, u, du);
+}
+
+extern "C" int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, int32_t on_device) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, u && du, "fvm_rhs: null argument");
+    int32_t rc = fvm_ensure_state(h);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * h->N * h->neq;
+    const double* src = u;
+    if (!on_device) {
+        FVM_CUDA(h, cudaMemcpyAsync(h->d_io, u, bytes, cudaMemcpyHostToDevice, h->stream));
+        src = h->d_io;
+    }
+    if ((rc = fvm_launch_permute(h, src, h->d_u, true))) return rc;
+    if ((rc = fvm_launch_rhs(h, t, h->d_u, h->d_du))) return rc;
+    if (on_device) {
+        if ((rc = fvm_launch_permute(h, h->d_du, du, false))) return rc;
+    } else {
+        if ((rc = fvm_launch_permute(h, h->d_du, h->d_io, false))) return rc;
+        FVM_CUDA(h, cudaMemcpyAsync(du, h->d_io, bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_apply_dirichlet_native(fvm_handle h, double t, double* u) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, u, "fvm_apply_dirichlet_native: null argument");
+    return fvm_launch_dirichlet(h, t, u);
+}
+
+extern "C" int32_t fvm_apply_dirichlet(fvm_handle h, double t, double* u, int32_t on_device) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, u, "fvm_apply_dirichlet: null argument");
+    int32_t rc = fvm_ensure_state(h);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * h->N * h->neq;
+    double* src = u;
+    if (!on_device) {
+        FVM_CUDA(h, cudaMemcpyAsync(h->d_io, u, bytes, cudaMemcpyHostToDevice, h->stream));
+        src = h->d_io;
+    }
+    if ((rc = fvm_launch_permute(h, src, h->d_u, true))) return rc;
+    if ((rc = fvm_launch_dirichlet(h, t, h->d_u))) return rc;
+    if ((rc = fvm_launch_permute(h, h->d_u, src, false))) return rc;
+    if (!on_device) FVM_CUDA(h, cudaMemcpyAsync(u, h->d_io, bytes, cudaMemcpyDeviceToHost, h->stream));
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_to_native(fvm_handle h, const double* v_caller, double* v_native) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, v_caller && v_native && v_caller != v_native, "fvm_to_native: bad arguments");
+    return fvm_launch_permute(h, v_caller, v_native, true);
+}
+
+extern "C" int32_t fvm_from_native(fvm_handle h, const double* v_native, double* v_caller) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, v_caller && v_native && v_caller != v_native, "fvm_from_native: bad arguments");
+    return fvm_launch_permute(h, v_native, v_caller, false);
+}
+
+extern "C" int32_t fvm_stream_synchronize(fvm_handle h) {
+    NEED_FINAL(h);
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_get_stream(fvm_handle h, void** stream) {
+    if (!h || !stream) return FVM_ERR_ARG;
+    *stream = (void*)h->stream;
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_get_geometry(fvm_handle h, double* V, double* s9, double* mid6, double* nrm6, double* len3) {
+    NEED_FINAL(h);
+    const int64_t N = h->N, T = h->T;
+    int32_t rc;
+    if (V) {
+        if ((rc = fvm_ensure_state(h))) return rc;
+        // vol is a scalar-per-node array: permute with neq = 1
+        double* tmp = nullptr;
+        FVM_CUDA(h, cudaMalloc((void**)&tmp, sizeof(double) * N));
+        permute_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(h->d_node_old_of_new, h->dm.vol, tmp, N, 1, 0);
+        cudaError_t e = cudaMemcpyAsync(V, tmp, sizeof(double) * N, cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+        FVM_CUDA(h, e);
+    }
+    if (s9 || mid6 || nrm6 || len3) {
+        int32_t* d_perm = nullptr;
+        FVM_CUDA(h, cudaMalloc((void**)&d_perm, sizeof(int32_t) * T));
+        FVM_CUDA(h, cudaMemcpyAsync(d_perm, h->tri_old_of_new.data(), sizeof(int32_t) * T, cudaMemcpyHostToDevice, h->stream));
+        double* outs[4] = {s9, mid6, nrm6, len3};
+        const int width[4] = {9, 6, 6, 3};
+        for (int q = 0; q < 4; ++q) {  // one array at a time bounds the temporary device memory
+            if (!outs[q]) continue;
+            double* tmp = nullptr;
+            cudaError_t e = cudaMalloc((void**)&tmp, sizeof(double) * T * width[q]);
+            if (e != cudaSuccess) {
+                cudaFree(d_perm);
+                FVM_CUDA(h, e);
+            }
+            export_geometry_kernel<<<(unsigned)((T + 255) / 256), 256, 0, h->stream>>>(
+                h->dm, h->d_tri_native, d_perm, q == 0 ? tmp : nullptr, q == 1 ? tmp : nullptr, q == 2 ? tmp : nullptr,
+                q == 3 ? tmp : nullptr);
+            e = cudaMemcpyAsync(outs[q], tmp, sizeof(double) * T * width[q], cudaMemcpyDeviceToHost, h->stream);
+            cudaStreamSynchronize(h->stream);
+            cudaFree(tmp);
+            if (e != cudaSuccess) {
+                cudaFree(d_perm);
+                FVM_CUDA(h, e);
+            }
+        }
+        cudaFree(d_perm);
+    }
+    return FVM_OK;
+}

@@ -1,0 +1,642 @@
+// libfvmcuda: handle lifecycle and the one-off mesh preprocessing ("finalize").
+//
+// finalize() replaces the reference's hash containers (Dict{NTuple{3,Int},TriangleProperties},
+// Set of triangles, Dicts of conditions; /root/reference/src/geometry.jl:44-49,
+// src/conditions.jl:310-316) by flat device arrays laid out for one streaming pass:
+//   * triangles are sorted along a Hilbert curve through their centroids and cut into tiles of
+//     TT consecutive triangles (a tile is a compact 2-D patch of the mesh);
+//   * nodes are renumbered tile-major: a tile's interior nodes (all incident triangles inside
+//     the tile) first, then the interface nodes it owns; a tile's nodes are one contiguous range;
+//   * every tile gets a node -> (triangle, slot) gather list, so the per-vertex scatter of
+//     src/equations/triangle_contributions.jl:10-15 becomes a fixed-order gather in shared
+//     memory: deterministic, no fp64 atomics, `du` written exactly once;
+//   * interface and boundary nodes are finished by a second small kernel from a buffer of
+//     per-tile partial sums whose slots are assigned here.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <parallel/algorithm>
+#include <unordered_map>
+
+#include "fvm_internal.h"
+
+int32_t fvm_fail(fvm_ctx* h, int32_t code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+
+static thread_local std::string g_create_err;
+
+extern "C" const char* fvm_version(void) { return "fvmcuda 0.1 (sm_100a)"; }
+
+extern "C" const char* fvm_last_error(fvm_handle h) {
+    if (!h) return g_create_err.c_str();
+    return h->err.c_str();
+}
+
+extern "C" int32_t fvm_create(const double* xy, int64_t N, const int32_t* tri, int64_t T, int32_t index_base,
+                              int32_t neq, int32_t device, fvm_handle* out) {
+    if (!out) return FVM_ERR_ARG;
+    *out = nullptr;
+    auto bad = [&](int32_t code, const std::string& m) {
+        g_create_err = m;
+        return code;
+    };
+    if (!xy || !tri || N <= 0 || T <= 0) return bad(FVM_ERR_ARG, "fvm_create: empty mesh");
+    if (N >= INT32_MAX / 2 || 3 * T >= (int64_t)INT32_MAX * 2)
+        return bad(FVM_ERR_ARG, "fvm_create: mesh too large for int32 indices");
+    if (neq < 1 || neq > FVM_MAX_NEQ) return bad(FVM_ERR_ARG, "fvm_create: neq must be in 1..4");
+    if (index_base != 0 && index_base != 1) return bad(FVM_ERR_ARG, "fvm_create: index_base must be 0 or 1");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return bad(FVM_ERR_CUDA, std::string("fvm_create: no CUDA device (") + cudaGetErrorString(ce) +
+                                     "); libfvmcuda has no CPU fallback");
+    if (device < 0 || device >= ndev) return bad(FVM_ERR_ARG, "fvm_create: bad device ordinal");
+    fvm_ctx* h = new fvm_ctx();
+    h->device = device;
+    h->neq = neq;
+    h->N = N;
+    h->T = T;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return bad(FVM_ERR_CUDA, "fvm_create: cannot create stream");
+    }
+    h->h_xy.assign(xy, xy + 2 * N);
+    h->h_tri.resize(3 * T);
+    for (int64_t i = 0; i < 3 * T; ++i) {
+        int32_t v = tri[i] - index_base;
+        if (v < 0 || v >= N) {
+            cudaStreamDestroy(h->stream);
+            delete h;
+            return bad(FVM_ERR_ARG, "fvm_create: triangle vertex out of range");
+        }
+        h->h_tri[i] = v;
+    }
+    for (int v = 0; v < neq; ++v) {
+        h->h_nkind[v].assign(N, 0);
+        h->h_nfidx[v].assign(N, 0);
+    }
+    h->h_cond.assign((size_t)neq * FVM_MAX_COND_FN, CondFn{FVM_COND_CONST, {0, 0, 0, 0}});
+    h->flux.model = FVM_FLUX_DIFF_CONST;
+    h->flux.nparams = neq;
+    for (int v = 0; v < FVM_MAX_PARAMS; ++v) h->flux.p[v] = 1.0;
+    h->source.model = FVM_SRC_ZERO;
+    h->h_index_base = index_base;
+    *out = h;
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_destroy(fvm_handle h) {
+    if (!h) return FVM_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    fvm_shard_release(h);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return FVM_OK;
+}
+
+#define NOT_FINAL(h)                                                                      \
+    do {                                                                                  \
+        if (!(h)) return FVM_ERR_ARG;                                                     \
+        if ((h)->finalized) return fvm_fail((h), FVM_ERR_STATE, "mesh already finalized"); \
+    } while (0)
+
+extern "C" int32_t fvm_set_boundary_edges(fvm_handle h, const int32_t* uv, int64_t n_edges) {
+    NOT_FINAL(h);
+    FVM_REQUIRE(h, n_edges >= 0 && (uv || n_edges == 0), "fvm_set_boundary_edges: null edges");
+    h->Eb = n_edges;
+    h->h_bedge.resize(2 * n_edges);
+    for (int64_t i = 0; i < 2 * n_edges; ++i) {
+        int32_t v = uv[i] - h->h_index_base;
+        FVM_REQUIRE(h, v >= 0 && v < h->N, "fvm_set_boundary_edges: vertex out of range");
+        h->h_bedge[i] = v;
+    }
+    for (int v = 0; v < h->neq; ++v) {
+        h->h_ekind[v].assign(n_edges, 0);
+        h->h_efidx[v].assign(n_edges, 0);
+    }
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_set_edge_conditions(fvm_handle h, int32_t var, const uint8_t* kind, const int32_t* fidx) {
+    NOT_FINAL(h);
+    FVM_REQUIRE(h, var >= 0 && var < h->neq, "fvm_set_edge_conditions: bad species index");
+    FVM_REQUIRE(h, kind && fidx, "fvm_set_edge_conditions: null argument");
+    for (int64_t e = 0; e < h->Eb; ++e) {
+        FVM_REQUIRE(h, kind[e] <= FVM_EDGE_CONSTRAINED, "fvm_set_edge_conditions: bad kind");
+        FVM_REQUIRE(h, fidx[e] >= 0 && fidx[e] < FVM_MAX_COND_FN, "fvm_set_edge_conditions: fidx out of range");
+    }
+    h->h_ekind[var].assign(kind, kind + h->Eb);
+    h->h_efidx[var].assign(fidx, fidx + h->Eb);
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_set_node_conditions(fvm_handle h, int32_t var, const uint8_t* kind, const int32_t* fidx) {
+    NOT_FINAL(h);
+    FVM_REQUIRE(h, var >= 0 && var < h->neq, "fvm_set_node_conditions: bad species index");
+    FVM_REQUIRE(h, kind && fidx, "fvm_set_node_conditions: null argument");
+    for (int64_t i = 0; i < h->N; ++i) {
+        FVM_REQUIRE(h, kind[i] <= FVM_NODE_DUDT, "fvm_set_node_conditions: bad kind");
+        FVM_REQUIRE(h, fidx[i] >= 0 && fidx[i] < FVM_MAX_COND_FN, "fvm_set_node_conditions: fidx out of range");
+    }
+    h->h_nkind[var].assign(kind, kind + h->N);
+    h->h_nfidx[var].assign(fidx, fidx + h->N);
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_set_condition_fn(fvm_handle h, int32_t var, int32_t fidx, int32_t fn_id, const double* params,
+                                        int32_t nparams) {
+    if (!h) return FVM_ERR_ARG;
+    FVM_REQUIRE(h, var >= 0 && var < h->neq, "fvm_set_condition_fn: bad species index");
+    FVM_REQUIRE(h, fidx >= 0 && fidx < FVM_MAX_COND_FN, "fvm_set_condition_fn: fidx out of range");
+    if (fn_id < FVM_COND_CONST || fn_id > FVM_COND_LINEAR_XY)
+        return fvm_fail(h, FVM_ERR_UNSUPPORTED,
+                        "fvm_set_condition_fn: condition function is not in the compiled registry "
+                        "(arbitrary closures cannot run on the device)");
+    static const int need[] = {1, 2, 2, 3};
+    FVM_REQUIRE(h, nparams == need[fn_id] && params, "fvm_set_condition_fn: wrong parameter count");
+    CondFn c{fn_id, {0, 0, 0, 0}};
+    for (int i = 0; i < nparams; ++i) c.p[i] = params[i];
+    h->h_cond[(size_t)var * FVM_MAX_COND_FN + fidx] = c;
+    if (h->finalized) {  // condition parameters may change between solves
+        FVM_CUDA(h, cudaMemcpyAsync((void*)(h->dm.cond + (size_t)var * FVM_MAX_COND_FN + fidx), &c, sizeof(CondFn),
+                                    cudaMemcpyHostToDevice, h->stream));
+        FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_set_flux(fvm_handle h, int32_t model, const double* params, int32_t nparams) {
+    if (!h) return FVM_ERR_ARG;
+    const int neq = h->neq;
+    int need = -1;
+    switch (model) {
+        case FVM_FLUX_DIFF_CONST: need = neq; break;
+        case FVM_FLUX_DIFF_TABLE: need = 0; break;
+        case FVM_FLUX_DIFF_POWER: need = 3 * neq; break;
+        case FVM_FLUX_ADVDIFF: need = 3 * neq; break;
+        case FVM_FLUX_KELLER_SEGEL: need = 2; break;
+        default:
+            return fvm_fail(h, FVM_ERR_UNSUPPORTED,
+                            "fvm_set_flux: flux model is not in the compiled registry "
+                            "(arbitrary closures cannot run on the device)");
+    }
+    if (model == FVM_FLUX_KELLER_SEGEL && neq != 2)
+        return fvm_fail(h, FVM_ERR_ARG, "fvm_set_flux: Keller-Segel needs neq == 2");
+    FVM_REQUIRE(h, nparams == need && (params || need == 0), "fvm_set_flux: wrong parameter count");
+    if (h->finalized && model == FVM_FLUX_DIFF_TABLE && !h->dm.dtab)
+        return fvm_fail(h, FVM_ERR_STATE, "fvm_set_flux: table model needs fvm_set_flux_table before finalize");
+    h->flux.model = model;
+    h->flux.nparams = nparams;
+    for (int i = 0; i < nparams; ++i) h->flux.p[i] = params[i];
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_set_flux_table(fvm_handle h, const double* d_cv_edge, const double* d_bnd) {
+    NOT_FINAL(h);
+    FVM_REQUIRE(h, d_cv_edge, "fvm_set_flux_table: null table");
+    FVM_REQUIRE(h, d_bnd || h->Eb == 0, "fvm_set_flux_table: boundary table missing (set boundary edges first)");
+    h->h_dtab.assign(d_cv_edge, d_cv_edge + 3 * h->T);
+    if (h->Eb) h->h_dbnd.assign(d_bnd, d_bnd + 2 * h->Eb);
+    h->flux.model = FVM_FLUX_DIFF_TABLE;
+    h->flux.nparams = 0;
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_set_source(fvm_handle h, int32_t model, const double* params, int32_t nparams) {
+    if (!h) return FVM_ERR_ARG;
+    const int neq = h->neq;
+    int need = -1;
+    switch (model) {
+        case FVM_SRC_ZERO: need = 0; break;
+        case FVM_SRC_LINEAR: need = 2 * neq; break;
+        case FVM_SRC_LOGISTIC: need = neq; break;
+        case FVM_SRC_TABLE: need = 0; break;
+        case FVM_SRC_GRAY_SCOTT: need = 2; break;
+        case FVM_SRC_BRUSSELATOR: need = 0; break;
+        case FVM_SRC_KELLER_SEGEL: need = 1; break;
+        default:
+            return fvm_fail(h, FVM_ERR_UNSUPPORTED,
+                            "fvm_set_source: source model is not in the compiled registry "
+                            "(arbitrary closures cannot run on the device)");
+    }
+    if (model >= FVM_SRC_GRAY_SCOTT && neq != 2) return fvm_fail(h, FVM_ERR_ARG, "fvm_set_source: model needs neq == 2");
+    FVM_REQUIRE(h, nparams == need && (params || need == 0), "fvm_set_source: wrong parameter count");
+    if (model == FVM_SRC_TABLE && h->finalized && !h->dm.src_tab)
+        return fvm_fail(h, FVM_ERR_STATE, "fvm_set_source: table model needs fvm_set_source_table before finalize");
+    h->source.model = model;
+    h->source.nparams = nparams;
+    for (int i = 0; i < nparams; ++i) h->source.p[i] = params[i];
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_set_source_table(fvm_handle h, const double* s_node) {
+    NOT_FINAL(h);
+    FVM_REQUIRE(h, s_node, "fvm_set_source_table: null table");
+    h->h_srctab.assign(s_node, s_node + h->N * h->neq);
+    h->source.model = FVM_SRC_TABLE;
+    h->source.nparams = 0;
+    return FVM_OK;
+}
+
+// ---- Hilbert curve index of a 16-bit lattice point --------------------------------------
+static inline uint32_t hilbert_xy2d(uint32_t x, uint32_t y) {
+    uint32_t d = 0;
+    for (uint32_t s = 1u << 15; s > 0; s >>= 1) {
+        uint32_t rx = (x & s) ? 1u : 0u;
+        uint32_t ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (ry == 0) {
+            if (rx == 1) {
+                x = 65535u - x;
+                y = 65535u - y;
+            }
+            uint32_t tmp = x;
+            x = y;
+            y = tmp;
+        }
+    }
+    return d;
+}
+
+extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t geometry_mode) {
+    NOT_FINAL(h);
+    FVM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t N = h->N, T = h->T, Eb = h->Eb;
+    const int neq = h->neq;
+    int TT = tile_triangles > 0 ? tile_triangles : 1024;
+    FVM_REQUIRE(h, TT >= 64 && TT <= 4096 && TT % 64 == 0, "fvm_finalize: tile_triangles must be a multiple of 64 in 64..4096");
+    FVM_REQUIRE(h, geometry_mode == 0 || geometry_mode == 1, "fvm_finalize: geometry_mode must be 0 or 1");
+    if (h->flux.model == FVM_FLUX_DIFF_TABLE && h->h_dtab.empty())
+        return fvm_fail(h, FVM_ERR_STATE, "fvm_finalize: table flux model without fvm_set_flux_table");
+    h->geometry_mode = geometry_mode;
+    const double* xy = h->h_xy.data();
+    const int32_t* tri = h->h_tri.data();
+
+    // ---- 1. Hilbert sort of triangles by centroid ------------------------------------
+    double minx = xy[0], maxx = xy[0], miny = xy[1], maxy = xy[1];
+    for (int64_t i = 0; i < N; ++i) {
+        minx = std::min(minx, xy[2 * i]);
+        maxx = std::max(maxx, xy[2 * i]);
+        miny = std::min(miny, xy[2 * i + 1]);
+        maxy = std::max(maxy, xy[2 * i + 1]);
+    }
+    const double ext = std::max(maxx - minx, maxy - miny);
+    const double scale = ext > 0 ? 65535.0 / ext : 0.0;
+    std::vector<uint64_t> keys(T);
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < T; ++t) {
+        const int32_t a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+        double cx = (xy[2 * a] + xy[2 * b] + xy[2 * c]) / 3.0, cy = (xy[2 * a + 1] + xy[2 * b + 1] + xy[2 * c + 1]) / 3.0;
+        uint32_t ix = (uint32_t)std::min(65535.0, std::max(0.0, (cx - minx) * scale));
+        uint32_t iy = (uint32_t)std::min(65535.0, std::max(0.0, (cy - miny) * scale));
+        keys[t] = ((uint64_t)hilbert_xy2d(ix, iy) << 32) | (uint64_t)t;
+    }
+    __gnu_parallel::sort(keys.begin(), keys.end());
+    h->tri_old_of_new.resize(T);
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < T; ++t) h->tri_old_of_new[t] = (int32_t)(keys[t] & 0xffffffffu);
+    std::vector<uint64_t>().swap(keys);
+    const int32_t* told = h->tri_old_of_new.data();
+    const int64_t n_tiles = (T + TT - 1) / TT;
+    FVM_REQUIRE(h, n_tiles < INT32_MAX, "too many tiles");
+
+    // ---- 2. boundary edges: adjacent triangle, live flag --------------------------------
+    std::vector<uint8_t> forced(N, 0);  // nodes that must be finished by the interface kernel
+    std::vector<int32_t> live_edges;
+    for (int64_t e = 0; e < Eb; ++e) {
+        const int32_t i = h->h_bedge[2 * e], j = h->h_bedge[2 * e + 1];
+        bool live = false;
+        for (int v = 0; v < neq; ++v) live = live || h->h_nkind[v][i] == FVM_NODE_FREE || h->h_nkind[v][j] == FVM_NODE_FREE;
+        if (live) {  // dead work on conditioned edges is skipped
+            live_edges.push_back((int32_t)e);
+            forced[i] = forced[j] = 1;
+        }
+    }
+    std::vector<int32_t> edge_tri(live_edges.size(), -1), edge_rot(live_edges.size(), 0);
+    if (!live_edges.empty()) {
+        std::unordered_map<uint64_t, int32_t> emap;
+        emap.reserve(live_edges.size() * 2);
+        std::vector<uint8_t> is_src(N, 0);
+        for (size_t k = 0; k < live_edges.size(); ++k) {
+            const int32_t e = live_edges[k];
+            emap[((uint64_t)(uint32_t)h->h_bedge[2 * e] << 32) | (uint32_t)h->h_bedge[2 * e + 1]] = (int32_t)k;
+            is_src[h->h_bedge[2 * e]] = 1;
+        }
+        for (int64_t t = 0; t < T; ++t) {
+            for (int r = 0; r < 3; ++r) {
+                const int32_t a = tri[3 * t + r];
+                if (!is_src[a]) continue;
+                const int32_t b = tri[3 * t + (r + 1) % 3];
+                auto it = emap.find(((uint64_t)(uint32_t)a << 32) | (uint32_t)b);
+                if (it != emap.end()) {
+                    edge_tri[it->second] = (int32_t)t;
+                    edge_rot[it->second] = r;
+                }
+            }
+        }
+        for (size_t k = 0; k < live_edges.size(); ++k)
+            FVM_REQUIRE(h, edge_tri[k] >= 0, "fvm_finalize: a boundary edge (u,v) is not a ccw edge of any triangle");
+    }
+
+    // ---- 3. node classification and tile-major renumbering -------------------------------
+    std::vector<int32_t> min_tile(N, INT32_MAX), max_tile(N, -1);
+    for (int64_t nt = 0; nt < T; ++nt) {
+        const int32_t tile = (int32_t)(nt / TT);
+        const int32_t* v = tri + 3 * (int64_t)told[nt];
+        for (int r = 0; r < 3; ++r) {
+            if (tile < min_tile[v[r]]) min_tile[v[r]] = tile;
+            if (tile > max_tile[v[r]]) max_tile[v[r]] = tile;
+        }
+    }
+    std::vector<int32_t> tile_node0(n_tiles), tile_nint(n_tiles), tile_nown(n_tiles), tile_nloc(n_tiles);
+    h->node_new_of_old.assign(N, -1);
+    h->node_old_of_new.assign(N, -1);
+    int32_t* new_of_old = h->node_new_of_old.data();
+    {
+        std::vector<int32_t> ilist, flist;
+        int32_t cursor = 0;
+        std::vector<uint8_t> seen(N, 0);
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            ilist.clear();
+            flist.clear();
+            const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
+            for (int64_t nt = t0; nt < t1; ++nt) {
+                const int32_t* v = tri + 3 * (int64_t)told[nt];
+                for (int r = 0; r < 3; ++r) {
+                    const int32_t g = v[r];
+                    if (min_tile[g] != b || seen[g]) continue;
+                    seen[g] = 1;
+                    if (max_tile[g] == b && !forced[g]) ilist.push_back(g);
+                    else flist.push_back(g);
+                }
+            }
+            tile_node0[b] = cursor;
+            tile_nint[b] = (int32_t)ilist.size();
+            tile_nown[b] = (int32_t)(ilist.size() + flist.size());
+            for (int32_t g : ilist) new_of_old[g] = cursor++;
+            for (int32_t g : flist) new_of_old[g] = cursor++;
+        }
+        h->dm.n_vertices = cursor;
+        for (int64_t g = 0; g < N; ++g)
+            if (new_of_old[g] < 0) new_of_old[g] = cursor++;  // points that are not vertices
+    }
+    for (int64_t g = 0; g < N; ++g) h->node_old_of_new[new_of_old[g]] = (int32_t)g;
+    const int32_t n_vertices = h->dm.n_vertices;
+
+    // ---- 4. tile-local indices, gather lists, interface bookkeeping -----------------------
+    const int64_t tpad = n_tiles * TT;
+    std::vector<ushort4> tri_loc(tpad, make_ushort4(0, 0, 0, 0));
+    std::vector<int32_t> tri_native(3 * T);  // native node ids per native triangle (geometry kernel input)
+    std::vector<int32_t> tile_ext0(n_tiles + 1), tile_loc0(n_tiles + 1), tile_pp0(n_tiles + 1);
+    std::vector<int32_t> ext_ids;
+    std::vector<uint16_t> inc_ptr, inc((size_t)3 * tpad, 0);
+    std::vector<int32_t> ifc_of_new(N, -1);  // compact interface index by native id
+    std::vector<int32_t> ifc_node;
+    for (int64_t b = 0; b < n_tiles; ++b)
+        for (int32_t l = tile_nint[b]; l < tile_nown[b]; ++l) {
+            ifc_of_new[tile_node0[b] + l] = (int32_t)ifc_node.size();
+            ifc_node.push_back(tile_node0[b] + l);
+        }
+    const int32_t n_ifc = (int32_t)ifc_node.size();
+    std::vector<int32_t> ifc_cnt(n_ifc + 1, 0);
+    int32_t max_nloc = 0;
+    {
+        std::vector<int32_t> stamp(N, -1), loc(N, 0);
+        std::vector<int32_t> cnt, fill;
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
+            const int32_t node0 = tile_node0[b], nown = tile_nown[b];
+            tile_ext0[b] = (int32_t)ext_ids.size();
+            int32_t next = 0;
+            for (int64_t nt = t0; nt < t1; ++nt) {
+                const int32_t* v = tri + 3 * (int64_t)told[nt];
+                uint16_t l3[3];
+                for (int r = 0; r < 3; ++r) {
+                    const int32_t g = v[r];
+                    const int32_t gn = new_of_old[g];
+                    tri_native[3 * nt + r] = gn;
+                    int32_t l;
+                    if (min_tile[g] == b) l = gn - node0;
+                    else {
+                        if (stamp[g] != b) {
+                            stamp[g] = (int32_t)b;
+                            loc[g] = nown + next++;
+                            ext_ids.push_back(gn);
+                        }
+                        l = loc[g];
+                    }
+                    l3[r] = (uint16_t)l;
+                }
+                tri_loc[nt] = make_ushort4(l3[0], l3[1], l3[2], 0);
+            }
+            const int32_t nloc = nown + next;
+            FVM_REQUIRE(h, nloc < 65535, "fvm_finalize: tile has too many nodes for 16-bit local ids");
+            tile_nloc[b] = nloc;
+            max_nloc = std::max(max_nloc, nloc);
+            // gather list: local node -> (local triangle, slot), ascending triangle order
+            tile_loc0[b] = (int32_t)inc_ptr.size();
+            cnt.assign(nloc + 1, 0);
+            for (int64_t nt = t0; nt < t1; ++nt) {
+                const ushort4 q = tri_loc[nt];
+                cnt[q.x + 1]++;
+                cnt[q.y + 1]++;
+                cnt[q.z + 1]++;
+            }
+            for (int32_t l = 0; l < nloc; ++l) cnt[l + 1] += cnt[l];
+            for (int32_t l = 0; l <= nloc; ++l) inc_ptr.push_back((uint16_t)cnt[l]);
+            fill.assign(cnt.begin(), cnt.end() - 1);
+            uint16_t* tinc = inc.data() + (size_t)3 * TT * b;
+            for (int64_t nt = t0; nt < t1; ++nt) {
+                const ushort4 q = tri_loc[nt];
+                const uint16_t lt = (uint16_t)(nt - t0);
+                tinc[fill[q.x]++] = (uint16_t)(lt << 2 | 0);
+                tinc[fill[q.y]++] = (uint16_t)(lt << 2 | 1);
+                tinc[fill[q.z]++] = (uint16_t)(lt << 2 | 2);
+            }
+            // interface locals of this tile contribute one partial each
+            for (int32_t l = tile_nint[b]; l < nown; ++l) ifc_cnt[ifc_of_new[node0 + l]]++;
+            for (int32_t k = 0; k < next; ++k) ifc_cnt[ifc_of_new[ext_ids[tile_ext0[b] + k]]]++;
+        }
+        tile_ext0[n_tiles] = (int32_t)ext_ids.size();
+        tile_loc0[n_tiles] = (int32_t)inc_ptr.size();
+    }
+    for (size_t k = 0; k < live_edges.size(); ++k) {
+        const int32_t e = live_edges[k];
+        ifc_cnt[ifc_of_new[new_of_old[h->h_bedge[2 * e]]]]++;
+        ifc_cnt[ifc_of_new[new_of_old[h->h_bedge[2 * e + 1]]]]++;
+    }
+    std::vector<int32_t> ifc_pptr(n_ifc + 1, 0);
+    for (int32_t k = 0; k < n_ifc; ++k) ifc_pptr[k + 1] = ifc_pptr[k] + ifc_cnt[k];
+    const int64_t n_partial = ifc_pptr[n_ifc];
+    std::vector<int32_t> pfill(ifc_pptr.begin(), ifc_pptr.end() - 1);
+    std::vector<int32_t> ppos;
+    for (int64_t b = 0; b < n_tiles; ++b) {  // ascending tile order = fixed summation order
+        tile_pp0[b] = (int32_t)ppos.size();
+        for (int32_t l = tile_nint[b]; l < tile_nown[b]; ++l) ppos.push_back(pfill[ifc_of_new[tile_node0[b] + l]]++);
+        for (int32_t k = tile_ext0[b]; k < tile_ext0[b + 1]; ++k) ppos.push_back(pfill[ifc_of_new[ext_ids[k]]]++);
+    }
+    tile_pp0[n_tiles] = (int32_t)ppos.size();
+
+    // ---- 5. live boundary-edge records ------------------------------------------------------
+    std::vector<BndEdge> bnd(live_edges.size());
+    std::vector<double> dbnd_live;
+    for (size_t k = 0; k < live_edges.size(); ++k) {
+        const int32_t e = live_edges[k];
+        BndEdge& r = bnd[k];
+        const int32_t i = h->h_bedge[2 * e], j = h->h_bedge[2 * e + 1];
+        const int32_t* v = tri + 3 * (int64_t)edge_tri[k];
+        for (int q = 0; q < 3; ++q) r.v[q] = new_of_old[v[q]];
+        r.pi = edge_rot[k];
+        r.pj = (edge_rot[k] + 1) % 3;
+        r.slot_i = pfill[ifc_of_new[new_of_old[i]]]++;
+        r.slot_j = pfill[ifc_of_new[new_of_old[j]]]++;
+        r.orig = e;
+        r.px = xy[2 * i];
+        r.py = xy[2 * i + 1];
+        r.qx = xy[2 * j];
+        r.qy = xy[2 * j + 1];
+        for (int s = 0; s < FVM_MAX_NEQ; ++s) {
+            r.kind[s] = s < neq ? h->h_ekind[s][e] : 0;
+            r.fidx[s] = s < neq ? h->h_efidx[s][e] : 0;
+        }
+        if (!h->h_dbnd.empty()) {
+            dbnd_live.push_back(h->h_dbnd[2 * e]);
+            dbnd_live.push_back(h->h_dbnd[2 * e + 1]);
+        }
+    }
+    // ---- 6. upload --------------------------------------------------------------------------
+    DevMesh& m = h->dm;
+    m.neq = neq;
+    m.n_nodes = (int32_t)N;
+    m.n_tris = (int32_t)T;
+    m.n_tiles = (int32_t)n_tiles;
+    m.tile_tris = TT;
+    m.tpad = tpad;
+    int32_t rc;
+#define UP(dst, vec)                                               \
+    do {                                                           \
+        std::remove_const<std::remove_pointer<decltype(dst)>::type>::type* p__ = nullptr; \
+        if ((rc = fvm_dev_upload(h, &p__, vec))) return rc;        \
+        dst = p__;                                                 \
+    } while (0)
+    UP(m.tri_loc, tri_loc);
+    UP(m.tile_node0, tile_node0);
+    UP(m.tile_nint, tile_nint);
+    UP(m.tile_nown, tile_nown);
+    UP(m.tile_nloc, tile_nloc);
+    UP(m.tile_ext0, tile_ext0);
+    UP(m.tile_loc0, tile_loc0);
+    UP(m.tile_pp0, tile_pp0);
+    UP(m.ext_ids, ext_ids);
+    UP(m.inc_ptr, inc_ptr);
+    UP(m.inc, inc);
+    UP(m.ppos, ppos);
+    UP(m.ifc_node, ifc_node);
+    UP(m.ifc_pptr, ifc_pptr);
+    m.n_ifc = n_ifc;
+    m.n_partial = n_partial;
+    if ((rc = fvm_dev_alloc(h, &m.partial, (size_t)n_partial * neq))) return rc;
+    // per-node arrays in native order
+    {
+        std::vector<double> xyn(2 * N);
+        std::vector<uint8_t> kn((size_t)neq * N);
+        std::vector<int32_t> fn((size_t)neq * N);
+        std::vector<int32_t> dir;
+#pragma omp parallel for schedule(static)
+        for (int64_t g = 0; g < N; ++g) {
+            const int32_t o = h->node_old_of_new[g];
+            xyn[2 * g] = xy[2 * o];
+            xyn[2 * g + 1] = xy[2 * o + 1];
+            for (int v = 0; v < neq; ++v) {
+                kn[(size_t)v * N + g] = g < n_vertices ? h->h_nkind[v][o] : (uint8_t)3;  // 3: not a vertex
+                fn[(size_t)v * N + g] = h->h_nfidx[v][o];
+            }
+        }
+        for (int v = 0; v < neq; ++v)
+            for (int64_t g = 0; g < n_vertices; ++g)
+                if (kn[(size_t)v * N + g] == FVM_NODE_DIRICHLET) {
+                    dir.push_back((int32_t)g);
+                    dir.push_back(v);
+                }
+        UP(m.xy, xyn);
+        UP(m.kind, kn);
+        UP(m.fidx, fn);
+        h->n_dir = (int32_t)(dir.size() / 2);
+        if ((rc = fvm_dev_upload(h, &h->d_dir_nodes, dir))) return rc;
+        if (!h->h_srctab.empty()) {
+            std::vector<double> sn((size_t)N * neq);
+#pragma omp parallel for schedule(static)
+            for (int64_t g = 0; g < N; ++g)
+                for (int v = 0; v < neq; ++v) sn[g * neq + v] = h->h_srctab[(int64_t)h->node_old_of_new[g] * neq + v];
+            UP(m.src_tab, sn);
+        }
+    }
+    if (!h->h_dtab.empty()) {
+        std::vector<double> dt((size_t)3 * tpad, 0.0);
+#pragma omp parallel for schedule(static)
+        for (int64_t nt = 0; nt < T; ++nt)
+            for (int e = 0; e < 3; ++e) dt[(size_t)e * tpad + nt] = h->h_dtab[3 * (int64_t)told[nt] + e];
+        UP(m.dtab, dt);
+    }
+    UP(m.cond, h->h_cond);
+    if ((rc = fvm_dev_upload(h, &h->d_node_old_of_new, h->node_old_of_new))) return rc;
+    if ((rc = fvm_dev_upload(h, &h->d_node_new_of_old, h->node_new_of_old))) return rc;
+    h->n_bnd_live = (int32_t)bnd.size();
+    if ((rc = fvm_dev_upload(h, &h->d_bnd, bnd))) return rc;
+    if (!dbnd_live.empty() && (rc = fvm_dev_upload(h, &h->d_dbnd, dbnd_live))) return rc;
+    {
+        double* vol = nullptr;
+        if ((rc = fvm_dev_alloc(h, &vol, (size_t)N))) return rc;
+        m.vol = vol;
+    }
+    h->max_nloc = max_nloc;
+
+    // ---- 7. geometry on the device ----------------------------------------------------------
+    int32_t* d_tri_native = nullptr;
+    FVM_CUDA(h, cudaMalloc((void**)&d_tri_native, sizeof(int32_t) * 3 * T));
+    FVM_CUDA(h, cudaMemcpyAsync(d_tri_native, tri_native.data(), sizeof(int32_t) * 3 * T, cudaMemcpyHostToDevice, h->stream));
+    h->d_tri_native = d_tri_native;  // kept: assembly and geometry export read it
+    h->allocs.push_back(d_tri_native);
+    rc = fvm_launch_geometry(h, d_tri_native);
+    if (rc) return rc;
+    rc = fvm_launch_volumes(h);
+    if (rc) return rc;
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+
+    h->stats[0] = n_tiles;
+    h->stats[1] = TT;
+    h->stats[2] = n_vertices;
+    h->stats[3] = n_ifc;
+    h->stats[4] = n_partial;
+    h->stats[5] = (int64_t)ext_ids.size();
+    h->stats[6] = max_nloc;
+    h->stats[7] = h->n_bnd_live;
+    h->stats[8] = h->n_dir;
+    h->stats[9] = h->smem_rhs;
+    h->finalized = true;
+    // the big host copies are no longer needed
+    std::vector<double>().swap(h->h_dtab);
+    std::vector<double>().swap(h->h_srctab);
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_get_permutation(fvm_handle h, int32_t* node_perm, int32_t* tri_perm) {
+    if (!h) return FVM_ERR_ARG;
+    if (!h->finalized) return fvm_fail(h, FVM_ERR_STATE, "fvm_get_permutation: finalize first");
+    if (node_perm) std::memcpy(node_perm, h->node_old_of_new.data(), sizeof(int32_t) * h->N);
+    if (tri_perm) std::memcpy(tri_perm, h->tri_old_of_new.data(), sizeof(int32_t) * h->T);
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_get_stats(fvm_handle h, int64_t* stats) {
+    if (!h || !stats) return FVM_ERR_ARG;
+    for (int i = 0; i < 16; ++i) stats[i] = h->stats[i];
+    return FVM_OK;
+}

@@ -1,0 +1,370 @@
+"""FVMGeometry / FVMProblem / FVMSystem / SteadyFVMProblem and the GPU `fvm_eqs!`.
+
+Mirrors /root/reference/src/geometry.jl, src/problem.jl and src/solve.jl:1-42: the constructors
+keep the reference's names, keyword arguments and assertions; `get_cuda_parameters(prob)` is the
+sibling of `get_multithreading_parameters` that holds the libfvmcuda handle, and
+`fvm_eqs(du, u, p, t)` is `fvm_eqs!` for `p.parallel == "cuda"`."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import functors as F
+from .conditions import BoundaryConditions, Conditions, InternalConditions
+
+
+class FVMGeometry:
+    """geometry.jl:44-49.  The control-volume data lives on the device; `cv_volumes` and
+    `triangle_props` are read back on demand (parity checks, host-side tabulation)."""
+
+    def __init__(self, tri):
+        self.triangulation = tri
+        self._geom = None
+
+    def _fetch(self):
+        if self._geom is None:
+            tri = self.triangulation
+            h = _create_handle(tri, 1)
+            try:
+                L.check(h, L.lib().fvm_finalize(h, 0, 0))
+                N, T = tri.num_points, tri.num_triangles
+                V = np.empty(N)
+                s9 = np.empty((T, 9))
+                mid = np.empty((T, 3, 2))
+                nrm = np.empty((T, 3, 2))
+                ln = np.empty((T, 3))
+                L.check(h, L.lib().fvm_get_geometry(h, L.dp(V), L.dp(s9), L.dp(mid), L.dp(nrm), L.dp(ln)))
+                self._geom = dict(cv_volumes=V, s=s9, mid=mid, nrm=nrm, len=ln)
+            finally:
+                L.lib().fvm_destroy(h)
+        return self._geom
+
+    @property
+    def cv_volumes(self):
+        return self._fetch()["cv_volumes"]
+
+    @property
+    def triangle_props(self):
+        """dict of arrays in the caller's triangle order: s (T,9), mid (T,3,2), nrm (T,3,2), len (T,3)"""
+        return self._fetch()
+
+    # host-side evaluation points for (x,y)-only coefficient tabulation, geometry.jl:114-151
+    def cv_edge_midpoints(self):
+        P, Tr = self.triangulation.points, self.triangulation.triangles
+        p, q, r = P[Tr[:, 0]], P[Tr[:, 1]], P[Tr[:, 2]]
+        c = (p + q + r) / 3
+        out = np.empty((len(Tr), 3, 2))
+        for e, (a, b) in enumerate(((p, q), (q, r), (r, p))):
+            out[:, e, :] = ((a + b) / 2 + c) / 2
+        return out
+
+    def boundary_quarter_points(self, uv):
+        """control_volumes.jl:41-56: m_i, m_j of every boundary edge, shape (Eb,2,2)."""
+        P = self.triangulation.points
+        p, q = P[uv[:, 0]], P[uv[:, 1]]
+        mij = (p + q) / 2
+        return np.stack([(p + mij) / 2, (q + mij) / 2], axis=1)
+
+
+def _create_handle(tri, neq, device=None):
+    if device is None:
+        device = _current_device()
+    h = L.H()
+    pts = L.f64(tri.points)
+    tr = L.i32(tri.triangles)
+    rc = L.lib().fvm_create(L.dp(pts), tri.num_points, L.ip(tr), tri.num_triangles, 0, neq, device, C.byref(h))
+    if rc != L.OK:
+        raise L.FVMCudaError(rc, L.lib().fvm_last_error(None).decode())
+    return h
+
+
+def _current_device():
+    import os
+    return int(os.environ.get("FVM_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def construct_flux_function(q, D, Dp=None):
+    """problem.jl:425-440: a diffusion function is turned into a flux spec."""
+    if q is not None:
+        return q
+    if D is None:
+        raise AssertionError("either flux_function or diffusion_function must be given")
+    if isinstance(D, (int, float)):
+        return F.ConstantDiffusion(float(D))
+    return D
+
+
+_FLUX_TYPES = (F.ConstantDiffusion, F.TabulatedDiffusion, F.PowerDiffusion, F.AdvectionDiffusionFlux, F.KellerSegelFlux)
+_SRC_TYPES = (F.ZeroSource, F.LinearSource, F.LogisticSource, F.TabulatedSource, F.GrayScottSource, F.BrusselatorSource,
+              F.KellerSegelSource)
+
+
+class FVMProblem:
+    """problem.jl:96-163."""
+
+    def __init__(self, mesh, boundary_conditions, internal_conditions=None, *,
+                 diffusion_function=None, diffusion_parameters=None,
+                 source_function=None, source_parameters=None,
+                 flux_function=None, flux_parameters=None,
+                 initial_condition, initial_time=0.0, final_time):
+        ic = np.ascontiguousarray(initial_condition, dtype=np.float64)
+        if ic.ndim != 1 or len(ic) != mesh.triangulation.num_points:
+            raise AssertionError("The initial condition must have the same number of elements as the number of nodes "
+                                 "in the mesh (including nodes that aren't vertices in the mesh itself).")
+        self.mesh = mesh
+        if isinstance(boundary_conditions, Conditions):
+            self.conditions = boundary_conditions
+        else:
+            self.conditions = Conditions(mesh, boundary_conditions, internal_conditions or InternalConditions())
+        self.flux_function = construct_flux_function(flux_function, diffusion_function, diffusion_parameters)
+        self.flux_parameters = flux_parameters
+        self.source_function = source_function if source_function is not None else F.ZeroSource()
+        self.source_parameters = source_parameters
+        self.initial_condition = ic
+        self.initial_time = float(initial_time)
+        self.final_time = float(final_time)
+        _check_registry(self.flux_function, _FLUX_TYPES, "flux/diffusion")
+        _check_registry(self.source_function, _SRC_TYPES, "source")
+
+    neqs = 0
+    problems = property(lambda self: (self,))
+
+    def __repr__(self):
+        nv = int(self.mesh.triangulation.solid_vertex_mask().sum())
+        return "FVMProblem with %d nodes and time span (%s, %s)" % (nv, self.initial_time, self.final_time)
+
+
+def _check_registry(fn, types, what):
+    if not isinstance(fn, types):
+        raise L.UnsupportedClosureError(
+            L.ERR_UNSUPPORTED,
+            "%s function %r is not in the compiled device registry (%s); arbitrary closures cannot run on the GPU. "
+            "(x,y)-only functions can be wrapped in TabulatedDiffusion / TabulatedSource."
+            % (what, fn, ", ".join(t.__name__ for t in types)))
+
+
+class FVMSystem:
+    """problem.jl:233-279, 359-411: state is (N, neq) C-order == Julia's Matrix(neq, N)."""
+
+    def __init__(self, *probs):
+        if len(probs) == 0:
+            raise AssertionError("There must be at least one problem.")
+        self.problems = tuple(probs)
+        self.mesh = probs[0].mesh
+        if not all(p.mesh is self.mesh for p in probs):
+            raise AssertionError("All problems must have the same mesh.")
+        if not all(p.initial_time == probs[0].initial_time for p in probs):
+            raise AssertionError("All problems must have the same initial time.")
+        if not all(p.final_time == probs[0].final_time for p in probs):
+            raise AssertionError("All problems must have the same final time.")
+        self.initial_time, self.final_time = probs[0].initial_time, probs[0].final_time
+        self.neqs = len(probs)
+        self.initial_condition = np.ascontiguousarray(np.stack([p.initial_condition for p in probs], axis=1))
+        self.conditions = tuple(p.conditions for p in probs)
+        nf = [len(p.conditions.functions) for p in probs]
+        self.cnum_fncs = tuple(int(x) for x in np.concatenate([[0], np.cumsum(nf)[:-1]]))  # problem.jl:380-383
+
+    def __repr__(self):
+        return "FVMSystem with %d equations and time span (%s, %s)" % (self.neqs, self.initial_time, self.final_time)
+
+
+class SteadyFVMProblem:
+    """problem.jl:174-180."""
+
+    def __init__(self, prob):
+        self.problem = prob
+        self.neqs = prob.neqs
+
+
+# ---------------------------------------------------------------------------------------------
+class Engine:
+    """Owns one libfvmcuda handle for a problem (RHS) or a template (linear operator)."""
+
+    def __init__(self, mesh, neq, conditions, flux=None, source=None, tile_triangles=0, geometry_mode=0, device=None):
+        lib = L.lib()
+        tri = mesh.triangulation
+        self.mesh, self.neq = mesh, neq
+        self.N, self.T = tri.num_points, tri.num_triangles
+        self.h = _create_handle(tri, neq, device)
+        self._keep = []
+        try:
+            uv = conditions[0].boundary_edges
+            self.boundary_edges = uv
+            L.check(self.h, lib.fvm_set_boundary_edges(self.h, L.ip(L.i32(uv)), len(uv)))
+            for v, c in enumerate(conditions):
+                ek, ef = np.ascontiguousarray(c.edge_kind, np.uint8), L.i32(c.edge_fidx)
+                nk, nf = np.ascontiguousarray(c.node_kind, np.uint8), L.i32(c.node_fidx)
+                L.check(self.h, lib.fvm_set_edge_conditions(self.h, v, L.bp(ek), L.ip(ef)))
+                L.check(self.h, lib.fvm_set_node_conditions(self.h, v, L.bp(nk), L.ip(nf)))
+                used = set(np.unique(nf[nk != 0]).tolist()) | set(np.unique(ef[ek == 1]).tolist())
+                for fidx in sorted(used):
+                    fid, params = F.cond_spec(c.functions[fidx])
+                    p = L.f64(params)
+                    L.check(self.h, lib.fvm_set_condition_fn(self.h, v, fidx, fid, L.dp(p), len(p)))
+            if flux is not None:
+                self._set_flux(flux, uv)
+            if source is not None:
+                self._set_source(source)
+            L.check(self.h, lib.fvm_finalize(self.h, tile_triangles, geometry_mode))
+        except Exception:
+            lib.fvm_destroy(self.h)
+            self.h = None
+            raise
+
+    def _set_flux(self, specs, uv):
+        lib = L.lib()
+        s0 = specs[0]
+        if not all(type(s) is type(s0) for s in specs):
+            raise L.UnsupportedClosureError(L.ERR_UNSUPPORTED, "all species of an FVMSystem must use the same flux model class")
+        if isinstance(s0, F.ConstantDiffusion):
+            model, p = F.FLUX_DIFF_CONST, [s.D for s in specs]
+        elif isinstance(s0, F.TabulatedDiffusion):
+            if not all(s.fn is s0.fn for s in specs):
+                raise L.UnsupportedClosureError(L.ERR_UNSUPPORTED, "a tabulated diffusion function must be shared by all species")
+            mid = self.mesh.cv_edge_midpoints()
+            dt = L.f64(np.broadcast_to(s0.fn(mid[..., 0], mid[..., 1]), mid.shape[:2]))
+            qp = self.mesh.boundary_quarter_points(uv) if len(uv) else np.zeros((0, 2, 2))
+            db = L.f64(np.broadcast_to(s0.fn(qp[..., 0], qp[..., 1]), qp.shape[:2]))
+            L.check(self.h, lib.fvm_set_flux_table(self.h, L.dp(dt), L.dp(db)))
+            return
+        elif isinstance(s0, F.PowerDiffusion):
+            model, p = F.FLUX_DIFF_POWER, [x for s in specs for x in (s.D0, s.m, 1.0 if s.use_abs else 0.0)]
+        elif isinstance(s0, F.AdvectionDiffusionFlux):
+            model, p = F.FLUX_ADVDIFF, [x for s in specs for x in (s.D, s.nu_x, s.nu_y)]
+        elif isinstance(s0, F.KellerSegelFlux):
+            if not all(s == s0 for s in specs):
+                raise AssertionError("KellerSegelFlux must be the same spec on every species")
+            model, p = F.FLUX_KELLER_SEGEL, [s0.c, s0.D]
+        else:
+            _check_registry(s0, _FLUX_TYPES, "flux/diffusion")
+        p = L.f64(p)
+        L.check(self.h, lib.fvm_set_flux(self.h, model, L.dp(p), len(p)))
+
+    def _set_source(self, specs):
+        lib = L.lib()
+        s0 = specs[0]
+        system_specs = (F.GrayScottSource, F.BrusselatorSource, F.KellerSegelSource)
+        if isinstance(s0, system_specs):
+            if not all(s == s0 for s in specs):
+                raise AssertionError("%s must be the same spec on every species" % type(s0).__name__)
+            model = {F.GrayScottSource: F.SRC_GRAY_SCOTT, F.BrusselatorSource: F.SRC_BRUSSELATOR,
+                     F.KellerSegelSource: F.SRC_KELLER_SEGEL}[type(s0)]
+            p = {F.GrayScottSource: lambda s: [s.b, s.d], F.BrusselatorSource: lambda s: [],
+                 F.KellerSegelSource: lambda s: [s.a]}[type(s0)](s0)
+        elif all(isinstance(s, F.ZeroSource) for s in specs):
+            return
+        elif any(isinstance(s, F.TabulatedSource) for s in specs):
+            P = self.mesh.triangulation.points
+            tab = np.zeros((self.N, self.neq))
+            for v, s in enumerate(specs):
+                if isinstance(s, F.TabulatedSource):
+                    tab[:, v] = s.fn(P[:, 0], P[:, 1])
+                elif not isinstance(s, F.ZeroSource):
+                    raise L.UnsupportedClosureError(L.ERR_UNSUPPORTED, "tabulated sources can only be mixed with ZeroSource")
+            tab = L.f64(tab)
+            L.check(self.h, lib.fvm_set_source_table(self.h, L.dp(tab)))
+            return
+        elif all(isinstance(s, (F.LinearSource, F.ZeroSource)) for s in specs):
+            model = F.SRC_LINEAR
+            p = [x for s in specs for x in ((s.lam, s.mu) if isinstance(s, F.LinearSource) else (0.0, 0.0))]
+        elif all(isinstance(s, (F.LogisticSource, F.ZeroSource)) for s in specs):
+            model = F.SRC_LOGISTIC
+            p = [s.lam if isinstance(s, F.LogisticSource) else 0.0 for s in specs]
+        else:
+            raise L.UnsupportedClosureError(L.ERR_UNSUPPORTED, "this combination of per-species source models is not compiled")
+        p = L.f64(p)
+        L.check(self.h, lib.fvm_set_source(self.h, model, L.dp(p) if len(p) else None, len(p)))
+
+    # ---- calls ----
+    def rhs(self, du, u, t):
+        L.check(self.h, L.lib().fvm_rhs(self.h, float(t), u.ctypes.data, du.ctypes.data, 0))
+        return du
+
+    def rhs_device(self, du_ptr, u_ptr, t, native=False):
+        if native:
+            L.check(self.h, L.lib().fvm_rhs_native(self.h, float(t), u_ptr, du_ptr))
+        else:
+            L.check(self.h, L.lib().fvm_rhs(self.h, float(t), u_ptr, du_ptr, 1))
+
+    def apply_dirichlet(self, u, t):
+        L.check(self.h, L.lib().fvm_apply_dirichlet(self.h, float(t), u.ctypes.data, 0))
+        return u
+
+    def synchronize(self):
+        L.check(self.h, L.lib().fvm_stream_synchronize(self.h))
+
+    def stream(self):
+        s = C.c_void_p()
+        L.check(self.h, L.lib().fvm_get_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def stats(self):
+        st = np.zeros(16, dtype=np.int64)
+        L.check(self.h, L.lib().fvm_get_stats(self.h, st.ctypes.data_as(L.c_lp)))
+        keys = ["n_tiles", "tile_triangles", "n_vertices", "n_interface", "n_partial", "n_external", "max_local_nodes",
+                "n_live_boundary_edges", "n_dirichlet", "smem_bytes"]
+        return dict(zip(keys, st.tolist()))
+
+    def permutation(self):
+        node = np.empty(self.N, dtype=np.int32)
+        tri = np.empty(self.T, dtype=np.int32)
+        L.check(self.h, L.lib().fvm_get_permutation(self.h, L.ip(node), L.ip(tri)))
+        return node, tri
+
+    def geometry(self):
+        V = np.empty(self.N)
+        s9 = np.empty((self.T, 9))
+        mid = np.empty((self.T, 3, 2))
+        nrm = np.empty((self.T, 3, 2))
+        ln = np.empty((self.T, 3))
+        L.check(self.h, L.lib().fvm_get_geometry(self.h, L.dp(V), L.dp(s9), L.dp(mid), L.dp(nrm), L.dp(ln)))
+        return dict(cv_volumes=V, s=s9, mid=mid, nrm=nrm, len=ln)
+
+    def close(self):
+        if getattr(self, "h", None):
+            L.lib().fvm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaParameters:
+    """The `p` of fvm_eqs!(du,u,p,t) (main_equations.jl:8-26) for the GPU path."""
+    parallel = "cuda"
+
+    def __init__(self, prob, engine):
+        self.prob = prob
+        self.engine = engine
+
+
+def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None):
+    """Sibling of get_multithreading_parameters (solve.jl:1-27): builds the device state once."""
+    if isinstance(prob, SteadyFVMProblem):
+        prob = prob.problem
+    probs = prob.problems
+    neq = max(1, prob.neqs)
+    conds = [p.conditions for p in probs]
+    eng = Engine(prob.mesh, neq, conds, [p.flux_function for p in probs], [p.source_function for p in probs],
+                 tile_triangles, geometry_mode, device)
+    return CudaParameters(prob, eng)
+
+
+def fvm_eqs(du, u, p, t):
+    """fvm_eqs!(du, u, p, t) (main_equations.jl:28-35) for p.parallel == "cuda".  `u`/`du` are host
+    float64 arrays of shape (N,) or (N, neq) in the caller's node order; mutates and returns du."""
+    if u.dtype != np.float64 or du.dtype != np.float64:
+        raise TypeError("the GPU path supports Float64 only (ForwardDiff duals are rejected)")
+    if u.shape != p.prob.initial_condition.shape or du.shape != u.shape:
+        raise AssertionError("u and du must have the shape of the initial condition")
+    if not (u.flags.c_contiguous and du.flags.c_contiguous):
+        raise AssertionError("u and du must be contiguous")
+    return p.engine.rhs(du, u, t)
+
+
+def update_dirichlet_nodes(u, t, p):
+    """update_dirichlet_nodes!(integrator) (dirichlet.jl:78-86)."""
+    return p.engine.apply_dirichlet(u, t)

@@ -1,0 +1,187 @@
+/*
+ * fvmcuda.h — C ABI of libfvmcuda.so, the B200 (sm_100a) engine behind
+ * FiniteVolumeMethod.jl's semi-discrete right-hand side `fvm_eqs!` and its
+ * linear-template operator path.
+ *
+ * Conventions
+ *  - every call returns an int32 status (FVM_OK == 0); fvm_last_error(h) gives
+ *    the message of the last failing call on that handle;
+ *  - the caller owns every host buffer, the library owns every device buffer
+ *    behind the handle; a handle is bound to one device and one stream and is
+ *    not thread-safe; distinct handles may be used from distinct host threads;
+ *  - vectors cross the ABI in the CALLER's node/triangle numbering and in the
+ *    reference's memory layout: a system state `u::Matrix(neq, N)` (column
+ *    major) is species-interleaved per node.  The tile/Hilbert renumbering is
+ *    internal ("native" order); the *_native entry points expose it so an
+ *    integrator can keep its state resident without a permutation per call;
+ *  - `on_device` != 0 means the pointer arguments are device pointers on the
+ *    handle's device;
+ *  - there is no CPU fallback: without a CUDA device every compute call fails
+ *    with FVM_ERR_CUDA.
+ *
+ * File:line citations are relative to /root/reference (FiniteVolumeMethod.jl v1.2.3).
+ */
+#ifndef FVMCUDA_H
+#define FVMCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fvm_ctx* fvm_handle;
+
+enum fvm_status {
+    FVM_OK = 0,
+    FVM_ERR_ARG = 1,         /* invalid argument (the reference's @assert / ArgumentError) */
+    FVM_ERR_CUDA = 2,        /* CUDA runtime failure, including "no device" */
+    FVM_ERR_UNSUPPORTED = 3, /* functor / closure outside the registry (north_star b) */
+    FVM_ERR_STATE = 4,       /* call order violated (e.g. rhs before finalize) */
+    FVM_ERR_NCCL = 5
+};
+
+/* node condition kinds: src/conditions.jl:36-41, flattened per node / per boundary edge */
+enum fvm_node_kind { FVM_NODE_FREE = 0, FVM_NODE_DIRICHLET = 1, FVM_NODE_DUDT = 2 };
+enum fvm_edge_kind { FVM_EDGE_NONE = 0, FVM_EDGE_NEUMANN = 1, FVM_EDGE_CONSTRAINED = 2 };
+
+/* Flux models q(x,y,t,alpha,beta,gamma,p): the registry that replaces Julia closures
+ * (src/problem.jl:113-116, 425-440).  One model per handle; parameters are per species. */
+enum fvm_flux_model {
+    FVM_FLUX_DIFF_CONST = 0,  /* q_v = -D_v grad u_v                 params: D_v (neq)            */
+    FVM_FLUX_DIFF_TABLE = 1,  /* q_v = -D(x_e) grad u_v, D tabulated by fvm_set_flux_table        */
+    FVM_FLUX_DIFF_POWER = 2,  /* D = D0_v |u_v|^(m_v-1)              params: (D0_v, m_v) per v    */
+    FVM_FLUX_ADVDIFF = 3,     /* q_v = nu_v u_v - D_v grad u_v       params: (D_v, nux_v, nuy_v)  */
+    FVM_FLUX_KELLER_SEGEL = 4 /* neq=2: q_u = chi(u) grad v - grad u, chi = c u/(1+u^2);
+                                 q_v = -D grad v                    params: (c, D)               */
+};
+
+/* Source models S(x,y,t,u,p): src/problem.jl:10-13, 342-345 */
+enum fvm_source_model {
+    FVM_SRC_ZERO = 0,
+    FVM_SRC_LINEAR = 1,      /* S_v = lam_v u_v + mu_v              params: (lam_v, mu_v) per v   */
+    FVM_SRC_LOGISTIC = 2,    /* S_v = lam_v u_v (1 - u_v)           params: lam_v                 */
+    FVM_SRC_TABLE = 3,       /* S_v(x_i) tabulated by fvm_set_source_table                        */
+    FVM_SRC_GRAY_SCOTT = 4,  /* neq=2: b(1-u) - u v^2 ; -d v + u v^2        params: (b, d)        */
+    FVM_SRC_BRUSSELATOR = 5, /* neq=2: u^2 v - (b+1)... as the tutorial: u^2 v - 2u ; -u^2 v + u  */
+    FVM_SRC_KELLER_SEGEL = 6 /* neq=2: u(1-u) ; u - a v                     params: a             */
+};
+
+/* Boundary / internal condition functions a(x,y,t,u,p): src/conditions.jl:16-20 */
+enum fvm_cond_fn {
+    FVM_COND_CONST = 0,    /* c0                                   */
+    FVM_COND_AFFINE_U = 1, /* c0 + c1 * u_var                      */
+    FVM_COND_EXP_SAT = 2,  /* c0 * (1 - exp(-t / c1))              */
+    FVM_COND_LINEAR_XY = 3 /* c0 + c1 x + c2 y                     */
+};
+
+/* Linear templates: src/specific_problems/*.jl */
+enum fvm_template {
+    FVM_TPL_DIFFUSION = 0,                 /* diffusion_equation.jl:69-101 */
+    FVM_TPL_LINEAR_REACTION_DIFFUSION = 1, /* linear_reaction_diffusion_equations.jl:76-125 */
+    FVM_TPL_MEAN_EXIT_TIME = 2,            /* mean_exit_time.jl:57-94 */
+    FVM_TPL_POISSON = 3,                   /* poissons_equation.jl:58-88 */
+    FVM_TPL_LAPLACE = 4                    /* laplaces_equation.jl:51-78 */
+};
+
+enum fvm_krylov_method { FVM_KRYLOV_PCG = 0, FVM_KRYLOV_BICGSTAB = 1 };
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+
+/* Replaces FVMGeometry(tri) (src/geometry.jl:99-169): takes the triangulation's points
+ * (interleaved x,y) and solid triangles (ccw, stored rotation kept), `index_base` 1 for
+ * Julia.  neq = 1 for FVMProblem, N for FVMSystem{N} (src/problem.jl:233-279). */
+int32_t fvm_create(const double* xy, int64_t n_points, const int32_t* triangles, int64_t n_triangles,
+                   int32_t index_base, int32_t neq, int32_t device, fvm_handle* out);
+
+/* keys(get_boundary_edge_map(tri)) as directed ccw edges (u,v)
+ * (src/equations/boundary_edge_contributions.jl:89-94). */
+int32_t fvm_set_boundary_edges(fvm_handle h, const int32_t* uv, int64_t n_edges);
+
+/* Conditions flattened per species (src/conditions.jl:506-544, src/problem.jl:322-357):
+ * kind/fidx per boundary edge, in the order given to fvm_set_boundary_edges ... */
+int32_t fvm_set_edge_conditions(fvm_handle h, int32_t var, const uint8_t* kind, const int32_t* fidx);
+/* ... and per node (Dirichlet takes precedence over Dudt: resolve before calling,
+ * src/equations/source_contributions.jl:5-12). */
+int32_t fvm_set_node_conditions(fvm_handle h, int32_t var, const uint8_t* kind, const int32_t* fidx);
+/* condition function `fidx` of species `var` (0-based) from the registry. */
+int32_t fvm_set_condition_fn(fvm_handle h, int32_t var, int32_t fidx, int32_t fn_id, const double* params,
+                             int32_t nparams);
+
+int32_t fvm_set_flux(fvm_handle h, int32_t model, const double* params, int32_t nparams);
+/* D at the 3T cv-edge midpoints (layout [T][3], caller triangle order) and at the 2 quarter
+ * points of every boundary edge (layout [Eb][2]); for (x,y)-only diffusion functions. */
+int32_t fvm_set_flux_table(fvm_handle h, const double* d_cv_edge, const double* d_bnd);
+int32_t fvm_set_source(fvm_handle h, int32_t model, const double* params, int32_t nparams);
+int32_t fvm_set_source_table(fvm_handle h, const double* s_node /* [N][neq] */);
+
+/* Freezes the mesh: Hilbert-sorts triangles into tiles, renumbers nodes tile-major, builds the
+ * per-tile gather lists that make the scatter deterministic (no fp64 atomics), computes the
+ * geometry SoA on the device.  Options: tile_triangles (0 = default 1024),
+ * geometry_mode 0 = stored SoA (north_star layout), 1 = recomputed from vertex coordinates. */
+int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t geometry_mode);
+int32_t fvm_destroy(fvm_handle h);
+const char* fvm_last_error(fvm_handle h);
+const char* fvm_version(void);
+
+/* ---- the right-hand side (src/equations/main_equations.jl:28-44) -------------------- */
+
+/* du = fvm_eqs!(du, u, p, t): triangle pass, boundary-edge pass, node pass. */
+int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, int32_t on_device);
+/* same on device vectors already in native order (see fvm_to_native) */
+int32_t fvm_rhs_native(fvm_handle h, double t, const double* u_native, double* du_native);
+/* update_dirichlet_nodes! (src/equations/dirichlet.jl:78-86): u[i] = a(x_i,y_i,t,u[i]) */
+int32_t fvm_apply_dirichlet(fvm_handle h, double t, double* u, int32_t on_device);
+int32_t fvm_apply_dirichlet_native(fvm_handle h, double t, double* u_native);
+int32_t fvm_to_native(fvm_handle h, const double* v_caller_dev, double* v_native_dev);
+int32_t fvm_from_native(fvm_handle h, const double* v_native_dev, double* v_caller_dev);
+/* the *_native calls are asynchronous on the handle's stream */
+int32_t fvm_stream_synchronize(fvm_handle h);
+int32_t fvm_get_stream(fvm_handle h, void** cuda_stream);
+
+/* ---- geometry / connectivity read-back for parity (src/geometry.jl:21-49) ----------- */
+/* caller order; any pointer may be NULL.  V[N]; s9[T][9]; mid6[T][3][2]; nrm6[T][3][2]; len3[T][3] */
+int32_t fvm_get_geometry(fvm_handle h, double* V, double* s9, double* mid6, double* nrm6, double* len3);
+/* native permutations: node_perm[new] = old (N), tri_perm[new] = old (T); tile layout stats */
+int32_t fvm_get_permutation(fvm_handle h, int32_t* node_perm, int32_t* tri_perm);
+int32_t fvm_get_stats(fvm_handle h, int64_t* stats /* [16] */);
+
+/* ---- linear templates (src/specific_problems/abstract_templates.jl:73-325) ---------- */
+
+/* Assembles A (CSR on the structural pattern of jacobian_sparsity, src/solve.jl:56-77) and b on
+ * the device.  d_const is used when d_cv_edge == NULL.  node_value[N]: value of the node's
+ * condition function (Dirichlet value for u0 / steady b, Dudt value for b); edge_value[Eb][2]:
+ * Neumann function at the quarter points; source[N]: f(x_i) for Poisson, the diagonal term for
+ * linear reaction-diffusion; pointers may be NULL where the template does not use them.
+ * reference_quirks != 0 reproduces abstract_templates.jl:262 (j row scaled by 1/V_i). */
+int32_t fvm_assemble(fvm_handle h, int32_t template_id, double d_const, const double* d_cv_edge,
+                     const double* d_bnd, const double* node_value, const double* edge_value,
+                     const double* source, int32_t reference_quirks);
+int32_t fvm_get_csr_size(fvm_handle h, int64_t* n_rows, int64_t* nnz);
+/* caller numbering, columns sorted within a row, explicit zeros kept on the structural pattern */
+int32_t fvm_get_csr(fvm_handle h, int32_t* rowptr, int32_t* col, double* val, double* b);
+/* y = A x + b (add_b != 0) or y = A x : the MatrixOperator mul! of diffusion_equation.jl:93-94 */
+int32_t fvm_spmv(fvm_handle h, const double* x, double* y, int32_t add_b, int32_t on_device);
+int32_t fvm_spmv_native(fvm_handle h, const double* x_native, double* y_native, int32_t add_b);
+
+/* Device-resident fixed-step Tsit5 (solve(prob, Tsit5(); adaptive=false, dt)).  use_operator != 0
+ * integrates du/dt = A u + b (templates), else du/dt = fvm_eqs!(u,t) with the Dirichlet callback
+ * after every step.  u: in u0, out u(t1), caller order, host or device.  usave[nsave][len] receives
+ * the states at tsave (each must be a step boundary). */
+int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, double t0, double t1, double dt,
+                  int64_t nsave, const double* tsave, double* usave, int32_t on_device);
+
+/* Steady templates: solves A x = b with Jacobi-preconditioned CG (on the symmetrised system
+ * -V A, Dirichlet-consistent start) or BiCGStab.  x: in initial guess, out solution. */
+int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rtol, int32_t maxit, int32_t* iters,
+                   double* relres, int32_t on_device);
+
+/* ---- multi-GPU: row-strip / tile-range sharding with a one-layer node halo ---------- */
+/* nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 and broadcast by the host. */
+int32_t fvm_shard_init(fvm_handle h, const void* nccl_unique_id, int32_t rank, int32_t nranks);
+int32_t fvm_nccl_unique_id(void* out128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FVMCUDA_H */

@@ -1,0 +1,122 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol of include/fvmcuda.h, the host
+mirror reproduces the reference's constructors/assertions/condition flattening, integer mesh arrays
+are bit-exact against the oracle, and the product fails loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fvm_b200 as G
+from oracle import fvm_oracle as O
+from tests.common import Pair, delaunay_mesh
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "fvmcuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(fvm_[a-z0-9_]+)\s*\(", hdr)))
+    assert set(declared) == set(G.exported_symbols())
+    lib = ctypes.CDLL(G.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    lib.fvm_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.fvm_version()
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "finitevolumemethod.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src, f
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-device failure path")
+def test_no_cpu_fallback_without_device():
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 4, 4, single_boundary=True))
+    gp, _ = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(1.0))
+    with pytest.raises(G.FVMCudaError) as e:
+        G.get_cuda_parameters(gp)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_lattice_connectivity_bit_exact():
+    """Integer mesh/connectivity arrays bit-exact vs the oracle."""
+    for single in (True, False):
+        g = G.triangulate_rectangle(0.0, 2.0, -1.0, 3.0, 12, 19, single_boundary=single)
+        o = O.triangulate_rectangle(0.0, 2.0, -1.0, 3.0, 12, 19, single_boundary=single)
+        assert np.array_equal(g.points, o.points)
+        assert np.array_equal(g.triangles, o.triangles)
+        assert len(g.boundary_sections) == len(o.boundary_sections)
+        for a, b in zip(g.boundary_sections, o.boundary_sections):
+            assert np.array_equal(a, b)
+        uv, _ = g.boundary_edges()
+        assert [tuple(e) for e in uv.tolist()] == list(o.boundary_edge_map.keys())
+    # test/test_functions.jl:112: 7+(i-1)*12 is a vertical node line for nx = 12 (1-based)
+    assert np.all(g.points[6 + 12 * np.arange(19), 0] == g.points[6, 0])
+    # test/equations.jl:42: (1,2,201) is a stored triangle for nx = 200
+    assert (G.triangulate_rectangle(0, 1, 0, 1, 200, 200).triangles[0] == [0, 1, 200]).all()
+
+
+def test_chained_boundary_matches_oracle():
+    g = delaunay_mesh(300, 2)
+    o = O.Triangulation(g.points, g.triangles.astype(np.int64))
+    assert len(g.boundary_sections) == len(o.boundary_sections) == 1
+    assert np.array_equal(g.boundary_sections[0], o.boundary_sections[0])
+
+
+def test_conditions_flattening_matches_reference_dicts():
+    """merge_conditions! (conditions.jl:506-544): same edge/node maps as the oracle's Dicts."""
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 9, 7, single_boundary=False))
+    specs = (G.Const(1.0), G.Const(2.0), G.Const(3.0), G.Const(4.0))
+    types = (G.Neumann, G.Dirichlet, G.Dudt, G.Constrained)
+    internal = ((G.Const(5.0),), {20: 0, 21: 0}, {22: 0, 20: 0})
+    gp, op = pair.problem(specs, types, G.ConstantDiffusion(1.0), internal=internal)
+    gc, oc = gp.conditions, op.conditions
+    assert gc.get_dirichlet_nodes() == dict(sorted(oc.dirichlet_nodes.items()))
+    assert gc.get_dudt_nodes() == dict(sorted(oc.dudt_nodes.items()))
+    assert gc.get_neumann_edges() == oc.neumann_edges
+    assert len(gc.functions) == len(oc.functions) == 5
+    for i in range(pair.gtri.num_points):
+        assert gc.has_condition(i) == oc.has_condition(i)
+        if oc.is_dirichlet_node(i):
+            assert gc.node_kind[i] == 1 and gc.node_fidx[i] == oc.dirichlet_nodes[i]
+        elif oc.is_dudt_node(i):
+            assert gc.node_kind[i] == 2 and gc.node_fidx[i] == oc.dudt_nodes[i]
+    assert gc.has_constrained_edges() and gc.has_neumann_edges() and gc.has_dudt_nodes()
+
+
+def test_constructor_errors_mirror_the_reference():
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 5, 5, single_boundary=True))
+    mesh = pair.gmesh
+    BCs = G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet)
+    with pytest.raises(AssertionError):  # problem.jl:131-132
+        G.FVMProblem(mesh, BCs, diffusion_function=1.0, initial_condition=np.zeros(24), final_time=1.0)
+    with pytest.raises(AssertionError):  # one function per boundary section
+        G.BoundaryConditions(mesh, (G.Const(0.0), G.Const(1.0)), (G.Dirichlet, G.Dirichlet))
+    with pytest.raises(G.UnsupportedClosureError):  # closures cannot run on the device
+        G.FVMProblem(mesh, BCs, diffusion_function=lambda x, y, t, u, p: 1.0, initial_condition=np.zeros(25), final_time=1.0)
+    with pytest.raises(G.UnsupportedClosureError):
+        G.FVMProblem(mesh, BCs, diffusion_function=1.0, source_function=lambda x, y, t, u, p: u,
+                     initial_condition=np.zeros(25), final_time=1.0)
+    p1 = G.FVMProblem(mesh, BCs, diffusion_function=1.0, initial_condition=np.zeros(25), final_time=1.0)
+    p2 = G.FVMProblem(mesh, BCs, diffusion_function=1.0, initial_condition=np.zeros(25), final_time=2.0)
+    with pytest.raises(AssertionError):  # problem.jl:249-271
+        G.FVMSystem(p1, p2)
+    with pytest.raises(AssertionError):
+        G.FVMSystem()
+    sys_ = G.FVMSystem(p1, p1)
+    assert sys_.initial_condition.shape == (25, 2) and sys_.cnum_fncs == (0, 1)
+    assert "FVMProblem with 25 nodes" in repr(p1)

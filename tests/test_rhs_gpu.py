@@ -1,0 +1,186 @@
+"""GPU parity of the right-hand side: libfvmcuda (through the C ABI) vs the CPU oracle on the
+same seeded inputs.  Bar (BASELINE.json): one RHS evaluation within 1e-12 relative error (fp64,
+only the summation order differs); geometry bit-exact; integer connectivity bit-exact."""
+import numpy as np
+import pytest
+
+import fvm_b200 as G
+from oracle import fvm_oracle as O
+from tests.common import RTOL_RHS, Pair, delaunay_mesh, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def run_both(gp, op, u, t=0.0, **kw):
+    p = G.get_cuda_parameters(gp, **kw)
+    du = G.fvm_eqs(np.zeros_like(u), u, p, t)
+    ref = O.fvm_eqs_vec(np.zeros_like(u), u, op, t)
+    return du, ref, p
+
+
+@pytest.mark.parametrize("geometry_mode", [0, 1])
+@pytest.mark.parametrize("tile", [64, 256, 1024])
+def test_readme_diffusion_50x50(geometry_mode, tile):
+    """BASELINE config 1: triangulate_rectangle 50x50 on [0,2]^2, Dirichlet u=0, D=1/9."""
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True))
+    ic = np.where(pair.gtri.points[:, 1] <= 1.0, 50.0, 0.0)
+    gp, op = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(1 / 9), ic=ic, final_time=0.5)
+    for u in (ic, 50 * np.random.default_rng(20240517).random(len(ic))):
+        du, ref, p = run_both(gp, op, u, tile_triangles=tile, geometry_mode=geometry_mode)
+        assert rel_err(du, ref) <= RTOL_RHS
+        # loop oracle == vectorised oracle (bitwise) on this config
+        assert np.array_equal(ref, O.fvm_eqs(np.zeros_like(u), u, op, 0.0))
+        st = p.engine.stats()
+        assert st["n_vertices"] == 2500 and st["n_dirichlet"] == 196 and st["n_live_boundary_edges"] == 0
+
+
+def test_geometry_bit_exact_and_connectivity():
+    """FVMGeometry (geometry.jl:99-169): s, cv-edge midpoints, normals, lengths bit-exact against the
+    oracle; cv volumes to the ulp level (summation order); permutations are bijections."""
+    for gtri in (G.triangulate_rectangle(0, 2, 0, 2, 37, 23, single_boundary=False), delaunay_mesh(700, 1, extra_points=5)):
+        pair = Pair(gtri)
+        gp, _ = pair.problem((G.Const(0.0),) * len(gtri.boundary_sections), (G.Neumann,) * len(gtri.boundary_sections),
+                             G.ConstantDiffusion(1.0))
+        p = G.get_cuda_parameters(gp, tile_triangles=128)
+        geo = p.engine.geometry()
+        om = pair.omesh
+        assert np.array_equal(geo["s"], om.s)
+        assert np.array_equal(geo["mid"], om.mid)
+        assert np.array_equal(geo["nrm"], om.nrm)
+        assert np.array_equal(geo["len"], om.len)
+        assert rel_err(geo["cv_volumes"], om.cv_volumes) <= 4e-16
+        node_perm, tri_perm = p.engine.permutation()
+        assert np.array_equal(np.sort(node_perm), np.arange(gtri.num_points))
+        assert np.array_equal(np.sort(tri_perm), np.arange(gtri.num_triangles))
+        # FVMGeometry read-back without a problem
+        assert np.array_equal(pair.gmesh.cv_volumes, geo["cv_volumes"])
+
+
+def test_convection_all_neumann_robin():
+    """test/test_functions.jl:339-374 (heat convection): four Neumann sections, constant flux at the
+    bottom, Robin (affine in u) at the top."""
+    L, k, T0, Tinf, alpha, q, h = 1.0, 237.0, 10.0, 10.0, 80.0e-6, 10.0, 25.0
+    pair = Pair(G.triangulate_rectangle(0, L, 0, L, 61, 47, single_boundary=False))
+    specs = (G.Const(-alpha * q / k), G.Const(0.0), G.AffineU(-alpha * h / k * Tinf, alpha * h / k), G.Const(0.0))
+    gp, op = pair.problem(specs, (G.Neumann,) * 4, G.ConstantDiffusion(alpha))
+    u = T0 + np.random.default_rng(7).random(pair.gtri.num_points)
+    for mode in (0, 1):
+        du, ref, p = run_both(gp, op, u, tile_triangles=256, geometry_mode=mode)
+        assert rel_err(du, ref) <= RTOL_RHS
+        assert p.engine.stats()["n_live_boundary_edges"] == 2 * 60 + 2 * 46
+
+
+def _split_loop(gtri, k=4):
+    loop = gtri.boundary_sections[0]
+    n = len(loop) - 1
+    cuts = [round(i * n / k) for i in range(k + 1)]
+    secs = [loop[cuts[i]:cuts[i + 1] + 1] for i in range(k)]
+    return G.Triangulation(gtri.points, gtri.triangles, secs)
+
+
+@pytest.mark.parametrize("geometry_mode", [0, 1])
+def test_unstructured_mixed_conditions_power_diffusion(geometry_mode):
+    """Delaunay mesh with points that are not vertices; Dirichlet, Dudt, Neumann and Constrained
+    sections; internal Dirichlet and Dudt nodes; porous-medium diffusion D0*u^(m-1) with a
+    logistic source (docs tutorials porous_medium_equation.jl:50, porous_fisher_equation...jl:60-61)."""
+    gtri = _split_loop(delaunay_mesh(1500, 3, extra_points=7))
+    pair = Pair(gtri)
+    specs = (G.Const(0.25), G.AffineU(0.1, -0.5), G.LinearXY(0.3, 0.2, -0.1), G.Const(0.0))
+    types = (G.Dirichlet, G.Dudt, G.Neumann, G.Constrained)
+    internal = ((G.Const(0.7), G.AffineU(0.0, 1.0)), {200: 0, 201: 0}, {300: 1, 200: 1})
+    rng = np.random.default_rng(11)
+    u = 0.2 + rng.random(gtri.num_points)
+    for flux in (G.PowerDiffusion(0.3, 2.0), G.PowerDiffusion(0.3, 2.5, use_abs=True), G.PowerDiffusion(0.3, 1.0)):
+        gp, op = pair.problem(specs, types, flux, source=G.LogisticSource(1.3), internal=internal)
+        du, ref, p = run_both(gp, op, u, t=0.3, tile_triangles=128, geometry_mode=geometry_mode)
+        assert rel_err(du, ref) <= RTOL_RHS
+        assert np.all(du[-7:] == 0.0)  # points that are not vertices
+        # loop oracle agrees with the vectorised oracle
+        assert rel_err(ref, O.fvm_eqs(np.zeros_like(u), u, op, 0.3)) <= 1e-15
+
+
+def test_tabulated_diffusion_and_source():
+    """(x,y)-only D and S are tabulated per cv-edge / node at setup (north_star b)."""
+    gtri = delaunay_mesh(900, 5)
+    pair = Pair(gtri)
+    Dfn = lambda x, y: 1.0 + 0.5 * np.sin(3 * x) * np.cos(2 * y)
+    Sfn = lambda x, y: np.exp(-x) * y
+    gp, op = pair.problem(G.Const(0.0), G.Neumann, G.TabulatedDiffusion(Dfn), source=G.TabulatedSource(Sfn))
+    u = np.random.default_rng(5).random(gtri.num_points)
+    du, ref, _ = run_both(gp, op, u, tile_triangles=64)
+    assert rel_err(du, ref) <= RTOL_RHS
+
+
+def test_advection_diffusion_and_linear_source():
+    """docs tutorial piecewise_linear_and_natural_neighbour...jl:80-88: q = (nu u - D u_x, -D u_y)."""
+    pair = Pair(G.triangulate_rectangle(-1, 1, -0.5, 0.5, 48, 31, single_boundary=True))
+    gp, op = pair.problem(G.Const(0.0), G.Dirichlet, G.AdvectionDiffusionFlux(0.02, 0.05, 0.0), source=G.LinearSource(-0.2, 0.1))
+    P = pair.gtri.points
+    u = np.exp(-(P[:, 0] ** 2 + P[:, 1] ** 2) / 0.01) / (0.01 * np.pi)
+    for mode in (0, 1):
+        du, ref, _ = run_both(gp, op, u, geometry_mode=mode, tile_triangles=256)
+        assert rel_err(du, ref) <= RTOL_RHS
+
+
+@pytest.mark.parametrize("geometry_mode", [0, 1])
+def test_system_gray_scott_and_keller_segel(geometry_mode):
+    """FVMSystem (problem.jl:233-279): species-interleaved state, per-species conditions, fluxes that
+    see every species (Keller-Segel, src/FiniteVolumeMethod.jl:92-138) and coupled sources."""
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 40, 33, single_boundary=True))
+    N = pair.gtri.num_points
+    rng = np.random.default_rng(13)
+    U = np.ascontiguousarray(np.stack([0.5 + 0.5 * rng.random(N), 0.25 * rng.random(N)], axis=1))
+    # Gray-Scott: zero-flux Neumann, constant per-species diffusion
+    src = G.GrayScottSource(0.04, 0.1)
+    g1, o1 = pair.problem(G.Const(0.0), G.Neumann, G.ConstantDiffusion(2e-5), source=src, var=0, ic=U[:, 0])
+    g2, o2 = pair.problem(G.Const(0.0), G.Neumann, G.ConstantDiffusion(1e-5), source=src, var=1, ic=U[:, 1])
+    du, ref, _ = run_both(G.FVMSystem(g1, g2), O.FVMSystem(o1, o2), U, tile_triangles=256, geometry_mode=geometry_mode)
+    assert du.shape == (N, 2) and rel_err(du, ref) <= RTOL_RHS
+    # Keller-Segel with a Dirichlet condition on species 0 only and a Robin Neumann edge on species 1
+    ks, kss = G.KellerSegelFlux(4.0, 1.0), G.KellerSegelSource(0.1)
+    g1, o1 = pair.problem(G.Const(0.3), G.Dirichlet, ks, source=kss, var=0, ic=U[:, 0])
+    g2, o2 = pair.problem(G.AffineU(0.01, -0.2), G.Neumann, ks, source=kss, var=1, ic=U[:, 1])
+    du, ref, p = run_both(G.FVMSystem(g1, g2), O.FVMSystem(o1, o2), U, t=1.5, tile_triangles=128, geometry_mode=geometry_mode)
+    assert rel_err(du[:, 0], ref[:, 0]) <= RTOL_RHS and rel_err(du[:, 1], ref[:, 1]) <= RTOL_RHS
+    # system of two identical diffusion problems reproduces the scalar problem (test/equations.jl:106-121)
+    g1, o1 = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(1 / 9), var=0, ic=U[:, 0])
+    g2, o2 = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(1 / 9), var=1, ic=U[:, 0])
+    gs, _ = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(1 / 9), ic=U[:, 0])
+    UU = np.ascontiguousarray(np.stack([U[:, 0], U[:, 0]], axis=1))
+    dsys = G.fvm_eqs(np.zeros_like(UU), UU, G.get_cuda_parameters(G.FVMSystem(g1, g2)), 0.0)
+    dsc = G.fvm_eqs(np.zeros(N), np.ascontiguousarray(U[:, 0]), G.get_cuda_parameters(gs), 0.0)
+    assert rel_err(dsys[:, 0], dsc) <= 1e-14 and np.array_equal(dsys[:, 0], dsys[:, 1])
+
+
+def test_dirichlet_callback_time_dependent():
+    """update_dirichlet_nodes! (dirichlet.jl:78-86) with the annulus tutorial's 50(1-exp(-t/2))."""
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 20, 20, single_boundary=False))
+    specs = (G.ExpSaturation(50.0, 2.0), G.Const(1.0), G.LinearXY(0.0, 1.0, 2.0), G.AffineU(0.5, 0.5))
+    gp, op = pair.problem(specs, (G.Dirichlet,) * 4, G.ConstantDiffusion(1.0))
+    u = np.random.default_rng(3).random(400)
+    p = G.get_cuda_parameters(gp)
+    got = G.update_dirichlet_nodes(u.copy(), 0.7, p)
+    ref = O.update_dirichlet_nodes(u.copy(), 0.7, op)
+    # corners belong to two sections: the later section wins in both implementations
+    assert rel_err(got, ref) <= 1e-15
+
+
+def test_determinism_and_midsize_lattice():
+    """512x512 lattice (262k nodes): parity at a size the vectorised oracle finishes in seconds,
+    and bitwise run-to-run determinism (no atomics)."""
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 512, 512, single_boundary=True))
+    N = pair.gtri.num_points
+    u = 50 * np.random.default_rng(20240517).random(N)
+    gp, op = pair.problem(G.Const(0.0), G.Dirichlet, G.PowerDiffusion(1 / 9, 1.0))
+    du, ref, p = run_both(gp, op, u)
+    assert rel_err(du, ref) <= RTOL_RHS
+    du2 = G.fvm_eqs(np.zeros_like(u), u, p, 0.0)
+    assert np.array_equal(du, du2)
+    # linearity of the constant-coefficient operator: F(a u + b w) = a F(u) + b F(w)
+    w = np.random.default_rng(1).random(N)
+    for g in (u, w):
+        g[p.prob.conditions.node_kind != 0] = 0.0
+    Fu = G.fvm_eqs(np.zeros_like(u), u, p, 0.0)
+    Fw = G.fvm_eqs(np.zeros_like(u), w, p, 0.0)
+    Fc = G.fvm_eqs(np.zeros_like(u), 2.0 * u - 3.0 * w, p, 0.0)
+    assert rel_err(Fc, 2.0 * Fu - 3.0 * Fw) <= 1e-12
