@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- fvm_eqs! triangle-updates/s (+ template SpMV GB/s) on a 16.7M-node lattice, B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (libfvmcuda)
+    python bench.py --impl reference --steps K --warmup W    # CPU arm: the oracle port on host cores
+
+A step = one pass of the hot path over the whole mesh: one `fvm_eqs!` evaluation (boundary-edge,
+tile and interface kernels) on the README diffusion problem scaled to BASELINE configs[1]'s mesh
+(triangulate_rectangle 4096x4096 on [0,2]^2, Dirichlet u=0, D=1/9).  `value` times it with `u`
+resident in HBM (native order); `e2e` times the public `fvm_eqs(du,u,p,t)` call with pinned HOST
+buffers (H2D + permutation + kernels + D2H).  N>1: weak scaling, each rank owns a 4096-row strip.
+One JSON line on stdout (rank 0)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20240517
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def lattice_problem(G, nx, ny, flux, y0=0.0, y1=2.0):
+    tri = G.triangulate_rectangle(0.0, 2.0, y0, y1, nx, ny, single_boundary=True)
+    mesh = G.FVMGeometry(tri)
+    BCs = G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet)
+    ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
+    prob = G.FVMProblem(mesh, BCs, diffusion_function=flux, initial_condition=ic, final_time=0.5)
+    return prob
+
+
+def rhs_bytes(T, N, neq, layout):
+    """Algorithmic bytes of one RHS (BASELINE.md section 2 / SURVEY.md 8d)."""
+    if layout == "general":      # north_star SoA: 3 idx + 9 s + 6 midpoints + 6 scaled normals
+        return 180 * T + (17 * neq + 8) * N
+    if layout == "reduced":      # flux independent of (x,y,u): s1..s6 + scaled normals
+        return 108 * T + (17 * neq + 8) * N
+    if layout == "recompute":    # geometry recomputed from vertex coordinates
+        return 12 * T + (24 + 17 * neq) * N
+    raise ValueError(layout)
+
+
+VARIANTS = {
+    # name: (flux spec factory, geometry_mode, byte layout)
+    "general_stored": (lambda G: G.PowerDiffusion(1 / 9, 1.0), 0, "general"),
+    "const_stored": (lambda G: G.ConstantDiffusion(1 / 9), 0, "reduced"),
+    "general_recompute": (lambda G: G.PowerDiffusion(1 / 9, 1.0), 1, "recompute"),
+    "const_recompute": (lambda G: G.ConstantDiffusion(1 / 9), 1, "recompute"),
+}
+
+
+def time_rhs(torch, eng, u_d, du_d, steps, warmup):
+    """CUDA events on the handle's stream; returns (ms per step, dominant-kernel ms per launch)."""
+    stream = torch.cuda.ExternalStream(eng.stream())
+    for _ in range(warmup):
+        eng.rhs_device(du_d.data_ptr(), u_d.data_ptr(), 0.0, native=True)
+    eng.synchronize()
+    eng.set_profiling(steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        eng.rhs_device(du_d.data_ptr(), u_d.data_ptr(), 0.0, native=True)
+    e1.record(stream)
+    eng.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    kms, kn = eng.get_profile()
+    eng.set_profiling(0)
+    return ms, (kms / kn if kn else float("nan"))
+
+
+def cpu_baseline(nx, target_s=12.0, impl_reference=False, steps=None, warmup=1):
+    """The oracle port (oracle/fvm_oracle_c.c, reference-structured: hash-table triangle props,
+    per-thread du copies, serial combine) timed on the host cores on a bounded sample."""
+    from oracle.c_oracle import COracle
+    import fvm_b200 as G
+    tri = G.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, nx, nx, single_boundary=True)
+    uv, _ = tri.boundary_edges()
+    co = COracle(tri.points, tri.triangles, np.unique(uv), 1 / 9)
+    u = 50 * np.random.default_rng(SEED).random(tri.num_points)
+    du = np.empty_like(u)
+    for _ in range(max(1, warmup)):
+        co.fvm_eqs_threaded(u, du)
+    t0 = time.perf_counter()
+    co.fvm_eqs_threaded(u, du)
+    one = time.perf_counter() - t0
+    reps = steps if steps else max(3, min(200, int(target_s / max(one, 1e-4))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        co.fvm_eqs_threaded(u, du)
+    dt = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(max(2, reps // 4)):
+        co.fvm_eqs_flat(u, du)
+    dt_flat = (time.perf_counter() - t0) / max(2, reps // 4)
+    T = tri.num_triangles
+    out = {"value": T / dt / 1e6, "unit": "Mtriangle-updates/s", "cores": co.nthreads, "kind": "port",
+           "sample": "%dx%d lattice (%d triangles), %d threaded fvm_eqs! calls of the reference-structured C port; "
+                     "flat-array variant: %.1f Mtri/s" % (nx, nx, T, reps, T / dt_flat / 1e6),
+           "ms_per_step": dt * 1e3}
+    co.close()
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args.ref_nx, impl_reference=True, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": "fvm_eqs! Mtriangle-updates/s", "value": cb["value"], "unit": cb["unit"],
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "README diffusion fvm_eqs! (D=1/9, Dirichlet u=0); CPU arm on a bounded %dx%d sample of "
+                                   "the 4096x4096 lattice" % (args.ref_nx, args.ref_nx)},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nx", type=int, default=4096)
+    ap.add_argument("--ref-nx", type=int, default=1024)
+    ap.add_argument("--variant", default="general_stored", choices=sorted(VARIANTS))
+    ap.add_argument("--all-variants", action="store_true")
+    ap.add_argument("--tile", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import fvm_b200 as G
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libfvmcuda has no CPU fallback")
+    torch.cuda.set_device(local)
+    os.environ["FVM_DEVICE"] = str(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    nx = args.nx
+    peak, peak_src = measured_peak()
+    names = sorted(VARIANTS) if args.all_variants else [args.variant]
+    if args.variant in names:
+        names.remove(args.variant)
+        names.append(args.variant)  # headline variant last: its engine stays alive for e2e
+    results = {}
+    eng = p = None
+    for name in names:
+        flux_f, gmode, layout = VARIANTS[name]
+        if eng is not None:
+            eng.close()
+        t0 = time.perf_counter()
+        prob = lattice_problem(G, nx, nx, flux_f(G), 2.0 * rank, 2.0 * (rank + 1))
+        p = G.get_cuda_parameters(prob, tile_triangles=args.tile, geometry_mode=gmode, device=local)
+        eng = p.engine
+        setup_s = time.perf_counter() - t0
+        N, T = eng.N, eng.T
+        g = torch.Generator(device="cuda")
+        g.manual_seed(SEED + rank)
+        u_d = 50.0 * torch.rand(N, dtype=torch.float64, device="cuda", generator=g)
+        du_d = torch.empty_like(u_d)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if rank == 0 and name == names[-1] else None
+        ms, kms = time_rhs(torch, eng, u_d, du_d, args.steps, args.warmup)
+        torch.cuda.synchronize()
+        if dist is not None:
+            tmax = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms = float(tmax.item())
+        clocks = sampler.stop() if sampler else None
+        B = rhs_bytes(T, N, 1, layout)
+        results[name] = {"ms_per_step": ms, "mtri_s": world * T / ms / 1e3, "kernel_ms": kms, "layout": layout,
+                         "alg_bytes": B, "kernel_gbs": B / kms / 1e6, "frac": B / kms / 1e6 / peak, "setup_s": setup_s,
+                         "tiles": eng.stats()}
+        if rank == 0:
+            sys.stderr.write("[bench] %-18s %.3f ms/step  %.1f Mtri/s  tile-kernel %.3f ms  %.0f GB/s (%.2f of %s)\n"
+                             % (name, ms, results[name]["mtri_s"], kms, results[name]["kernel_gbs"], results[name]["frac"], peak_src))
+    head = results[args.variant]
+    N, T = eng.N, eng.T
+
+    # ---- e2e: the public call with pinned host buffers -------------------------------------
+    u_h = torch.empty(N, dtype=torch.float64).pin_memory()
+    du_h = torch.empty(N, dtype=torch.float64).pin_memory()
+    u_h.copy_(u_d.cpu())
+    un, dun = u_h.numpy(), du_h.numpy()
+    G.fvm_eqs(dun, un, p, 0.0)
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        G.fvm_eqs(dun, un, p, 0.0)  # synchronous: H2D, to-native, kernels, from-native, D2H
+    e2e_ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
+    if dist is not None:
+        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tmax.item())
+
+    if rank != 0:
+        dist.destroy_process_group()
+        return
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_baseline(args.ref_nx)
+    st = eng.stats()
+    launches_per_step = 1 + (1 if st["n_interface"] + (N - st["n_vertices"]) > 0 else 0) + (1 if st["n_live_boundary_edges"] else 0)
+    line = {
+        "metric": "fvm_eqs! Mtriangle-updates/s", "value": head["mtri_s"], "unit": "Mtriangle-updates/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": head["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "README diffusion FVMProblem fvm_eqs! on triangulate_rectangle %dx%d per GPU ([0,2]x[0,2] strip, "
+                               "Dirichlet u=0, D=1/9, u=50*U(0,1)); %d nodes, %d triangles per GPU" % (nx, nx, N, T),
+                   "variant": args.variant, "l2": "inputs larger than L2 (%.2f GB streamed per step vs 126 MB L2)" % (head["alg_bytes"] / 1e9),
+                   "tile_triangles": st["tile_triangles"], "n_tiles": st["n_tiles"]},
+        "roofline": {"bound": "hbm", "kernel": "rhs_tile_kernel", "achieved": head["kernel_gbs"], "peak": peak, "unit": "GB/s",
+                     "frac": head["frac"], "traffic": None, "peak_source": peak_src,
+                     "bytes_formula": {"general": "180*T + 25*N", "reduced": "108*T + 25*N", "recompute": "12*T + 41*N"}[head["layout"]],
+                     "alg_bytes_per_launch": head["alg_bytes"], "kernel_ms": head["kernel_ms"]},
+        "e2e": {"value": world * T / e2e_ms / 1e3, "unit": "Mtriangle-updates/s", "h2d_bytes_per_step": 8 * N,
+                "d2h_bytes_per_step": 8 * N, "ms_per_step": e2e_ms},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+        "setup_s": head["setup_s"],
+    }
+    if cb:
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if len(results) > 1:
+        line["variants"] = {k: {kk: v[kk] for kk in ("ms_per_step", "mtri_s", "kernel_ms", "kernel_gbs", "frac", "layout")}
+                            for k, v in results.items()}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ _SIGS = {
     "fvm_from_native": [H, C.c_void_p, C.c_void_p],
     "fvm_stream_synchronize": [H],
     "fvm_get_stream": [H, C.POINTER(C.c_void_p)],
+    "fvm_set_profiling": [H, C.c_int32],
+    "fvm_get_profile": [H, c_dp, c_lp],
     "fvm_get_geometry": [H, c_dp, c_dp, c_dp, c_dp, c_dp],
     "fvm_get_permutation": [H, c_ip, c_ip],
     "fvm_get_stats": [H, c_lp],

@@ -139,6 +139,10 @@ struct fvm_ctx {
     double* d_work[12] = {nullptr};
     double* d_red = nullptr;  // reduction scratch
     int64_t stats[16] = {0};
+    // optional per-kernel timing of the dominant kernels (bench.py's roofline leg)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+    int64_t prof_used = 0;
     // sharding
     void* nccl_comm = nullptr;
     int32_t rank = 0, nranks = 1;
@@ -185,3 +189,5 @@ int32_t fvm_launch_permute(fvm_ctx* h, const double* src, double* dst, bool to_n
 int32_t fvm_export_geometry(fvm_ctx* h, double* s9, double* mid6, double* nrm6, double* len3);  // device, native tri order
 int32_t fvm_ensure_state(fvm_ctx* h);
 void fvm_shard_release(fvm_ctx* h);
+void fvm_prof_begin(fvm_ctx* h);
+void fvm_prof_end(fvm_ctx* h);

@@ -357,7 +357,9 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du) {
         configured = smem;
     }
     h->smem_rhs = smem;
+    fvm_prof_begin(h);
     kern<<<h->dm.n_tiles, RHS_BLOCK, smem, h->stream>>>(h->dm, h->flux, h->source, t, u, du, h->max_nloc);
+    fvm_prof_end(h);
     FVM_CUDA(h, cudaGetLastError());
     return FVM_OK;
 }
@@ -536,6 +538,48 @@ extern "C" int32_t fvm_from_native(fvm_handle h, const double* v_native, double*
     NEED_FINAL(h);
     FVM_REQUIRE(h, v_caller && v_native && v_caller != v_native, "fvm_from_native: bad arguments");
     return fvm_launch_permute(h, v_native, v_caller, false);
+}
+
+// ---- optional CUDA-event timing of the dominant kernel, on the launching stream ---------------
+void fvm_prof_begin(fvm_ctx* h) {
+    if (!h->profiling || h->prof_used + 2 > (int64_t)h->prof_ev.size()) return;
+    cudaEventRecord(h->prof_ev[h->prof_used], h->stream);
+}
+void fvm_prof_end(fvm_ctx* h) {
+    if (!h->profiling || h->prof_used + 2 > (int64_t)h->prof_ev.size()) return;
+    cudaEventRecord(h->prof_ev[h->prof_used + 1], h->stream);
+    h->prof_used += 2;
+}
+
+extern "C" int32_t fvm_set_profiling(fvm_handle h, int32_t max_launches) {
+    if (!h) return FVM_ERR_ARG;
+    FVM_CUDA(h, cudaSetDevice(h->device));
+    for (cudaEvent_t e : h->prof_ev) cudaEventDestroy(e);
+    h->prof_ev.clear();
+    h->prof_used = 0;
+    h->profiling = max_launches > 0;
+    for (int i = 0; i < 2 * max_launches; ++i) {
+        cudaEvent_t e;
+        FVM_CUDA(h, cudaEventCreate(&e));
+        h->prof_ev.push_back(e);
+    }
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_get_profile(fvm_handle h, double* total_ms, int64_t* launches) {
+    if (!h || !total_ms || !launches) return FVM_ERR_ARG;
+    FVM_CUDA(h, cudaSetDevice(h->device));
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    for (int64_t i = 0; i + 1 < h->prof_used; i += 2) {
+        float ms = 0.f;
+        FVM_CUDA(h, cudaEventElapsedTime(&ms, h->prof_ev[i], h->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = h->prof_used / 2;
+    h->prof_used = 0;
+    return FVM_OK;
 }
 
 extern "C" int32_t fvm_stream_synchronize(fvm_handle h) {

@@ -298,6 +298,16 @@ class Engine:
         L.check(self.h, L.lib().fvm_get_stream(self.h, C.byref(s)))
         return s.value or 0
 
+    def set_profiling(self, max_launches):
+        L.check(self.h, L.lib().fvm_set_profiling(self.h, int(max_launches)))
+
+    def get_profile(self):
+        """(summed ms, launches) of the dominant kernel since profiling was armed"""
+        ms = C.c_double()
+        n = C.c_int64()
+        L.check(self.h, L.lib().fvm_get_profile(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def stats(self):
         st = np.zeros(16, dtype=np.int64)
         L.check(self.h, L.lib().fvm_get_stats(self.h, st.ctypes.data_as(L.c_lp)))

@@ -138,6 +138,10 @@ int32_t fvm_from_native(fvm_handle h, const double* v_native_dev, double* v_call
 /* the *_native calls are asynchronous on the handle's stream */
 int32_t fvm_stream_synchronize(fvm_handle h);
 int32_t fvm_get_stream(fvm_handle h, void** cuda_stream);
+/* CUDA-event timing of the dominant kernel (RHS tile kernel / SpMV) on the launching stream:
+ * arm with the number of launches to record, read back the summed duration. */
+int32_t fvm_set_profiling(fvm_handle h, int32_t max_launches);
+int32_t fvm_get_profile(fvm_handle h, double* total_ms, int64_t* launches);
 
 /* ---- geometry / connectivity read-back for parity (src/geometry.jl:21-49) ----------- */
 /* caller order; any pointer may be NULL.  V[N]; s9[T][9]; mid6[T][3][2]; nrm6[T][3][2]; len3[T][3] */

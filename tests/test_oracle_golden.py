@@ -398,3 +398,19 @@ def test_jacobian_sparsity_counts():
     tri = O.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True)
     r, c = O.jacobian_sparsity(tri)
     assert len(r) == 17102
+
+
+def test_c_oracle_matches_numpy_oracle():
+    """oracle/fvm_oracle_c.c (the timed CPU arm) against the NumPy restatement: serial bitwise,
+    threaded/flat to summation order (test/test_functions.jl:653-656 uses the same bar)."""
+    from oracle.c_oracle import COracle
+    prob = example_diffusion_problem()
+    tri = prob.mesh.triangulation
+    dn = np.array(sorted(prob.conditions.dirichlet_nodes), dtype=np.int32)
+    co = COracle(tri.points, tri.triangles, dn, 1 / 9, nthreads=4)
+    assert np.array_equal(co.volumes(), prob.mesh.cv_volumes)
+    u = 50 * np.random.default_rng(8).random(tri.num_points)
+    ref = O.fvm_eqs(np.zeros_like(u), u, prob, 0.0)
+    assert np.array_equal(co.fvm_eqs_serial(u), ref)
+    assert isapprox(co.fvm_eqs_threaded(u), ref, rtol=1e-14)
+    assert isapprox(co.fvm_eqs_flat(u), ref, rtol=1e-14)
