@@ -8,3 +8,6 @@ from .functors import *  # noqa: F401,F403
 from .mesh import Triangulation, triangulate_rectangle  # noqa: F401
 from .problem import (CudaParameters, Engine, FVMGeometry, FVMProblem, FVMSystem,  # noqa: F401
                       SteadyFVMProblem, fvm_eqs, get_cuda_parameters, update_dirichlet_nodes)
+from .templates import (DiffusionEquation, KrylovJacobi, LaplacesEquation,  # noqa: F401
+                        LinearReactionDiffusionEquation, MeanExitTimeProblem, PoissonsEquation, Solution, Tsit5)
+from .solve import solve  # noqa: F401

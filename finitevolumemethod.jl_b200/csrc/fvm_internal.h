@@ -85,6 +85,13 @@ struct SourceParams {
 struct Csr {
     int64_t nnz = 0;
     int32_t n = 0;
+    int32_t max_row = 0;
+    bool pattern = false;
+    int32_t* n2t_ptr = nullptr;  // node -> incident (triangle << 2 | slot), native ids
+    int32_t* n2t = nullptr;
+    double* diag_inv = nullptr;  // Jacobi preconditioner of the (scaled) system
+    int32_t chunk_rows = 0;      // SpMV: rows per CTA
+    int32_t chunk_smem = 0;
     int32_t* rowptr = nullptr;  // native numbering
     int32_t* col = nullptr;
     double* val = nullptr;
@@ -114,6 +121,7 @@ struct fvm_ctx {
     std::vector<uint8_t> h_nkind[FVM_MAX_NEQ];
     std::vector<int32_t> h_nfidx[FVM_MAX_NEQ];
     std::vector<double> h_dtab, h_dbnd, h_srctab;
+    std::vector<int32_t> h_edge_tri, h_edge_rot;  // adjacent triangle (caller id) / rotation per boundary edge
     std::vector<CondFn> h_cond;  // [neq][FVM_MAX_COND_FN]
     FluxParams flux{};
     SourceParams source{};
@@ -189,5 +197,6 @@ int32_t fvm_launch_permute(fvm_ctx* h, const double* src, double* dst, bool to_n
 int32_t fvm_export_geometry(fvm_ctx* h, double* s9, double* mid6, double* nrm6, double* len3);  // device, native tri order
 int32_t fvm_ensure_state(fvm_ctx* h);
 void fvm_shard_release(fvm_ctx* h);
+int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale);
 void fvm_prof_begin(fvm_ctx* h);
 void fvm_prof_end(fvm_ctx* h);

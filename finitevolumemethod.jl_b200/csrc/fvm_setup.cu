@@ -319,14 +319,18 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
             forced[i] = forced[j] = 1;
         }
     }
-    std::vector<int32_t> edge_tri(live_edges.size(), -1), edge_rot(live_edges.size(), 0);
-    if (!live_edges.empty()) {
+    // adjacent triangle (get_adjacent) and stored rotation of EVERY boundary edge; the template
+    // assembly needs the dead ones too (abstract_templates.jl:237-267)
+    std::vector<int32_t>& all_tri = h->h_edge_tri;
+    std::vector<int32_t>& all_rot = h->h_edge_rot;
+    all_tri.assign(Eb, -1);
+    all_rot.assign(Eb, 0);
+    if (Eb > 0) {
         std::unordered_map<uint64_t, int32_t> emap;
-        emap.reserve(live_edges.size() * 2);
+        emap.reserve(Eb * 2);
         std::vector<uint8_t> is_src(N, 0);
-        for (size_t k = 0; k < live_edges.size(); ++k) {
-            const int32_t e = live_edges[k];
-            emap[((uint64_t)(uint32_t)h->h_bedge[2 * e] << 32) | (uint32_t)h->h_bedge[2 * e + 1]] = (int32_t)k;
+        for (int64_t e = 0; e < Eb; ++e) {
+            emap[((uint64_t)(uint32_t)h->h_bedge[2 * e] << 32) | (uint32_t)h->h_bedge[2 * e + 1]] = (int32_t)e;
             is_src[h->h_bedge[2 * e]] = 1;
         }
         for (int64_t t = 0; t < T; ++t) {
@@ -336,13 +340,18 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
                 const int32_t b = tri[3 * t + (r + 1) % 3];
                 auto it = emap.find(((uint64_t)(uint32_t)a << 32) | (uint32_t)b);
                 if (it != emap.end()) {
-                    edge_tri[it->second] = (int32_t)t;
-                    edge_rot[it->second] = r;
+                    all_tri[it->second] = (int32_t)t;
+                    all_rot[it->second] = r;
                 }
             }
         }
-        for (size_t k = 0; k < live_edges.size(); ++k)
-            FVM_REQUIRE(h, edge_tri[k] >= 0, "fvm_finalize: a boundary edge (u,v) is not a ccw edge of any triangle");
+        for (int64_t e = 0; e < Eb; ++e)
+            FVM_REQUIRE(h, all_tri[e] >= 0, "fvm_finalize: a boundary edge (u,v) is not a ccw edge of any triangle");
+    }
+    std::vector<int32_t> edge_tri(live_edges.size(), -1), edge_rot(live_edges.size(), 0);
+    for (size_t k = 0; k < live_edges.size(); ++k) {
+        edge_tri[k] = all_tri[live_edges[k]];
+        edge_rot[k] = all_rot[live_edges[k]];
     }
 
     // ---- 3. node classification and tile-major renumbering -------------------------------

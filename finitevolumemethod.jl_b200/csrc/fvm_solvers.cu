@@ -1,0 +1,500 @@
+// libfvmcuda: device-resident solvers on top of the RHS / SpMV kernels.
+//
+//   fvm_tsit5   fixed-step Tsit5 (OrdinaryDiffEq tableau) with FSAL and the
+//               Dirichlet callback of /root/reference/src/solve.jl:133-165; the state never leaves
+//               the device between steps.
+//   fvm_krylov  Jacobi-preconditioned CG on the symmetrised system (-V A) x = -V b, or BiCGStab on
+//               A x = b.  Dot products: warp-shuffle + fixed-shape block reduction into per-block
+//               partials, summed by one block in a fixed order -> deterministic, no atomics; all
+//               scalars stay on the device, the host only polls a convergence flag.
+#include <cmath>
+
+#include "fvm_device.cuh"
+
+int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale);
+
+#define NEED_FINAL(h)                                                                       \
+    do {                                                                                    \
+        if (!(h)) return FVM_ERR_ARG;                                                       \
+        if (!(h)->finalized) return fvm_fail((h), FVM_ERR_STATE, "call fvm_finalize first"); \
+        FVM_CUDA(h, cudaSetDevice((h)->device));                                            \
+    } while (0)
+
+static int32_t ensure_work(fvm_ctx* h, int count) {
+    const size_t n = (size_t)h->N * h->neq;
+    for (int i = 0; i < count; ++i)
+        if (!h->d_work[i]) {
+            int32_t rc = fvm_dev_alloc(h, &h->d_work[i], n);
+            if (rc) return rc;
+        }
+    if (!h->d_red) return fvm_dev_alloc(h, &h->d_red, (size_t)8 * 2048 + 64);
+    return FVM_OK;
+}
+
+// ---- Tsit5 -----------------------------------------------------------------------------------
+static const double TS_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+static const double TS_A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+
+struct LinComb {
+    const double* k[6];
+    double c[6];
+};
+
+template <int S>
+__global__ void __launch_bounds__(256) lincomb_kernel(const int64_t n, double* __restrict__ out, const double* __restrict__ u,
+                                                       const double dt, const LinComb lc) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double acc = lc.c[0] * lc.k[0][i];
+#pragma unroll
+        for (int j = 1; j < S; ++j) acc += lc.c[j] * lc.k[j][i];
+        out[i] = u[i] + dt * acc;
+    }
+}
+
+static int32_t launch_lincomb(fvm_ctx* h, int S, int64_t n, double* out, const double* u, double dt, double* const* K,
+                              const double* coef) {
+    LinComb lc{};
+    for (int j = 0; j < S; ++j) {
+        lc.k[j] = K[j];
+        lc.c[j] = coef[j];
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    switch (S) {
+        case 1: lincomb_kernel<1><<<grid, 256, 0, h->stream>>>(n, out, u, dt, lc); break;
+        case 2: lincomb_kernel<2><<<grid, 256, 0, h->stream>>>(n, out, u, dt, lc); break;
+        case 3: lincomb_kernel<3><<<grid, 256, 0, h->stream>>>(n, out, u, dt, lc); break;
+        case 4: lincomb_kernel<4><<<grid, 256, 0, h->stream>>>(n, out, u, dt, lc); break;
+        case 5: lincomb_kernel<5><<<grid, 256, 0, h->stream>>>(n, out, u, dt, lc); break;
+        default: lincomb_kernel<6><<<grid, 256, 0, h->stream>>>(n, out, u, dt, lc); break;
+    }
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, double t0, double t1, double dt, int64_t nsave,
+                             const double* tsave, double* usave, int32_t on_device) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, u, "fvm_tsit5: null state");
+    FVM_REQUIRE(h, dt > 0 && t1 >= t0, "fvm_tsit5: need dt > 0 and t1 >= t0");
+    FVM_REQUIRE(h, nsave == 0 || (tsave && usave), "fvm_tsit5: save buffers missing");
+    if (use_operator && !h->csr.assembled) return fvm_fail(h, FVM_ERR_STATE, "fvm_tsit5: call fvm_assemble first");
+    const int64_t nsteps = llround((t1 - t0) / dt);
+    FVM_REQUIRE(h, std::fabs(t0 + nsteps * dt - t1) <= 1e-9 * std::max(1.0, std::fabs(t1)),
+                "fvm_tsit5: dt must divide the time span (fixed-step integration)");
+    int32_t rc = ensure_work(h, 9);
+    if (rc) return rc;
+    if ((rc = fvm_ensure_state(h))) return rc;
+    const int64_t n = h->N * h->neq;
+    const size_t bytes = sizeof(double) * n;
+    double* U = h->d_work[0];
+    double* K[7];
+    for (int s = 0; s < 7; ++s) K[s] = h->d_work[1 + s];
+    double* TMP = h->d_work[8];
+
+    const double* src = u;
+    if (!on_device) {
+        FVM_CUDA(h, cudaMemcpyAsync(h->d_io, u, bytes, cudaMemcpyHostToDevice, h->stream));
+        src = h->d_io;
+    }
+    if ((rc = fvm_launch_permute(h, src, U, true))) return rc;
+
+    auto f = [&](double* out, const double* x, double t) -> int32_t {
+        return use_operator ? fvm_launch_spmv(h, x, out, true, false) : fvm_launch_rhs(h, t, x, out);
+    };
+    int64_t next_save = 0;
+    auto save = [&](double tn) -> int32_t {
+        while (next_save < nsave && std::fabs(tsave[next_save] - tn) < 0.5 * dt) {
+            double* dst = usave + next_save * n;
+            if (on_device) {
+                int32_t r = fvm_launch_permute(h, U, dst, false);
+                if (r) return r;
+            } else {
+                int32_t r = fvm_launch_permute(h, U, h->d_io, false);
+                if (r) return r;
+                FVM_CUDA(h, cudaMemcpyAsync(dst, h->d_io, bytes, cudaMemcpyDeviceToHost, h->stream));
+                FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+            }
+            ++next_save;
+        }
+        return FVM_OK;
+    };
+    if ((rc = save(t0))) return rc;
+    const bool has_callback = !use_operator && h->n_dir > 0;
+    bool have_k1 = false;
+    for (int64_t step = 0; step < nsteps; ++step) {
+        const double t = t0 + step * dt;
+        if (!have_k1 && (rc = f(K[0], U, t))) return rc;
+        for (int s = 1; s < 6; ++s) {
+            if ((rc = launch_lincomb(h, s, n, TMP, U, dt, K, TS_A[s]))) return rc;
+            if ((rc = f(K[s], TMP, t + TS_C[s] * dt))) return rc;
+        }
+        if ((rc = launch_lincomb(h, 6, n, U, U, dt, K, TS_A[6]))) return rc;
+        const double tn = t0 + (step + 1) * dt;
+        if (has_callback) {
+            // the DiscreteCallback modifies u, so the FSAL value is discarded and k1 is re-evaluated
+            if ((rc = fvm_launch_dirichlet(h, tn, U))) return rc;
+            have_k1 = false;
+        } else {
+            if ((rc = f(K[6], U, tn))) return rc;
+            std::swap(K[0], K[6]);
+            have_k1 = true;
+        }
+        if ((rc = save(tn))) return rc;
+    }
+    if (on_device) {
+        if ((rc = fvm_launch_permute(h, U, u, false))) return rc;
+    } else {
+        if ((rc = fvm_launch_permute(h, U, h->d_io, false))) return rc;
+        FVM_CUDA(h, cudaMemcpyAsync(u, h->d_io, bytes, cudaMemcpyDeviceToHost, h->stream));
+    }
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return FVM_OK;
+}
+
+// ---- Krylov ----------------------------------------------------------------------------------
+#define RED_BLOCKS 1184  // 148 SMs x 8
+#define RED_THREADS 256
+enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_N };
+
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partial) {
+    __shared__ double sh[NV][RED_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+        if (lane == 0) sh[q][warp] = v[q];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+            double s = lane < RED_THREADS / 32 ? sh[q][lane] : 0.0;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) partial[q * RED_BLOCKS + blockIdx.x] = s;
+        }
+    }
+}
+
+// sums the per-block partials of `nv` slots in a fixed order; one block
+__device__ __forceinline__ double final_sum(const double* __restrict__ partial, int slot) {
+    __shared__ double sh[RED_THREADS / 32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < RED_BLOCKS; i += RED_THREADS) s += partial[slot * RED_BLOCKS + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+    for (int w = 0; w < RED_THREADS / 32; ++w) tot += sh[w];
+    return tot;
+}
+
+#define GRID_STRIDE(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// PCG -------------------------------------------------------------------------------------------
+__global__ void pcg_init1_kernel(int64_t n, const double* b, const double* rowscale, double* x) {
+    GRID_STRIDE(i, n) if (rowscale[i] == 1.0) x[i] = b[i];  // identity rows: Dirichlet-consistent start
+}
+__global__ void __launch_bounds__(RED_THREADS)
+    pcg_init2_kernel(int64_t n, const double* b, const double* rowscale, const double* Ax_scaled, const double* dinv, double* r,
+                     double* z, double* p, double* partial) {
+    double v[3] = {0, 0, 0};
+    GRID_STRIDE(i, n) {
+        const double c = rowscale[i] * b[i];
+        const double ri = c - Ax_scaled[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri;
+        z[i] = zi;
+        p[i] = zi;
+        v[0] += ri * zi;
+        v[1] += ri * ri;
+        v[2] += c * c;
+    }
+    block_reduce_store<3>(v, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS) pcg_init3_kernel(const double* partial, double* sc, double rtol) {
+    const double rz = final_sum(partial, 0), rr = final_sum(partial, 1), bb = final_sum(partial, 2);
+    if (threadIdx.x == 0) {
+        sc[SC_RZ] = rz;
+        sc[SC_RR] = rr;
+        sc[SC_BNORM2] = bb;
+        sc[SC_TOL2] = rtol * rtol * bb;
+        sc[SC_ITER] = 0.0;
+        sc[SC_DONE] = (rr <= rtol * rtol * bb) ? 1.0 : 0.0;
+    }
+}
+__global__ void __launch_bounds__(RED_THREADS) dot_kernel(int64_t n, const double* a, const double* b, double* partial, const double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    double v[1] = {0};
+    GRID_STRIDE(i, n) v[0] += a[i] * b[i];
+    block_reduce_store<1>(v, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS) pcg_alpha_kernel(const double* partial, double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double pq = final_sum(partial, 0);
+    if (threadIdx.x == 0) {
+        sc[SC_PQ] = pq;
+        sc[SC_ALPHA] = sc[SC_RZ] / pq;
+    }
+}
+__global__ void __launch_bounds__(RED_THREADS)
+    pcg_update_kernel(int64_t n, const double* p, const double* q, const double* dinv, double* x, double* r, double* z,
+                      double* partial, const double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double alpha = sc[SC_ALPHA];
+    double v[2] = {0, 0};
+    GRID_STRIDE(i, n) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri;
+        z[i] = zi;
+        v[0] += ri * zi;
+        v[1] += ri * ri;
+    }
+    block_reduce_store<2>(v, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS) pcg_beta_kernel(const double* partial, double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double rz = final_sum(partial, 0), rr = final_sum(partial, 1);
+    if (threadIdx.x == 0) {
+        sc[SC_BETA] = rz / sc[SC_RZ];
+        sc[SC_RZ] = rz;
+        sc[SC_RR] = rr;
+        sc[SC_ITER] += 1.0;
+        if (rr <= sc[SC_TOL2] || !(rr == rr)) sc[SC_DONE] = 1.0;
+    }
+}
+__global__ void pcg_p_kernel(int64_t n, const double* z, double* p, const double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double beta = sc[SC_BETA];
+    GRID_STRIDE(i, n) p[i] = z[i] + beta * p[i];
+}
+
+// BiCGStab ----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS)
+    bicg_init_kernel(int64_t n, const double* b, const double* Ax, double* r, double* rhat, double* p, double* v, double* partial) {
+    double s[2] = {0, 0};
+    GRID_STRIDE(i, n) {
+        const double ri = b[i] - Ax[i];
+        r[i] = ri;
+        rhat[i] = ri;
+        p[i] = 0.0;
+        v[i] = 0.0;
+        s[0] += ri * ri;
+        s[1] += b[i] * b[i];
+    }
+    block_reduce_store<2>(s, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS) bicg_init2_kernel(const double* partial, double* sc, double rtol) {
+    const double rr = final_sum(partial, 0), bb = final_sum(partial, 1);
+    if (threadIdx.x == 0) {
+        sc[SC_RR] = rr;
+        sc[SC_BNORM2] = bb;
+        sc[SC_TOL2] = rtol * rtol * bb;
+        sc[SC_RHO] = 1.0;
+        sc[SC_ALPHA] = 1.0;
+        sc[SC_OMEGA] = 1.0;
+        sc[SC_RZ] = rr;  // rhat . r
+        sc[SC_ITER] = 0.0;
+        sc[SC_DONE] = (rr <= rtol * rtol * bb) ? 1.0 : 0.0;
+    }
+}
+// beta = (rho_new/rho)(alpha/omega); p = r + beta (p - omega v); y = K^-1 p
+__global__ void bicg_p_kernel(int64_t n, const double* r, const double* v, const double* kinv, double* p, double* y, const double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double beta = (sc[SC_RZ] / sc[SC_RHO]) * (sc[SC_ALPHA] / sc[SC_OMEGA]);
+    const double omega = sc[SC_OMEGA];
+    GRID_STRIDE(i, n) {
+        const double pi = r[i] + beta * (p[i] - omega * v[i]);
+        p[i] = pi;
+        y[i] = kinv[i] * pi;
+    }
+}
+__global__ void __launch_bounds__(RED_THREADS) bicg_alpha_kernel(const double* partial, double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double rhv = final_sum(partial, 0);
+    if (threadIdx.x == 0) {
+        sc[SC_RHO] = sc[SC_RZ];
+        sc[SC_ALPHA] = sc[SC_RZ] / rhv;
+    }
+}
+// s = r - alpha v ; z = K^-1 s
+__global__ void bicg_s_kernel(int64_t n, const double* r, const double* v, const double* kinv, double* s, double* z, const double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double alpha = sc[SC_ALPHA];
+    GRID_STRIDE(i, n) {
+        const double si = r[i] - alpha * v[i];
+        s[i] = si;
+        z[i] = kinv[i] * si;
+    }
+}
+__global__ void __launch_bounds__(RED_THREADS) bicg_ts_kernel(int64_t n, const double* t, const double* s, double* partial, const double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    double v[2] = {0, 0};
+    GRID_STRIDE(i, n) {
+        v[0] += t[i] * s[i];
+        v[1] += t[i] * t[i];
+    }
+    block_reduce_store<2>(v, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS) bicg_omega_kernel(const double* partial, double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double ts = final_sum(partial, 0), tt = final_sum(partial, 1);
+    if (threadIdx.x == 0) sc[SC_OMEGA] = tt != 0.0 ? ts / tt : 0.0;
+}
+// x += alpha y + omega z ; r = s - omega t ; dots rhat.r, r.r
+__global__ void __launch_bounds__(RED_THREADS)
+    bicg_x_kernel(int64_t n, const double* y, const double* z, const double* s, const double* t, const double* rhat, double* x,
+                  double* r, double* partial, const double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA];
+    double v[2] = {0, 0};
+    GRID_STRIDE(i, n) {
+        x[i] += alpha * y[i] + omega * z[i];
+        const double ri = s[i] - omega * t[i];
+        r[i] = ri;
+        v[0] += rhat[i] * ri;
+        v[1] += ri * ri;
+    }
+    block_reduce_store<2>(v, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS) bicg_end_kernel(const double* partial, double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double rhr = final_sum(partial, 0), rr = final_sum(partial, 1);
+    if (threadIdx.x == 0) {
+        sc[SC_RZ] = rhr;
+        sc[SC_RR] = rr;
+        sc[SC_ITER] += 1.0;
+        if (rr <= sc[SC_TOL2] || !(rr == rr) || rhr == 0.0) sc[SC_DONE] = 1.0;
+    }
+}
+__global__ void kinv_kernel(int64_t n, const double* dinv, const double* rowscale, double* kinv) {
+    GRID_STRIDE(i, n) kinv[i] = dinv[i] * rowscale[i];
+}
+__global__ void __launch_bounds__(RED_THREADS) resid_kernel(int64_t n, const double* b, const double* Ax, double* partial) {
+    double v[2] = {0, 0};
+    GRID_STRIDE(i, n) {
+        const double ri = b[i] - Ax[i];
+        v[0] += ri * ri;
+        v[1] += b[i] * b[i];
+    }
+    block_reduce_store<2>(v, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS) resid_final_kernel(const double* partial, double* sc) {
+    const double rr = final_sum(partial, 0), bb = final_sum(partial, 1);
+    if (threadIdx.x == 0) {
+        sc[SC_RR] = rr;
+        sc[SC_BNORM2] = bb;
+    }
+}
+
+extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rtol, int32_t maxit, int32_t* iters,
+                              double* relres, int32_t on_device) {
+    NEED_FINAL(h);
+    if (!h->csr.assembled) return fvm_fail(h, FVM_ERR_STATE, "fvm_krylov: call fvm_assemble first");
+    FVM_REQUIRE(h, x && rtol > 0 && maxit > 0, "fvm_krylov: bad arguments");
+    FVM_REQUIRE(h, method == FVM_KRYLOV_PCG || method == FVM_KRYLOV_BICGSTAB, "fvm_krylov: unknown method");
+    int32_t rc = ensure_work(h, 10);
+    if (rc) return rc;
+    if ((rc = fvm_ensure_state(h))) return rc;
+    const Csr& c = h->csr;
+    const int64_t n = h->N;
+    const size_t bytes = sizeof(double) * n;
+    double* X = h->d_work[0];
+    double* partial = h->d_red;
+    double* sc = h->d_red + 8 * 2048;
+    cudaStream_t st = h->stream;
+    const double* src = x;
+    if (!on_device) {
+        FVM_CUDA(h, cudaMemcpyAsync(h->d_io, x, bytes, cudaMemcpyHostToDevice, st));
+        src = h->d_io;
+    }
+    if ((rc = fvm_launch_permute(h, src, X, true))) return rc;
+    const int G = RED_BLOCKS, B = RED_THREADS;
+    const int check_every = 25;
+    double hsc[SC_N];
+    auto poll = [&]() -> int32_t {
+        FVM_CUDA(h, cudaMemcpyAsync(hsc, sc, sizeof(double) * SC_N, cudaMemcpyDeviceToHost, st));
+        FVM_CUDA(h, cudaStreamSynchronize(st));
+        return FVM_OK;
+    };
+    if (method == FVM_KRYLOV_PCG) {
+        double *R = h->d_work[1], *Z = h->d_work[2], *P = h->d_work[3], *Q = h->d_work[4];
+        pcg_init1_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, X);
+        if ((rc = fvm_launch_spmv(h, X, Q, false, true))) return rc;
+        pcg_init2_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, Q, c.diag_inv, R, Z, P, partial);
+        pcg_init3_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
+        for (int it = 0; it < maxit; ++it) {
+            if ((rc = fvm_launch_spmv(h, P, Q, false, true))) return rc;
+            dot_kernel<<<G, B, 0, st>>>(n, P, Q, partial, sc);
+            pcg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
+            pcg_update_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, X, R, Z, partial, sc);
+            pcg_beta_kernel<<<1, B, 0, st>>>(partial, sc);
+            pcg_p_kernel<<<G, B, 0, st>>>(n, Z, P, sc);
+            if ((it + 1) % check_every == 0 || it + 1 == maxit) {
+                if ((rc = poll())) return rc;
+                if (hsc[SC_DONE] != 0.0) break;
+            }
+        }
+    } else {
+        double *R = h->d_work[1], *RH = h->d_work[2], *P = h->d_work[3], *V = h->d_work[4], *Y = h->d_work[5], *S = h->d_work[6],
+               *Z = h->d_work[7], *T = h->d_work[8], *KI = h->d_work[9];
+        kinv_kernel<<<G, B, 0, st>>>(n, c.diag_inv, c.rowscale, KI);
+        if ((rc = fvm_launch_spmv(h, X, V, false, false))) return rc;
+        bicg_init_kernel<<<G, B, 0, st>>>(n, c.b, V, R, RH, P, V, partial);
+        bicg_init2_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
+        for (int it = 0; it < maxit; ++it) {
+            bicg_p_kernel<<<G, B, 0, st>>>(n, R, V, KI, P, Y, sc);
+            if ((rc = fvm_launch_spmv(h, Y, V, false, false))) return rc;
+            dot_kernel<<<G, B, 0, st>>>(n, RH, V, partial, sc);
+            bicg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
+            bicg_s_kernel<<<G, B, 0, st>>>(n, R, V, KI, S, Z, sc);
+            if ((rc = fvm_launch_spmv(h, Z, T, false, false))) return rc;
+            bicg_ts_kernel<<<G, B, 0, st>>>(n, T, S, partial, sc);
+            bicg_omega_kernel<<<1, B, 0, st>>>(partial, sc);
+            bicg_x_kernel<<<G, B, 0, st>>>(n, Y, Z, S, T, RH, X, R, partial, sc);
+            bicg_end_kernel<<<1, B, 0, st>>>(partial, sc);
+            if ((it + 1) % check_every == 0 || it + 1 == maxit) {
+                if ((rc = poll())) return rc;
+                if (hsc[SC_DONE] != 0.0) break;
+            }
+        }
+    }
+    FVM_CUDA(h, cudaGetLastError());
+    if ((rc = poll())) return rc;
+    const int32_t done_iters = (int32_t)hsc[SC_ITER];
+    // true (unscaled) residual of A x = b
+    double* AX = h->d_work[4];
+    if ((rc = fvm_launch_spmv(h, X, AX, false, false))) return rc;
+    resid_kernel<<<G, B, 0, st>>>(n, c.b, AX, partial);
+    resid_final_kernel<<<1, B, 0, st>>>(partial, sc);
+    if ((rc = poll())) return rc;
+    if (iters) *iters = done_iters;
+    if (relres) *relres = hsc[SC_BNORM2] > 0 ? std::sqrt(hsc[SC_RR] / hsc[SC_BNORM2]) : std::sqrt(hsc[SC_RR]);
+    if (on_device) {
+        if ((rc = fvm_launch_permute(h, X, x, false))) return rc;
+    } else {
+        if ((rc = fvm_launch_permute(h, X, h->d_io, false))) return rc;
+        FVM_CUDA(h, cudaMemcpyAsync(x, h->d_io, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    FVM_CUDA(h, cudaStreamSynchronize(st));
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_shard_init(fvm_handle h, const void*, int32_t, int32_t) {
+    if (!h) return FVM_ERR_ARG;
+    return fvm_fail(h, FVM_ERR_STATE, "fvm_shard_init: not implemented yet");
+}
+extern "C" int32_t fvm_nccl_unique_id(void*) { return FVM_ERR_NCCL; }

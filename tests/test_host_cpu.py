@@ -120,3 +120,21 @@ def test_constructor_errors_mirror_the_reference():
     sys_ = G.FVMSystem(p1, p1)
     assert sys_.initial_condition.shape == (25, 2) and sys_.cnum_fncs == (0, 1)
     assert "FVMProblem with 25 nodes" in repr(p1)
+
+
+def test_template_argument_errors_mirror_the_reference():
+    """poissons_equation.jl:69-70, mean_exit_time.jl:66-69: ArgumentError before any device work."""
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 5, 5, single_boundary=False))
+    mesh = pair.gmesh
+    dudt = G.BoundaryConditions(mesh, (G.Const(0.0),) * 4, (G.Dirichlet, G.Dudt, G.Dirichlet, G.Dirichlet))
+    cons = G.BoundaryConditions(mesh, (G.Const(0.0),) * 4, (G.Dirichlet, G.Constrained, G.Dirichlet, G.Dirichlet))
+    with pytest.raises(ValueError, match="PoissonsEquation does not support Dudt nodes"):
+        G.PoissonsEquation(mesh, dudt, source_function=lambda x, y, p: 0 * x)
+    with pytest.raises(ValueError, match="PoissonsEquation does not support Dudt nodes"):  # sic, laplaces_equation.jl:62
+        G.LaplacesEquation(mesh, dudt)
+    with pytest.raises(ValueError, match="MeanExitTimeProblem does not support Dudt nodes"):
+        G.MeanExitTimeProblem(mesh, dudt, diffusion_function=1.0)
+    with pytest.raises(ValueError, match="MeanExitTimeProblem does not support Constrained edges"):
+        G.MeanExitTimeProblem(mesh, cons, diffusion_function=1.0)
+    with pytest.raises(NotImplementedError):
+        G.Tsit5(0.1, adaptive=True)

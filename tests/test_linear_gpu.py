@@ -1,0 +1,198 @@
+"""GPU parity of the linear-template path: device assembly (CSR A, b), SpMV, device Tsit5 and the
+Jacobi-Krylov steady solves, against the CPU oracle's restatement of
+/root/reference/src/specific_problems/*.jl.  Tolerances: operator application 1e-12 (BASELINE.json),
+fixed-step end state 1e-10, steady solves to the Krylov tolerance, closed forms at the reference's
+own tolerances."""
+import math
+
+import numpy as np
+import pytest
+
+import fvm_b200 as G
+from oracle import fvm_oracle as O
+from tests.common import RTOL_RHS, RTOL_TSIT5, Pair, cond_closure, delaunay_mesh, rel_err
+from tests.test_rhs_gpu import _split_loop
+
+pytestmark = pytest.mark.gpu
+
+
+def xy_cond(spec):
+    c = cond_closure(spec)
+    return lambda x, y, t, u, p: c(x, y, 0.0, 0.0, p)
+
+
+def assert_system_matches(tpl, ref, rtol=1e-12):
+    A, b = tpl.A, tpl.b
+    D = (A - ref.A).tocoo()
+    scale = abs(ref.A).max()
+    assert (abs(D.data).max() if D.nnz else 0.0) <= rtol * scale
+    assert rel_err(b, ref.b) <= rtol if np.abs(ref.b).max() > 0 else np.abs(b).max() == 0
+
+
+def test_diffusion_equation_readme_operator():
+    """BASELINE configs[0]/[1] shape: DiffusionEquation on the README mesh; A, b, u0, A*u+b."""
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True))
+    ic = np.where(pair.gtri.points[:, 1] <= 1.0, 50.0, 0.0)
+    gBC = G.BoundaryConditions(pair.gmesh, G.Const(0.0), G.Dirichlet)
+    oBC = O.BoundaryConditions(pair.omesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet)
+    tpl = G.DiffusionEquation(pair.gmesh, gBC, diffusion_function=1 / 9, initial_condition=ic, final_time=0.5)
+    ref = O.DiffusionEquation(pair.omesh, oBC, diffusion_function=lambda x, y, p: 1 / 9, initial_condition=ic, final_time=0.5)
+    assert tpl.A.nnz == 17102  # structural pattern N + 2E
+    assert_system_matches(tpl, ref)
+    assert np.array_equal(tpl.u0, ref.u0)
+    u = 50 * np.random.default_rng(20240517).random(len(ic))
+    du = tpl.mul(np.empty_like(u), u)
+    assert rel_err(du, ref.A @ u + ref.b) <= RTOL_RHS
+    # the template operator equals the generic RHS (docs/src/literate_wyos/diffusion_equations.jl:436-438)
+    gp, _ = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(1 / 9), ic=ic)
+    rhs = G.fvm_eqs(np.zeros_like(u), u, G.get_cuda_parameters(gp), 0.0)
+    assert rel_err(du, rhs) <= RTOL_RHS
+
+
+@pytest.mark.parametrize("kind", ["diffusion", "lrd"])
+def test_assembly_unstructured_mixed_conditions(kind):
+    """Tabulated D(x,y), Neumann with a non-zero function, Dirichlet, Dudt and Constrained sections
+    (with the reference's V_i quirk, abstract_templates.jl:262), internal conditions, points that are
+    not vertices (fix_missing_vertices!)."""
+    gtri = _split_loop(delaunay_mesh(1200, 21, extra_points=4))
+    pair = Pair(gtri)
+    specs = (G.LinearXY(0.5, 1.0, -2.0), G.Const(0.3), G.LinearXY(0.1, 0.2, 0.3), G.Const(0.0))
+    types = (G.Dirichlet, G.Dudt, G.Neumann, G.Constrained)
+    dn, tn = {200: 0, 201: 0}, {300: 0, 200: 0}
+    gBC = G.BoundaryConditions(pair.gmesh, specs, types)
+    oBC = O.BoundaryConditions(pair.omesh, tuple(xy_cond(s) for s in specs), types)
+    gIC = G.InternalConditions((G.Const(0.7),), dirichlet_nodes=dn, dudt_nodes=tn)
+    oIC = O.InternalConditions((xy_cond(G.Const(0.7)),), dirichlet_nodes=dn, dudt_nodes=tn)
+    Dfn = lambda x, y, p: 1.0 + 0.5 * np.sin(3 * x) * np.cos(2 * y) + p
+    Sfn = lambda x, y, p: -0.3 + x * y
+    ic = np.random.default_rng(2).random(gtri.num_points)
+    if kind == "diffusion":
+        tpl = G.DiffusionEquation(pair.gmesh, gBC, gIC, diffusion_function=Dfn, diffusion_parameters=0.25,
+                                  initial_condition=ic, final_time=1.0, tile_triangles=128)
+        ref = O.DiffusionEquation(pair.omesh, oBC, oIC, diffusion_function=Dfn, diffusion_parameters=0.25,
+                                  initial_condition=ic, final_time=1.0)
+    else:
+        tpl = G.LinearReactionDiffusionEquation(pair.gmesh, gBC, gIC, diffusion_function=Dfn, diffusion_parameters=0.25,
+                                                source_function=Sfn, initial_condition=ic, final_time=1.0)
+        ref = O.LinearReactionDiffusionEquation(pair.omesh, oBC, oIC, diffusion_function=Dfn, diffusion_parameters=0.25,
+                                                source_function=Sfn, initial_condition=ic, final_time=1.0)
+    assert_system_matches(tpl, ref)
+    assert rel_err(tpl.u0, ref.u0) == 0.0
+    u = np.random.default_rng(3).random(gtri.num_points)
+    assert rel_err(tpl.mul(np.empty_like(u), u), ref.A @ u + ref.b) <= RTOL_RHS
+    assert rel_err(tpl.mul(np.empty_like(u), u, add_b=False), ref.A @ u) <= RTOL_RHS
+
+
+def test_tsit5_operator_readme():
+    """DiffusionEquation + fixed-step Tsit5 to t = 0.5 (README, BASELINE configs[0]) vs the oracle's
+    fixed-step Tsit5 on (A, b); end state within 1e-10, trailing augmented 1 (Appendix D-2)."""
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True))
+    ic = np.where(pair.gtri.points[:, 1] <= 1.0, 50.0, 0.0)
+    gBC = G.BoundaryConditions(pair.gmesh, G.Const(0.0), G.Dirichlet)
+    oBC = O.BoundaryConditions(pair.omesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet)
+    tpl = G.DiffusionEquation(pair.gmesh, gBC, diffusion_function=1 / 9, initial_condition=ic, final_time=0.5)
+    ref = O.DiffusionEquation(pair.omesh, oBC, diffusion_function=lambda x, y, p: 1 / 9, initial_condition=ic, final_time=0.5)
+    dt = 0.0025  # stable: dt < 3.3 h^2 / (8 D)
+    sol = G.solve(tpl, G.Tsit5(dt), saveat=[0.0, 0.25, 0.5])
+
+    def f(du, u, t):
+        du[...] = ref.A @ u + ref.b
+
+    uref, saves = O.tsit5_fixed(f, ref.u0, 0.0, 0.5, dt, saveat=[0.25, 0.5])
+    assert len(sol.u) == 3 and all(len(s) == 2501 and s[-1] == 1.0 for s in sol.u)
+    assert np.array_equal(sol.u[0][:-1], ref.u0)
+    assert rel_err(sol.u[1][:-1], saves[0]) <= RTOL_TSIT5
+    assert rel_err(sol.u[2][:-1], uref) <= RTOL_TSIT5
+    end = G.solve(tpl, G.Tsit5(dt))
+    assert np.array_equal(end.u, sol.u[2])
+    assert 1.0 < uref.max() < 50.0  # the heat has diffused but not vanished
+
+
+def test_tsit5_rhs_with_dirichlet_callback():
+    """FVMProblem + device Tsit5: time-dependent Dirichlet values re-applied after every step
+    (solve.jl:133-165), FSAL discarded after the callback; nonlinear diffusion + logistic source."""
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 24, 24, single_boundary=False))
+    specs = (G.ExpSaturation(2.0, 0.5), G.Const(0.2), G.Const(0.0), G.AffineU(0.0, 1.0))
+    types = (G.Dirichlet, G.Dirichlet, G.Neumann, G.Dudt)
+    P = pair.gtri.points
+    ic = 0.2 + 0.1 * np.sin(3 * P[:, 0]) * np.cos(2 * P[:, 1])
+    gp, op = pair.problem(specs, types, G.PowerDiffusion(0.05, 2.0), source=G.LogisticSource(0.7), ic=ic, final_time=0.2)
+    dt = 0.001
+    sol = G.solve(gp, G.Tsit5(dt), saveat=[0.1, 0.2], tile_triangles=128)
+    uref, saves = O.tsit5_fixed(lambda du, u, t: O.fvm_eqs_vec(du, u, op, t), ic, 0.0, 0.2, dt,
+                                callback=lambda u, t: (O.update_dirichlet_nodes(u, t, op), True)[1], saveat=[0.1, 0.2])
+    assert rel_err(sol.u[0], saves[0]) <= RTOL_TSIT5 and rel_err(sol.u[1], uref) <= RTOL_TSIT5
+    assert abs(uref[0] - 2.0 * (1 - math.exp(-0.2 / 0.5))) < 1e-12  # the Dirichlet value at t = 0.2
+
+
+def test_tsit5_system_no_callback_uses_fsal():
+    """Gray-Scott FVMSystem, all-Neumann: no Dirichlet nodes, so k7 is reused as k1 (FSAL)."""
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 20, 17, single_boundary=True))
+    N = pair.gtri.num_points
+    rng = np.random.default_rng(4)
+    U = np.ascontiguousarray(np.stack([0.5 + 0.5 * rng.random(N), 0.25 * rng.random(N)], axis=1))
+    src = G.GrayScottSource(0.04, 0.1)
+    g1, o1 = pair.problem(G.Const(0.0), G.Neumann, G.ConstantDiffusion(2e-3), source=src, var=0, ic=U[:, 0], final_time=2.0)
+    g2, o2 = pair.problem(G.Const(0.0), G.Neumann, G.ConstantDiffusion(1e-3), source=src, var=1, ic=U[:, 1], final_time=2.0)
+    gs, os_ = G.FVMSystem(g1, g2), O.FVMSystem(o1, o2)
+    sol = G.solve(gs, G.Tsit5(0.05))
+    uref = O.tsit5_fixed(lambda du, u, t: O.fvm_eqs_vec(du, u, os_, t), U, 0.0, 2.0, 0.05)
+    assert sol.u.shape == (N, 2) and rel_err(sol.u, uref) <= RTOL_TSIT5
+
+
+def test_poisson_closed_form_pcg():
+    """docs/src/literate_wyos/poissons_equation.jl:92-116,159-162 on 100x100, plus parity with the
+    oracle's sparse-direct solve (SuperLU standing in for KLU)."""
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 100, 100, single_boundary=True))
+    gBC = G.BoundaryConditions(pair.gmesh, G.Const(0.0), G.Dirichlet)
+    oBC = O.BoundaryConditions(pair.omesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet)
+    src = lambda x, y, p: -np.sin(np.pi * x) * np.sin(np.pi * y)
+    tpl = G.PoissonsEquation(pair.gmesh, gBC, source_function=src)
+    ref = O.PoissonsEquation(pair.omesh, oBC, source_function=src)
+    assert_system_matches(tpl, ref)
+    sol = G.solve(tpl, G.KrylovJacobi("pcg", rtol=1e-13))
+    P = pair.gtri.points
+    exact = 1 / (2 * np.pi**2) * np.sin(np.pi * P[:, 0]) * np.sin(np.pi * P[:, 1])
+    assert np.linalg.norm(sol.u - exact) <= 1e-4 * np.linalg.norm(exact)
+    assert sol.relres <= 1e-12 and sol.iters < 2000
+    assert rel_err(sol.u, O.solve_steady(ref)) <= 1e-9
+    # BiCGStab reaches the same answer
+    sol2 = G.solve(tpl, G.KrylovJacobi("bicgstab", rtol=1e-13))
+    assert sol2.relres <= 1e-11 and rel_err(sol2.u, sol.u) <= 1e-8
+
+
+def test_laplace_variable_diffusion_bicgstab():
+    """docs/src/literate_wyos/laplaces_equation.jl:160-193: D = (x+1)(y+2), mixed Neumann/Dirichlet,
+    exact solution 5 log6(1+x) at rtol 1e-3; non-symmetric operator -> BiCGStab."""
+    pair = Pair(G.triangulate_rectangle(0, 5, 0, 5, 100, 100, single_boundary=False))
+    specs = (G.Const(0.0), G.Const(5.0), G.Const(0.0), G.Const(0.0))
+    types = (G.Neumann, G.Dirichlet, G.Neumann, G.Dirichlet)
+    gBC = G.BoundaryConditions(pair.gmesh, specs, types)
+    oBC = O.BoundaryConditions(pair.omesh, tuple(xy_cond(s) for s in specs), types)
+    Dfn = lambda x, y, p: (x + 1) * (y + 2)
+    tpl = G.LaplacesEquation(pair.gmesh, gBC, diffusion_function=Dfn)
+    ref = O.LaplacesEquation(pair.omesh, oBC, diffusion_function=Dfn)
+    assert_system_matches(tpl, ref)
+    sol = G.solve(tpl)
+    exact = 5 * np.log(1 + pair.gtri.points[:, 0]) / math.log(6)
+    assert np.linalg.norm(sol.u - exact) <= 1e-3 * np.linalg.norm(exact)
+    assert sol.relres <= 1e-11
+    assert rel_err(sol.u, O.solve_steady(ref)) <= 1e-8
+
+
+def test_mean_exit_time_unstructured():
+    """mean_exit_time.jl:57-94: b = -1 on free vertices, identity rows on Dirichlet nodes, Neumann
+    section ignored by the assembly, BC functions never evaluated."""
+    gtri = _split_loop(delaunay_mesh(2500, 8, extra_points=2), k=2)
+    pair = Pair(gtri)
+    gBC = G.BoundaryConditions(pair.gmesh, (G.Const(99.0), G.Const(99.0)), (G.Neumann, G.Dirichlet))
+    oBC = O.BoundaryConditions(pair.omesh, (xy_cond(G.Const(99.0)),) * 2, (O.Neumann, O.Dirichlet))
+    tpl = G.MeanExitTimeProblem(pair.gmesh, gBC, diffusion_function=6.25e-4)
+    ref = O.MeanExitTimeProblem(pair.omesh, oBC, diffusion_function=lambda x, y, p: 6.25e-4)
+    assert_system_matches(tpl, ref)
+    sol = G.solve(tpl, G.KrylovJacobi(rtol=1e-13))
+    uref = O.solve_steady(ref)
+    assert sol.relres <= 1e-12
+    assert rel_err(sol.u, uref) <= 1e-9
+    assert uref.max() > 10  # exit times are positive and large for a small D
+    assert np.all(sol.u[-2:] == 0.0)  # points that are not vertices: A[i,i] = 1, b[i] = 0
