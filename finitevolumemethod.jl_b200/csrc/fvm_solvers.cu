@@ -161,7 +161,7 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
 // ---- Krylov ----------------------------------------------------------------------------------
 #define RED_BLOCKS 1184  // 148 SMs x 8
 #define RED_THREADS 256
-enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_N };
+enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_N };
 
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partial) {
@@ -217,9 +217,10 @@ __global__ void __launch_bounds__(RED_THREADS)
         r[i] = ri;
         z[i] = zi;
         p[i] = zi;
+        const double ru = ri / rowscale[i];  // residual of the unscaled system A x = b
         v[0] += ri * zi;
-        v[1] += ri * ri;
-        v[2] += c * c;
+        v[1] += ru * ru;
+        v[2] += b[i] * b[i];
     }
     block_reduce_store<3>(v, partial);
 }
@@ -249,8 +250,8 @@ __global__ void __launch_bounds__(RED_THREADS) pcg_alpha_kernel(const double* pa
     }
 }
 __global__ void __launch_bounds__(RED_THREADS)
-    pcg_update_kernel(int64_t n, const double* p, const double* q, const double* dinv, double* x, double* r, double* z,
-                      double* partial, const double* sc) {
+    pcg_update_kernel(int64_t n, const double* p, const double* q, const double* dinv, const double* rowscale, double* x,
+                      double* r, double* z, double* partial, const double* sc) {
     if (sc[SC_DONE] != 0.0) return;
     const double alpha = sc[SC_ALPHA];
     double v[2] = {0, 0};
@@ -260,8 +261,9 @@ __global__ void __launch_bounds__(RED_THREADS)
         const double zi = dinv[i] * ri;
         r[i] = ri;
         z[i] = zi;
+        const double ru = ri / rowscale[i];
         v[0] += ri * zi;
-        v[1] += ri * ri;
+        v[1] += ru * ru;
     }
     block_reduce_store<2>(v, partial);
 }
@@ -308,12 +310,23 @@ __global__ void __launch_bounds__(RED_THREADS) bicg_init2_kernel(const double* p
         sc[SC_OMEGA] = 1.0;
         sc[SC_RZ] = rr;  // rhat . r
         sc[SC_ITER] = 0.0;
+        sc[SC_RESTART] = 0.0;
         sc[SC_DONE] = (rr <= rtol * rtol * bb) ? 1.0 : 0.0;
     }
 }
 // beta = (rho_new/rho)(alpha/omega); p = r + beta (p - omega v); y = K^-1 p
-__global__ void bicg_p_kernel(int64_t n, const double* r, const double* v, const double* kinv, double* p, double* y, const double* sc) {
+__global__ void bicg_p_kernel(int64_t n, const double* r, const double* v, const double* kinv, double* p, double* y, double* rhat,
+                              const double* sc) {
     if (sc[SC_DONE] != 0.0) return;
+    if (sc[SC_RESTART] != 0.0) {  // rhat . r vanished: restart the recurrence with rhat = r
+        GRID_STRIDE(i, n) {
+            const double ri = r[i];
+            rhat[i] = ri;
+            p[i] = ri;
+            y[i] = kinv[i] * ri;
+        }
+        return;
+    }
     const double beta = (sc[SC_RZ] / sc[SC_RHO]) * (sc[SC_ALPHA] / sc[SC_OMEGA]);
     const double omega = sc[SC_OMEGA];
     GRID_STRIDE(i, n) {
@@ -328,6 +341,7 @@ __global__ void __launch_bounds__(RED_THREADS) bicg_alpha_kernel(const double* p
     if (threadIdx.x == 0) {
         sc[SC_RHO] = sc[SC_RZ];
         sc[SC_ALPHA] = sc[SC_RZ] / rhv;
+        sc[SC_RESTART] = 0.0;
     }
 }
 // s = r - alpha v ; z = K^-1 s
@@ -377,7 +391,13 @@ __global__ void __launch_bounds__(RED_THREADS) bicg_end_kernel(const double* par
         sc[SC_RZ] = rhr;
         sc[SC_RR] = rr;
         sc[SC_ITER] += 1.0;
-        if (rr <= sc[SC_TOL2] || !(rr == rr) || rhr == 0.0) sc[SC_DONE] = 1.0;
+        if (rr <= sc[SC_TOL2] || !(rr == rr)) {
+            sc[SC_DONE] = 1.0;
+        } else if (fabs(rhr) <= 1e-28 * rr || sc[SC_OMEGA] == 0.0) {
+            sc[SC_RZ] = rr;
+            sc[SC_RHO] = sc[SC_ALPHA] = sc[SC_OMEGA] = 1.0;
+            sc[SC_RESTART] = 1.0;
+        }
     }
 }
 __global__ void kinv_kernel(int64_t n, const double* dinv, const double* rowscale, double* kinv) {
@@ -430,51 +450,65 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
         FVM_CUDA(h, cudaStreamSynchronize(st));
         return FVM_OK;
     };
-    if (method == FVM_KRYLOV_PCG) {
-        double *R = h->d_work[1], *Z = h->d_work[2], *P = h->d_work[3], *Q = h->d_work[4];
-        pcg_init1_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, X);
-        if ((rc = fvm_launch_spmv(h, X, Q, false, true))) return rc;
-        pcg_init2_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, Q, c.diag_inv, R, Z, P, partial);
-        pcg_init3_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
-        for (int it = 0; it < maxit; ++it) {
-            if ((rc = fvm_launch_spmv(h, P, Q, false, true))) return rc;
-            dot_kernel<<<G, B, 0, st>>>(n, P, Q, partial, sc);
-            pcg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
-            pcg_update_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, X, R, Z, partial, sc);
-            pcg_beta_kernel<<<1, B, 0, st>>>(partial, sc);
-            pcg_p_kernel<<<G, B, 0, st>>>(n, Z, P, sc);
-            if ((it + 1) % check_every == 0 || it + 1 == maxit) {
-                if ((rc = poll())) return rc;
-                if (hsc[SC_DONE] != 0.0) break;
+    // Outer loop = residual replacement: every cycle starts from the TRUE residual b - A x, so the
+    // recurrence drift of CG / BiCGStab cannot hide a residual above the tolerance.
+    int32_t total_iters = 0;
+    double last_rr = -1.0;
+    for (int cycle = 0; cycle < 8 && total_iters < maxit; ++cycle) {
+        const int budget = maxit - total_iters;
+        if (method == FVM_KRYLOV_PCG) {
+            double *R = h->d_work[1], *Z = h->d_work[2], *P = h->d_work[3], *Q = h->d_work[4];
+            pcg_init1_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, X);
+            if ((rc = fvm_launch_spmv(h, X, Q, false, true))) return rc;
+            pcg_init2_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, Q, c.diag_inv, R, Z, P, partial);
+            pcg_init3_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
+            for (int it = 0; it < budget; ++it) {
+                if ((rc = fvm_launch_spmv(h, P, Q, false, true))) return rc;
+                dot_kernel<<<G, B, 0, st>>>(n, P, Q, partial, sc);
+                pcg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
+                pcg_update_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, c.rowscale, X, R, Z, partial, sc);
+                pcg_beta_kernel<<<1, B, 0, st>>>(partial, sc);
+                pcg_p_kernel<<<G, B, 0, st>>>(n, Z, P, sc);
+                if ((it + 1) % check_every == 0 || it + 1 == budget) {
+                    if ((rc = poll())) return rc;
+                    if (hsc[SC_DONE] != 0.0) break;
+                }
+            }
+        } else {
+            double *R = h->d_work[1], *RH = h->d_work[2], *P = h->d_work[3], *V = h->d_work[4], *Y = h->d_work[5],
+                   *S = h->d_work[6], *Z = h->d_work[7], *T = h->d_work[8], *KI = h->d_work[9];
+            kinv_kernel<<<G, B, 0, st>>>(n, c.diag_inv, c.rowscale, KI);
+            pcg_init1_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, X);  // identity rows are satisfied from the start
+            if ((rc = fvm_launch_spmv(h, X, V, false, false))) return rc;
+            bicg_init_kernel<<<G, B, 0, st>>>(n, c.b, V, R, RH, P, V, partial);
+            bicg_init2_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
+            for (int it = 0; it < budget; ++it) {
+                bicg_p_kernel<<<G, B, 0, st>>>(n, R, V, KI, P, Y, RH, sc);
+                if ((rc = fvm_launch_spmv(h, Y, V, false, false))) return rc;
+                dot_kernel<<<G, B, 0, st>>>(n, RH, V, partial, sc);
+                bicg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
+                bicg_s_kernel<<<G, B, 0, st>>>(n, R, V, KI, S, Z, sc);
+                if ((rc = fvm_launch_spmv(h, Z, T, false, false))) return rc;
+                bicg_ts_kernel<<<G, B, 0, st>>>(n, T, S, partial, sc);
+                bicg_omega_kernel<<<1, B, 0, st>>>(partial, sc);
+                bicg_x_kernel<<<G, B, 0, st>>>(n, Y, Z, S, T, RH, X, R, partial, sc);
+                bicg_end_kernel<<<1, B, 0, st>>>(partial, sc);
+                if ((it + 1) % check_every == 0 || it + 1 == budget) {
+                    if ((rc = poll())) return rc;
+                    if (hsc[SC_DONE] != 0.0) break;
+                }
             }
         }
-    } else {
-        double *R = h->d_work[1], *RH = h->d_work[2], *P = h->d_work[3], *V = h->d_work[4], *Y = h->d_work[5], *S = h->d_work[6],
-               *Z = h->d_work[7], *T = h->d_work[8], *KI = h->d_work[9];
-        kinv_kernel<<<G, B, 0, st>>>(n, c.diag_inv, c.rowscale, KI);
-        if ((rc = fvm_launch_spmv(h, X, V, false, false))) return rc;
-        bicg_init_kernel<<<G, B, 0, st>>>(n, c.b, V, R, RH, P, V, partial);
-        bicg_init2_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
-        for (int it = 0; it < maxit; ++it) {
-            bicg_p_kernel<<<G, B, 0, st>>>(n, R, V, KI, P, Y, sc);
-            if ((rc = fvm_launch_spmv(h, Y, V, false, false))) return rc;
-            dot_kernel<<<G, B, 0, st>>>(n, RH, V, partial, sc);
-            bicg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
-            bicg_s_kernel<<<G, B, 0, st>>>(n, R, V, KI, S, Z, sc);
-            if ((rc = fvm_launch_spmv(h, Z, T, false, false))) return rc;
-            bicg_ts_kernel<<<G, B, 0, st>>>(n, T, S, partial, sc);
-            bicg_omega_kernel<<<1, B, 0, st>>>(partial, sc);
-            bicg_x_kernel<<<G, B, 0, st>>>(n, Y, Z, S, T, RH, X, R, partial, sc);
-            bicg_end_kernel<<<1, B, 0, st>>>(partial, sc);
-            if ((it + 1) % check_every == 0 || it + 1 == maxit) {
-                if ((rc = poll())) return rc;
-                if (hsc[SC_DONE] != 0.0) break;
-            }
-        }
+        FVM_CUDA(h, cudaGetLastError());
+        if ((rc = poll())) return rc;
+        const int32_t cyc_iters = (int32_t)hsc[SC_ITER];
+        total_iters += cyc_iters;
+        if (cyc_iters == 0) break;  // the true residual at the start of this cycle already met the tolerance
+        if (!(hsc[SC_RR] == hsc[SC_RR])) break;
+        if (last_rr >= 0.0 && hsc[SC_RR] >= last_rr && cycle > 1) break;  // no further progress possible
+        last_rr = hsc[SC_RR];
     }
-    FVM_CUDA(h, cudaGetLastError());
-    if ((rc = poll())) return rc;
-    const int32_t done_iters = (int32_t)hsc[SC_ITER];
+    const int32_t done_iters = total_iters;
     // true (unscaled) residual of A x = b
     double* AX = h->d_work[4];
     if ((rc = fvm_launch_spmv(h, X, AX, false, false))) return rc;

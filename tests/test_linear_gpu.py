@@ -21,6 +21,12 @@ def xy_cond(spec):
     return lambda x, y, t, u, p: c(x, y, 0.0, 0.0, p)
 
 
+def direct_relres(ref):
+    """relative residual the oracle's sparse-direct solve attains: the fp64 floor eps*|A||x|/|b|"""
+    x = O.solve_steady(ref)
+    return x, np.linalg.norm(ref.b - ref.A @ x) / np.linalg.norm(ref.b)
+
+
 def assert_system_matches(tpl, ref, rtol=1e-12):
     A, b = tpl.A, tpl.b
     D = (A - ref.A).tocoo()
@@ -158,7 +164,7 @@ def test_poisson_closed_form_pcg():
     assert rel_err(sol.u, O.solve_steady(ref)) <= 1e-9
     # BiCGStab reaches the same answer
     sol2 = G.solve(tpl, G.KrylovJacobi("bicgstab", rtol=1e-13))
-    assert sol2.relres <= 1e-11 and rel_err(sol2.u, sol.u) <= 1e-8
+    assert sol2.relres <= 1e-12 and rel_err(sol2.u, sol.u) <= 1e-8
 
 
 def test_laplace_variable_diffusion_bicgstab():
@@ -173,11 +179,12 @@ def test_laplace_variable_diffusion_bicgstab():
     tpl = G.LaplacesEquation(pair.gmesh, gBC, diffusion_function=Dfn)
     ref = O.LaplacesEquation(pair.omesh, oBC, diffusion_function=Dfn)
     assert_system_matches(tpl, ref)
-    sol = G.solve(tpl)
+    sol = G.solve(tpl, G.KrylovJacobi(rtol=1e-13))
     exact = 5 * np.log(1 + pair.gtri.points[:, 0]) / math.log(6)
     assert np.linalg.norm(sol.u - exact) <= 1e-3 * np.linalg.norm(exact)
-    assert sol.relres <= 1e-11
-    assert rel_err(sol.u, O.solve_steady(ref)) <= 1e-8
+    uref, floor = direct_relres(ref)
+    assert sol.relres <= max(1e-12, 10 * floor)  # |b| is tiny here: 1e-12 |b| is below the fp64 floor
+    assert rel_err(sol.u, uref) <= 1e-8
 
 
 def test_mean_exit_time_unstructured():
@@ -191,8 +198,8 @@ def test_mean_exit_time_unstructured():
     ref = O.MeanExitTimeProblem(pair.omesh, oBC, diffusion_function=lambda x, y, p: 6.25e-4)
     assert_system_matches(tpl, ref)
     sol = G.solve(tpl, G.KrylovJacobi(rtol=1e-13))
-    uref = O.solve_steady(ref)
-    assert sol.relres <= 1e-12
+    uref, floor = direct_relres(ref)
+    assert sol.relres <= max(1e-12, 10 * floor)
     assert rel_err(sol.u, uref) <= 1e-9
     assert uref.max() > 10  # exit times are positive and large for a small D
     assert np.all(sol.u[-2:] == 0.0)  # points that are not vertices: A[i,i] = 1, b[i] = 0
