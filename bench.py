@@ -12,6 +12,7 @@ buffers (H2D + permutation + kernels + D2H).  N>1: weak scaling, each rank owns 
 One JSON line on stdout (rank 0)."""
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -125,6 +126,57 @@ def time_rhs(torch, eng, u_d, du_d, steps, warmup):
     return ms, (kms / kn if kn else float("nan"))
 
 
+def time_template(torch, G, prob, steps, warmup, peak):
+    """BASELINE configs[1]: DiffusionEquation template on the same mesh: y = A x + b SpMV and the
+    device-resident fixed-step Tsit5 (6 SpMV + 6 stage combinations per step)."""
+    mesh = prob.mesh
+    tri = mesh.triangulation
+    BCs = G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet)
+    t0 = time.perf_counter()
+    tpl = G.DiffusionEquation(mesh, BCs, diffusion_function=1 / 9, initial_condition=prob.initial_condition, final_time=1.0)
+    setup_s = time.perf_counter() - t0
+    eng = tpl.engine
+    N = eng.N
+    st = eng.stats()
+    nnz = st["nnz"]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED)
+    x = 50.0 * torch.rand(N, dtype=torch.float64, device="cuda", generator=g)
+    y = torch.empty_like(x)
+    stream = torch.cuda.ExternalStream(eng.stream())
+    for _ in range(warmup):
+        eng.spmv_device(y.data_ptr(), x.data_ptr(), True, native=True)
+    eng.synchronize()
+    eng.set_profiling(steps)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        eng.spmv_device(y.data_ptr(), x.data_ptr(), True, native=True)
+    e1.record(stream)
+    eng.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    kms, kn = eng.get_profile()
+    eng.set_profiling(0)
+    kms = kms / kn if kn else float("nan")
+    B = 12 * nnz + 4 * (N + 1) + 24 * N
+    # fixed-step Tsit5 at a stable dt (|lambda|max ~ 8 D / h^2, dt < 3.3 / |lambda|max)
+    h = 2.0 / (int(round(math.sqrt(N))) - 1)
+    dt = 0.2 * 3.3 * h * h / (8.0 / 9.0)
+    nst = 20
+    u = torch.from_numpy(tpl.u0).cuda()
+    eng.tsit5_device(u.data_ptr(), 0.0, 2 * dt, dt, True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.tsit5_device(u.data_ptr(), 0.0, nst * dt, dt, True)
+    torch.cuda.synchronize()
+    ts_ms = (time.perf_counter() - t0) / nst * 1e3
+    out = {"spmv_ms": ms, "spmv_kernel_ms": kms, "spmv_gbs": B / kms / 1e6, "spmv_frac": B / kms / 1e6 / peak, "spmv_alg_bytes": B,
+           "nnz": nnz, "assemble_setup_s": setup_s, "tsit5_ms_per_step": ts_ms, "tsit5_steps": nst, "tsit5_dt": dt,
+           "tsit5_launches": nst * 12 + 3, "finite": bool(torch.isfinite(u).all().item())}
+    eng.close()
+    return out
+
+
 def cpu_baseline(nx, target_s=12.0, impl_reference=False, steps=None, warmup=1):
     """The oracle port (oracle/fvm_oracle_c.c, reference-structured: hash-table triangle props,
     per-thread du copies, serial combine) timed on the host cores on a bounded sample."""
@@ -185,6 +237,7 @@ def main():
     ap.add_argument("--all-variants", action="store_true")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-template", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -264,13 +317,20 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = float(tmax.item())
 
+    tplres = None
+    st = eng.stats()
+    if not args.no_template:
+        eng.close()
+        tplres = time_template(torch, G, p.prob, args.steps, args.warmup, peak)
+        if rank == 0:
+            sys.stderr.write("[bench] template SpMV %.3f ms  %.0f GB/s (%.2f of peak)  Tsit5 %.3f ms/step\n"
+                             % (tplres["spmv_kernel_ms"], tplres["spmv_gbs"], tplres["spmv_frac"], tplres["tsit5_ms_per_step"]))
     if rank != 0:
         dist.destroy_process_group()
         return
     cb = None
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_baseline(args.ref_nx)
-    st = eng.stats()
     launches_per_step = 1 + (1 if st["n_interface"] + (N - st["n_vertices"]) > 0 else 0) + (1 if st["n_live_boundary_edges"] else 0)
     line = {
         "metric": "fvm_eqs! Mtriangle-updates/s", "value": head["mtri_s"], "unit": "Mtriangle-updates/s",
@@ -290,6 +350,14 @@ def main():
         "clocks": clocks,
         "setup_s": head["setup_s"],
     }
+    if tplres:
+        line["spmv"] = {"metric": "DiffusionEquation template y = A x + b, fp64 CSR SpMV", "gbs": tplres["spmv_gbs"],
+                        "frac": tplres["spmv_frac"], "kernel_ms": tplres["spmv_kernel_ms"], "ms_per_step": tplres["spmv_ms"],
+                        "alg_bytes_per_launch": tplres["spmv_alg_bytes"], "bytes_formula": "12*nnz + 4*(N+1) + 24*N",
+                        "nnz": tplres["nnz"], "assemble_setup_s": tplres["assemble_setup_s"]}
+        line["tsit5"] = {"ms_per_step": tplres["tsit5_ms_per_step"], "steps": tplres["tsit5_steps"], "dt": tplres["tsit5_dt"],
+                         "spmv_per_step": 6, "finite": tplres["finite"]}
+        line["gpu_launches"] += args.steps + tplres["tsit5_launches"]
     if cb:
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if len(results) > 1:

@@ -11,3 +11,5 @@ from .problem import (CudaParameters, Engine, FVMGeometry, FVMProblem, FVMSystem
 from .templates import (DiffusionEquation, KrylovJacobi, LaplacesEquation,  # noqa: F401
                         LinearReactionDiffusionEquation, MeanExitTimeProblem, PoissonsEquation, Solution, Tsit5)
 from .solve import solve  # noqa: F401
+from .sharding import (LocalMesh, extract_local, get_sharded_cuda_parameters, install_halo,  # noqa: F401
+                       lattice_strip_local, partition_rcb, partition_strips, shard_problem)

@@ -62,6 +62,9 @@ _SIGS = {
     "fvm_tsit5": [H, C.c_int32, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int64, c_dp, C.c_void_p, C.c_int32],
     "fvm_krylov": [H, C.c_int32, C.c_void_p, C.c_double, C.c_int32, c_ip, c_dp, C.c_int32],
     "fvm_shard_init": [H, C.c_void_p, C.c_int32, C.c_int32],
+    "fvm_set_ghost_nodes": [H, c_bp],
+    "fvm_set_halo": [H, C.c_int32, c_ip, c_ip, c_ip, c_ip, c_ip],
+    "fvm_halo_exchange_native": [H, C.c_void_p],
     "fvm_nccl_unique_id": [C.c_void_p],
 }
 

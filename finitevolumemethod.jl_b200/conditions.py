@@ -16,7 +16,7 @@ class BoundaryConditions:
             functions = (functions,)
         if isinstance(condition_types, str):
             condition_types = (condition_types,)
-        nsec = len(mesh.triangulation.boundary_sections)
+        nsec = mesh.triangulation.num_sections
         if not (len(functions) == len(condition_types) == nsec):
             raise AssertionError("The number of boundary conditions must match the number of boundary sections (%d)." % nsec)
         for t in condition_types:
@@ -51,6 +51,7 @@ class Conditions:
         tri = mesh.triangulation
         N = tri.num_points
         nif = len(ic.functions)
+        self.nif, self.condition_types, self.internal = nif, tuple(bc.condition_types), ic
         self.functions = tuple(ic.functions) + tuple(bc.functions)
         dir_f = np.full(N, -1, dtype=np.int32)
         dudt_f = np.full(N, -1, dtype=np.int32)

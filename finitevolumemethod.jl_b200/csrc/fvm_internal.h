@@ -151,8 +151,10 @@ struct fvm_ctx {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
     int64_t prof_used = 0;
-    // sharding
-    void* nccl_comm = nullptr;
+    // sharding (fvm_shard.cu)
+    void* shard = nullptr;
+    bool halo_ready = false;
+    std::vector<uint8_t> h_ghost;  // caller order: 1 = ghost node owned by another rank
     int32_t rank = 0, nranks = 1;
 };
 
@@ -197,6 +199,9 @@ int32_t fvm_launch_permute(fvm_ctx* h, const double* src, double* dst, bool to_n
 int32_t fvm_export_geometry(fvm_ctx* h, double* s9, double* mid6, double* nrm6, double* len3);  // device, native tri order
 int32_t fvm_ensure_state(fvm_ctx* h);
 void fvm_shard_release(fvm_ctx* h);
+int32_t fvm_halo_exchange(fvm_ctx* h, double* u_native);
+int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);
+#define FVM_NODE_GHOST 4
 int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale);
 void fvm_prof_begin(fvm_ctx* h);
 void fvm_prof_end(fvm_ctx* h);

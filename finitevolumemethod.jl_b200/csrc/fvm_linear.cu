@@ -506,6 +506,8 @@ extern "C" int32_t fvm_get_csr(fvm_handle h, int32_t* rowptr, int32_t* col, doub
 extern "C" int32_t fvm_spmv_native(fvm_handle h, const double* x, double* y, int32_t add_b) {
     NEED_ASSEMBLED(h);
     FVM_REQUIRE(h, x && y && x != y, "fvm_spmv_native: bad arguments");
+    int32_t rc = fvm_halo_exchange(h, const_cast<double*>(x));
+    if (rc) return rc;
     return fvm_launch_spmv(h, x, y, add_b != 0, false);
 }
 
@@ -521,6 +523,7 @@ extern "C" int32_t fvm_spmv(fvm_handle h, const double* x, double* y, int32_t ad
         src = h->d_io;
     }
     if ((rc = fvm_launch_permute(h, src, h->d_u, true))) return rc;
+    if ((rc = fvm_halo_exchange(h, h->d_u))) return rc;
     if ((rc = fvm_launch_spmv(h, h->d_u, h->d_du, add_b != 0, false))) return rc;
     if (on_device) {
         if ((rc = fvm_launch_permute(h, h->d_du, y, false))) return rc;

@@ -477,6 +477,8 @@ int32_t fvm_ensure_state(fvm_ctx* h) {
 extern "C" int32_t fvm_rhs_native(fvm_handle h, double t, const double* u, double* du) {
     NEED_FINAL(h);
     FVM_REQUIRE(h, u && du, "fvm_rhs_native: null argument");
+    int32_t rc = fvm_halo_exchange(h, const_cast<double*>(u));  // sharded: ghost entries of u are refreshed in place
+    if (rc) return rc;
     return fvm_launch_rhs(h, t, u, du);
 }
 
@@ -492,6 +494,7 @@ extern "C" int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, 
         src = h->d_io;
     }
     if ((rc = fvm_launch_permute(h, src, h->d_u, true))) return rc;
+    if ((rc = fvm_halo_exchange(h, h->d_u))) return rc;
     if ((rc = fvm_launch_rhs(h, t, h->d_u, h->d_du))) return rc;
     if (on_device) {
         if ((rc = fvm_launch_permute(h, h->d_du, du, false))) return rc;

@@ -150,6 +150,15 @@ extern "C" int32_t fvm_set_node_conditions(fvm_handle h, int32_t var, const uint
     return FVM_OK;
 }
 
+// Sharded meshes: flags the ghost layer (nodes owned by another rank).  Ghost nodes take part in the
+// triangle pass as inputs only; their du is 0 and they are never treated as Dirichlet nodes.
+extern "C" int32_t fvm_set_ghost_nodes(fvm_handle h, const uint8_t* is_ghost) {
+    NOT_FINAL(h);
+    FVM_REQUIRE(h, is_ghost, "fvm_set_ghost_nodes: null argument");
+    h->h_ghost.assign(is_ghost, is_ghost + h->N);
+    return FVM_OK;
+}
+
 extern "C" int32_t fvm_set_condition_fn(fvm_handle h, int32_t var, int32_t fidx, int32_t fn_id, const double* params,
                                         int32_t nparams) {
     if (!h) return FVM_ERR_ARG;
@@ -307,6 +316,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     const int64_t n_tiles = (T + TT - 1) / TT;
     FVM_REQUIRE(h, n_tiles < INT32_MAX, "too many tiles");
 
+    if (!h->h_ghost.empty())  // ghost nodes are neither free nor Dirichlet
+        for (int v = 0; v < neq; ++v)
+            for (int64_t i = 0; i < N; ++i)
+                if (h->h_ghost[i]) h->h_nkind[v][i] = FVM_NODE_GHOST;
     // ---- 2. boundary edges: adjacent triangle, live flag --------------------------------
     std::vector<uint8_t> forced(N, 0);  // nodes that must be finished by the interface kernel
     std::vector<int32_t> live_edges;

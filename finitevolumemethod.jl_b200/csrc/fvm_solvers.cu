@@ -105,7 +105,9 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
     }
     if ((rc = fvm_launch_permute(h, src, U, true))) return rc;
 
-    auto f = [&](double* out, const double* x, double t) -> int32_t {
+    auto f = [&](double* out, double* x, double t) -> int32_t {
+        int32_t r = fvm_halo_exchange(h, x);  // sharded: refresh the ghost layer of the stage vector
+        if (r) return r;
         return use_operator ? fvm_launch_spmv(h, x, out, true, false) : fvm_launch_rhs(h, t, x, out);
     };
     int64_t next_save = 0;
@@ -527,8 +529,3 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
     return FVM_OK;
 }
 
-extern "C" int32_t fvm_shard_init(fvm_handle h, const void*, int32_t, int32_t) {
-    if (!h) return FVM_ERR_ARG;
-    return fvm_fail(h, FVM_ERR_STATE, "fvm_shard_init: not implemented yet");
-}
-extern "C" int32_t fvm_nccl_unique_id(void*) { return FVM_ERR_NCCL; }

@@ -10,12 +10,19 @@ class Triangulation:
     """points (N,2) f64, triangles (T,3) i32 (0-based, ccw, stored rotation kept),
     boundary_sections: list of ccw node sequences; section s has ghost vertex -(s+1)."""
 
-    def __init__(self, points, triangles, boundary_sections=None):
+    def __init__(self, points, triangles, boundary_sections=None, boundary_edge_list=None, num_sections=None):
         self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 2)
         self.triangles = np.ascontiguousarray(triangles, dtype=np.int32).reshape(-1, 3)
         if boundary_sections is None:
             boundary_sections = _chain_boundary(self.triangles)
         self.boundary_sections = [np.ascontiguousarray(s, dtype=np.int32) for s in boundary_sections]
+        # rank-local meshes (sharding.py) carry an explicit edge list: only the part of the global
+        # boundary that belongs to a local triangle, with the global section of every edge
+        self._edge_list = None
+        if boundary_edge_list is not None:
+            uv, sec = boundary_edge_list
+            self._edge_list = (np.ascontiguousarray(uv, dtype=np.int32).reshape(-1, 2), np.ascontiguousarray(sec, dtype=np.int32))
+        self.num_sections = len(self.boundary_sections) if num_sections is None else int(num_sections)
 
     @property
     def num_points(self):
@@ -27,6 +34,8 @@ class Triangulation:
 
     def boundary_edges(self):
         """keys(get_boundary_edge_map(tri)): (Eb,2) directed ccw edges and their section."""
+        if self._edge_list is not None:
+            return self._edge_list
         uv, sec = [], []
         for s, nodes in enumerate(self.boundary_sections):
             uv.append(np.stack([nodes[:-1], nodes[1:]], axis=1))

@@ -180,7 +180,7 @@ class SteadyFVMProblem:
 class Engine:
     """Owns one libfvmcuda handle for a problem (RHS) or a template (linear operator)."""
 
-    def __init__(self, mesh, neq, conditions, flux=None, source=None, tile_triangles=0, geometry_mode=0, device=None):
+    def __init__(self, mesh, neq, conditions, flux=None, source=None, tile_triangles=0, geometry_mode=0, device=None, ghost=None):
         lib = L.lib()
         tri = mesh.triangulation
         self.mesh, self.neq = mesh, neq
@@ -205,6 +205,9 @@ class Engine:
                 self._set_flux(flux, uv)
             if source is not None:
                 self._set_source(source)
+            if ghost is not None:
+                gh = np.ascontiguousarray(ghost, dtype=np.uint8)
+                L.check(self.h, lib.fvm_set_ghost_nodes(self.h, L.bp(gh)))
             L.check(self.h, lib.fvm_finalize(self.h, tile_triangles, geometry_mode))
         except Exception:
             lib.fvm_destroy(self.h)
@@ -286,6 +289,16 @@ class Engine:
         else:
             L.check(self.h, L.lib().fvm_rhs(self.h, float(t), u_ptr, du_ptr, 1))
 
+    def spmv_device(self, y_ptr, x_ptr, add_b=True, native=False):
+        if native:
+            L.check(self.h, L.lib().fvm_spmv_native(self.h, x_ptr, y_ptr, 1 if add_b else 0))
+        else:
+            L.check(self.h, L.lib().fvm_spmv(self.h, x_ptr, y_ptr, 1 if add_b else 0, 1))
+
+    def tsit5_device(self, u_ptr, t0, t1, dt, use_operator):
+        """device-resident fixed-step Tsit5 on a device vector in caller order"""
+        L.check(self.h, L.lib().fvm_tsit5(self.h, 1 if use_operator else 0, u_ptr, float(t0), float(t1), float(dt), 0, None, None, 1))
+
     def apply_dirichlet(self, u, t):
         L.check(self.h, L.lib().fvm_apply_dirichlet(self.h, float(t), u.ctypes.data, 0))
         return u
@@ -312,7 +325,7 @@ class Engine:
         st = np.zeros(16, dtype=np.int64)
         L.check(self.h, L.lib().fvm_get_stats(self.h, st.ctypes.data_as(L.c_lp)))
         keys = ["n_tiles", "tile_triangles", "n_vertices", "n_interface", "n_partial", "n_external", "max_local_nodes",
-                "n_live_boundary_edges", "n_dirichlet", "smem_bytes"]
+                "n_live_boundary_edges", "n_dirichlet", "smem_bytes", "nnz", "max_row"]
         return dict(zip(keys, st.tolist()))
 
     def permutation(self):
@@ -351,7 +364,7 @@ class CudaParameters:
         self.engine = engine
 
 
-def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None):
+def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None, ghost=None):
     """Sibling of get_multithreading_parameters (solve.jl:1-27): builds the device state once."""
     if isinstance(prob, SteadyFVMProblem):
         prob = prob.problem
@@ -359,7 +372,7 @@ def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None):
     neq = max(1, prob.neqs)
     conds = [p.conditions for p in probs]
     eng = Engine(prob.mesh, neq, conds, [p.flux_function for p in probs], [p.source_function for p in probs],
-                 tile_triangles, geometry_mode, device)
+                 tile_triangles, geometry_mode, device, ghost)
     return CudaParameters(prob, eng)
 
 

@@ -66,7 +66,7 @@ class AbstractFVMTemplate:
     steady = False
 
     def _setup(self, mesh, BCs, ICs, diffusion_function, diffusion_parameters, source_function=None, source_parameters=None,
-               tile_triangles=0, reference_quirks=True):
+               tile_triangles=0, reference_quirks=True, ghost=None):
         self.mesh = mesh
         self.conditions = Conditions(mesh, BCs, ICs or InternalConditions())
         self.diffusion_function, self.diffusion_parameters = diffusion_function, diffusion_parameters
@@ -105,7 +105,7 @@ class AbstractFVMTemplate:
         source = None
         if source_function is not None:
             source = L.f64(_eval_xy(source_function, P[:, 0], P[:, 1], source_parameters))
-        self.engine = Engine(mesh, 1, [c], tile_triangles=tile_triangles)
+        self.engine = Engine(mesh, 1, [c], tile_triangles=tile_triangles, geometry_mode=1, ghost=ghost)  # assembly recomputes geometry; no SoA kept
         self.node_value = node_value
         node_value, edge_value = L.f64(node_value), L.f64(edge_value)
         L.check(self.engine.h, L.lib().fvm_assemble(self.engine.h, self.template_id, d_const, L.dp(d_edge), L.dp(d_bnd),

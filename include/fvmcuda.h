@@ -180,10 +180,21 @@ int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, double t0, doub
 int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rtol, int32_t maxit, int32_t* iters,
                    double* relres, int32_t on_device);
 
-/* ---- multi-GPU: row-strip / tile-range sharding with a one-layer node halo ---------- */
+/* ---- multi-GPU: node partition + one-layer ghost halo per rank ---------------- */
+/* Each rank creates its handle on the LOCAL mesh: owned nodes + ghost nodes, and every triangle that
+ * touches an owned node.  Call order: fvm_create, setters, fvm_set_ghost_nodes, fvm_finalize,
+ * fvm_shard_init, fvm_set_halo.  Afterwards fvm_rhs*, fvm_spmv* and fvm_tsit5 refresh the ghost
+ * entries of their input vector with grouped ncclSend/ncclRecv before computing; outputs are valid
+ * on owned nodes (ghost rows are 0). */
+int32_t fvm_set_ghost_nodes(fvm_handle h, const uint8_t* is_ghost /* [N], 1 = owned by another rank */);
 /* nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 and broadcast by the host. */
-int32_t fvm_shard_init(fvm_handle h, const void* nccl_unique_id, int32_t rank, int32_t nranks);
 int32_t fvm_nccl_unique_id(void* out128);
+int32_t fvm_shard_init(fvm_handle h, const void* nccl_unique_id, int32_t rank, int32_t nranks);
+/* neighbours and the (local) node lists to send to / receive from each; both sides of a pair must
+ * list the shared nodes in the same order (ascending global node id). */
+int32_t fvm_set_halo(fvm_handle h, int32_t n_neighbours, const int32_t* neighbour_ranks, const int32_t* send_ptr,
+                     const int32_t* send_nodes, const int32_t* recv_ptr, const int32_t* recv_nodes);
+int32_t fvm_halo_exchange_native(fvm_handle h, double* u_native);
 
 #ifdef __cplusplus
 }

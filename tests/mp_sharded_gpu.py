@@ -1,0 +1,84 @@
+"""Multi-rank GPU parity (run under torchrun, one rank per GPU): the sharded fvm_eqs!, template
+SpMV and device Tsit5 with NCCL halo exchange must reproduce the single-domain ORACLE on the owned
+nodes of every rank."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import fvm_b200 as G
+    from oracle import fvm_oracle as O
+    from tests.common import RTOL_RHS, RTOL_TSIT5, rel_err
+    from tests.sharding_worker import build_case
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    errs = {}
+    for kind in ("lattice", "delaunay"):
+        pair, gp, op, owner = build_case(kind)
+        if world != 2:
+            owner = G.partition_rcb(pair.gtri.points, world)
+        local = G.extract_local(pair.gtri, owner, rank, world)
+        lp = G.shard_problem(gp, local)
+        p = G.get_sharded_cuda_parameters(lp, local, dist, tile_triangles=128, device=local_rank)
+        N = pair.gtri.num_points
+        u = 0.2 + np.random.default_rng(5).random(N)
+        ref = O.fvm_eqs_vec(np.zeros(N), u, op, 0.3)
+        ul = u[local.global_nodes].copy()
+        ul[local.n_owned:] = 1e300  # ghosts must come from the NCCL exchange
+        du = G.fvm_eqs(np.zeros_like(ul), ul, p, 0.3)
+        own = local.global_nodes[:local.n_owned]
+        errs["rhs_" + kind] = rel_err(du[:local.n_owned], ref[own]) if np.abs(ref).max() > 0 else 0.0
+        assert errs["rhs_" + kind] <= RTOL_RHS, errs
+        # device Tsit5 on the sharded RHS vs the single-domain oracle
+        if kind == "delaunay":
+            dt, t1 = 2e-5, 2e-4
+            ul = gp.initial_condition[local.global_nodes] + 0.3 + 0.1 * np.sin(7 * pair.gtri.points[local.global_nodes, 0])
+            ug = gp.initial_condition + 0.3 + 0.1 * np.sin(7 * pair.gtri.points[:, 0])
+            from fvm_b200 import _lib as L
+            ul = np.ascontiguousarray(ul)
+            L.check(p.engine.h, L.lib().fvm_tsit5(p.engine.h, 0, ul.ctypes.data, 0.0, t1, dt, 0, None, None, 0))
+            uref = O.tsit5_fixed(lambda d, x, t: O.fvm_eqs_vec(d, x, op, t), ug, 0.0, t1, dt,
+                                 callback=lambda x, t: (O.update_dirichlet_nodes(x, t, op), True)[1])
+            errs["tsit5_" + kind] = rel_err(ul[:local.n_owned], uref[own])
+            assert errs["tsit5_" + kind] <= RTOL_TSIT5, errs
+        p.engine.close()
+    # template operator: sharded SpMV y = A x + b and Tsit5 on the lattice
+    tri = G.triangulate_rectangle(0, 2, 0, 2, 40, 32, single_boundary=True)
+    owner = G.partition_strips(tri.points, world)
+    local = G.extract_local(tri, owner, rank, world)
+    lmesh = G.FVMGeometry(local.triangulation)
+    ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
+    tpl = G.DiffusionEquation(lmesh, G.BoundaryConditions(lmesh, G.Const(0.0), G.Dirichlet), diffusion_function=1 / 9,
+                              initial_condition=ic[local.global_nodes], final_time=0.02, ghost=local.is_ghost)
+    G.install_halo(tpl.engine, local, dist)
+    otri = O.triangulate_rectangle(0, 2, 0, 2, 40, 32, single_boundary=True)
+    omesh = O.FVMGeometry(otri)
+    ref = O.DiffusionEquation(omesh, O.BoundaryConditions(omesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet),
+                              diffusion_function=lambda x, y, p: 1 / 9, initial_condition=ic, final_time=0.02)
+    x = np.random.default_rng(9).random(tri.num_points)
+    xl = x[local.global_nodes].copy()
+    xl[local.n_owned:] = 1e300
+    y = tpl.mul(np.empty_like(xl), xl)
+    own = local.global_nodes[:local.n_owned]
+    errs["spmv"] = rel_err(y[:local.n_owned], (ref.A @ x + ref.b)[own])
+    assert errs["spmv"] <= RTOL_RHS, errs
+    sol = G.solve(tpl, G.Tsit5(0.001))
+    uref = O.tsit5_fixed(lambda d, v, t: d.__setitem__(Ellipsis, ref.A @ v + ref.b), ref.u0, 0.0, 0.02, 0.001)
+    errs["tsit5_operator"] = rel_err(sol.u[:local.n_owned], uref[own])
+    assert errs["tsit5_operator"] <= RTOL_TSIT5, errs
+    tpl.engine.close()
+    dist.barrier()
+    print("rank %d/%d sharded parity OK: %s" % (rank, world, {k: float("%.2e" % v) for k, v in errs.items()}), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

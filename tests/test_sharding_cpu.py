@@ -1,0 +1,64 @@
+"""N > 1 path on CPU (gloo, world_size 2): partitioners, rank-local meshes, halo plan and the
+exchange schedule; the sharded ORACLE right-hand side must equal the single-domain one on every
+owned node (only the summation order differs)."""
+import socket
+
+import numpy as np
+import pytest
+
+import fvm_b200 as G
+from oracle import fvm_oracle as O
+from tests.common import rel_err
+from tests.sharding_worker import build_case, worker
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("kind", ["lattice", "delaunay"])
+def test_sharded_oracle_rhs_two_ranks(kind, tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(worker, args=(2, _free_port(), kind, str(tmp_path)), nprocs=2, join=True)
+    pair, gp, op, owner = build_case(kind)
+    N = pair.gtri.num_points
+    u = 0.2 + np.random.default_rng(5).random(N)
+    ref = O.fvm_eqs_vec(np.zeros(N), u, op, 0.3)
+    got = np.full(N, np.nan)
+    for r in range(2):
+        got[np.load(tmp_path / ("own_%s_%d.npy" % (kind, r)))] = np.load(tmp_path / ("du_%s_%d.npy" % (kind, r)))
+    assert not np.isnan(got).any()  # every node is owned by exactly one rank
+    assert rel_err(got, ref) <= 1e-13
+
+
+def test_partitioners_and_local_meshes():
+    tri = G.triangulate_rectangle(0, 2, 0, 2, 33, 32, single_boundary=True)
+    for nparts in (2, 4, 8):
+        for owner in (G.partition_strips(tri.points, nparts), G.partition_rcb(tri.points, nparts)):
+            cnt = np.bincount(owner, minlength=nparts)
+            assert cnt.min() >= len(owner) // nparts - 1 and cnt.max() <= len(owner) // nparts + 1
+            locs = [G.extract_local(tri, owner, r, nparts) for r in range(nparts)]
+            # every triangle touching an owned node is local; ghosts are exactly the non-owned vertices
+            for r, lm in enumerate(locs):
+                gt = lm.global_nodes[lm.triangulation.triangles]
+                assert ((owner[gt] == r).any(axis=1)).all()
+                assert (owner[lm.global_nodes[:lm.n_owned]] == r).all() and (owner[lm.global_nodes[lm.n_owned:]] != r).all()
+                # send/recv lists pair up across ranks in the same (global id) order
+                for q, snd in zip(lm.neighbours, lm.send_nodes):
+                    other = locs[q]
+                    rcv = other.recv_nodes[other.neighbours.index(r)]
+                    assert np.array_equal(lm.global_nodes[snd], other.global_nodes[rcv])
+            assert sum(lm.n_owned for lm in locs) == tri.num_points
+    # analytic strips used by bench.py equal the generic extraction
+    owner = G.partition_strips(tri.points, 4)
+    for r in range(4):
+        a, b = G.lattice_strip_local(0, 2, 0, 2, 33, 8, r, 4), G.extract_local(tri, owner, r, 4)
+        assert np.array_equal(a.global_nodes, b.global_nodes) and np.array_equal(a.triangulation.points, b.triangulation.points)
+        assert sorted(map(tuple, a.triangulation.triangles.tolist())) == sorted(map(tuple, b.triangulation.triangles.tolist()))
+        assert sorted(map(tuple, a.triangulation.boundary_edges()[0].tolist())) == sorted(map(tuple, b.triangulation.boundary_edges()[0].tolist()))
+        assert a.neighbours == b.neighbours
+        assert all(np.array_equal(x, y) for x, y in zip(a.send_nodes + a.recv_nodes, b.send_nodes + b.recv_nodes))
