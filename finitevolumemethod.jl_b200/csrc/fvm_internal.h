@@ -201,6 +201,7 @@ int32_t fvm_ensure_state(fvm_ctx* h);
 void fvm_shard_release(fvm_ctx* h);
 int32_t fvm_halo_exchange(fvm_ctx* h, double* u_native);
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);
+int32_t fvm_global_or(fvm_ctx* h, bool local, bool* global);
 #define FVM_NODE_GHOST 4
 int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale);
 void fvm_prof_begin(fvm_ctx* h);

@@ -164,3 +164,25 @@ int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n) {
     FVM_NCCL(h, ncclAllReduce(d_vals, d_vals, n, ncclDouble, ncclSum, s->comm, h->stream));
     return FVM_OK;
 }
+
+// logical OR over ranks of a host flag (e.g. "some rank has Dirichlet nodes"): every rank must take
+// the same control-flow decisions, or the halo exchanges no longer pair up
+int32_t fvm_global_or(fvm_ctx* h, bool local, bool* global) {
+    *global = local;
+    ShardState* s = (ShardState*)h->shard;
+    if (!s || !s->comm || h->nranks == 1) return FVM_OK;
+    double* d = nullptr;
+    FVM_CUDA(h, cudaMalloc((void**)&d, sizeof(double)));
+    const double v = local ? 1.0 : 0.0;
+    double out = 0.0;
+    cudaError_t e = cudaMemcpyAsync(d, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    ncclResult_t r = ncclSuccess;
+    if (e == cudaSuccess) r = ncclAllReduce(d, d, 1, ncclDouble, ncclSum, s->comm, h->stream);
+    if (e == cudaSuccess && r == ncclSuccess) e = cudaMemcpyAsync(&out, d, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    if (r != ncclSuccess) return fvm_fail(h, FVM_ERR_NCCL, ncclGetErrorString(r));
+    FVM_CUDA(h, e);
+    *global = out > 0.5;
+    return FVM_OK;
+}

@@ -128,7 +128,8 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
         return FVM_OK;
     };
     if ((rc = save(t0))) return rc;
-    const bool has_callback = !use_operator && h->n_dir > 0;
+    bool has_callback = false;  // sharded: the same FSAL / callback schedule on every rank
+    if ((rc = fvm_global_or(h, !use_operator && h->n_dir > 0, &has_callback))) return rc;
     bool have_k1 = false;
     for (int64_t step = 0; step < nsteps; ++step) {
         const double t = t0 + step * dt;

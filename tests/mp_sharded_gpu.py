@@ -21,7 +21,13 @@ def main():
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     errs = {}
+
+    def log(msg):
+        sys.stderr.write("[rank %d] %s\n" % (rank, msg))
+        sys.stderr.flush()
+
     for kind in ("lattice", "delaunay"):
+        log("case " + kind)
         pair, gp, op, owner = build_case(kind)
         if world != 2:
             owner = G.partition_rcb(pair.gtri.points, world)
@@ -33,7 +39,9 @@ def main():
         ref = O.fvm_eqs_vec(np.zeros(N), u, op, 0.3)
         ul = u[local.global_nodes].copy()
         ul[local.n_owned:] = 1e300  # ghosts must come from the NCCL exchange
+        log("halo installed")
         du = G.fvm_eqs(np.zeros_like(ul), ul, p, 0.3)
+        log("rhs done")
         own = local.global_nodes[:local.n_owned]
         errs["rhs_" + kind] = rel_err(du[:local.n_owned], ref[own]) if np.abs(ref).max() > 0 else 0.0
         assert errs["rhs_" + kind] <= RTOL_RHS, errs
@@ -58,6 +66,7 @@ def main():
     ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
     tpl = G.DiffusionEquation(lmesh, G.BoundaryConditions(lmesh, G.Const(0.0), G.Dirichlet), diffusion_function=1 / 9,
                               initial_condition=ic[local.global_nodes], final_time=0.02, ghost=local.is_ghost)
+    log("template assembled")
     G.install_halo(tpl.engine, local, dist)
     otri = O.triangulate_rectangle(0, 2, 0, 2, 40, 32, single_boundary=True)
     omesh = O.FVMGeometry(otri)
@@ -81,4 +90,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # a failing rank must not hang its peers inside an NCCL call
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+    os._exit(0)
