@@ -182,8 +182,7 @@ __device__ __forceinline__ double cond_eval(const CondFn& c, double x, double y,
 // ---- node pass, src/equations/source_contributions.jl:33-68 --------------------------------
 template <int NEQ>
 __device__ __forceinline__ void node_finish(const DevMesh& m, const SourceParams& sp, double t, int g, const double* acc,
-                                            const double* uv, double* __restrict__ du) {
-    const double V = m.vol[g];
+                                            const double* uv, double* __restrict__ du, const double V, const uint8_t* kinds) {
     double tab[NEQ];
     if (sp.model == FVM_SRC_TABLE) {
 #pragma unroll
@@ -191,7 +190,7 @@ __device__ __forceinline__ void node_finish(const DevMesh& m, const SourceParams
     }
 #pragma unroll
     for (int v = 0; v < NEQ; ++v) {
-        const uint8_t kind = m.kind[(size_t)v * m.n_nodes + g];
+        const uint8_t kind = kinds[v];
         double out;
         if (kind == FVM_NODE_FREE) {
             out = acc[v] / V + source_eval<NEQ>(sp, v, uv, tab);
@@ -203,4 +202,13 @@ __device__ __forceinline__ void node_finish(const DevMesh& m, const SourceParams
         }
         du[(size_t)g * NEQ + v] = out;
     }
+}
+
+template <int NEQ>
+__device__ __forceinline__ void node_finish(const DevMesh& m, const SourceParams& sp, double t, int g, const double* acc,
+                                            const double* uv, double* __restrict__ du) {
+    uint8_t kinds[NEQ];
+#pragma unroll
+    for (int v = 0; v < NEQ; ++v) kinds[v] = m.kind[(size_t)v * m.n_nodes + g];
+    node_finish<NEQ>(m, sp, t, g, acc, uv, du, m.vol[g], kinds);
 }

@@ -33,6 +33,7 @@ struct DevMesh {
     const double* geo;       // [FVM_NGEO][tpad]
     const double* dtab;      // [3][tpad] tabulated D at cv-edge midpoints (or null)
     // per tile
+    const int4* tile_meta;       // 2 x int4 per tile: {node0, nint, nown, nloc}, {ext0, loc0, pp0, ntri}
     const int32_t* tile_node0;   // first own node (native id)
     const int32_t* tile_nint;    // interior nodes
     const int32_t* tile_nown;    // interior + owned interface nodes
@@ -92,6 +93,25 @@ struct Csr {
     double* diag_inv = nullptr;  // Jacobi preconditioner of the (scaled) system
     int32_t chunk_rows = 0;      // SpMV: rows per CTA
     int32_t chunk_smem = 0;
+    // tile-local SpMV: interior rows of a tile are contiguous in native order, so their val/col span is
+    // contiguous too; col16 holds the tile-local column of every entry of an interior row
+    uint16_t* col16 = nullptr;
+    int32_t* tail_rows = nullptr;  // interface rows + points that are not vertices (generic CSR path)
+    int32_t n_tail = 0;
+    int32_t tile_prod_cap = 0, tile_max_nint = 0, tile_smem = 0;
+    int32_t use_tile_spmv = 1;
+    // sliced-ELL copy of the interior rows (32 rows per slice, entry k of the 32 rows contiguous)
+    int32_t* tile_slice0 = nullptr;  // [n_tiles + 1] first slice of each tile
+    int32_t* sell_ptr = nullptr;     // [n_slices + 1] offset of each slice (units of entries)
+    double* sell_val = nullptr;
+    uint16_t* sell_col = nullptr;
+    int64_t sell_entries = 0;
+    int32_t n_slices = 0;
+    // sliced-ELL copy of the tail rows (global int32 columns)
+    int32_t* tsell_ptr = nullptr;
+    double* tsell_val = nullptr;
+    int32_t* tsell_col = nullptr;
+    int32_t n_tslices = 0;
     int32_t* rowptr = nullptr;  // native numbering
     int32_t* col = nullptr;
     double* val = nullptr;

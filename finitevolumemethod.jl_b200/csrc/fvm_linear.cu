@@ -228,21 +228,208 @@ __global__ void __launch_bounds__(SPMV_BLOCK)
     }
 }
 
-int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale) {
+// Warp-granular CSR SpMV: a warp owns 32 consecutive rows whose val/col entries are one contiguous
+// span; lanes stream the span coalesced (all lanes busy, ~7 independent loads each), park the
+// products in a warp-private shared-memory segment, then every lane sums its own row in CSR order.
+// No block-level barrier: warps never wait for each other.
+template <bool ADD_B, bool SCALE>
+__global__ void __launch_bounds__(SPMV_BLOCK)
+    spmv_warp_kernel(const int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                     const double* __restrict__ val, const double* __restrict__ b, const double* __restrict__ rowscale,
+                     const double* __restrict__ x, double* __restrict__ y, const int cap) {
+    extern __shared__ double prod_all[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* prod = prod_all + (size_t)warp * cap;
+    const int r0 = (blockIdx.x * (SPMV_BLOCK / 32) + warp) * 32;
+    if (r0 >= n) return;
+    const int row = r0 + lane;
+    const int rp = __ldg(rowptr + min(row, n));
+    const int rp_next = __ldg(rowptr + min(row + 1, n));
+    const int base = __shfl_sync(0xffffffffu, rp, 0);
+    const int end = __shfl_sync(0xffffffffu, rp_next, 31);
+    const int cnt = end - base;
+#pragma unroll 8
+    for (int q = lane; q < cnt; q += 32) prod[q] = __ldg(val + base + q) * __ldg(x + __ldg(col + base + q));
+    __syncwarp();
+    if (row < n) {
+        double s = 0.0;
+        for (int q = rp - base; q < rp_next - base; ++q) s += prod[q];
+        if (ADD_B) s += b[row];
+        if (SCALE) s *= rowscale[row];
+        y[row] = s;
+    }
+}
+
+// ---- tile-local SpMV ---------------------------------------------------------------------------
+// Reuses the RHS tiling: a CTA owns the interior rows of one tile.  x of the tile's local nodes is
+// staged in shared memory (own range coalesced, external interface nodes gathered), columns are
+// 16-bit tile-local ids: 10 B per nonzero instead of 12, and no global gather of x at all.
+template <bool ADD_B, bool SCALE>
+__global__ void __launch_bounds__(SPMV_BLOCK)
+    spmv_tile_kernel(const DevMesh m, const int32_t* __restrict__ tile_slice0, const int32_t* __restrict__ sell_ptr,
+                     const uint16_t* __restrict__ sell_col, const double* __restrict__ sell_val, const double* __restrict__ b,
+                     const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y) {
+    extern __shared__ double x_s[];  // [max_nloc]
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int4 m0 = __ldg(m.tile_meta + 2 * tile), m1 = __ldg(m.tile_meta + 2 * tile + 1);
+    const int node0 = m0.x, nint = m0.y, nown = m0.z, nloc = m0.w, ext0 = m1.x;
+    if (nint == 0) return;
+    for (int i = tid; i < nown; i += SPMV_BLOCK) x_s[i] = x[node0 + i];
+    for (int k = tid; k < nloc - nown; k += SPMV_BLOCK) x_s[nown + k] = x[m.ext_ids[ext0 + k]];
+    const int s0 = __ldg(tile_slice0 + tile), s1 = __ldg(tile_slice0 + tile + 1);
+    __syncthreads();
+    // sliced ELL: entry k of the 32 rows of a slice is contiguous -> every load below is coalesced,
+    // all 2*len loads of a row are independent, and the row is summed in CSR order in a register
+    for (int sl = s0 + warp; sl < s1; sl += SPMV_BLOCK / 32) {
+        const int p0 = __ldg(sell_ptr + sl), len = (__ldg(sell_ptr + sl + 1) - p0) >> 5;
+        const double* __restrict__ v = sell_val + p0 + lane;
+        const uint16_t* __restrict__ c = sell_col + p0 + lane;
+        double acc = 0.0;
+        int k = 0;
+        for (; k + 8 <= len; k += 8) {
+            double vv[8];
+            uint16_t cc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                vv[q] = __ldg(v + (k + q) * 32);
+                cc[q] = __ldg(c + (k + q) * 32);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += vv[q] * x_s[cc[q]];
+        }
+        {
+            double vv[8];
+            uint16_t cc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const bool on = k + q < len;
+                vv[q] = on ? __ldg(v + (k + q) * 32) : 0.0;
+                cc[q] = on ? __ldg(c + (k + q) * 32) : (uint16_t)0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (k + q < len) acc += vv[q] * x_s[cc[q]];
+        }
+        const int l = (sl - s0) * 32 + lane;
+        if (l < nint) {
+            if (ADD_B) acc += b[node0 + l];
+            if (SCALE) acc *= rowscale[node0 + l];
+            y[node0 + l] = acc;
+        }
+    }
+}
+
+// fills the sliced-ELL arrays of the interior rows from the CSR arrays (cols once, vals per assembly)
+__global__ void sell_pack_kernel(const DevMesh m, const int32_t* __restrict__ tile_slice0, const int32_t* __restrict__ sell_ptr,
+                                 const int32_t* __restrict__ rowptr, const uint16_t* __restrict__ col16,
+                                 const double* __restrict__ val, uint16_t* __restrict__ sell_col, double* __restrict__ sell_val) {
+    const int tile = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int4 m0 = m.tile_meta[2 * tile];
+    const int node0 = m0.x, nint = m0.y;
+    const int s0 = tile_slice0[tile], s1 = tile_slice0[tile + 1];
+    for (int sl = s0 + warp; sl < s1; sl += blockDim.x / 32) {
+        const int p0 = sell_ptr[sl], len = (sell_ptr[sl + 1] - p0) >> 5;
+        const int l = (sl - s0) * 32 + lane;
+        const int rb = l < nint ? rowptr[node0 + l] : 0, rl = l < nint ? rowptr[node0 + l + 1] - rb : 0;
+        for (int k = 0; k < len; ++k) {
+            if (sell_col) sell_col[p0 + k * 32 + lane] = k < rl ? col16[rb + k] : (uint16_t)0;
+            if (sell_val) sell_val[p0 + k * 32 + lane] = k < rl ? val[rb + k] : 0.0;
+        }
+    }
+}
+
+// interface rows and points that are not vertices: sliced ELL with global columns, one lane per row
+template <bool ADD_B, bool SCALE>
+__global__ void __launch_bounds__(128)
+    spmv_rows_kernel(const int n_rows, const int32_t* __restrict__ rows, const int32_t* __restrict__ sptr,
+                     const int32_t* __restrict__ scol, const double* __restrict__ sval, const double* __restrict__ b,
+                     const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y) {
+    const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (sl * 32 >= n_rows) return;
+    const int p0 = __ldg(sptr + sl), len = (__ldg(sptr + sl + 1) - p0) >> 5;
+    const int k = sl * 32 + lane;
+    double acc = 0.0;
+#pragma unroll 4
+    for (int q = 0; q < len; ++q) acc += __ldg(sval + p0 + q * 32 + lane) * __ldg(x + __ldg(scol + p0 + q * 32 + lane));
+    if (k < n_rows) {
+        const int g = rows[k];
+        if (ADD_B) acc += b[g];
+        if (SCALE) acc *= rowscale[g];
+        y[g] = acc;
+    }
+}
+
+__global__ void tsell_pack_kernel(const int n_rows, const int32_t* __restrict__ rows, const int32_t* __restrict__ sptr,
+                                  const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                  const double* __restrict__ val, int32_t* __restrict__ scol, double* __restrict__ sval) {
+    const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (sl * 32 >= n_rows) return;
+    const int p0 = sptr[sl], len = (sptr[sl + 1] - p0) >> 5;
+    const int k = sl * 32 + lane;
+    const int g = k < n_rows ? rows[k] : -1;
+    const int rb = g >= 0 ? rowptr[g] : 0, rl = g >= 0 ? rowptr[g + 1] - rb : 0;
+    for (int q = 0; q < len; ++q) {
+        if (scol) scol[p0 + q * 32 + lane] = q < rl ? col[rb + q] : (g >= 0 ? g : 0);
+        if (sval) sval[p0 + q * 32 + lane] = q < rl ? val[rb + q] : 0.0;
+    }
+}
+
+// tile-local column ids of the entries of interior rows (one-off, at pattern build)
+__global__ void col16_kernel(const DevMesh m, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                             uint16_t* __restrict__ col16) {
+    const int tile = blockIdx.x;
+    const int4 m0 = m.tile_meta[2 * tile], m1 = m.tile_meta[2 * tile + 1];
+    const int node0 = m0.x, nint = m0.y, nown = m0.z, nloc = m0.w, ext0 = m1.x;
+    if (nint == 0) return;
+    const int base = rowptr[node0], end = rowptr[node0 + nint];
+    for (int q = base + threadIdx.x; q < end; q += blockDim.x) {
+        const int g = col[q];
+        int l = g - node0;
+        if (l < 0 || l >= nown) {
+            l = 0xffff;
+            for (int k = 0; k < nloc - nown; ++k)
+                if (m.ext_ids[ext0 + k] == g) {
+                    l = nown + k;
+                    break;
+                }
+        }
+        col16[q] = (uint16_t)l;
+    }
+}
+
+template <bool ADD_B, bool SCALE>
+static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y) {
     Csr& c = h->csr;
-    const int grid = (c.n + SPMV_ROWS - 1) / SPMV_ROWS;
-    fvm_prof_begin(h);
-    if (add_b && !scale)
-        spmv_kernel<true, false><<<grid, SPMV_BLOCK, c.chunk_smem, h->stream>>>(c.n, c.rowptr, c.col, c.val, c.b, c.rowscale, x, y);
-    else if (!add_b && !scale)
-        spmv_kernel<false, false><<<grid, SPMV_BLOCK, c.chunk_smem, h->stream>>>(c.n, c.rowptr, c.col, c.val, c.b, c.rowscale, x, y);
-    else if (add_b && scale)
-        spmv_kernel<true, true><<<grid, SPMV_BLOCK, c.chunk_smem, h->stream>>>(c.n, c.rowptr, c.col, c.val, c.b, c.rowscale, x, y);
-    else
-        spmv_kernel<false, true><<<grid, SPMV_BLOCK, c.chunk_smem, h->stream>>>(c.n, c.rowptr, c.col, c.val, c.b, c.rowscale, x, y);
-    fvm_prof_end(h);
+    if (c.use_tile_spmv) {
+        fvm_prof_begin(h);
+        spmv_tile_kernel<ADD_B, SCALE><<<h->dm.n_tiles, SPMV_BLOCK, c.tile_smem, h->stream>>>(
+            h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale, x, y);
+        fvm_prof_end(h);
+        if (c.n_tail > 0)
+            spmv_rows_kernel<ADD_B, SCALE><<<(c.n_tslices * 32 + 127) / 128, 128, 0, h->stream>>>(
+                c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b, c.rowscale, x, y);
+    } else if (c.use_tile_spmv == 0 && c.chunk_rows > 0 && getenv("FVM_SPMV_BLOCK")) {
+        const int grid = (c.n + SPMV_ROWS - 1) / SPMV_ROWS;
+        fvm_prof_begin(h);
+        spmv_kernel<ADD_B, SCALE><<<grid, SPMV_BLOCK, c.chunk_smem, h->stream>>>(c.n, c.rowptr, c.col, c.val, c.b, c.rowscale, x, y);
+        fvm_prof_end(h);
+    } else {
+        const int cap = 32 * c.max_row;
+        const int grid = (c.n + SPMV_BLOCK - 1) / SPMV_BLOCK;
+        fvm_prof_begin(h);
+        spmv_warp_kernel<ADD_B, SCALE><<<grid, SPMV_BLOCK, sizeof(double) * cap * (SPMV_BLOCK / 32), h->stream>>>(
+            c.n, c.rowptr, c.col, c.val, c.b, c.rowscale, x, y, cap);
+        fvm_prof_end(h);
+    }
     FVM_CUDA(h, cudaGetLastError());
     return FVM_OK;
+}
+
+int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale) {
+    if (add_b && !scale) return launch_spmv_t<true, false>(h, x, y);
+    if (!add_b && !scale) return launch_spmv_t<false, false>(h, x, y);
+    if (add_b && scale) return launch_spmv_t<true, true>(h, x, y);
+    return launch_spmv_t<false, true>(h, x, y);
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -299,7 +486,7 @@ static int32_t build_pattern(fvm_ctx* h) {
     if (c.chunk_smem > 200 * 1024) return fvm_fail(h, FVM_ERR_ARG, "fvm_assemble: SpMV row chunk exceeds shared memory");
     if ((rc = fvm_dev_upload(h, &c.rowptr, rp))) return rc;
     if ((rc = fvm_dev_alloc(h, &c.col, (size_t)nnz))) return rc;
-    if ((rc = fvm_dev_alloc(h, &c.val, (size_t)nnz))) return rc;
+    if ((rc = fvm_dev_alloc(h, &c.val, (size_t)nnz + 8))) return rc;  // slack: quads are read whole
     if ((rc = fvm_dev_alloc(h, &c.b, (size_t)N))) return rc;
     if ((rc = fvm_dev_alloc(h, &c.rowscale, (size_t)N))) return rc;
     if ((rc = fvm_dev_alloc(h, &c.diag_inv, (size_t)N))) return rc;
@@ -310,6 +497,86 @@ static int32_t build_pattern(fvm_ctx* h) {
         FVM_CUDA(h, cudaFuncSetAttribute(spmv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.chunk_smem));
         FVM_CUDA(h, cudaFuncSetAttribute(spmv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.chunk_smem));
         FVM_CUDA(h, cudaFuncSetAttribute(spmv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.chunk_smem));
+    }
+    {   // tile-local SpMV structures
+        const int64_t n_tiles = h->dm.n_tiles;
+        std::vector<int4> meta(2 * n_tiles);
+        FVM_CUDA(h, cudaMemcpyAsync(meta.data(), h->dm.tile_meta, sizeof(int4) * 2 * n_tiles, cudaMemcpyDeviceToHost, h->stream));
+        FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+        int32_t cap = 0, max_nint = 0;
+        std::vector<int32_t> tail;
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            const int node0 = meta[2 * b].x, nint = meta[2 * b].y, nown = meta[2 * b].z;
+            cap = std::max(cap, rp[node0 + nint] - rp[node0]);
+            max_nint = std::max(max_nint, nint);
+            for (int l = nint; l < nown; ++l) tail.push_back(node0 + l);
+        }
+        for (int64_t g = h->dm.n_vertices; g < N; ++g) tail.push_back((int32_t)g);
+        c.n_tail = (int32_t)tail.size();
+        c.tile_prod_cap = cap;
+        c.tile_max_nint = max_nint;
+        c.tile_smem = (int32_t)((sizeof(double) * (size_t)h->max_nloc + 15) & ~(size_t)15);
+        // sliced-ELL layout of the interior rows
+        std::vector<int32_t> slice0(n_tiles + 1, 0), sptr(1, 0);
+        int64_t entries = 0;
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            const int node0 = meta[2 * b].x, nint = meta[2 * b].y;
+            slice0[b] = (int32_t)(sptr.size() - 1);
+            for (int l0 = 0; l0 < nint; l0 += 32) {
+                int mx = 0;
+                for (int l = l0; l < std::min(nint, l0 + 32); ++l) mx = std::max(mx, rp[node0 + l + 1] - rp[node0 + l]);
+                entries += (int64_t)32 * mx;
+                if (entries >= INT32_MAX) return fvm_fail(h, FVM_ERR_ARG, "fvm_assemble: sliced-ELL size exceeds int32");
+                sptr.push_back((int32_t)entries);
+            }
+        }
+        slice0[n_tiles] = (int32_t)(sptr.size() - 1);
+        c.n_slices = slice0[n_tiles];
+        c.sell_entries = entries;
+        if ((rc = fvm_dev_upload(h, &c.tile_slice0, slice0))) return rc;
+        if ((rc = fvm_dev_upload(h, &c.sell_ptr, sptr))) return rc;
+        if ((rc = fvm_dev_alloc(h, &c.sell_val, (size_t)entries + 32))) return rc;
+        if ((rc = fvm_dev_alloc(h, &c.sell_col, (size_t)entries + 32))) return rc;
+        h->stats[12] = entries;
+        if ((rc = fvm_dev_upload(h, &c.tail_rows, tail))) return rc;
+        {
+            std::vector<int32_t> tp(1, 0);
+            int64_t te = 0;
+            for (size_t k0 = 0; k0 < tail.size(); k0 += 32) {
+                int mx = 0;
+                for (size_t k = k0; k < std::min(tail.size(), k0 + 32); ++k) mx = std::max(mx, rp[tail[k] + 1] - rp[tail[k]]);
+                te += (int64_t)32 * mx;
+                tp.push_back((int32_t)te);
+            }
+            c.n_tslices = (int32_t)tp.size() - 1;
+            if ((rc = fvm_dev_upload(h, &c.tsell_ptr, tp))) return rc;
+            if ((rc = fvm_dev_alloc(h, &c.tsell_val, (size_t)te + 32))) return rc;
+            if ((rc = fvm_dev_alloc(h, &c.tsell_col, (size_t)te + 32))) return rc;
+        }
+        if ((rc = fvm_dev_alloc(h, &c.col16, (size_t)nnz + 8))) return rc;
+        FVM_CUDA(h, cudaMemsetAsync(c.col16, 0, sizeof(uint16_t) * ((size_t)nnz + 8), h->stream));
+        col16_kernel<<<(unsigned)n_tiles, 256, 0, h->stream>>>(h->dm, c.rowptr, c.col, c.col16);
+        sell_pack_kernel<<<(unsigned)n_tiles, 256, 0, h->stream>>>(h->dm, c.tile_slice0, c.sell_ptr, c.rowptr, c.col16, nullptr,
+                                                                   c.sell_col, nullptr);
+        if (c.n_tail > 0)
+            tsell_pack_kernel<<<(c.n_tslices * 32 + 127) / 128, 128, 0, h->stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.rowptr, c.col,
+                                                                                      nullptr, c.tsell_col, nullptr);
+        FVM_CUDA(h, cudaGetLastError());
+        if (c.tile_smem > 200 * 1024) c.use_tile_spmv = 0;
+        else if (c.tile_smem > 48 * 1024) {
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
+        }
+        if (const char* e = getenv("FVM_SPMV_GENERIC")) c.use_tile_spmv = (e[0] == '1') ? 0 : c.use_tile_spmv;
+        if (sizeof(double) * 32 * maxrow * (SPMV_BLOCK / 32) > 48 * 1024) {
+            const int wb = (int)(sizeof(double) * 32 * maxrow * (SPMV_BLOCK / 32));
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb));
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb));
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb));
+            FVM_CUDA(h, cudaFuncSetAttribute(spmv_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb));
+        }
     }
     c.pattern = true;
     h->stats[10] = nnz;
@@ -439,6 +706,11 @@ extern "C" int32_t fvm_assemble(fvm_handle h, int32_t template_id, double d_cons
         const int n_bn = (int)bn_node.size();
         assemble_boundary_kernel<<<(n_bn + 127) / 128, 128, 0, h->stream>>>(h->dm, a, d_edges, d_bn, d_bp, d_bi, n_bn);
     }
+    sell_pack_kernel<<<(unsigned)h->dm.n_tiles, 256, 0, h->stream>>>(h->dm, c.tile_slice0, c.sell_ptr, c.rowptr, c.col16, c.val, nullptr,
+                                                                     c.sell_val);
+    if (c.n_tail > 0)
+        tsell_pack_kernel<<<(c.n_tslices * 32 + 127) / 128, 128, 0, h->stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.rowptr, c.col, c.val,
+                                                                                  nullptr, c.tsell_val);
     jacobi_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>((int)N, c.rowptr, c.col, c.val, c.rowscale, c.diag_inv);
     cudaError_t ce = cudaGetLastError();
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);

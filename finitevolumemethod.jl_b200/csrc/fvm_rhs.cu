@@ -12,6 +12,8 @@
 //   rhs_interface_kernel sums the partials of interface/boundary nodes in slot order, node pass.
 //
 // No atomics anywhere: every output word has exactly one writer and a fixed summation order.
+#include <cuda_pipeline.h>
+
 #include "fvm_device.cuh"
 
 #define RHS_BLOCK 256
@@ -29,16 +31,48 @@ __global__ void __launch_bounds__(RHS_BLOCK)
     double* u_s = smem;                                            // [smem_nloc][NEQ]
     double* xy_s = u_s + (VOL ? 0 : (size_t)smem_nloc * NEQ);      // [smem_nloc][2]
     double* c_s = xy_s + (NEED_XY ? 2 * (size_t)smem_nloc : 0);    // [3][TT][NEQ]
+    uint16_t* inc_s = reinterpret_cast<uint16_t*>(c_s + (size_t)3 * TT * (VOL ? 1 : NEQ));  // [3*TT] gather list
+    uint16_t* iptr_s = inc_s + 3 * TT;                                                      // [smem_nloc + 1]
 
     const int tile = blockIdx.x;
     const int tid = threadIdx.x;
-    const int node0 = m.tile_node0[tile];
-    const int nint = m.tile_nint[tile];
-    const int nown = m.tile_nown[tile];
-    const int nloc = m.tile_nloc[tile];
-    const int ext0 = m.tile_ext0[tile];
+    const int4 m0 = __ldg(m.tile_meta + 2 * tile), m1 = __ldg(m.tile_meta + 2 * tile + 1);
+    const int node0 = m0.x, nint = m0.y, nown = m0.z, nloc = m0.w;
+    const int ext0 = m1.x, loc0 = m1.y, pp0 = m1.z, ntri = m1.w;
     const int64_t t0 = (int64_t)tile * TT;
-    const int ntri = (int)min((int64_t)TT, (int64_t)m.n_tris - t0);
+
+    // ---- stage the tile's gather list early: it is consumed after the second barrier, so its
+    // latency overlaps the triangle pass instead of stalling the node pass ----------------------
+    {   // cp.async (LDGSTS): no register staging, completion awaited just before the node pass
+        const uint32_t* __restrict__ src = reinterpret_cast<const uint32_t*>(m.inc + (size_t)3 * TT * tile);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(inc_s);
+        for (int k = tid; k < (3 * ntri + 1) / 2; k += RHS_BLOCK) __pipeline_memcpy_async(dst + k, src + k, 4);
+        const uint32_t* __restrict__ ip = reinterpret_cast<const uint32_t*>(m.inc_ptr + loc0);
+        uint32_t* dp = reinterpret_cast<uint32_t*>(iptr_s);
+        for (int k = tid; k < (nloc + 2) / 2; k += RHS_BLOCK) __pipeline_memcpy_async(dp + k, ip + k, 4);
+        __pipeline_commit();
+    }
+    // ---- register prefetch of everything else this thread will need from global memory, so the
+    // DRAM latency is paid once per tile (overlapped with the staging) instead of once per use ----
+    // (only where registers are cheap: the recompute kernels of flux models without (x,y,u) terms;
+    // measured: -16 % there, but the extra registers cost the stored-geometry kernels occupancy)
+    constexpr bool PREFETCH = !VOL && GEOM == 1 && !FluxTraits<VOL ? 0 : MODEL>::full;
+    constexpr int TPF = 4, NPF = 3;
+    ushort4 vpf[TPF];
+    double Vpf[NPF];
+    uint8_t kpf[NPF][NEQ];
+    if constexpr (PREFETCH) {
+#pragma unroll
+        for (int r = 0; r < TPF; ++r)
+            vpf[r] = (tid + r * RHS_BLOCK < ntri) ? __ldg(m.tri_loc + t0 + tid + r * RHS_BLOCK) : make_ushort4(0, 0, 0, 0);
+#pragma unroll
+        for (int r = 0; r < NPF; ++r) {
+            const int l = tid + r * RHS_BLOCK;
+            Vpf[r] = l < nint ? __ldg(m.vol + node0 + l) : 1.0;
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) kpf[r][v] = l < nint ? __ldg(m.kind + (size_t)v * m.n_nodes + node0 + l) : (uint8_t)0;
+        }
+    }
 
     // ---- stage node data: own range is contiguous, external interface nodes are gathered ----
     if constexpr (!VOL) {
@@ -60,9 +94,23 @@ __global__ void __launch_bounds__(RHS_BLOCK)
     __syncthreads();
 
     // ---- triangle pass ------------------------------------------------------------------------
-    for (int lt = tid; lt < ntri; lt += RHS_BLOCK) {
+    const int n_iter = (ntri - tid + RHS_BLOCK - 1) / RHS_BLOCK;
+#pragma unroll 1
+    for (int r = 0; r < n_iter; ++r) {
+        const int lt = tid + r * RHS_BLOCK;
         const int64_t gt = t0 + lt;
-        const ushort4 vv = m.tri_loc[gt];
+        ushort4 vv;
+        if constexpr (PREFETCH) {
+            switch (r) {  // prefetched ids for the first TPF rounds
+                case 0: vv = vpf[0]; break;
+                case 1: vv = vpf[1]; break;
+                case 2: vv = vpf[2]; break;
+                case 3: vv = vpf[3]; break;
+                default: vv = m.tri_loc[gt]; break;
+            }
+        } else {
+            vv = m.tri_loc[gt];
+        }
         if constexpr (VOL) {
             TriGeom G;
             double S[3];
@@ -136,13 +184,14 @@ __global__ void __launch_bounds__(RHS_BLOCK)
             }
         }
     }
+    __pipeline_wait_prior(0);
     __syncthreads();
 
     // ---- per-node gather in ascending triangle order, then node pass --------------------------
-    const uint16_t* __restrict__ iptr = m.inc_ptr + m.tile_loc0[tile];
-    const uint16_t* __restrict__ inc = m.inc + (size_t)3 * TT * tile;
-    const int pp0 = m.tile_pp0[tile];
-    for (int l = tid; l < nloc; l += RHS_BLOCK) {
+    const uint16_t* iptr = iptr_s;
+    const uint16_t* inc = inc_s;
+    int round = 0;
+    for (int l = tid; l < nloc; l += RHS_BLOCK, ++round) {
         const int beg = iptr[l], end = iptr[l + 1];
         double acc[NEQ];
 #pragma unroll
@@ -155,7 +204,15 @@ __global__ void __launch_bounds__(RHS_BLOCK)
         }
         if (l < nint) {
             if constexpr (VOL) du[node0 + l] = acc[0];
-            else node_finish<NEQ>(m, sp, t, node0 + l, acc, u_s + l * NEQ, du);
+            else if constexpr (!PREFETCH) node_finish<NEQ>(m, sp, t, node0 + l, acc, u_s + l * NEQ, du);
+            else {
+                switch (round) {
+                    case 0: node_finish<NEQ>(m, sp, t, node0 + l, acc, u_s + l * NEQ, du, Vpf[0], kpf[0]); break;
+                    case 1: node_finish<NEQ>(m, sp, t, node0 + l, acc, u_s + l * NEQ, du, Vpf[1], kpf[1]); break;
+                    case 2: node_finish<NEQ>(m, sp, t, node0 + l, acc, u_s + l * NEQ, du, Vpf[2], kpf[2]); break;
+                    default: node_finish<NEQ>(m, sp, t, node0 + l, acc, u_s + l * NEQ, du); break;
+                }
+            }
         } else {
             const size_t p = (size_t)m.ppos[pp0 + (l - nint)] * NEQ;
 #pragma unroll
@@ -342,7 +399,9 @@ static int32_t rhs_smem_bytes(const fvm_ctx* h, int neq, bool vol, bool need_xy)
     if (!vol) d += (size_t)h->max_nloc * neq;
     if (need_xy) d += 2 * (size_t)h->max_nloc;
     d += (size_t)3 * h->dm.tile_tris * (vol ? 1 : neq);
-    return (int32_t)(d * sizeof(double));
+    size_t bytes = d * sizeof(double);
+    bytes += sizeof(uint16_t) * ((size_t)3 * h->dm.tile_tris + h->max_nloc + 4);  // staged gather list
+    return (int32_t)((bytes + 15) & ~(size_t)15);
 }
 
 template <int MODEL, int NEQ, int GEOM>

@@ -279,7 +279,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     FVM_CUDA(h, cudaSetDevice(h->device));
     const int64_t N = h->N, T = h->T, Eb = h->Eb;
     const int neq = h->neq;
-    int TT = tile_triangles > 0 ? tile_triangles : 1024;
+    // default tile size (measured on B200, 4096^2): kernels that stream the full 21-component SoA are
+    // register-limited to 3 CTAs/SM and like big tiles; the reduced stream wants 8 small CTAs per SM
+    const bool full_flux = h->flux.model == FVM_FLUX_DIFF_POWER || h->flux.model == FVM_FLUX_ADVDIFF || h->flux.model == FVM_FLUX_KELLER_SEGEL;
+    int TT = tile_triangles > 0 ? tile_triangles : ((geometry_mode == 0 && !full_flux) ? 512 : 1024);
     FVM_REQUIRE(h, TT >= 64 && TT <= 4096 && TT % 64 == 0, "fvm_finalize: tile_triangles must be a multiple of 64 in 64..4096");
     FVM_REQUIRE(h, geometry_mode == 0 || geometry_mode == 1, "fvm_finalize: geometry_mode must be 0 or 1");
     if (h->flux.model == FVM_FLUX_DIFF_TABLE && h->h_dtab.empty())
@@ -463,6 +466,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
             tile_nloc[b] = nloc;
             max_nloc = std::max(max_nloc, nloc);
             // gather list: local node -> (local triangle, slot), ascending triangle order
+            if (inc_ptr.size() & 1) inc_ptr.push_back(0);  // 4-byte aligned per tile (staged with cp.async)
             tile_loc0[b] = (int32_t)inc_ptr.size();
             cnt.assign(nloc + 1, 0);
             for (int64_t nt = t0; nt < t1; ++nt) {
@@ -488,6 +492,8 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         }
         tile_ext0[n_tiles] = (int32_t)ext_ids.size();
         tile_loc0[n_tiles] = (int32_t)inc_ptr.size();
+        inc_ptr.push_back(0);
+        inc_ptr.push_back(0);  // slack for the 4-byte granular copy of the last tile
     }
     for (size_t k = 0; k < live_edges.size(); ++k) {
         const int32_t e = live_edges[k];
@@ -549,6 +555,14 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         dst = p__;                                                 \
     } while (0)
     UP(m.tri_loc, tri_loc);
+    {
+        std::vector<int4> meta(2 * n_tiles);
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            meta[2 * b] = make_int4(tile_node0[b], tile_nint[b], tile_nown[b], tile_nloc[b]);
+            meta[2 * b + 1] = make_int4(tile_ext0[b], tile_loc0[b], tile_pp0[b], (int)std::min<int64_t>(TT, T - b * TT));
+        }
+        UP(m.tile_meta, meta);
+    }
     UP(m.tile_node0, tile_node0);
     UP(m.tile_nint, tile_nint);
     UP(m.tile_nown, tile_nown);

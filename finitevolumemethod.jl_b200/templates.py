@@ -105,7 +105,9 @@ class AbstractFVMTemplate:
         source = None
         if source_function is not None:
             source = L.f64(_eval_xy(source_function, P[:, 0], P[:, 1], source_parameters))
-        self.engine = Engine(mesh, 1, [c], tile_triangles=tile_triangles, geometry_mode=1, ghost=ghost)  # assembly recomputes geometry; no SoA kept
+        # big tiles: the sliced-ELL SpMV keeps only x of a tile in shared memory, and fewer interface rows
+        # (3 % at 4096 triangles per tile) mean less gather traffic in the tail kernel
+        self.engine = Engine(mesh, 1, [c], tile_triangles=tile_triangles or 4096, geometry_mode=1, ghost=ghost)  # assembly recomputes geometry; no SoA kept
         self.node_value = node_value
         node_value, edge_value = L.f64(node_value), L.f64(edge_value)
         L.check(self.engine.h, L.lib().fvm_assemble(self.engine.h, self.template_id, d_const, L.dp(d_edge), L.dp(d_bnd),
