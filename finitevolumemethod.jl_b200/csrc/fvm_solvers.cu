@@ -164,7 +164,7 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
 // ---- Krylov ----------------------------------------------------------------------------------
 #define RED_BLOCKS 1184  // 148 SMs x 8
 #define RED_THREADS 256
-enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_N };
+enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_SUM0, SC_SUM1, SC_SUM2, SC_N };
 
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partial) {
@@ -203,6 +203,18 @@ __device__ __forceinline__ double final_sum(const double* __restrict__ partial, 
     return tot;
 }
 
+// local sums of the per-block partials -> sc[SC_SUM0 + slot]; sharded runs all-reduce them next
+__global__ void __launch_bounds__(RED_THREADS) reduce_partials_kernel(const double* partial, int nslots, double* sc, int guard) {
+    if (guard && sc[SC_DONE] != 0.0) {
+        if (threadIdx.x < nslots) sc[SC_SUM0 + threadIdx.x] = 0.0;  // keep the collective matched, values unused
+        return;
+    }
+    for (int q = 0; q < nslots; ++q) {
+        const double v = final_sum(partial, q);
+        if (threadIdx.x == 0) sc[SC_SUM0 + q] = v;
+    }
+}
+
 #define GRID_STRIDE(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
 
 // PCG -------------------------------------------------------------------------------------------
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(RED_THREADS)
     block_reduce_store<3>(v, partial);
 }
 __global__ void __launch_bounds__(RED_THREADS) pcg_init3_kernel(const double* partial, double* sc, double rtol) {
-    const double rz = final_sum(partial, 0), rr = final_sum(partial, 1), bb = final_sum(partial, 2);
+    const double rz = sc[SC_SUM0], rr = sc[SC_SUM1], bb = sc[SC_SUM2];
     if (threadIdx.x == 0) {
         sc[SC_RZ] = rz;
         sc[SC_RR] = rr;
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(RED_THREADS) dot_kernel(int64_t n, const doubl
 }
 __global__ void __launch_bounds__(RED_THREADS) pcg_alpha_kernel(const double* partial, double* sc) {
     if (sc[SC_DONE] != 0.0) return;
-    const double pq = final_sum(partial, 0);
+    const double pq = sc[SC_SUM0];
     if (threadIdx.x == 0) {
         sc[SC_PQ] = pq;
         sc[SC_ALPHA] = sc[SC_RZ] / pq;
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 }
 __global__ void __launch_bounds__(RED_THREADS) pcg_beta_kernel(const double* partial, double* sc) {
     if (sc[SC_DONE] != 0.0) return;
-    const double rz = final_sum(partial, 0), rr = final_sum(partial, 1);
+    const double rz = sc[SC_SUM0], rr = sc[SC_SUM1];
     if (threadIdx.x == 0) {
         sc[SC_BETA] = rz / sc[SC_RZ];
         sc[SC_RZ] = rz;
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(RED_THREADS)
     block_reduce_store<2>(s, partial);
 }
 __global__ void __launch_bounds__(RED_THREADS) bicg_init2_kernel(const double* partial, double* sc, double rtol) {
-    const double rr = final_sum(partial, 0), bb = final_sum(partial, 1);
+    const double rr = sc[SC_SUM0], bb = sc[SC_SUM1];
     if (threadIdx.x == 0) {
         sc[SC_RR] = rr;
         sc[SC_BNORM2] = bb;
@@ -340,7 +352,7 @@ __global__ void bicg_p_kernel(int64_t n, const double* r, const double* v, const
 }
 __global__ void __launch_bounds__(RED_THREADS) bicg_alpha_kernel(const double* partial, double* sc) {
     if (sc[SC_DONE] != 0.0) return;
-    const double rhv = final_sum(partial, 0);
+    const double rhv = sc[SC_SUM0];
     if (threadIdx.x == 0) {
         sc[SC_RHO] = sc[SC_RZ];
         sc[SC_ALPHA] = sc[SC_RZ] / rhv;
@@ -368,7 +380,7 @@ __global__ void __launch_bounds__(RED_THREADS) bicg_ts_kernel(int64_t n, const d
 }
 __global__ void __launch_bounds__(RED_THREADS) bicg_omega_kernel(const double* partial, double* sc) {
     if (sc[SC_DONE] != 0.0) return;
-    const double ts = final_sum(partial, 0), tt = final_sum(partial, 1);
+    const double ts = sc[SC_SUM0], tt = sc[SC_SUM1];
     if (threadIdx.x == 0) sc[SC_OMEGA] = tt != 0.0 ? ts / tt : 0.0;
 }
 // x += alpha y + omega z ; r = s - omega t ; dots rhat.r, r.r
@@ -389,7 +401,7 @@ __global__ void __launch_bounds__(RED_THREADS)
 }
 __global__ void __launch_bounds__(RED_THREADS) bicg_end_kernel(const double* partial, double* sc) {
     if (sc[SC_DONE] != 0.0) return;
-    const double rhr = final_sum(partial, 0), rr = final_sum(partial, 1);
+    const double rhr = sc[SC_SUM0], rr = sc[SC_SUM1];
     if (threadIdx.x == 0) {
         sc[SC_RZ] = rhr;
         sc[SC_RR] = rr;
@@ -416,7 +428,7 @@ __global__ void __launch_bounds__(RED_THREADS) resid_kernel(int64_t n, const dou
     block_reduce_store<2>(v, partial);
 }
 __global__ void __launch_bounds__(RED_THREADS) resid_final_kernel(const double* partial, double* sc) {
-    const double rr = final_sum(partial, 0), bb = final_sum(partial, 1);
+    const double rr = sc[SC_SUM0], bb = sc[SC_SUM1];
     if (threadIdx.x == 0) {
         sc[SC_RR] = rr;
         sc[SC_BNORM2] = bb;
@@ -447,6 +459,17 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
     if ((rc = fvm_launch_permute(h, src, X, true))) return rc;
     const int G = RED_BLOCKS, B = RED_THREADS;
     const int check_every = 25;
+    // local block partials -> local sums -> (sharded) NCCL all-reduce; ghost rows of A, b are zero, so
+    // r, z, q, v, t vanish on ghost nodes and the local dot products count every node exactly once
+    auto reduce = [&](int nslots, int guard) -> int32_t {
+        reduce_partials_kernel<<<1, B, 0, st>>>(partial, nslots, sc, guard);
+        return fvm_allreduce_sum(h, sc + SC_SUM0, nslots);
+    };
+    auto spmv = [&](double* in, double* out, bool scale) -> int32_t {
+        int32_t r = fvm_halo_exchange(h, in);
+        if (r) return r;
+        return fvm_launch_spmv(h, in, out, false, scale);
+    };
     double hsc[SC_N];
     auto poll = [&]() -> int32_t {
         FVM_CUDA(h, cudaMemcpyAsync(hsc, sc, sizeof(double) * SC_N, cudaMemcpyDeviceToHost, st));
@@ -462,14 +485,17 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
         if (method == FVM_KRYLOV_PCG) {
             double *R = h->d_work[1], *Z = h->d_work[2], *P = h->d_work[3], *Q = h->d_work[4];
             pcg_init1_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, X);
-            if ((rc = fvm_launch_spmv(h, X, Q, false, true))) return rc;
+            if ((rc = spmv(X, Q, true))) return rc;
             pcg_init2_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, Q, c.diag_inv, R, Z, P, partial);
+            if ((rc = reduce(3, 0))) return rc;
             pcg_init3_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
             for (int it = 0; it < budget; ++it) {
-                if ((rc = fvm_launch_spmv(h, P, Q, false, true))) return rc;
+                if ((rc = spmv(P, Q, true))) return rc;
                 dot_kernel<<<G, B, 0, st>>>(n, P, Q, partial, sc);
+                if ((rc = reduce(1, 1))) return rc;
                 pcg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
                 pcg_update_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, c.rowscale, X, R, Z, partial, sc);
+                if ((rc = reduce(2, 1))) return rc;
                 pcg_beta_kernel<<<1, B, 0, st>>>(partial, sc);
                 pcg_p_kernel<<<G, B, 0, st>>>(n, Z, P, sc);
                 if ((it + 1) % check_every == 0 || it + 1 == budget) {
@@ -482,19 +508,23 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
                    *S = h->d_work[6], *Z = h->d_work[7], *T = h->d_work[8], *KI = h->d_work[9];
             kinv_kernel<<<G, B, 0, st>>>(n, c.diag_inv, c.rowscale, KI);
             pcg_init1_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, X);  // identity rows are satisfied from the start
-            if ((rc = fvm_launch_spmv(h, X, V, false, false))) return rc;
+            if ((rc = spmv(X, V, false))) return rc;
             bicg_init_kernel<<<G, B, 0, st>>>(n, c.b, V, R, RH, P, V, partial);
+            if ((rc = reduce(2, 0))) return rc;
             bicg_init2_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
             for (int it = 0; it < budget; ++it) {
                 bicg_p_kernel<<<G, B, 0, st>>>(n, R, V, KI, P, Y, RH, sc);
-                if ((rc = fvm_launch_spmv(h, Y, V, false, false))) return rc;
+                if ((rc = spmv(Y, V, false))) return rc;
                 dot_kernel<<<G, B, 0, st>>>(n, RH, V, partial, sc);
+                if ((rc = reduce(1, 1))) return rc;
                 bicg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
                 bicg_s_kernel<<<G, B, 0, st>>>(n, R, V, KI, S, Z, sc);
-                if ((rc = fvm_launch_spmv(h, Z, T, false, false))) return rc;
+                if ((rc = spmv(Z, T, false))) return rc;
                 bicg_ts_kernel<<<G, B, 0, st>>>(n, T, S, partial, sc);
+                if ((rc = reduce(2, 1))) return rc;
                 bicg_omega_kernel<<<1, B, 0, st>>>(partial, sc);
                 bicg_x_kernel<<<G, B, 0, st>>>(n, Y, Z, S, T, RH, X, R, partial, sc);
+                if ((rc = reduce(2, 1))) return rc;
                 bicg_end_kernel<<<1, B, 0, st>>>(partial, sc);
                 if ((it + 1) % check_every == 0 || it + 1 == budget) {
                     if ((rc = poll())) return rc;
@@ -514,8 +544,9 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
     const int32_t done_iters = total_iters;
     // true (unscaled) residual of A x = b
     double* AX = h->d_work[4];
-    if ((rc = fvm_launch_spmv(h, X, AX, false, false))) return rc;
+    if ((rc = spmv(X, AX, false))) return rc;
     resid_kernel<<<G, B, 0, st>>>(n, c.b, AX, partial);
+    if ((rc = reduce(2, 0))) return rc;
     resid_final_kernel<<<1, B, 0, st>>>(partial, sc);
     if ((rc = poll())) return rc;
     if (iters) *iters = done_iters;

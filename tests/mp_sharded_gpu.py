@@ -84,6 +84,26 @@ def main():
     errs["tsit5_operator"] = rel_err(sol.u[:local.n_owned], uref[own])
     assert errs["tsit5_operator"] <= RTOL_TSIT5, errs
     tpl.engine.close()
+    # sharded steady solve: Poisson on the lattice, PCG and BiCGStab with NCCL all-reduced dot products
+    log("sharded krylov")
+    tri = G.triangulate_rectangle(0, 1, 0, 1, 60, 48, single_boundary=True)
+    owner = G.partition_rcb(tri.points, world)
+    local = G.extract_local(tri, owner, rank, world)
+    lmesh = G.FVMGeometry(local.triangulation)
+    src = lambda x, y, p: -np.sin(np.pi * x) * np.sin(np.pi * y)
+    otri = O.triangulate_rectangle(0, 1, 0, 1, 60, 48, single_boundary=True)
+    omesh = O.FVMGeometry(otri)
+    ref = O.PoissonsEquation(omesh, O.BoundaryConditions(omesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet), source_function=src)
+    uref = O.solve_steady(ref)
+    own = local.global_nodes[:local.n_owned]
+    for method in ("pcg", "bicgstab"):
+        tpl = G.PoissonsEquation(lmesh, G.BoundaryConditions(lmesh, G.Const(0.0), G.Dirichlet), source_function=src,
+                                 ghost=local.is_ghost, tile_triangles=256)
+        G.install_halo(tpl.engine, local, dist)
+        sol = G.solve(tpl, G.KrylovJacobi(method, rtol=1e-13))
+        errs["krylov_" + method] = rel_err(sol.u[:local.n_owned], uref[own])
+        assert errs["krylov_" + method] <= 1e-9 and sol.relres <= 1e-11, (errs, sol.relres, sol.iters)
+        tpl.engine.close()
     dist.barrier()
     print("rank %d/%d sharded parity OK: %s" % (rank, world, {k: float("%.2e" % v) for k, v in errs.items()}), flush=True)
     dist.destroy_process_group()
