@@ -195,6 +195,77 @@ def time_template(torch, G, prob, nx, steps, warmup, peak, lmesh=None, dist=None
     return out
 
 
+def time_extras(torch, G, nx, steps, warmup, peak):
+    """The other BASELINE configs, at full size on one GPU: config 4 (2-species Keller-Segel FVMSystem
+    RHS, 4096^2), config 3 (MeanExitTimeProblem, 2048^2, Jacobi-PCG) and config 1 (README 50x50)."""
+    out = {}
+    # ---- config 4: FVMSystem, registered u-dependent flux, all-Neumann zero flux -------------------
+    tri = G.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, nx, nx, single_boundary=True)
+    mesh = G.FVMGeometry(tri)
+    N = tri.num_points
+    rng = np.random.default_rng(SEED)
+    ks, kss = G.KellerSegelFlux(4.0, 1.0), G.KellerSegelSource(0.1)
+    BC = G.BoundaryConditions(mesh, G.Const(0.0), G.Neumann)
+    pu = G.FVMProblem(mesh, BC, flux_function=ks, source_function=kss, initial_condition=0.01 * rng.random(N), final_time=1.0)
+    pv = G.FVMProblem(mesh, BC, flux_function=ks, source_function=kss, initial_condition=np.zeros(N), final_time=1.0)
+    p = G.get_cuda_parameters(G.FVMSystem(pu, pv))
+    eng = p.engine
+    g = torch.Generator(device="cuda")
+    g.manual_seed(SEED)
+    u_d = 0.01 * torch.rand(2 * N, dtype=torch.float64, device="cuda", generator=g)
+    du_d = torch.empty_like(u_d)
+    ms, kms = time_rhs(torch, eng, u_d, du_d, steps, warmup)
+    B = 180 * eng.T + (17 * 2 + 8) * N
+    out["system_rhs"] = {"config": "FVMSystem 2-species Keller-Segel (chi(u) grad v - grad u; -D grad v), all-Neumann, %dx%d" % (nx, nx),
+                         "mtri_s": eng.T / ms / 1e3, "ms_per_step": ms, "tile_kernel_ms": kms, "alg_bytes": B,
+                         "bytes_formula": "180*T + 42*N", "gbs": B / kms / 1e6, "frac": B / kms / 1e6 / peak,
+                         "finite": bool(torch.isfinite(du_d).all().item())}
+    eng.close()
+    del u_d, du_d, p, eng
+    # ---- config 3: steady MeanExitTimeProblem, 2048^2, Jacobi-PCG -----------------------------------
+    n3 = max(64, nx // 2)
+    tri = G.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, n3, n3, single_boundary=True)
+    mesh = G.FVMGeometry(tri)
+    t0 = time.perf_counter()
+    met = G.MeanExitTimeProblem(mesh, G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet), diffusion_function=1 / 9)
+    t_asm = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sol = G.solve(met, G.KrylovJacobi("pcg", rtol=1e-10, maxiter=40000))
+    t_solve = time.perf_counter() - t0
+    # closed form on the square [0,L]^2: T(x,y) = (16 L^2 / (D pi^4)) sum_odd sin(m pi x/L) sin(n pi y/L) / (m n (m^2+n^2))
+    c = n3 // 2 * n3 + n3 // 2
+    L = 2.0
+    mm = np.arange(1, 400, 2, dtype=np.float64)
+    xc, yc = tri.points[c]
+    series = 16 * L * L / ((1 / 9) * np.pi**4) * np.sum(
+        np.sin(mm[:, None] * np.pi * xc / L) * np.sin(mm[None, :] * np.pi * yc / L) / (mm[:, None] * mm[None, :] * (mm[:, None]**2 + mm[None, :]**2)))
+    out["steady_pcg"] = {"config": "MeanExitTimeProblem %dx%d, D=1/9, Jacobi-PCG rtol 1e-10" % (n3, n3), "iters": sol.iters,
+                         "relres": sol.relres, "solve_s": t_solve, "assemble_s": t_asm, "ms_per_iter": 1e3 * t_solve / max(1, sol.iters),
+                         "centre_value": float(sol.u[c]), "centre_closed_form": float(series)}
+    met.engine.close()
+    # ---- config 1: README, 50x50, Tsit5 to t = 0.5 (launch-bound) -----------------------------------
+    tri = G.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, 50, 50, single_boundary=True)
+    mesh = G.FVMGeometry(tri)
+    BCs = G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet)
+    ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
+    prob = G.FVMProblem(mesh, BCs, diffusion_function=G.ConstantDiffusion(1 / 9), initial_condition=ic, final_time=0.5)
+    pp = G.get_cuda_parameters(prob)
+    G.solve(prob, G.Tsit5(0.0025), p=pp)
+    t0 = time.perf_counter()
+    G.solve(prob, G.Tsit5(0.0025), p=pp)
+    t_fvm = time.perf_counter() - t0
+    tpl = G.DiffusionEquation(mesh, BCs, diffusion_function=1 / 9, initial_condition=ic, final_time=0.5)
+    G.solve(tpl, G.Tsit5(0.0025))
+    t0 = time.perf_counter()
+    G.solve(tpl, G.Tsit5(0.0025))
+    t_tpl = time.perf_counter() - t0
+    out["readme_50x50"] = {"config": "README diffusion, Tsit5 fixed dt=0.0025 to t=0.5 (200 steps)", "fvmproblem_solve_ms": 1e3 * t_fvm,
+                           "template_solve_ms": 1e3 * t_tpl}
+    pp.engine.close()
+    tpl.engine.close()
+    return out
+
+
 def cpu_baseline(nx, target_s=12.0, impl_reference=False, steps=None, warmup=1):
     """The oracle port (oracle/fvm_oracle_c.c, reference-structured: hash-table triangle props,
     per-thread du copies, serial combine) timed on the host cores on a bounded sample."""
@@ -256,6 +327,7 @@ def main():
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-template", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -355,6 +427,10 @@ def main():
         if rank == 0:
             sys.stderr.write("[bench] template SpMV %.3f ms (tile kernel %.3f)  %.0f GB/s (%.2f of peak)  Tsit5 %.3f ms/step\n"
                              % (tplres["spmv_ms"], tplres["spmv_kernel_ms"], tplres["spmv_gbs"], tplres["spmv_frac"], tplres["tsit5_ms_per_step"]))
+    extras = None
+    if not args.no_extras and world == 1:
+        extras = time_extras(torch, G, nx, max(10, args.steps // 4), args.warmup, peak)
+        sys.stderr.write("[bench] extras: %s\n" % json.dumps(extras))
     if rank != 0:
         dist.destroy_process_group()
         return
@@ -391,6 +467,8 @@ def main():
         line["tsit5"] = {"ms_per_step": tplres["tsit5_ms_per_step"], "steps": tplres["tsit5_steps"], "dt": tplres["tsit5_dt"],
                          "spmv_per_step": 6, "finite": tplres["finite"]}
         line["gpu_launches"] += 2 * args.steps + tplres["tsit5_launches"]
+    if extras:
+        line["other_configs"] = extras
     if cb:
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if len(results) > 1:

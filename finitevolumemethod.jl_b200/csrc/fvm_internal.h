@@ -126,6 +126,7 @@ struct fvm_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     bool finalized = false;
+    bool time_dependent = false;  // some registered condition function reads t
     int32_t neq = 1;
     int32_t h_index_base = 0;
     void* graph_exec = nullptr;

@@ -20,8 +20,22 @@
 #define MODEL_VOLUME 100
 
 // ------------------------------------------------------------------------------------------
+// register budget (CTAs of 256 threads per SM): the kernels that stream the full SoA keep 3 resident
+// (<= 85 registers; measured best), the reduced-stream kernel wants 8 small CTAs, recompute kernels 4
+template <int MODEL, int NEQ>
+struct TileOcc {
+    static constexpr bool vol = (MODEL == MODEL_VOLUME);
+    static constexpr bool full = FluxTraits<vol ? 0 : MODEL>::full;
+    template <int GEOM>
+    static constexpr int min_blocks() {
+        if (vol) return 1;
+        if (NEQ == 1) return full ? 3 : (GEOM == 1 ? 4 : 8);
+        if (NEQ == 2) return 3;
+        return 2;
+    }
+};
 template <int MODEL, int NEQ, int GEOM>
-__global__ void __launch_bounds__(RHS_BLOCK)
+__global__ void __launch_bounds__(RHS_BLOCK, TileOcc<MODEL, NEQ>::template min_blocks<GEOM>())
     rhs_tile_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t,
                     const double* __restrict__ u, double* __restrict__ du, const int smem_nloc) {
     extern __shared__ double smem[];

@@ -173,6 +173,8 @@ extern "C" int32_t fvm_set_condition_fn(fvm_handle h, int32_t var, int32_t fidx,
     CondFn c{fn_id, {0, 0, 0, 0}};
     for (int i = 0; i < nparams; ++i) c.p[i] = params[i];
     h->h_cond[(size_t)var * FVM_MAX_COND_FN + fidx] = c;
+    h->time_dependent = false;
+    for (const CondFn& q : h->h_cond) h->time_dependent = h->time_dependent || q.id == FVM_COND_EXP_SAT;
     if (h->finalized) {  // condition parameters may change between solves
         FVM_CUDA(h, cudaMemcpyAsync((void*)(h->dm.cond + (size_t)var * FVM_MAX_COND_FN + fidx), &c, sizeof(CondFn),
                                     cudaMemcpyHostToDevice, h->stream));

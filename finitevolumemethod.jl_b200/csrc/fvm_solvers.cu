@@ -131,25 +131,81 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
     bool has_callback = false;  // sharded: the same FSAL / callback schedule on every rank
     if ((rc = fvm_global_or(h, !use_operator && h->n_dir > 0, &has_callback))) return rc;
     bool have_k1 = false;
-    for (int64_t step = 0; step < nsteps; ++step) {
+    int parity = 0, graph_parity = 0;  // k1/k7 buffer arrangement; a graph only replays in the one it was captured in
+    auto do_step = [&](int64_t step) -> int32_t {
         const double t = t0 + step * dt;
-        if (!have_k1 && (rc = f(K[0], U, t))) return rc;
+        int32_t r;
+        if (!have_k1 && (r = f(K[0], U, t))) return r;
         for (int s = 1; s < 6; ++s) {
-            if ((rc = launch_lincomb(h, s, n, TMP, U, dt, K, TS_A[s]))) return rc;
-            if ((rc = f(K[s], TMP, t + TS_C[s] * dt))) return rc;
+            if ((r = launch_lincomb(h, s, n, TMP, U, dt, K, TS_A[s]))) return r;
+            if ((r = f(K[s], TMP, t + TS_C[s] * dt))) return r;
         }
-        if ((rc = launch_lincomb(h, 6, n, U, U, dt, K, TS_A[6]))) return rc;
+        if ((r = launch_lincomb(h, 6, n, U, U, dt, K, TS_A[6]))) return r;
         const double tn = t0 + (step + 1) * dt;
         if (has_callback) {
             // the DiscreteCallback modifies u, so the FSAL value is discarded and k1 is re-evaluated
-            if ((rc = fvm_launch_dirichlet(h, tn, U))) return rc;
+            if ((r = fvm_launch_dirichlet(h, tn, U))) return r;
             have_k1 = false;
         } else {
-            if ((rc = f(K[6], U, tn))) return rc;
+            if ((r = f(K[6], U, tn))) return r;
             std::swap(K[0], K[6]);
+            parity ^= 1;
             have_k1 = true;
         }
-        if ((rc = save(tn))) return rc;
+        return FVM_OK;
+    };
+    // Launch-bound meshes (the README 50x50 config runs ~20 kernels of a few microseconds per step):
+    // the steady-state step is captured once into a CUDA graph and replayed.  Two steps per graph
+    // when FSAL swaps k1/k7 (the pointer arrangement repeats with period 2).  Not used when a kernel
+    // argument changes per step (time-dependent condition functions), when sharded (NCCL in the
+    // step) or while the per-kernel profiling events are armed.
+    const bool graph_ok = (use_operator || !h->time_dependent) && h->nranks == 1 && !h->halo_ready && !h->profiling && nsteps >= 6 &&
+                          !getenv("FVM_NO_GRAPH");
+    const int per = has_callback ? 1 : 2;
+    cudaGraphExec_t exec = nullptr;
+    auto save_due = [&](double tn) { return next_save < nsave && std::fabs(tsave[next_save] - tn) < 0.5 * dt; };
+    int64_t step = 0;
+    while (step < nsteps) {
+        const bool can = graph_ok && step >= 1 && step + per <= nsteps && (per == 1 || !save_due(t0 + (step + 1) * dt)) &&
+                         (!exec || parity == graph_parity);
+        if (can) {
+            if (!exec) {
+                graph_parity = parity;
+                cudaGraph_t graph = nullptr;
+                FVM_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                rc = FVM_OK;
+                for (int q = 0; q < per && !rc; ++q) rc = do_step(step + q);
+                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                if (rc) {
+                    if (graph) cudaGraphDestroy(graph);
+                    return rc;
+                }
+                FVM_CUDA(h, ce);
+                ce = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                FVM_CUDA(h, ce);
+            }
+            cudaError_t ce = cudaGraphLaunch(exec, h->stream);
+            if (ce != cudaSuccess) {
+                cudaGraphExecDestroy(exec);
+                FVM_CUDA(h, ce);
+            }
+            step += per;
+        } else {
+            if ((rc = do_step(step))) {
+                if (exec) cudaGraphExecDestroy(exec);
+                return rc;
+            }
+            step += 1;
+        }
+        if ((rc = save(t0 + step * dt))) {
+            if (exec) cudaGraphExecDestroy(exec);
+            return rc;
+        }
+    }
+    if (exec) {
+        FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+        cudaGraphExecDestroy(exec);
     }
     if (on_device) {
         if ((rc = fvm_launch_permute(h, U, u, false))) return rc;
