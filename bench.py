@@ -381,9 +381,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         sampler = ClockSampler(local) if rank == 0 and name == names[-1] else None
-        if sampler:  # nvidia-smi needs ~0.3 s to start sampling: keep the GPU under the same load meanwhile
-            t_end = time.perf_counter() + 0.5
-            while time.perf_counter() < t_end:
+        if name == names[-1]:
+            # nvidia-smi needs ~0.3 s to start sampling: keep the GPU under the same load meanwhile.  A FIXED
+            # number of calls on EVERY rank: sharded calls contain NCCL send/recv and must pair up across ranks.
+            for _ in range(400):
                 eng.rhs_device(du_d.data_ptr(), u_d.data_ptr(), 0.0, native=True)
             eng.synchronize()
         ms, kms = time_rhs(torch, eng, u_d, du_d, args.steps, args.warmup)

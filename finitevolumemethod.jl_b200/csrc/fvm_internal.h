@@ -175,6 +175,10 @@ struct fvm_ctx {
     // sharding (fvm_shard.cu)
     void* shard = nullptr;
     bool halo_ready = false;
+    bool overlap = false;            // exchange overlapped with the tiles that touch no ghost node
+    int32_t* d_tile_order = nullptr; // independent tiles first, then the halo-dependent ones
+    int32_t n_tiles_indep = 0;
+    std::vector<int32_t> h_tile_node0, h_tile_nown, h_tile_ext0, h_ext_ids;  // host copies for the classification
     std::vector<uint8_t> h_ghost;  // caller order: 1 = ghost node owned by another rank
     int32_t rank = 0, nranks = 1;
 };
@@ -221,6 +225,14 @@ int32_t fvm_export_geometry(fvm_ctx* h, double* s9, double* mid6, double* nrm6, 
 int32_t fvm_ensure_state(fvm_ctx* h);
 void fvm_shard_release(fvm_ctx* h);
 int32_t fvm_halo_exchange(fvm_ctx* h, double* u_native);
+int32_t fvm_halo_begin(fvm_ctx* h, double* u_native);
+int32_t fvm_halo_wait(fvm_ctx* h);
+// operator applications with the ghost refresh (overlapped with the independent tiles when possible)
+int32_t fvm_apply_rhs(fvm_ctx* h, double t, double* x, double* out);
+int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* out, bool add_b, bool scale);
+// part: 0 = everything, 1 = independent tiles only, 2 = halo-dependent tiles + boundary/interface/tail kernels
+int32_t fvm_launch_rhs_part(fvm_ctx* h, double t, const double* u, double* du, int part);
+int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part);
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);
 int32_t fvm_global_or(fvm_ctx* h, bool local, bool* global);
 #define FVM_NODE_GHOST 4

@@ -268,9 +268,11 @@ template <bool ADD_B, bool SCALE>
 __global__ void __launch_bounds__(SPMV_BLOCK)
     spmv_tile_kernel(const DevMesh m, const int32_t* __restrict__ tile_slice0, const int32_t* __restrict__ sell_ptr,
                      const uint16_t* __restrict__ sell_col, const double* __restrict__ sell_val, const double* __restrict__ b,
-                     const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y) {
+                     const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y,
+                     const int32_t* __restrict__ tile_list, const int tile_off) {
     extern __shared__ double x_s[];  // [max_nloc]
-    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = tile_list ? tile_list[blockIdx.x + tile_off] : (int)blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int4 m0 = __ldg(m.tile_meta + 2 * tile), m1 = __ldg(m.tile_meta + 2 * tile + 1);
     const int node0 = m0.x, nint = m0.y, nown = m0.z, nloc = m0.w, ext0 = m1.x;
     if (nint == 0) return;
@@ -398,16 +400,30 @@ __global__ void col16_kernel(const DevMesh m, const int32_t* __restrict__ rowptr
 }
 
 template <bool ADD_B, bool SCALE>
-static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y) {
+static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part) {
     Csr& c = h->csr;
     if (c.use_tile_spmv) {
-        fvm_prof_begin(h);
-        spmv_tile_kernel<ADD_B, SCALE><<<h->dm.n_tiles, SPMV_BLOCK, c.tile_smem, h->stream>>>(
-            h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale, x, y);
-        fvm_prof_end(h);
-        if (c.n_tail > 0)
+        int grid = h->dm.n_tiles, off = 0;
+        const int32_t* list = nullptr;
+        if (part == 1) {
+            list = h->d_tile_order;
+            grid = h->n_tiles_indep;
+        } else if (part == 2) {
+            list = h->d_tile_order;
+            off = h->n_tiles_indep;
+            grid = h->dm.n_tiles - h->n_tiles_indep;
+        }
+        if (grid > 0) {
+            fvm_prof_begin(h);
+            spmv_tile_kernel<ADD_B, SCALE><<<grid, SPMV_BLOCK, c.tile_smem, h->stream>>>(
+                h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale, x, y, list, off);
+            fvm_prof_end(h);
+        }
+        if (c.n_tail > 0 && part != 1)
             spmv_rows_kernel<ADD_B, SCALE><<<(c.n_tslices * 32 + 127) / 128, 128, 0, h->stream>>>(
                 c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b, c.rowscale, x, y);
+    } else if (part == 1) {
+        return FVM_OK;  // the generic kernels have no tile split: everything runs in part 2
     } else if (c.use_tile_spmv == 0 && c.chunk_rows > 0 && getenv("FVM_SPMV_BLOCK")) {
         const int grid = (c.n + SPMV_ROWS - 1) / SPMV_ROWS;
         fvm_prof_begin(h);
@@ -425,11 +441,28 @@ static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y) {
     return FVM_OK;
 }
 
+int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part) {
+    if (add_b && !scale) return launch_spmv_t<true, false>(h, x, y, part);
+    if (!add_b && !scale) return launch_spmv_t<false, false>(h, x, y, part);
+    if (add_b && scale) return launch_spmv_t<true, true>(h, x, y, part);
+    return launch_spmv_t<false, true>(h, x, y, part);
+}
+
 int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale) {
-    if (add_b && !scale) return launch_spmv_t<true, false>(h, x, y);
-    if (!add_b && !scale) return launch_spmv_t<false, false>(h, x, y);
-    if (add_b && scale) return launch_spmv_t<true, true>(h, x, y);
-    return launch_spmv_t<false, true>(h, x, y);
+    return fvm_launch_spmv_part(h, x, y, add_b, scale, 0);
+}
+
+int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* y, bool add_b, bool scale) {
+    if (!h->halo_ready) return fvm_launch_spmv_part(h, x, y, add_b, scale, 0);
+    int32_t rc;
+    if (!h->overlap) {
+        if ((rc = fvm_halo_exchange(h, x))) return rc;
+        return fvm_launch_spmv_part(h, x, y, add_b, scale, 0);
+    }
+    if ((rc = fvm_halo_begin(h, x))) return rc;
+    if ((rc = fvm_launch_spmv_part(h, x, y, add_b, scale, 1))) return rc;
+    if ((rc = fvm_halo_wait(h))) return rc;
+    return fvm_launch_spmv_part(h, x, y, add_b, scale, 2);
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -778,9 +811,7 @@ extern "C" int32_t fvm_get_csr(fvm_handle h, int32_t* rowptr, int32_t* col, doub
 extern "C" int32_t fvm_spmv_native(fvm_handle h, const double* x, double* y, int32_t add_b) {
     NEED_ASSEMBLED(h);
     FVM_REQUIRE(h, x && y && x != y, "fvm_spmv_native: bad arguments");
-    int32_t rc = fvm_halo_exchange(h, const_cast<double*>(x));
-    if (rc) return rc;
-    return fvm_launch_spmv(h, x, y, add_b != 0, false);
+    return fvm_apply_spmv(h, const_cast<double*>(x), y, add_b != 0, false);
 }
 
 extern "C" int32_t fvm_spmv(fvm_handle h, const double* x, double* y, int32_t add_b, int32_t on_device) {
@@ -795,8 +826,7 @@ extern "C" int32_t fvm_spmv(fvm_handle h, const double* x, double* y, int32_t ad
         src = h->d_io;
     }
     if ((rc = fvm_launch_permute(h, src, h->d_u, true))) return rc;
-    if ((rc = fvm_halo_exchange(h, h->d_u))) return rc;
-    if ((rc = fvm_launch_spmv(h, h->d_u, h->d_du, add_b != 0, false))) return rc;
+    if ((rc = fvm_apply_spmv(h, h->d_u, h->d_du, add_b != 0, false))) return rc;
     if (on_device) {
         if ((rc = fvm_launch_permute(h, h->d_du, y, false))) return rc;
     } else {

@@ -37,7 +37,8 @@ struct TileOcc {
 template <int MODEL, int NEQ, int GEOM>
 __global__ void __launch_bounds__(RHS_BLOCK, TileOcc<MODEL, NEQ>::template min_blocks<GEOM>())
     rhs_tile_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t,
-                    const double* __restrict__ u, double* __restrict__ du, const int smem_nloc) {
+                    const double* __restrict__ u, double* __restrict__ du, const int smem_nloc,
+                    const int32_t* __restrict__ tile_list, const int tile_off) {
     extern __shared__ double smem[];
     constexpr bool VOL = (MODEL == MODEL_VOLUME);
     constexpr bool NEED_XY = VOL || GEOM == 1;
@@ -48,7 +49,7 @@ __global__ void __launch_bounds__(RHS_BLOCK, TileOcc<MODEL, NEQ>::template min_b
     uint16_t* inc_s = reinterpret_cast<uint16_t*>(c_s + (size_t)3 * TT * (VOL ? 1 : NEQ));  // [3*TT] gather list
     uint16_t* iptr_s = inc_s + 3 * TT;                                                      // [smem_nloc + 1]
 
-    const int tile = blockIdx.x;
+    const int tile = tile_list ? tile_list[blockIdx.x + tile_off] : (int)blockIdx.x;
     const int tid = threadIdx.x;
     const int4 m0 = __ldg(m.tile_meta + 2 * tile), m1 = __ldg(m.tile_meta + 2 * tile + 1);
     const int node0 = m0.x, nint = m0.y, nown = m0.z, nloc = m0.w;
@@ -419,7 +420,7 @@ static int32_t rhs_smem_bytes(const fvm_ctx* h, int neq, bool vol, bool need_xy)
 }
 
 template <int MODEL, int NEQ, int GEOM>
-static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du) {
+static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, int part = 0) {
     constexpr bool VOL = (MODEL == MODEL_VOLUME);
     const int32_t smem = rhs_smem_bytes(h, NEQ, VOL, VOL || GEOM == 1);
     auto kern = rhs_tile_kernel<MODEL, NEQ, GEOM>;
@@ -430,17 +431,28 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du) {
         configured = smem;
     }
     h->smem_rhs = smem;
+    int grid = h->dm.n_tiles, off = 0;
+    const int32_t* list = nullptr;
+    if (part == 1) {
+        list = h->d_tile_order;
+        grid = h->n_tiles_indep;
+    } else if (part == 2) {
+        list = h->d_tile_order;
+        off = h->n_tiles_indep;
+        grid = h->dm.n_tiles - h->n_tiles_indep;
+    }
+    if (grid == 0) return FVM_OK;
     fvm_prof_begin(h);
-    kern<<<h->dm.n_tiles, RHS_BLOCK, smem, h->stream>>>(h->dm, h->flux, h->source, t, u, du, h->max_nloc);
+    kern<<<grid, RHS_BLOCK, smem, h->stream>>>(h->dm, h->flux, h->source, t, u, du, h->max_nloc, list, off);
     fvm_prof_end(h);
     FVM_CUDA(h, cudaGetLastError());
     return FVM_OK;
 }
 
 template <int NEQ>
-static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du) {
+static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du, int part) {
     int32_t rc = FVM_OK;
-    if (h->n_bnd_live > 0) {
+    if (h->n_bnd_live > 0 && part != 1) {
         rhs_boundary_kernel<NEQ><<<(h->n_bnd_live + 127) / 128, 128, 0, h->stream>>>(h->dm, h->flux, t, h->d_bnd, h->d_dbnd,
                                                                                      h->n_bnd_live, u);
         FVM_CUDA(h, cudaGetLastError());
@@ -449,7 +461,7 @@ static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du)
     const int geom = h->geometry_mode;
 #define TILE_CASE(M)                                                        \
     case M:                                                                 \
-        rc = geom ? launch_tile<M, NEQ, 1>(h, t, u, du) : launch_tile<M, NEQ, 0>(h, t, u, du); \
+        rc = geom ? launch_tile<M, NEQ, 1>(h, t, u, du, part) : launch_tile<M, NEQ, 0>(h, t, u, du, part); \
         break;
     switch (model) {
         TILE_CASE(FVM_FLUX_DIFF_CONST)
@@ -458,8 +470,8 @@ static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du)
         TILE_CASE(FVM_FLUX_ADVDIFF)
         case FVM_FLUX_KELLER_SEGEL:
             if constexpr (NEQ == 2) {
-                rc = geom ? launch_tile<FVM_FLUX_KELLER_SEGEL, 2, 1>(h, t, u, du)
-                          : launch_tile<FVM_FLUX_KELLER_SEGEL, 2, 0>(h, t, u, du);
+                rc = geom ? launch_tile<FVM_FLUX_KELLER_SEGEL, 2, 1>(h, t, u, du, part)
+                          : launch_tile<FVM_FLUX_KELLER_SEGEL, 2, 0>(h, t, u, du, part);
             } else {
                 rc = fvm_fail(h, FVM_ERR_ARG, "Keller-Segel flux needs neq == 2");
             }
@@ -469,21 +481,37 @@ static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du)
 #undef TILE_CASE
     if (rc) return rc;
     const int n_tail = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
-    if (n_tail > 0) {
+    if (n_tail > 0 && part != 1) {
         rhs_interface_kernel<NEQ, false><<<(n_tail + 255) / 256, 256, 0, h->stream>>>(h->dm, h->source, t, u, du);
         FVM_CUDA(h, cudaGetLastError());
     }
     return FVM_OK;
 }
 
-int32_t fvm_launch_rhs(fvm_ctx* h, double t, const double* u, double* du) {
+int32_t fvm_launch_rhs_part(fvm_ctx* h, double t, const double* u, double* du, int part) {
     switch (h->neq) {
-        case 1: return launch_rhs_neq<1>(h, t, u, du);
-        case 2: return launch_rhs_neq<2>(h, t, u, du);
-        case 3: return launch_rhs_neq<3>(h, t, u, du);
-        case 4: return launch_rhs_neq<4>(h, t, u, du);
+        case 1: return launch_rhs_neq<1>(h, t, u, du, part);
+        case 2: return launch_rhs_neq<2>(h, t, u, du, part);
+        case 3: return launch_rhs_neq<3>(h, t, u, du, part);
+        case 4: return launch_rhs_neq<4>(h, t, u, du, part);
     }
     return fvm_fail(h, FVM_ERR_ARG, "unsupported neq");
+}
+
+int32_t fvm_launch_rhs(fvm_ctx* h, double t, const double* u, double* du) { return fvm_launch_rhs_part(h, t, u, du, 0); }
+
+// du = fvm_eqs!(u) with the ghost refresh; the exchange overlaps the tiles that touch no ghost node
+int32_t fvm_apply_rhs(fvm_ctx* h, double t, double* x, double* out) {
+    if (!h->halo_ready) return fvm_launch_rhs_part(h, t, x, out, 0);
+    int32_t rc;
+    if (!h->overlap) {
+        if ((rc = fvm_halo_exchange(h, x))) return rc;
+        return fvm_launch_rhs_part(h, t, x, out, 0);
+    }
+    if ((rc = fvm_halo_begin(h, x))) return rc;
+    if ((rc = fvm_launch_rhs_part(h, t, x, out, 1))) return rc;
+    if ((rc = fvm_halo_wait(h))) return rc;
+    return fvm_launch_rhs_part(h, t, x, out, 2);
 }
 
 int32_t fvm_launch_geometry(fvm_ctx* h, const int32_t* d_tri_native) {
@@ -505,7 +533,7 @@ int32_t fvm_launch_volumes(fvm_ctx* h) {
     // cv_volumes (geometry.jl:119-135) through the same tile gather: deterministic summation
     double* vol = const_cast<double*>(h->dm.vol);
     FVM_CUDA(h, cudaMemsetAsync(h->dm.partial, 0, sizeof(double) * h->dm.n_partial * h->neq, h->stream));
-    int32_t rc = launch_tile<MODEL_VOLUME, 1, 1>(h, 0.0, nullptr, vol);
+    int32_t rc = launch_tile<MODEL_VOLUME, 1, 1>(h, 0.0, nullptr, vol, 0);
     if (rc) return rc;
     const int n_tail = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
     if (n_tail > 0) {
@@ -550,9 +578,7 @@ int32_t fvm_ensure_state(fvm_ctx* h) {
 extern "C" int32_t fvm_rhs_native(fvm_handle h, double t, const double* u, double* du) {
     NEED_FINAL(h);
     FVM_REQUIRE(h, u && du, "fvm_rhs_native: null argument");
-    int32_t rc = fvm_halo_exchange(h, const_cast<double*>(u));  // sharded: ghost entries of u are refreshed in place
-    if (rc) return rc;
-    return fvm_launch_rhs(h, t, u, du);
+    return fvm_apply_rhs(h, t, const_cast<double*>(u), du);  // sharded: ghost entries of u are refreshed in place
 }
 
 extern "C" int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, int32_t on_device) {
@@ -567,8 +593,7 @@ extern "C" int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, 
         src = h->d_io;
     }
     if ((rc = fvm_launch_permute(h, src, h->d_u, true))) return rc;
-    if ((rc = fvm_halo_exchange(h, h->d_u))) return rc;
-    if ((rc = fvm_launch_rhs(h, t, h->d_u, h->d_du))) return rc;
+    if ((rc = fvm_apply_rhs(h, t, h->d_u, h->d_du))) return rc;
     if (on_device) {
         if ((rc = fvm_launch_permute(h, h->d_du, du, false))) return rc;
     } else {

@@ -565,6 +565,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         }
         UP(m.tile_meta, meta);
     }
+    h->h_tile_node0 = tile_node0;
+    h->h_tile_nown = tile_nown;
+    h->h_tile_ext0 = tile_ext0;
+    h->h_ext_ids = ext_ids;
     UP(m.tile_node0, tile_node0);
     UP(m.tile_nint, tile_nint);
     UP(m.tile_nown, tile_nown);

@@ -103,6 +103,27 @@ extern "C" int32_t fvm_set_halo(fvm_handle h, int32_t n_neigh, const int32_t* ne
         FVM_CUDA(h, cudaEventCreateWithFlags(&s->ev_packed, cudaEventDisableTiming));
         FVM_CUDA(h, cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
     }
+    // tiles whose local nodes (own range or external interface nodes) contain no received ghost node
+    // can run while the exchange is in flight
+    {
+        std::vector<uint8_t> is_recv(h->N, 0);
+        for (int32_t g : ri) is_recv[g] = 1;
+        std::vector<int32_t> pre(h->N + 1, 0);
+        for (int64_t g = 0; g < h->N; ++g) pre[g + 1] = pre[g] + is_recv[g];
+        const int64_t n_tiles = h->dm.n_tiles;
+        std::vector<int32_t> indep, dep;
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            const int32_t n0 = h->h_tile_node0[b], n1 = n0 + h->h_tile_nown[b];
+            bool d = pre[n1] - pre[n0] > 0;
+            for (int32_t k = h->h_tile_ext0[b]; !d && k < h->h_tile_ext0[b + 1]; ++k) d = is_recv[h->h_ext_ids[k]];
+            (d ? dep : indep).push_back((int32_t)b);
+        }
+        h->n_tiles_indep = (int32_t)indep.size();
+        indep.insert(indep.end(), dep.begin(), dep.end());
+        if ((rc = fvm_dev_upload(h, &h->d_tile_order, indep))) return rc;
+        h->overlap = n_neigh > 0 && !getenv("FVM_NO_OVERLAP");
+        h->stats[13] = h->n_tiles_indep;
+    }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->halo_ready = true;
     return FVM_OK;
@@ -147,6 +168,44 @@ int32_t fvm_halo_exchange(fvm_ctx* h, double* u_native) {
                                                                                              s->d_recv_buf, u_native);
         FVM_CUDA(h, cudaGetLastError());
     }
+    return FVM_OK;
+}
+
+// Overlapped variant: pack on the compute stream, exchange + unpack on the communication stream.
+// The compute stream keeps running kernels that read no ghost entry until fvm_halo_wait().
+int32_t fvm_halo_begin(fvm_ctx* h, double* u_native) {
+    ShardState* s = (ShardState*)h->shard;
+    if (!s || !h->halo_ready || s->n_neigh == 0) return FVM_OK;
+    if (!s->comm) return fvm_fail(h, FVM_ERR_STATE, "halo exchange needs fvm_shard_init");
+    const int neq = h->neq;
+    if (s->n_send) {
+        halo_pack_kernel<<<(unsigned)((s->n_send * neq + 255) / 256), 256, 0, h->stream>>>(s->d_send_idx, s->n_send, neq, u_native,
+                                                                                           s->d_send_buf);
+        FVM_CUDA(h, cudaGetLastError());
+    }
+    FVM_CUDA(h, cudaEventRecord(s->ev_packed, h->stream));
+    FVM_CUDA(h, cudaStreamWaitEvent(s->comm_stream, s->ev_packed, 0));
+    FVM_NCCL(h, ncclGroupStart());
+    for (int q = 0; q < s->n_neigh; ++q) {
+        const int64_t ns = (int64_t)(s->send_ptr[q + 1] - s->send_ptr[q]) * neq;
+        const int64_t nr = (int64_t)(s->recv_ptr[q + 1] - s->recv_ptr[q]) * neq;
+        if (ns) FVM_NCCL(h, ncclSend(s->d_send_buf + (int64_t)s->send_ptr[q] * neq, ns, ncclDouble, s->neigh[q], s->comm, s->comm_stream));
+        if (nr) FVM_NCCL(h, ncclRecv(s->d_recv_buf + (int64_t)s->recv_ptr[q] * neq, nr, ncclDouble, s->neigh[q], s->comm, s->comm_stream));
+    }
+    FVM_NCCL(h, ncclGroupEnd());
+    if (s->n_recv) {
+        halo_unpack_kernel<<<(unsigned)((s->n_recv * neq + 255) / 256), 256, 0, s->comm_stream>>>(s->d_recv_idx, s->n_recv, neq,
+                                                                                                  s->d_recv_buf, u_native);
+        FVM_CUDA(h, cudaGetLastError());
+    }
+    FVM_CUDA(h, cudaEventRecord(s->ev_done, s->comm_stream));
+    return FVM_OK;
+}
+
+int32_t fvm_halo_wait(fvm_ctx* h) {
+    ShardState* s = (ShardState*)h->shard;
+    if (!s || !h->halo_ready || s->n_neigh == 0) return FVM_OK;
+    FVM_CUDA(h, cudaStreamWaitEvent(h->stream, s->ev_done, 0));
     return FVM_OK;
 }
 

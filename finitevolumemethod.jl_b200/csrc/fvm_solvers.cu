@@ -106,9 +106,8 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
     if ((rc = fvm_launch_permute(h, src, U, true))) return rc;
 
     auto f = [&](double* out, double* x, double t) -> int32_t {
-        int32_t r = fvm_halo_exchange(h, x);  // sharded: refresh the ghost layer of the stage vector
-        if (r) return r;
-        return use_operator ? fvm_launch_spmv(h, x, out, true, false) : fvm_launch_rhs(h, t, x, out);
+        // sharded: the ghost layer of the stage vector is refreshed (overlapped with independent tiles)
+        return use_operator ? fvm_apply_spmv(h, x, out, true, false) : fvm_apply_rhs(h, t, x, out);
     };
     int64_t next_save = 0;
     auto save = [&](double tn) -> int32_t {
@@ -522,9 +521,7 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
         return fvm_allreduce_sum(h, sc + SC_SUM0, nslots);
     };
     auto spmv = [&](double* in, double* out, bool scale) -> int32_t {
-        int32_t r = fvm_halo_exchange(h, in);
-        if (r) return r;
-        return fvm_launch_spmv(h, in, out, false, scale);
+        return fvm_apply_spmv(h, in, out, false, scale);
     };
     double hsc[SC_N];
     auto poll = [&]() -> int32_t {
