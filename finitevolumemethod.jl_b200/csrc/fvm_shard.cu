@@ -121,7 +121,11 @@ extern "C" int32_t fvm_set_halo(fvm_handle h, int32_t n_neigh, const int32_t* ne
         h->n_tiles_indep = (int32_t)indep.size();
         indep.insert(indep.end(), dep.begin(), dep.end());
         if ((rc = fvm_dev_upload(h, &h->d_tile_order, indep))) return rc;
-        h->overlap = n_neigh > 0 && !getenv("FVM_NO_OVERLAP");
+        // measured on 2 B200s at 16.7M nodes per GPU: overlapped 1.133 ms/step vs serialised 1.121 ms/step (the
+        // exchange is ~20 us; a second tile launch and two event waits cost more than they hide), so the
+        // overlapped schedule is opt-in
+        const char* ov = getenv("FVM_HALO_OVERLAP");
+        h->overlap = n_neigh > 0 && ov && ov[0] == '1';
         h->stats[13] = h->n_tiles_indep;
     }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));

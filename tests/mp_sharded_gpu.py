@@ -18,6 +18,7 @@ def main():
     from tests.common import RTOL_RHS, RTOL_TSIT5, rel_err
     from tests.sharding_worker import build_case
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    os.environ.setdefault("FVM_HALO_OVERLAP", "1")  # exercise the overlapped schedule (opt-in) in the parity run
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     errs = {}
