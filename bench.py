@@ -328,6 +328,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-template", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--only-extras", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":

@@ -34,8 +34,8 @@ struct TileOcc {
         return 2;
     }
 };
-template <int MODEL, int NEQ, int GEOM>
-__global__ void __launch_bounds__(RHS_BLOCK, TileOcc<MODEL, NEQ>::template min_blocks<GEOM>())
+template <int MODEL, int NEQ, int GEOM, int OCC = 0>
+__global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::template min_blocks<GEOM>())
     rhs_tile_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t,
                     const double* __restrict__ u, double* __restrict__ du, const int smem_nloc,
                     const int32_t* __restrict__ tile_list, const int tile_off) {
@@ -424,6 +424,10 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
     constexpr bool VOL = (MODEL == MODEL_VOLUME);
     const int32_t smem = rhs_smem_bytes(h, NEQ, VOL, VOL || GEOM == 1);
     auto kern = rhs_tile_kernel<MODEL, NEQ, GEOM>;
+    if constexpr (NEQ == 2 && MODEL == FVM_FLUX_KELLER_SEGEL && GEOM == 0) {
+        static const char* e = getenv("FVM_SYS_MINB");  // experiment knob: 4 resident CTAs (<= 64 registers)
+        if (e && e[0] == '4') kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 4>;
+    }
     if (smem > 200 * 1024) return fvm_fail(h, FVM_ERR_ARG, "tile needs more than 200 KB of shared memory; lower tile_triangles");
     int32_t& configured = h->smem_configured[(const void*)kern];
     if (configured < smem) {

@@ -284,7 +284,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     // default tile size (measured on B200, 4096^2): kernels that stream the full 21-component SoA are
     // register-limited to 3 CTAs/SM and like big tiles; the reduced stream wants 8 small CTAs per SM
     const bool full_flux = h->flux.model == FVM_FLUX_DIFF_POWER || h->flux.model == FVM_FLUX_ADVDIFF || h->flux.model == FVM_FLUX_KELLER_SEGEL;
-    int TT = tile_triangles > 0 ? tile_triangles : ((geometry_mode == 0 && !full_flux) ? 512 : 1024);
+    // (systems: 768 measured best for the 2-species Keller-Segel kernel: 1.20 ms vs 1.45 ms at 1024)
+    int TT = tile_triangles > 0 ? tile_triangles : (neq >= 2 ? 768 : ((geometry_mode == 0 && !full_flux) ? 512 : 1024));
+    if (tile_triangles <= 0)
+        if (const char* e = getenv("FVM_TILE_TRIANGLES")) TT = atoi(e);
     FVM_REQUIRE(h, TT >= 64 && TT <= 4096 && TT % 64 == 0, "fvm_finalize: tile_triangles must be a multiple of 64 in 64..4096");
     FVM_REQUIRE(h, geometry_mode == 0 || geometry_mode == 1, "fvm_finalize: geometry_mode must be 0 or 1");
     if (h->flux.model == FVM_FLUX_DIFF_TABLE && h->h_dtab.empty())
