@@ -27,6 +27,14 @@ sys.path.insert(0, ROOT)
 SEED = 20240517
 
 
+def profiled_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -328,7 +336,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-template", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
-    ap.add_argument("--only-extras", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="skip the 400-launch pre-warm (for ncu captures)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
@@ -385,7 +393,7 @@ def main():
         if name == names[-1]:
             # nvidia-smi needs ~0.3 s to start sampling: keep the GPU under the same load meanwhile.  A FIXED
             # number of calls on EVERY rank: sharded calls contain NCCL send/recv and must pair up across ranks.
-            for _ in range(400):
+            for _ in range(0 if args.quick else 400):
                 eng.rhs_device(du_d.data_ptr(), u_d.data_ptr(), 0.0, native=True)
             eng.synchronize()
         ms, kms = time_rhs(torch, eng, u_d, du_d, args.steps, args.warmup)
@@ -451,7 +459,7 @@ def main():
                    "variant": args.variant, "l2": "inputs larger than L2 (%.2f GB streamed per step vs 126 MB L2)" % (head["alg_bytes"] / 1e9),
                    "tile_triangles": st["tile_triangles"], "n_tiles": st["n_tiles"]},
         "roofline": {"bound": "hbm", "kernel": "rhs_tile_kernel", "achieved": head["kernel_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": head["frac"], "traffic": None, "peak_source": peak_src,
+                     "frac": head["frac"], "traffic": profiled_traffic(args.variant) if nx == 4096 else None, "peak_source": peak_src,
                      "bytes_formula": {"general": "180*T + 25*N", "reduced": "108*T + 25*N", "recompute": "12*T + 41*N"}[head["layout"]],
                      "alg_bytes_per_launch": head["alg_bytes"], "kernel_ms": head["kernel_ms"]},
         "e2e": {"value": world * T / e2e_ms / 1e3, "unit": "Mtriangle-updates/s", "h2d_bytes_per_step": 8 * N,
@@ -463,7 +471,7 @@ def main():
     if tplres:
         line["spmv"] = {"metric": "DiffusionEquation template y = A x + b, fp64 CSR SpMV", "gbs": tplres["spmv_gbs"],
                         "frac": tplres["spmv_frac"], "tile_kernel_ms": tplres["spmv_kernel_ms"], "ms_per_step": tplres["spmv_ms"],
-                        "launches_per_spmv": 2, "format": "sliced ELL per tile, 16-bit tile-local columns, x staged in shared memory",
+                        "launches_per_spmv": 2, "traffic": profiled_traffic("spmv") if nx == 4096 else None, "format": "sliced ELL per tile, 16-bit tile-local columns, x staged in shared memory",
                         "alg_bytes_per_launch": tplres["spmv_alg_bytes"], "bytes_formula": "12*nnz + 4*(N+1) + 24*N",
                         "nnz": tplres["nnz"], "assemble_setup_s": tplres["assemble_setup_s"]}
         line["tsit5"] = {"ms_per_step": tplres["tsit5_ms_per_step"], "steps": tplres["tsit5_steps"], "dt": tplres["tsit5_dt"],
