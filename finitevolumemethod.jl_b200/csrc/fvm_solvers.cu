@@ -216,7 +216,7 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
     return FVM_OK;
 }
 
-// ---- Krylov ----------------------------------------------------------------------------------
+// ---- deterministic reductions (shared by the adaptive stepper and the Krylov solvers) ----------
 #define RED_BLOCKS 1184  // 148 SMs x 8
 #define RED_THREADS 256
 enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_SUM0, SC_SUM1, SC_SUM2, SC_N };
@@ -271,6 +271,191 @@ __global__ void __launch_bounds__(RED_THREADS) reduce_partials_kernel(const doub
 }
 
 #define GRID_STRIDE(i, n) for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (int64_t)gridDim.x * blockDim.x)
+
+// ---- adaptive Tsit5 --------------------------------------------------------------------------
+// Embedded 4th-order error estimate (btilde), OrdinaryDiffEq-style scaled RMS norm and PI step-size
+// controller (beta1 = 7/50, beta2 = 2/25, gamma = 0.9, qmin = 0.2, qmax = 10, no change for
+// 1 <= q <= 1.2).  saveat times are hit exactly (tstops).  SURVEY.md 8f rank 3 / Appendix C; the
+// controller constants live in OrdinaryDiffEq, which is not under /root/reference: parity unpinned.
+static const double TS_BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                                0.5823571654525552,      -0.45808210592918697,   0.015151515151515152};
+
+struct ErrComb {
+    const double* k[7];
+    double c[7];
+};
+
+__global__ void __launch_bounds__(RED_THREADS)
+    tsit5_err_kernel(const int64_t n, const double* __restrict__ u, const double* __restrict__ unew, const double dt,
+                     const ErrComb ec, const double abstol, const double reltol, const uint8_t* __restrict__ skip,
+                     double* __restrict__ partial) {
+    double v[1] = {0.0};
+    GRID_STRIDE(i, n) {
+        double e = ec.c[0] * ec.k[0][i];
+#pragma unroll
+        for (int j = 1; j < 7; ++j) e += ec.c[j] * ec.k[j][i];
+        e *= dt;
+        const double sc = abstol + fmax(fabs(u[i]), fabs(unew[i])) * reltol;
+        const double r = e / sc;
+        if (!skip || !skip[i]) v[0] += r * r;
+    }
+    block_reduce_store<1>(v, partial);
+}
+
+__global__ void __launch_bounds__(RED_THREADS) initdt_kernel(const int64_t n, const double* __restrict__ u, const double* __restrict__ f0,
+                                                             const double abstol, const double reltol, double* __restrict__ partial) {
+    double v[2] = {0.0, 0.0};
+    GRID_STRIDE(i, n) {
+        const double sc = abstol + fabs(u[i]) * reltol;
+        v[0] += (u[i] / sc) * (u[i] / sc);
+        v[1] += (f0[i] / sc) * (f0[i] / sc);
+    }
+    block_reduce_store<2>(v, partial);
+}
+
+extern "C" int32_t fvm_tsit5_adaptive(fvm_handle h, int32_t use_operator, double* u, double t0, double t1, double abstol,
+                                      double reltol, double dt0, int64_t nsave, const double* tsave, double* usave,
+                                      int32_t on_device, int64_t* n_accept, int64_t* n_reject) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, u && t1 >= t0 && abstol > 0 && reltol > 0, "fvm_tsit5_adaptive: bad arguments");
+    FVM_REQUIRE(h, nsave == 0 || (tsave && usave), "fvm_tsit5_adaptive: save buffers missing");
+    if (use_operator && !h->csr.assembled) return fvm_fail(h, FVM_ERR_STATE, "fvm_tsit5_adaptive: call fvm_assemble first");
+    int32_t rc = ensure_work(h, 10);
+    if (rc) return rc;
+    if ((rc = fvm_ensure_state(h))) return rc;
+    const int64_t n = h->N * h->neq;
+    const size_t bytes = sizeof(double) * n;
+    double* U = h->d_work[0];
+    double* K[7];
+    for (int s = 0; s < 7; ++s) K[s] = h->d_work[1 + s];
+    double* TMP = h->d_work[8];
+    double* UNEW = h->d_work[9];
+    double* partial = h->d_red;
+    double* sc = h->d_red + 8 * 2048;
+    cudaStream_t st = h->stream;
+    const double* src = u;
+    if (!on_device) {
+        FVM_CUDA(h, cudaMemcpyAsync(h->d_io, u, bytes, cudaMemcpyHostToDevice, st));
+        src = h->d_io;
+    }
+    if ((rc = fvm_launch_permute(h, src, U, true))) return rc;
+    auto f = [&](double* out, double* x, double t) -> int32_t {
+        return use_operator ? fvm_apply_spmv(h, x, out, true, false) : fvm_apply_rhs(h, t, x, out);
+    };
+    double hs[SC_N];
+    auto sums = [&](int nslots) -> int32_t {  // partials -> sums (all-reduced when sharded) -> host
+        reduce_partials_kernel<<<1, RED_THREADS, 0, st>>>(partial, nslots, sc, 0);
+        int32_t r = fvm_allreduce_sum(h, sc + SC_SUM0, nslots);
+        if (r) return r;
+        FVM_CUDA(h, cudaMemcpyAsync(hs, sc, sizeof(double) * SC_N, cudaMemcpyDeviceToHost, st));
+        FVM_CUDA(h, cudaStreamSynchronize(st));
+        return FVM_OK;
+    };
+    int64_t next_save = 0;
+    auto save = [&](double tn) -> int32_t {
+        while (next_save < nsave && std::fabs(tsave[next_save] - tn) <= 1e-12 * std::max(1.0, std::fabs(tn))) {
+            double* dst = usave + next_save * n;
+            int32_t r = fvm_launch_permute(h, U, on_device ? dst : h->d_io, false);
+            if (r) return r;
+            if (!on_device) {
+                FVM_CUDA(h, cudaMemcpyAsync(dst, h->d_io, bytes, cudaMemcpyDeviceToHost, st));
+                FVM_CUDA(h, cudaStreamSynchronize(st));
+            }
+            ++next_save;
+        }
+        return FVM_OK;
+    };
+    bool has_callback = false;
+    if ((rc = fvm_global_or(h, !use_operator && h->n_dir > 0, &has_callback))) return rc;
+    // sharded: every rank must see the same error norm -> global sums and a global entry count (ghost
+    // entries mirror owned values and are counted on both sides; the RMS weighting absorbs it)
+    double n_glob = (double)n;
+    if (h->nranks > 1) {
+        FVM_CUDA(h, cudaMemcpyAsync(sc + SC_SUM0, &n_glob, sizeof(double), cudaMemcpyHostToDevice, st));
+        if ((rc = fvm_allreduce_sum(h, sc + SC_SUM0, 1))) return rc;
+        FVM_CUDA(h, cudaMemcpyAsync(&n_glob, sc + SC_SUM0, sizeof(double), cudaMemcpyDeviceToHost, st));
+        FVM_CUDA(h, cudaStreamSynchronize(st));
+    }
+    double t = t0;
+    if ((rc = save(t))) return rc;
+    if ((rc = f(K[0], U, t))) return rc;
+    double dt = dt0;
+    if (!(dt > 0)) {  // Hairer's initial step from |u0| and |f(u0)|
+        initdt_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, U, K[0], abstol, reltol, partial);
+        if ((rc = sums(2))) return rc;
+        const double d0 = std::sqrt(hs[SC_SUM0] / n_glob), d1 = std::sqrt(hs[SC_SUM1] / n_glob);
+        dt = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        dt = std::min(dt, t1 - t0);
+    }
+    const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 0.9, qmin = 0.2, qmax = 10.0;
+    double qold = 1e-4;
+    int64_t nacc = 0, nrej = 0;
+    bool have_k1 = true;
+    const double t_eps = 1e-12 * std::max(1.0, std::fabs(t1));
+    while (t < t1 - t_eps) {
+        double tstop = t1;
+        if (next_save < nsave && tsave[next_save] > t + t_eps) tstop = std::min(tstop, tsave[next_save]);
+        bool clipped = false;
+        double dt_try = dt;
+        if (t + dt_try >= tstop - t_eps) {
+            dt_try = tstop - t;
+            clipped = true;
+        }
+        if (!have_k1 && (rc = f(K[0], U, t))) return rc;
+        have_k1 = true;
+        for (int s = 1; s < 6; ++s) {
+            if ((rc = launch_lincomb(h, s, n, TMP, U, dt_try, K, TS_A[s]))) return rc;
+            if ((rc = f(K[s], TMP, t + TS_C[s] * dt_try))) return rc;
+        }
+        if ((rc = launch_lincomb(h, 6, n, UNEW, U, dt_try, K, TS_A[6]))) return rc;
+        if ((rc = f(K[6], UNEW, t + dt_try))) return rc;
+        ErrComb ec{};
+        for (int j = 0; j < 7; ++j) {
+            ec.k[j] = K[j];
+            ec.c[j] = TS_BT[j];
+        }
+        tsit5_err_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, U, UNEW, dt_try, ec, abstol, reltol, nullptr, partial);
+        if ((rc = sums(1))) return rc;
+        const double EEst = std::sqrt(hs[SC_SUM0] / n_glob);
+        if (!(EEst == EEst)) return fvm_fail(h, FVM_ERR_ARG, "fvm_tsit5_adaptive: the error estimate is NaN (unstable step)");
+        // PI controller
+        double q;
+        if (EEst == 0.0) q = 1.0 / qmax;
+        else {
+            const double q11 = std::pow(EEst, beta1);
+            q = q11 / std::pow(qold, beta2);
+            q = std::max(1.0 / qmax, std::min(1.0 / qmin, q / gamma));
+        }
+        if (EEst <= 1.0) {
+            ++nacc;
+            t = clipped ? tstop : t + dt_try;
+            std::swap(U, UNEW);
+            qold = std::max(EEst, 1e-4);
+            double dt_new = dt_try / q;
+            if (dt_new >= dt_try && dt_new <= 1.2 * dt_try) dt_new = dt_try;  // qsteady_min = 1, qsteady_max = 1.2
+            if (!clipped || dt_new < dt) dt = dt_new;
+            if (has_callback) {
+                if ((rc = fvm_launch_dirichlet(h, t, U))) return rc;
+                have_k1 = false;
+            } else {
+                std::swap(K[0], K[6]);
+            }
+            if ((rc = save(t))) return rc;
+        } else {
+            ++nrej;
+            dt = dt_try / std::min(1.0 / qmin, q);
+            if (nrej > 100000) return fvm_fail(h, FVM_ERR_ARG, "fvm_tsit5_adaptive: too many rejected steps");
+        }
+    }
+    if ((rc = fvm_launch_permute(h, U, on_device ? u : h->d_io, false))) return rc;
+    if (!on_device) FVM_CUDA(h, cudaMemcpyAsync(u, h->d_io, bytes, cudaMemcpyDeviceToHost, st));
+    FVM_CUDA(h, cudaStreamSynchronize(st));
+    if (n_accept) *n_accept = nacc;
+    if (n_reject) *n_reject = nrej;
+    return FVM_OK;
+}
+
+// ---- Krylov ----------------------------------------------------------------------------------
 
 // PCG -------------------------------------------------------------------------------------------
 __global__ void pcg_init1_kernel(int64_t n, const double* b, const double* rowscale, double* x) {

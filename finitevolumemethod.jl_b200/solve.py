@@ -3,7 +3,7 @@ import numpy as np
 
 from . import _lib as L
 from .problem import FVMProblem, FVMSystem, SteadyFVMProblem, get_cuda_parameters
-from .templates import AbstractFVMTemplate, Solution, Tsit5, solve_template
+from .templates import AbstractFVMTemplate, Solution, Tsit5, run_tsit5, solve_template
 
 
 def solve(prob, alg=None, *, saveat=None, parallel="cuda", p=None, **kw):
@@ -24,13 +24,12 @@ def solve(prob, alg=None, *, saveat=None, parallel="cuda", p=None, **kw):
     if parallel != "cuda":
         raise ValueError("this package only provides the CUDA path (no CPU fallback)")
     if not isinstance(alg, Tsit5):
-        raise TypeError("only Tsit5(dt) runs on the device; other integrators call fvm_eqs through get_cuda_parameters")
+        raise TypeError("only Tsit5 runs on the device; other integrators call fvm_eqs through get_cuda_parameters")
     p = p or get_cuda_parameters(prob, **kw)
     u = np.ascontiguousarray(prob.initial_condition, dtype=np.float64).copy()
     ts = np.ascontiguousarray([] if saveat is None else saveat, dtype=np.float64)
     us = np.empty((len(ts),) + u.shape)
-    L.check(p.engine.h, L.lib().fvm_tsit5(p.engine.h, 0, u.ctypes.data, prob.initial_time, prob.final_time, alg.dt, len(ts),
-                                          L.dp(ts) if len(ts) else None, us.ctypes.data if len(ts) else None, 0))
+    run_tsit5(p.engine.h, alg, False, u, prob.initial_time, prob.final_time, ts, us)
     if saveat is None:
         return Solution(u, prob.final_time)
     return Solution(list(us), ts)

@@ -41,12 +41,32 @@ def _eval_xy(fn, x, y, p):
 
 
 class Tsit5:
-    """solve(prob, Tsit5(); adaptive=false, dt=dt) -- the fixed-step integrator of north_star (c)."""
+    """Device-resident Tsit5.  `Tsit5(dt)` is `solve(prob, Tsit5(); adaptive=false, dt=dt)`, the
+    fixed-step integrator of north_star (c); `Tsit5()` / `Tsit5(abstol=, reltol=)` is the adaptive
+    `solve(prob, Tsit5(); abstol, reltol, saveat)` with OrdinaryDiffEq's default tolerances."""
 
-    def __init__(self, dt, adaptive=False):
-        if adaptive:
-            raise NotImplementedError("only the fixed-step Tsit5 is device-resident (SURVEY 8f rank 3)")
-        self.dt = float(dt)
+    def __init__(self, dt=None, adaptive=None, abstol=1e-6, reltol=1e-3):
+        self.adaptive = (dt is None) if adaptive is None else bool(adaptive)
+        if not self.adaptive and dt is None:
+            raise ValueError("fixed-step Tsit5 needs dt")
+        self.dt = None if dt is None else float(dt)
+        self.abstol, self.reltol = float(abstol), float(reltol)
+        self.naccept = self.nreject = None
+
+
+def run_tsit5(h, alg, use_operator, u, t0, t1, ts, us):
+    """Dispatches to the fixed-step or the adaptive device stepper; u is updated in place."""
+    lib = L.lib()
+    nts = len(ts)
+    if alg.adaptive:
+        na, nr = C.c_int64(), C.c_int64()
+        L.check(h, lib.fvm_tsit5_adaptive(h, 1 if use_operator else 0, u.ctypes.data, t0, t1, alg.abstol, alg.reltol,
+                                          alg.dt or 0.0, nts, L.dp(ts) if nts else None, us.ctypes.data if nts else None, 0,
+                                          C.byref(na), C.byref(nr)))
+        alg.naccept, alg.nreject = na.value, nr.value
+    else:
+        L.check(h, lib.fvm_tsit5(h, 1 if use_operator else 0, u.ctypes.data, t0, t1, alg.dt, nts, L.dp(ts) if nts else None,
+                                 us.ctypes.data if nts else None, 0))
 
 
 class KrylovJacobi:
@@ -223,8 +243,7 @@ def solve_template(prob, alg=None, saveat=None, x0=None):
     u = prob.u0.copy()
     ts = np.ascontiguousarray([] if saveat is None else saveat, dtype=np.float64)
     us = np.empty((len(ts), prob.N))
-    L.check(h, lib.fvm_tsit5(h, 1, u.ctypes.data, prob.initial_time, prob.final_time, alg.dt, len(ts), L.dp(ts) if len(ts) else None,
-                             us.ctypes.data if len(ts) else None, 0))
+    run_tsit5(h, alg, True, u, prob.initial_time, prob.final_time, ts, us)
     # the reference's state is augmented by a trailing 1 that carries b (diffusion_equation.jl:82-94)
     if saveat is None:
         return Solution(np.append(u, 1.0), prob.final_time)

@@ -175,6 +175,13 @@ int32_t fvm_spmv_native(fvm_handle h, const double* x_native, double* y_native, 
 int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, double t0, double t1, double dt,
                   int64_t nsave, const double* tsave, double* usave, int32_t on_device);
 
+/* Adaptive Tsit5 (solve(prob, Tsit5(); abstol, reltol, saveat)): embedded error estimate, PI step
+ * controller with OrdinaryDiffEq's constants, saveat times hit exactly.  dt0 <= 0 selects the initial
+ * step automatically.  Returns the accepted / rejected step counts. */
+int32_t fvm_tsit5_adaptive(fvm_handle h, int32_t use_operator, double* u, double t0, double t1, double abstol,
+                           double reltol, double dt0, int64_t nsave, const double* tsave, double* usave,
+                           int32_t on_device, int64_t* n_accept, int64_t* n_reject);
+
 /* Steady templates: solves A x = b with Jacobi-preconditioned CG (on the symmetrised system
  * -V A, Dirichlet-consistent start) or BiCGStab.  x: in initial guess, out solution. */
 int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rtol, int32_t maxit, int32_t* iters,

@@ -984,3 +984,96 @@ def tsit5_fixed(f, u0, t0, t1, dt, callback=None, fsal=True, saveat=None):
     if saveat is not None:
         return u, saves
     return u
+
+
+TSIT5_BTILDE = (-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                0.5823571654525552, -0.45808210592918697, 0.015151515151515152)
+
+
+def tsit5_adaptive(f, u0, t0, t1, abstol=1e-6, reltol=1e-3, dt0=None, callback=None, saveat=None):
+    """Adaptive Tsit5 with the embedded error estimate, OrdinaryDiffEq's scaled RMS norm and PI
+    controller (beta1 = 7/50, beta2 = 2/25, gamma = 0.9, qmin = 0.2, qmax = 10, qsteady in [1, 1.2]),
+    Hairer's initial step, saveat times as tstops.  The controller lives in OrdinaryDiffEq (absent
+    from /root/reference): parity unpinned; this restates the documented algorithm.
+    Returns (u(t1), saves, n_accept, n_reject)."""
+    u = np.array(u0, dtype=np.float64)
+    n = u.size
+    k = [np.zeros_like(u) for _ in range(7)]
+    t = t0
+    saves = []
+    saveat = list(saveat or [])
+    nxt = 0
+    eps_t = 1e-12 * max(1.0, abs(t1))
+
+    def do_save():
+        nonlocal nxt
+        while nxt < len(saveat) and abs(saveat[nxt] - t) <= 1e-12 * max(1.0, abs(t)):
+            saves.append(u.copy())
+            nxt += 1
+
+    do_save()
+    f(k[0], u, t)
+    if dt0 is None or dt0 <= 0:
+        sc = abstol + np.abs(u) * reltol
+        d0 = math.sqrt(np.sum((u / sc) ** 2) / n)
+        d1 = math.sqrt(np.sum((k[0] / sc) ** 2) / n)
+        dt = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+        dt = min(dt, t1 - t0)
+    else:
+        dt = dt0
+    beta1, beta2, gamma, qmin, qmax = 7 / 50, 2 / 25, 0.9, 0.2, 10.0
+    qold = 1e-4
+    nacc = nrej = 0
+    have_k1 = True
+    while t < t1 - eps_t:
+        tstop = t1
+        if nxt < len(saveat) and saveat[nxt] > t + eps_t:
+            tstop = min(tstop, saveat[nxt])
+        clipped = False
+        h = dt
+        if t + h >= tstop - eps_t:
+            h = tstop - t
+            clipped = True
+        if not have_k1:
+            f(k[0], u, t)
+        have_k1 = True
+        for s in range(1, 6):
+            acc = TSIT5_A[s][0] * k[0]
+            for j in range(1, s):
+                acc = acc + TSIT5_A[s][j] * k[j]
+            f(k[s], u + h * acc, t + TSIT5_C[s] * h)
+        acc = TSIT5_A[6][0] * k[0]
+        for j in range(1, 6):
+            acc = acc + TSIT5_A[6][j] * k[j]
+        unew = u + h * acc
+        f(k[6], unew, t + h)
+        e = TSIT5_BTILDE[0] * k[0]
+        for j in range(1, 7):
+            e = e + TSIT5_BTILDE[j] * k[j]
+        e = e * h
+        sc = abstol + np.maximum(np.abs(u), np.abs(unew)) * reltol
+        EEst = math.sqrt(np.sum((e / sc) ** 2) / n)
+        if EEst == 0.0:
+            q = 1.0 / qmax
+        else:
+            q = EEst ** beta1 / qold ** beta2
+            q = max(1.0 / qmax, min(1.0 / qmin, q / gamma))
+        if EEst <= 1.0:
+            nacc += 1
+            t = tstop if clipped else t + h
+            u = unew
+            qold = max(EEst, 1e-4)
+            dt_new = h / q
+            if h <= dt_new <= 1.2 * h:
+                dt_new = h
+            if (not clipped) or dt_new < dt:
+                dt = dt_new
+            if callback is not None and callback(u, t):
+                have_k1 = False
+            else:
+                k[0], k[6] = k[6], k[0]
+            do_save()
+        else:
+            nrej += 1
+            dt = h / min(1.0 / qmin, q)
+    return u, saves, nacc, nrej

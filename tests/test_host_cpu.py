@@ -136,5 +136,6 @@ def test_template_argument_errors_mirror_the_reference():
         G.MeanExitTimeProblem(mesh, dudt, diffusion_function=1.0)
     with pytest.raises(ValueError, match="MeanExitTimeProblem does not support Constrained edges"):
         G.MeanExitTimeProblem(mesh, cons, diffusion_function=1.0)
-    with pytest.raises(NotImplementedError):
-        G.Tsit5(0.1, adaptive=True)
+    with pytest.raises(ValueError):
+        G.Tsit5(adaptive=False)
+    assert G.Tsit5().adaptive and not G.Tsit5(0.1).adaptive

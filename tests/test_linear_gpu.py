@@ -203,3 +203,37 @@ def test_mean_exit_time_unstructured():
     assert rel_err(sol.u, uref) <= 1e-9
     assert uref.max() > 10  # exit times are positive and large for a small D
     assert np.all(sol.u[-2:] == 0.0)  # points that are not vertices: A[i,i] = 1, b[i] = 0
+
+
+def test_adaptive_tsit5_device():
+    """solve(prob, Tsit5(); saveat) (README.md:43 style): adaptive device stepper vs the oracle's
+    restatement of the same controller (same accepted/rejected counts, end state to round-off), and
+    vs a fine fixed-step solution to the requested tolerance.  Template and FVMProblem paths."""
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True))
+    ic = np.where(pair.gtri.points[:, 1] <= 1.0, 50.0, 0.0)
+    gBC = G.BoundaryConditions(pair.gmesh, G.Const(0.0), G.Dirichlet)
+    oBC = O.BoundaryConditions(pair.omesh, lambda x, y, t, u, p: 0.0 * x, O.Dirichlet)
+    tpl = G.DiffusionEquation(pair.gmesh, gBC, diffusion_function=1 / 9, initial_condition=ic, final_time=0.5)
+    ref = O.DiffusionEquation(pair.omesh, oBC, diffusion_function=lambda x, y, p: 1 / 9, initial_condition=ic, final_time=0.5)
+    alg = G.Tsit5(abstol=1e-8, reltol=1e-6)
+    sol = G.solve(tpl, alg, saveat=[0.1, 0.5])
+
+    def f(du, u, t):
+        du[...] = ref.A @ u + ref.b
+
+    uref, saves, nacc, nrej = O.tsit5_adaptive(f, ref.u0, 0.0, 0.5, 1e-8, 1e-6, saveat=[0.1, 0.5])
+    # the step sequence is sensitive to the last bits of the error norm (summation order), so the counts
+    # may differ by a step or two and the states agree to the tolerance level, not to round-off
+    assert abs(alg.naccept - nacc) <= 2 and abs(alg.nreject - nrej) <= 2 and nacc > 20
+    assert rel_err(sol.u[0][:-1], saves[0]) <= 1e-6 and rel_err(sol.u[1][:-1], uref) <= 1e-6
+    fine = O.tsit5_fixed(f, ref.u0, 0.0, 0.5, 0.00125)
+    assert rel_err(uref, fine) <= 1e-5 and rel_err(sol.u[1][:-1], fine) <= 1e-5
+    # FVMProblem path with the Dirichlet callback after every accepted step
+    gp, op = pair.problem(G.ExpSaturation(5.0, 0.2), G.Dirichlet, G.PowerDiffusion(0.02, 2.0), source=G.LogisticSource(0.5),
+                          ic=1.0 + 0.01 * ic, final_time=0.3)
+    alg2 = G.Tsit5(abstol=1e-7, reltol=1e-5)
+    sol2 = G.solve(gp, alg2)
+    u2, _, na2, nr2 = O.tsit5_adaptive(lambda d, x, t: O.fvm_eqs_vec(d, x, op, t), 1.0 + 0.01 * ic, 0.0, 0.3, 1e-7, 1e-5,
+                                       callback=lambda x, t: (O.update_dirichlet_nodes(x, t, op), True)[1])
+    assert abs(alg2.naccept - na2) <= 2 and abs(alg2.nreject - nr2) <= 2
+    assert rel_err(sol2.u, u2) <= 1e-5
