@@ -101,10 +101,77 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return r;
 }
 
+// ---- forward-mode dual numbers: the analytic Jacobian of fvm_eqs! reuses the flux / source /
+// condition registry below unchanged
+template <int K>
+struct Dual {
+    double v;
+    double d[K];
+    __device__ __forceinline__ Dual() {}
+    __device__ __forceinline__ Dual(double c) : v(c) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) d[k] = 0.0;
+    }
+};
+#define DUAL_BIN(op, vexpr, dexpr)                                                            \
+    template <int K>                                                                          \
+    __device__ __forceinline__ Dual<K> operator op(const Dual<K>& a, const Dual<K>& b) {      \
+        Dual<K> r;                                                                            \
+        r.v = vexpr;                                                                          \
+        _Pragma("unroll") for (int k = 0; k < K; ++k) r.d[k] = dexpr;                         \
+        return r;                                                                             \
+    }
+DUAL_BIN(+, a.v + b.v, a.d[k] + b.d[k])
+DUAL_BIN(-, a.v - b.v, a.d[k] - b.d[k])
+DUAL_BIN(*, a.v * b.v, a.d[k] * b.v + a.v * b.d[k])
+#undef DUAL_BIN
+template <int K> __device__ __forceinline__ Dual<K> operator+(const Dual<K>& a, double b) { Dual<K> r = a; r.v += b; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator+(double b, const Dual<K>& a) { return a + b; }
+template <int K> __device__ __forceinline__ Dual<K> operator-(const Dual<K>& a, double b) { Dual<K> r = a; r.v -= b; return r; }
+template <int K> __device__ __forceinline__ Dual<K> operator-(const Dual<K>& a) {
+    Dual<K> r;
+    r.v = -a.v;
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.d[k] = -a.d[k];
+    return r;
+}
+template <int K> __device__ __forceinline__ Dual<K> operator-(double b, const Dual<K>& a) { return (-a) + b; }
+template <int K> __device__ __forceinline__ Dual<K> operator*(const Dual<K>& a, double b) {
+    Dual<K> r;
+    r.v = a.v * b;
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.d[k] = a.d[k] * b;
+    return r;
+}
+template <int K> __device__ __forceinline__ Dual<K> operator*(double b, const Dual<K>& a) { return a * b; }
+template <int K> __device__ __forceinline__ Dual<K> operator/(const Dual<K>& a, double b) { return a * (1.0 / b); }
+
+__device__ __forceinline__ double fabs_t(double x) { return fabs(x); }
+__device__ __forceinline__ double pow_t(double x, double e) { return pow(x, e); }
+__device__ __forceinline__ double exp_t(double x) { return exp(x); }
+template <int K> __device__ __forceinline__ Dual<K> fabs_t(const Dual<K>& a) { return a.v < 0.0 ? -a : a; }
+template <int K> __device__ __forceinline__ Dual<K> pow_t(const Dual<K>& a, double e) {
+    Dual<K> r;
+    r.v = pow(a.v, e);
+    const double g = e * pow(a.v, e - 1.0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.d[k] = g * a.d[k];
+    return r;
+}
+
+template <int K> __device__ __forceinline__ Dual<K> fast_rcp(const Dual<K>& a) {
+    Dual<K> r;
+    r.v = 1.0 / a.v;
+    const double g = -r.v * r.v;
+#pragma unroll
+    for (int k = 0; k < K; ++k) r.d[k] = g * a.d[k];
+    return r;
+}
+
 // ---- flux registry: q(x, y, t, alpha, beta, gamma, p), src/problem.jl:113-116, 425-440 ----
-template <int MODEL, int NEQ>
-__device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double y, double t, const double* a,
-                                          const double* b, const double* g, double dtab, double* qx, double* qy) {
+template <int MODEL, int NEQ, class T>
+__device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double y, double t, const T* a, const T* b, const T* g,
+                                          double dtab, T* qx, T* qy) {
     if constexpr (MODEL == FVM_FLUX_DIFF_CONST) {
 #pragma unroll
         for (int v = 0; v < NEQ; ++v) {
@@ -120,21 +187,21 @@ __device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double
     } else if constexpr (MODEL == FVM_FLUX_DIFF_POWER) {
 #pragma unroll
         for (int v = 0; v < NEQ; ++v) {
-            const double u = a[v] * x + b[v] * y + g[v];
+            const T u = a[v] * x + b[v] * y + g[v];
             const double D0 = fp.p[3 * v], mm = fp.p[3 * v + 1];
-            const double base = fp.p[3 * v + 2] != 0.0 ? fabs(u) : u;
-            double D;
-            if (mm == 1.0) D = D0;
+            const T base = fp.p[3 * v + 2] != 0.0 ? fabs_t(u) : u;
+            T D;
+            if (mm == 1.0) D = T(D0);
             else if (mm == 2.0) D = D0 * base;
             else if (mm == 3.0) D = D0 * base * base;
-            else D = D0 * pow(base, mm - 1.0);
-            qx[v] = -D * a[v];
-            qy[v] = -D * b[v];
+            else D = D0 * pow_t(base, mm - 1.0);
+            qx[v] = -(D * a[v]);
+            qy[v] = -(D * b[v]);
         }
     } else if constexpr (MODEL == FVM_FLUX_ADVDIFF) {
 #pragma unroll
         for (int v = 0; v < NEQ; ++v) {
-            const double u = a[v] * x + b[v] * y + g[v];
+            const T u = a[v] * x + b[v] * y + g[v];
             const double D = fp.p[3 * v];
             qx[v] = fp.p[3 * v + 1] * u - D * a[v];
             qy[v] = fp.p[3 * v + 2] * u - D * b[v];
@@ -142,8 +209,8 @@ __device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double
     } else if constexpr (MODEL == FVM_FLUX_KELLER_SEGEL) {
         // src/FiniteVolumeMethod.jl:98-110 : q_u = chi(u) grad v - grad u ; q_v = -D grad v
         static_assert(NEQ == 2 || MODEL != FVM_FLUX_KELLER_SEGEL, "Keller-Segel is a 2-species model");
-        const double u = a[0] * x + b[0] * y + g[0];
-        const double chi = fp.p[0] * u * fast_rcp(1.0 + u * u);
+        const T u = a[0] * x + b[0] * y + g[0];
+        const T chi = fp.p[0] * u * fast_rcp(u * u + 1.0);
         qx[0] = chi * a[1] - a[0];
         qy[0] = chi * b[1] - b[0];
         qx[1] = -fp.p[1] * a[1];
@@ -159,26 +226,39 @@ struct FluxTraits {
 };
 
 // ---- sources S(x, y, t, u, p), src/problem.jl:10-13, 342-345 -------------------------------
-template <int NEQ>
-__device__ __forceinline__ double source_eval(const SourceParams& sp, int v, const double* u, const double* tab) {
+template <int NEQ, class T>
+__device__ __forceinline__ T source_eval_t(const SourceParams& sp, int v, const T* u, const double* tab) {
     switch (sp.model) {
         case FVM_SRC_LINEAR: return sp.p[2 * v] * u[v] + sp.p[2 * v + 1];
         case FVM_SRC_LOGISTIC: return sp.p[v] * u[v] * (1.0 - u[v]);
-        case FVM_SRC_TABLE: return tab[v];
+        case FVM_SRC_TABLE: return T(tab[v]);
         case FVM_SRC_GRAY_SCOTT:
-            if constexpr (NEQ >= 2) return v == 0 ? sp.p[0] * (1.0 - u[0]) - u[0] * (u[1] * u[1]) : -sp.p[1] * u[1] + u[0] * (u[1] * u[1]);
-            return 0.0;
+            if constexpr (NEQ >= 2) return v == 0 ? sp.p[0] * (1.0 - u[0]) - u[0] * (u[1] * u[1]) : -(sp.p[1] * u[1]) + u[0] * (u[1] * u[1]);
+            return T(0.0);
         case FVM_SRC_BRUSSELATOR:
-            if constexpr (NEQ >= 2) return v == 0 ? (u[0] * u[0]) * u[1] - 2.0 * u[0] : -(u[0] * u[0]) * u[1] + u[0];
-            return 0.0;
+            if constexpr (NEQ >= 2) return v == 0 ? (u[0] * u[0]) * u[1] - 2.0 * u[0] : -((u[0] * u[0]) * u[1]) + u[0];
+            return T(0.0);
         case FVM_SRC_KELLER_SEGEL:
             if constexpr (NEQ >= 2) return v == 0 ? u[0] * (1.0 - u[0]) : u[0] - sp.p[0] * u[1];
-            return 0.0;
-        default: return 0.0;  // zero(eltype(u)), src/problem.jl:123
+            return T(0.0);
+        default: return T(0.0);  // zero(eltype(u)), src/problem.jl:123
     }
+}
+template <int NEQ>
+__device__ __forceinline__ double source_eval(const SourceParams& sp, int v, const double* u, const double* tab) {
+    return source_eval_t<NEQ, double>(sp, v, u, tab);
 }
 
 // ---- condition functions a(x, y, t, u, p), src/conditions.jl:16-20 -------------------------
+template <class T>
+__device__ __forceinline__ T cond_eval_t(const CondFn& c, double x, double y, double t, const T& u) {
+    switch (c.id) {
+        case FVM_COND_AFFINE_U: return c.p[1] * u + c.p[0];
+        case FVM_COND_EXP_SAT: return T(c.p[0] * (1.0 - exp(-t / c.p[1])));
+        case FVM_COND_LINEAR_XY: return T(c.p[0] + c.p[1] * x + c.p[2] * y);
+        default: return T(c.p[0]);
+    }
+}
 __device__ __forceinline__ double cond_eval(const CondFn& c, double x, double y, double t, double u) {
     switch (c.id) {
         case FVM_COND_AFFINE_U: return c.p[0] + c.p[1] * u;

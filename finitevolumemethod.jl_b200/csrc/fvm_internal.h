@@ -172,6 +172,11 @@ struct fvm_ctx {
     bool profiling = false;
     std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
     int64_t prof_used = 0;
+    // sparse Jacobian (fvm_jacobian.cu): block values on the CSR pattern, boundary edges by node
+    double* jac_val = nullptr;
+    void* jac_edges = nullptr;
+    int32_t *jac_bn_of = nullptr, *jac_bn_ptr = nullptr, *jac_bn_items = nullptr;
+    bool jac_ready = false;
     // sharding (fvm_shard.cu)
     void* shard = nullptr;
     bool halo_ready = false;

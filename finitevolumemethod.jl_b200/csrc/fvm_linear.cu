@@ -473,7 +473,7 @@ int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* y, bool add_b, bool scale)
         FVM_CUDA(h, cudaSetDevice((h)->device));                                            \
     } while (0)
 
-static int32_t build_pattern(fvm_ctx* h) {
+int32_t fvm_build_pattern(fvm_ctx* h) {
     Csr& c = h->csr;
     if (c.pattern) return FVM_OK;
     const int64_t N = h->N, T = h->T;
@@ -649,7 +649,7 @@ extern "C" int32_t fvm_assemble(fvm_handle h, int32_t template_id, double d_cons
         return fvm_fail(h, FVM_ERR_ARG, "MeanExitTimeProblem does not support Constrained edges.");
     FVM_REQUIRE(h, d_cv_edge == nullptr || d_bnd != nullptr || Eb == 0 || template_id == FVM_TPL_MEAN_EXIT_TIME,
                 "fvm_assemble: tabulated D needs the boundary quarter-point table too");
-    int32_t rc = build_pattern(h);
+    int32_t rc = fvm_build_pattern(h);
     if (rc) return rc;
     Csr& c = h->csr;
     std::vector<void*> temps;

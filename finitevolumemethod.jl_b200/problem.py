@@ -391,3 +391,31 @@ def fvm_eqs(du, u, p, t):
 def update_dirichlet_nodes(u, t, p):
     """update_dirichlet_nodes!(integrator) (dirichlet.jl:78-86)."""
     return p.engine.apply_dirichlet(u, t)
+
+
+def _jac_csr(p, with_values):
+    import scipy.sparse as sp
+    h = p.engine.h
+    n, nnz = C.c_int64(), C.c_int64()
+    L.check(h, L.lib().fvm_get_jacobian_size(h, C.byref(n), C.byref(nnz)))
+    rowptr = np.empty(n.value + 1, np.int32)
+    col = np.empty(nnz.value, np.int32)
+    val = np.empty(nnz.value) if with_values else None
+    L.check(h, L.lib().fvm_get_jacobian_csr(h, L.ip(rowptr), L.ip(col), L.dp(val)))
+    if val is None:
+        val = np.ones(nnz.value)
+    return sp.csr_matrix((val, col, rowptr), shape=(n.value, n.value))
+
+
+def jacobian_sparsity(p):
+    """jacobian_sparsity(prob) (solve.jl:50-131): the prototype (ones on the structural pattern); for an
+    FVMSystem rows/columns are node-major interleaved, (i-1)*neq + l in the reference's 1-based terms."""
+    return _jac_csr(p, False)
+
+
+def jacobian(u, p, t):
+    """Sparse Jacobian of fvm_eqs! at (u, t) as a SciPy CSR matrix, assembled on the device with exact
+    derivatives (what the reference obtains by pushing ForwardDiff duals through fvm_eqs!, solve.jl:5)."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    L.check(p.engine.h, L.lib().fvm_jacobian(p.engine.h, float(t), u.ctypes.data, 0))
+    return _jac_csr(p, True)

@@ -187,6 +187,14 @@ int32_t fvm_tsit5_adaptive(fvm_handle h, int32_t use_operator, double* u, double
 int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rtol, int32_t maxit, int32_t* iters,
                    double* relres, int32_t on_device);
 
+/* ---- sparse Jacobian of fvm_eqs! (jacobian_sparsity, src/solve.jl:56-131) ------------------------ */
+/* J = d(du)/du at (u, t), exact derivatives of the registered flux / source / condition functions
+ * (forward-mode duals on the device); pattern = jacobian_sparsity, systems node-major interleaved. */
+int32_t fvm_jacobian(fvm_handle h, double t, const double* u, int32_t on_device);
+int32_t fvm_get_jacobian_size(fvm_handle h, int64_t* n_rows, int64_t* nnz);
+/* caller numbering; val may be NULL to fetch the pattern only (the jac_prototype of solve.jl:170) */
+int32_t fvm_get_jacobian_csr(fvm_handle h, int32_t* rowptr, int32_t* col, double* val);
+
 /* ---- multi-GPU: node partition + one-layer ghost halo per rank ---------------- */
 /* Each rank creates its handle on the LOCAL mesh: owned nodes + ghost nodes, and every triangle that
  * touches an owned node.  Call order: fvm_create, setters, fvm_set_ghost_nodes, fvm_finalize,

@@ -184,3 +184,44 @@ def test_determinism_and_midsize_lattice():
     Fw = G.fvm_eqs(np.zeros_like(u), w, p, 0.0)
     Fc = G.fvm_eqs(np.zeros_like(u), 2.0 * u - 3.0 * w, p, 0.0)
     assert rel_err(Fc, 2.0 * Fu - 3.0 * Fw) <= 1e-12
+
+
+def test_sparse_jacobian_matches_finite_differences():
+    """d(fvm_eqs!)/du on the device (exact duals) vs central differences of the ORACLE right-hand side,
+    and its pattern vs jacobian_sparsity (solve.jl:56-131), scalar and FVMSystem."""
+    gtri = _split_loop(delaunay_mesh(600, 31, extra_points=2))
+    pair = Pair(gtri)
+    N = gtri.num_points
+    rng = np.random.default_rng(17)
+    specs = (G.Const(0.25), G.AffineU(0.1, -0.5), G.AffineU(0.3, 0.7), G.Const(0.0))
+    types = (G.Dirichlet, G.Dudt, G.Neumann, G.Constrained)
+    cases = [(G.PowerDiffusion(0.3, 2.5, use_abs=True), G.LogisticSource(1.3)), (G.AdvectionDiffusionFlux(0.02, 0.5, -0.3), G.LinearSource(-0.2, 0.1)),
+             (G.TabulatedDiffusion(lambda x, y: 1.0 + x * y), None)]
+    for flux, src in cases:
+        gp, op = pair.problem(specs, types, flux, source=src)
+        p = G.get_cuda_parameters(gp, tile_triangles=128)
+        u = 0.5 + rng.random(N)
+        J = G.jacobian(u, p, 0.2)
+        r, c = O.jacobian_sparsity(pair.otri)
+        P = G.jacobian_sparsity(p)
+        assert P.nnz == len(r) and (P[r, c] == 1).all()
+        v = rng.standard_normal(N)
+        eps = 1e-6
+        fd = (O.fvm_eqs_vec(np.zeros(N), u + eps * v, op, 0.2) - O.fvm_eqs_vec(np.zeros(N), u - eps * v, op, 0.2)) / (2 * eps)
+        assert rel_err(J @ v, fd) <= 1e-6
+    # FVMSystem: Keller-Segel flux + sources, Robin Neumann edge on species 1, Dirichlet on species 0
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 17, 13, single_boundary=True))
+    N = pair.gtri.num_points
+    U = np.ascontiguousarray(np.stack([0.5 + 0.5 * rng.random(N), 0.25 * rng.random(N)], axis=1))
+    ks, kss = G.KellerSegelFlux(4.0, 1.0), G.KellerSegelSource(0.1)
+    g1, o1 = pair.problem(G.Const(0.3), G.Dirichlet, ks, source=kss, var=0, ic=U[:, 0])
+    g2, o2 = pair.problem(G.AffineU(0.01, -0.2), G.Neumann, ks, source=kss, var=1, ic=U[:, 1])
+    gs, os_ = G.FVMSystem(g1, g2), O.FVMSystem(o1, o2)
+    p = G.get_cuda_parameters(gs, tile_triangles=128)
+    J = G.jacobian(U, p, 0.0)
+    r, c = O.jacobian_sparsity(pair.otri, 2)
+    assert J.shape == (2 * N, 2 * N) and G.jacobian_sparsity(p).nnz == len(r)
+    V = rng.standard_normal((N, 2))
+    eps = 1e-6
+    fd = (O.fvm_eqs_vec(np.zeros_like(U), U + eps * V, os_, 0.0) - O.fvm_eqs_vec(np.zeros_like(U), U - eps * V, os_, 0.0)) / (2 * eps)
+    assert rel_err((J @ V.ravel()).reshape(N, 2), fd) <= 1e-6
