@@ -50,12 +50,19 @@ __device__ __forceinline__ void tri_geometry(double px, double py, double qx, do
         S[1] = 0.5 * fabs(A::sub(A::mul(qcx, m21y), A::mul(qcy, m21x)));
         S[2] = 0.5 * fabs(A::sub(A::mul(rcx, m32y), A::mul(rcy, m32x)));
     }
-    // Delta = qx*ry - qy*rx - px*ry + rx*py + px*qy - qx*py   (left to right)
-    double D = A::sub(A::mul(qx, ry), A::mul(qy, rx));
-    D = A::sub(D, A::mul(px, ry));
-    D = A::add(D, A::mul(rx, py));
-    D = A::add(D, A::mul(px, qy));
-    D = A::sub(D, A::mul(qx, py));
+    // Delta = qx*ry - qy*rx - px*ry + rx*py + px*qy - qx*py   (left to right).  Delta and the numerators
+    // of s7..s9 cancel catastrophically in absolute coordinates (relative error ~ eps * |x|^2 / area:
+    // 1e-11 at h = 2e-3, 1e-9 on the 4096^2 lattice), so they are ALWAYS evaluated with the reference's
+    // individually rounded operations -- a contracted FMA would change the result at that level.
+    using E = Ar<true>;
+    double D = E::sub(E::mul(qx, ry), E::mul(qy, rx));
+    D = E::sub(D, E::mul(px, ry));
+    D = E::add(D, E::mul(rx, py));
+    D = E::add(D, E::mul(px, qy));
+    D = E::sub(D, E::mul(qx, py));
+    const double n7 = E::sub(E::mul(qx, ry), E::mul(rx, qy));
+    const double n8 = E::sub(E::mul(rx, py), E::mul(px, ry));
+    const double n9 = E::sub(E::mul(px, qy), E::mul(qx, py));
     if constexpr (EXACT) {
         G.s[0] = A::div(A::sub(qy, ry), D);
         G.s[1] = A::div(A::sub(ry, py), D);
@@ -63,20 +70,20 @@ __device__ __forceinline__ void tri_geometry(double px, double py, double qx, do
         G.s[3] = A::div(A::sub(rx, qx), D);
         G.s[4] = A::div(A::sub(px, rx), D);
         G.s[5] = A::div(A::sub(qx, px), D);
-        G.s[6] = A::div(A::sub(A::mul(qx, ry), A::mul(rx, qy)), D);
-        G.s[7] = A::div(A::sub(A::mul(rx, py), A::mul(px, ry)), D);
-        G.s[8] = A::div(A::sub(A::mul(px, qy), A::mul(qx, py)), D);
+        G.s[6] = A::div(n7, D);
+        G.s[7] = A::div(n8, D);
+        G.s[8] = A::div(n9, D);
     } else {
-        const double iD = 1.0 / D;
+        const double iD = 1.0 / D;  // one IEEE division; num * (1/D) differs from num / D by <= 1 ulp
         G.s[0] = (qy - ry) * iD;
         G.s[1] = (ry - py) * iD;
         G.s[2] = (py - qy) * iD;
         G.s[3] = (rx - qx) * iD;
         G.s[4] = (px - rx) * iD;
         G.s[5] = (qx - px) * iD;
-        G.s[6] = (qx * ry - rx * qy) * iD;
-        G.s[7] = (rx * py - px * ry) * iD;
-        G.s[8] = (px * qy - qx * py) * iD;
+        G.s[6] = n7 * iD;
+        G.s[7] = n8 * iD;
+        G.s[8] = n9 * iD;
     }
     G.mx[0] = A::mul(A::add(m1x, cx), 0.5);
     G.my[0] = A::mul(A::add(m1y, cy), 0.5);

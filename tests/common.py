@@ -141,16 +141,24 @@ class Pair:
         return gp, op
 
 
-def delaunay_mesh(n_points, seed, extra_points=0):
-    """Unstructured test mesh: Delaunay triangulation of random points in the unit square plus a
-    boundary ring (so no sliver boundary triangles); optionally trailing points that are not vertices."""
+def delaunay_mesh(n_points, seed, extra_points=0, jitter=None):
+    """Unstructured test mesh: Delaunay triangulation of points in the unit square plus a boundary ring;
+    optionally trailing points that are not vertices.  jitter=None: uniformly random interior points
+    (contains thin triangles); jitter=a: a lattice whose interior nodes are displaced by up to a*h, i.e.
+    a well-shaped mesh with unstructured connectivity (node degrees 4..8)."""
     from scipy.spatial import Delaunay
     rng = np.random.default_rng(seed)
     k = max(4, int(math.sqrt(n_points)))
     ring = np.linspace(0, 1, k, endpoint=False)
     bnd = np.concatenate([np.stack([ring, 0 * ring], 1), np.stack([1 + 0 * ring, ring], 1),
                           np.stack([1 - ring, 1 + 0 * ring], 1), np.stack([0 * ring, 1 - ring], 1)])
-    inner = 0.02 + 0.96 * rng.random((n_points, 2))
+    if jitter is None:
+        inner = 0.02 + 0.96 * rng.random((n_points, 2))
+    else:
+        h = 1.0 / k
+        g = (np.arange(1, k) * h)
+        X, Y = np.meshgrid(g, g)
+        inner = np.stack([X.ravel(), Y.ravel()], 1) + jitter * h * (2 * rng.random(((k - 1) ** 2, 2)) - 1)
     pts = np.concatenate([bnd, inner])
     dl = Delaunay(pts)
     tris = dl.simplices.astype(np.int32)

@@ -69,9 +69,10 @@ def test_linearity_and_operator_equals_rhs_4096(big):
 
 
 def test_unstructured_200k_vs_oracle():
-    """A Delaunay mesh of 200k random points (Hilbert tiling on a genuinely unstructured mesh, node
-    degrees 3..12) against the vectorised oracle."""
-    gtri = delaunay_mesh(200000, 77)
+    """A 200k-node unstructured mesh (jittered lattice, Delaunay connectivity, node degrees 4..8: Hilbert
+    tiling, gather lists and sliced-ELL slices with ragged rows) against the vectorised oracle.  (On
+    uniformly random points the thin triangles make |du| ~ 1e10 and the comparison meaningless.)"""
+    gtri = delaunay_mesh(200000, 77, jitter=0.35)
     pair = Pair(gtri)
     u = 0.2 + np.random.default_rng(3).random(gtri.num_points)
     for flux, src in ((G.PowerDiffusion(0.3, 2.0), G.LogisticSource(1.3)), (G.ConstantDiffusion(0.7), None)):
