@@ -65,6 +65,7 @@ _SIGS = {
     "fvm_jacobian": [H, C.c_double, C.c_void_p, C.c_int32],
     "fvm_get_jacobian_size": [H, c_lp, c_lp],
     "fvm_get_jacobian_csr": [H, c_ip, c_ip, c_dp],
+    "fvm_eval_points": [H, C.c_double, C.c_void_p, C.c_int32, C.c_int64, c_ip, c_dp, c_dp, c_dp],
     "fvm_krylov": [H, C.c_int32, C.c_void_p, C.c_double, C.c_int32, c_ip, c_dp, C.c_int32],
     "fvm_shard_init": [H, C.c_void_p, C.c_int32, C.c_int32],
     "fvm_set_ghost_nodes": [H, c_bp],

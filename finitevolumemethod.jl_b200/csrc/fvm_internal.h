@@ -147,7 +147,7 @@ struct fvm_ctx {
     FluxParams flux{};
     SourceParams source{};
     // permutations
-    std::vector<int32_t> node_new_of_old, node_old_of_new, tri_old_of_new;
+    std::vector<int32_t> node_new_of_old, node_old_of_new, tri_old_of_new, tri_new_of_old;
     int32_t* d_node_old_of_new = nullptr;
     int32_t* d_node_new_of_old = nullptr;
     // device mesh

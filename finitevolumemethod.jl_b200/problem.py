@@ -419,3 +419,62 @@ def jacobian(u, p, t):
     u = np.ascontiguousarray(u, dtype=np.float64)
     L.check(p.engine.h, L.lib().fvm_jacobian(p.engine.h, float(t), u.ctypes.data, 0))
     return _jac_csr(p, True)
+
+
+class _EdgeMap:
+    """directed edge (u,v) -> (triangle index, third vertex): get_adjacent of DelaunayTriangulation"""
+
+    def __init__(self, tri):
+        T = tri.triangles.astype(np.int64)
+        N = tri.num_points
+        e = np.concatenate([T[:, [0, 1]], T[:, [1, 2]], T[:, [2, 0]]])
+        self.N = N
+        keys = e[:, 0] * N + e[:, 1]
+        self.order = np.argsort(keys)
+        self.keys = keys[self.order]
+        self.tri = np.tile(np.arange(len(T)), 3)[self.order]
+        self.third = np.concatenate([T[:, 2], T[:, 0], T[:, 1]])[self.order]
+
+    def lookup(self, u, v):
+        k = np.asarray(u, np.int64) * self.N + np.asarray(v, np.int64)
+        pos = np.minimum(np.searchsorted(self.keys, k), len(self.keys) - 1)
+        hit = self.keys[pos] == k
+        return hit, np.where(hit, self.tri[pos], -1), np.where(hit, self.third[pos], -1)
+
+
+def pl_interpolate(p, T, u, x, y):
+    """pl_interpolate(prob, T, u, x, y) (utils.jl:23-27): piecewise-linear interpolant of u at points
+    (x, y) inside the triangles with caller indices T (arrays broadcast); (n,) or (n, neq)."""
+    T = np.atleast_1d(np.asarray(T, np.int32))
+    xy = L.f64(np.stack(np.broadcast_arrays(np.asarray(x, float), np.asarray(y, float)), -1).reshape(-1, 2))
+    T = L.i32(np.broadcast_to(T, (len(xy),)))
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty((len(xy), p.engine.neq))
+    L.check(p.engine.h, L.lib().fvm_eval_points(p.engine.h, 0.0, u.ctypes.data, 0, len(xy), L.ip(T), L.dp(xy), None, L.dp(out)))
+    return out[:, 0] if p.prob.neqs == 0 else out
+
+
+def compute_flux(p, i, j, u, t):
+    """compute_flux(prob, i, j, u, t) (problem.jl:458-487): q(midpoint) . n for the edges (i, j), n the
+    clockwise rotation of the edge (pointing right of i -> j), evaluated with the shape function of
+    the triangle on that side (or the other side for boundary edges).  Arrays of edges are accepted."""
+    mesh = p.prob.mesh
+    tri = mesh.triangulation
+    if getattr(mesh, "_edge_map", None) is None:
+        mesh._edge_map = _EdgeMap(tri)
+    i = np.atleast_1d(np.asarray(i, np.int64))
+    j = np.atleast_1d(np.asarray(j, np.int64))
+    P = tri.points
+    e = P[j] - P[i]
+    ell = np.sqrt(e[:, 0] * e[:, 0] + e[:, 1] * e[:, 1])
+    nrm = L.f64(np.stack([e[:, 1] / ell, -e[:, 0] / ell], 1))
+    hit, t_right, _ = mesh._edge_map.lookup(j, i)      # the vertex in the direction of the normal
+    hit2, t_left, _ = mesh._edge_map.lookup(i, j)
+    if not (hit | hit2).all():
+        raise KeyError("compute_flux: (i, j) is not an edge of the triangulation")
+    tq = L.i32(np.where(hit, t_right, t_left))
+    mid = L.f64((P[i] + P[j]) / 2)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.empty((len(i), p.engine.neq))
+    L.check(p.engine.h, L.lib().fvm_eval_points(p.engine.h, float(t), u.ctypes.data, 0, len(i), L.ip(tq), L.dp(mid), L.dp(nrm), L.dp(out)))
+    return out[:, 0] if p.prob.neqs == 0 else out

@@ -195,6 +195,13 @@ int32_t fvm_get_jacobian_size(fvm_handle h, int64_t* n_rows, int64_t* nnz);
 /* caller numbering; val may be NULL to fetch the pattern only (the jac_prototype of solve.jl:170) */
 int32_t fvm_get_jacobian_csr(fvm_handle h, int32_t* rowptr, int32_t* col, double* val);
 
+/* ---- post-processing (src/utils.jl:23-27 pl_interpolate, src/problem.jl:458-487 compute_flux) ---- */
+/* For n query points (x,y) lying in given triangles (caller triangle indices): the piecewise-linear
+ * interpolant alpha*x + beta*y + gamma of u (nrm == NULL), or q(x,y,t,alpha,beta,gamma) . nrm.
+ * tri_idx, xy, nrm, out are host buffers; out is [n][neq]. */
+int32_t fvm_eval_points(fvm_handle h, double t, const double* u, int32_t u_on_device, int64_t n, const int32_t* tri_idx,
+                        const double* xy, const double* nrm, double* out);
+
 /* ---- multi-GPU: node partition + one-layer ghost halo per rank ---------------- */
 /* Each rank creates its handle on the LOCAL mesh: owned nodes + ghost nodes, and every triangle that
  * touches an owned node.  Call order: fvm_create, setters, fvm_set_ghost_nodes, fvm_finalize,

@@ -1077,3 +1077,32 @@ def tsit5_adaptive(f, u0, t0, t1, abstol=1e-6, reltol=1e-3, dt0=None, callback=N
             nrej += 1
             dt = h / min(1.0 / qmin, q)
     return u, saves, nacc, nrej
+
+
+def pl_interpolate(prob, T, u, x, y):  # utils.jl:23-27
+    Ts, t_idx = prob.mesh.safe_get_triangle_props(tuple(int(v) for v in T))
+    a, b, g = get_shape_function_coefficients(prob.mesh, t_idx, Ts, u, prob.neqs)
+    if prob.neqs == 0:
+        return a * x + b * y + g
+    return tuple(a[v] * x + b[v] * y + g[v] for v in range(prob.neqs))
+
+
+def compute_flux(prob, i, j, u, t):  # problem.jl:458-487
+    tri = prob.mesh.triangulation
+    px, py = tri.points[i]
+    qx, qy = tri.points[j]
+    ex, ey = qx - px, qy - py
+    ell = math.sqrt(ex * ex + ey * ey)
+    nx, ny = ey / ell, -ex / ell
+    k = tri.adjacent.get((j, i), -1)
+    if k < 0:
+        k = tri.get_adjacent(i, j)
+    else:
+        i, j = j, i
+    Ts, t_idx = prob.mesh.safe_get_triangle_props((i, j, k))
+    a, b, g = get_shape_function_coefficients(prob.mesh, t_idx, Ts, u, prob.neqs)
+    mx, my = (px + qx) / 2, (py + qy) / 2
+    qv = prob.eval_flux_function(mx, my, t, a, b, g)
+    if prob.neqs == 0:
+        return nx * qv[0] + ny * qv[1]
+    return tuple(nx * qv[v][0] + ny * qv[v][1] for v in range(prob.neqs))

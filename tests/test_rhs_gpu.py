@@ -229,3 +229,82 @@ def test_sparse_jacobian_matches_finite_differences():
     eps = 1e-6
     fd = (O.fvm_eqs_vec(np.zeros_like(U), U + eps * V, os_, 0.0) - O.fvm_eqs_vec(np.zeros_like(U), U - eps * V, os_, 0.0)) / (2 * eps)
     assert rel_err((J @ V.ravel()).reshape(N, 2), fd) <= 1e-6
+
+
+def test_three_species_and_abi_error_codes():
+    """neq = 3 (FVMSystem{3}) reproduces three scalar problems; the ABI's error behaviour: call order,
+    unknown registry ids (the analogue of InvalidFluxError, problem.jl:291-316), bad sizes."""
+    import ctypes as C
+    from fvm_b200 import _lib as L
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 23, 19, single_boundary=True))
+    N = pair.gtri.num_points
+    rng = np.random.default_rng(23)
+    U = np.ascontiguousarray(rng.random((N, 3)))
+    Ds = (0.3, 0.7, 1.1)
+    gps, scal = [], []
+    for v, D in enumerate(Ds):
+        g, _ = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(D), source=G.LinearSource(-0.1 * (v + 1), 0.2), var=v, ic=U[:, v])
+        gps.append(g)
+        gs, os_ = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(D), source=G.LinearSource(-0.1 * (v + 1), 0.2), ic=U[:, v])
+        scal.append(O.fvm_eqs_vec(np.zeros(N), np.ascontiguousarray(U[:, v]), os_, 0.0))
+    p = G.get_cuda_parameters(G.FVMSystem(*gps))
+    dU = G.fvm_eqs(np.zeros_like(U), U, p, 0.0)
+    for v in range(3):
+        assert rel_err(dU[:, v], scal[v]) <= RTOL_RHS
+    # ---- error codes through the raw ABI ----
+    lib = L.lib()
+    tri = pair.gtri
+    h = L.H()
+    pts, tr = L.f64(tri.points), L.i32(tri.triangles)
+    assert lib.fvm_create(L.dp(pts), N, L.ip(tr), tri.num_triangles, 0, 1, 0, C.byref(h)) == L.OK
+    buf = np.zeros(N)
+    assert lib.fvm_rhs(h, 0.0, buf.ctypes.data, buf.ctypes.data, 0) == L.ERR_STATE      # rhs before finalize
+    assert b"finalize" in lib.fvm_last_error(h)
+    one = L.f64([1.0])
+    assert lib.fvm_set_flux(h, 99, L.dp(one), 1) == L.ERR_UNSUPPORTED                   # closure outside the registry
+    assert b"registry" in lib.fvm_last_error(h)
+    assert lib.fvm_set_flux(h, G.FLUX_KELLER_SEGEL, L.dp(L.f64([4.0, 1.0])), 2) == L.ERR_ARG  # needs neq == 2
+    assert lib.fvm_set_flux(h, G.FLUX_DIFF_CONST, L.dp(L.f64([1.0, 2.0])), 2) == L.ERR_ARG    # wrong parameter count
+    assert lib.fvm_finalize(h, 100, 0) == L.ERR_ARG                                     # tile size not a multiple of 64
+    assert lib.fvm_finalize(h, 0, 0) == L.OK
+    assert lib.fvm_finalize(h, 0, 0) == L.ERR_STATE                                     # already finalized
+    assert lib.fvm_spmv(h, buf.ctypes.data, buf.ctypes.data, 1, 0) == L.ERR_STATE       # spmv before assemble
+    bad = L.i32([[0, 1, N + 5]])
+    h2 = L.H()
+    assert lib.fvm_create(L.dp(pts), N, L.ip(bad), 1, 0, 1, 0, C.byref(h2)) == L.ERR_ARG  # vertex out of range
+    assert lib.fvm_create(L.dp(pts), N, L.ip(tr), tri.num_triangles, 0, 9, 0, C.byref(h2)) == L.ERR_ARG
+    lib.fvm_destroy(h)
+
+
+def test_pl_interpolate_and_compute_flux():
+    """pl_interpolate (utils.jl:23-27) and compute_flux on every edge (problem.jl:458-487;
+    test/test_functions.jl:659-747 checks it on every edge too), scalar and FVMSystem."""
+    gtri = delaunay_mesh(400, 41)
+    pair = Pair(gtri)
+    N = gtri.num_points
+    rng = np.random.default_rng(29)
+    u = 0.3 + rng.random(N)
+    gp, op = pair.problem(G.Const(0.0), G.Neumann, G.PowerDiffusion(0.3, 2.0))
+    p = G.get_cuda_parameters(gp, tile_triangles=64)
+    T = gtri.triangles
+    E = np.unique(np.sort(np.concatenate([T[:, [0, 1]], T[:, [1, 2]], T[:, [2, 0]]]), axis=1), axis=0)
+    E = np.concatenate([E, E[:, ::-1]])  # both orientations
+    got = G.compute_flux(p, E[:, 0], E[:, 1], u, 0.4)
+    ref = np.array([O.compute_flux(op, int(a), int(b), u, 0.4) for a, b in E])
+    assert rel_err(got, ref) <= 1e-12
+    tq = rng.integers(0, len(T), 300)
+    w = rng.dirichlet((1, 1, 1), 300)
+    pts = np.einsum("nk,nkd->nd", w, gtri.points[T[tq]])
+    got = G.pl_interpolate(p, tq, u, pts[:, 0], pts[:, 1])
+    ref = np.array([O.pl_interpolate(op, T[t], u, x, y) for t, (x, y) in zip(tq, pts)])
+    assert rel_err(got, ref) <= 1e-12
+    assert rel_err(got, np.einsum("nk,nk->n", w, u[T[tq]])) <= 1e-10  # barycentric interpolation
+    # system
+    U = np.ascontiguousarray(np.stack([u, 0.5 * u[::-1]], axis=1))
+    ks = G.KellerSegelFlux(4.0, 1.0)
+    g1, o1 = pair.problem(G.Const(0.0), G.Neumann, ks, var=0, ic=U[:, 0])
+    g2, o2 = pair.problem(G.Const(0.0), G.Neumann, ks, var=1, ic=U[:, 1])
+    ps = G.get_cuda_parameters(G.FVMSystem(g1, g2), tile_triangles=64)
+    got = G.compute_flux(ps, E[:50, 0], E[:50, 1], U, 0.0)
+    ref = np.array([O.compute_flux(O.FVMSystem(o1, o2), int(a), int(b), U, 0.0) for a, b in E[:50]])
+    assert got.shape == (50, 2) and rel_err(got, ref) <= 1e-12
