@@ -169,3 +169,24 @@ def delaunay_mesh(n_points, seed, extra_points=0, jitter=None):
     if extra_points:
         pts = np.concatenate([pts, 2.0 + rng.random((extra_points, 2))])
     return G.Triangulation(pts, tris)
+
+
+def annulus_mesh(nr, nt, r_in=0.2, r_out=1.0):
+    """Polar-grid triangulation of an annulus (the reference's tests and the 'diffusion equation on an
+    annulus' tutorial use annuli): two boundary loops, outer counter-clockwise and inner clockwise, so the
+    interior is on the left of both.  Sections are ordered by their smallest node id: inner first."""
+    r = np.linspace(r_in, r_out, nr)
+    th = np.linspace(0, 2 * np.pi, nt, endpoint=False)
+    pts = np.stack([np.outer(r, np.cos(th)).ravel(), np.outer(r, np.sin(th)).ravel()], 1)  # node = k*nt + m
+    tris = []
+    for k in range(nr - 1):
+        for m in range(nt):
+            a, b = k * nt + m, k * nt + (m + 1) % nt
+            c, d = (k + 1) * nt + m, (k + 1) * nt + (m + 1) % nt
+            tris.append((a, c, b) if False else (a, c, d))
+            tris.append((a, d, b))
+    tris = np.asarray(tris, dtype=np.int32)
+    p, q, s = pts[tris[:, 0]], pts[tris[:, 1]], pts[tris[:, 2]]
+    area2 = (q[:, 0] - p[:, 0]) * (s[:, 1] - p[:, 1]) - (q[:, 1] - p[:, 1]) * (s[:, 0] - p[:, 0])
+    tris[area2 < 0] = tris[area2 < 0][:, [0, 2, 1]]
+    return G.Triangulation(pts, tris)

@@ -237,3 +237,39 @@ def test_adaptive_tsit5_device():
                                        callback=lambda x, t: (O.update_dirichlet_nodes(x, t, op), True)[1])
     assert abs(alg2.naccept - na2) <= 2 and abs(alg2.nreject - nr2) <= 2
     assert rel_err(sol2.u, u2) <= 1e-5
+
+
+def test_annulus_two_boundary_loops():
+    """A domain with a hole (docs/src/literate_tutorials/diffusion_equation_on_an_annulus.jl:54-68):
+    inner loop Dirichlet 50(1-exp(-t/2)), outer loop zero-flux Neumann, D = 1.  RHS, device Tsit5 with
+    the time-dependent Dirichlet callback, and Laplace's equation against ln(r/R)/ln(r0/R)."""
+    from tests.common import annulus_mesh
+    gtri = annulus_mesh(24, 96)
+    assert len(gtri.boundary_sections) == 2
+    inner_first = np.allclose(np.hypot(*gtri.points[gtri.boundary_sections[0][0]]), 0.2)
+    pair = Pair(gtri)
+    N = gtri.num_points
+    specs = (G.ExpSaturation(50.0, 2.0), G.Const(0.0)) if inner_first else (G.Const(0.0), G.ExpSaturation(50.0, 2.0))
+    types = (G.Dirichlet, G.Neumann) if inner_first else (G.Neumann, G.Dirichlet)
+    u0 = 10.0 * np.exp(-25.0 * ((gtri.points[:, 0] + 0.5) ** 2 + (gtri.points[:, 1] + 0.5) ** 2))
+    gp, op = pair.problem(specs, types, G.ConstantDiffusion(1.0), ic=u0, final_time=0.02)
+    p = G.get_cuda_parameters(gp, tile_triangles=256)
+    u = u0 + np.random.default_rng(1).random(N)
+    assert rel_err(G.fvm_eqs(np.zeros(N), u, p, 0.3), O.fvm_eqs_vec(np.zeros(N), u, op, 0.3)) <= RTOL_RHS
+    dt = 2e-5
+    sol = G.solve(gp, G.Tsit5(dt), p=p)
+    uref = O.tsit5_fixed(lambda d, x, t: O.fvm_eqs_vec(d, x, op, t), u0, 0.0, 0.02, dt,
+                         callback=lambda x, t: (O.update_dirichlet_nodes(x, t, op), True)[1])
+    assert rel_err(sol.u, uref) <= RTOL_TSIT5
+    # steady: u = 1 on the inner circle, 0 on the outer one -> u(r) = ln(r/R)/ln(r0/R)
+    one = (G.Const(1.0), G.Const(0.0)) if inner_first else (G.Const(0.0), G.Const(1.0))
+    gBC = G.BoundaryConditions(pair.gmesh, one, (G.Dirichlet, G.Dirichlet))
+    oBC = O.BoundaryConditions(pair.omesh, tuple(xy_cond(s) for s in one), (O.Dirichlet, O.Dirichlet))
+    tpl = G.LaplacesEquation(pair.gmesh, gBC)
+    ref = O.LaplacesEquation(pair.omesh, oBC)
+    assert_system_matches(tpl, ref)
+    s2 = G.solve(tpl, G.KrylovJacobi("pcg", rtol=1e-13))
+    rr = np.hypot(gtri.points[:, 0], gtri.points[:, 1])
+    exact = np.log(rr / 1.0) / np.log(0.2 / 1.0)
+    assert rel_err(s2.u, O.solve_steady(ref)) <= 1e-9
+    assert np.abs(s2.u - exact).max() <= 5e-3
