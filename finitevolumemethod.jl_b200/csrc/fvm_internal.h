@@ -181,6 +181,8 @@ struct fvm_ctx {
     void* shard = nullptr;
     bool halo_ready = false;
     bool overlap = false;            // exchange overlapped with the tiles that touch no ghost node
+    cudaStream_t comm_stream = nullptr;   // communication stream (owned by the shard state)
+    cudaStream_t launch_stream = nullptr; // stream the kernel launchers use (compute stream by default)
     int32_t* d_tile_order = nullptr; // independent tiles first, then the halo-dependent ones
     int32_t n_tiles_indep = 0;
     std::vector<int32_t> h_tile_node0, h_tile_nown, h_tile_ext0, h_ext_ids;  // host copies for the classification
@@ -231,11 +233,13 @@ int32_t fvm_ensure_state(fvm_ctx* h);
 void fvm_shard_release(fvm_ctx* h);
 int32_t fvm_halo_exchange(fvm_ctx* h, double* u_native);
 int32_t fvm_halo_begin(fvm_ctx* h, double* u_native);
+int32_t fvm_halo_done(fvm_ctx* h);  // marks the end of the work queued on the communication stream
 int32_t fvm_halo_wait(fvm_ctx* h);
 // operator applications with the ghost refresh (overlapped with the independent tiles when possible)
 int32_t fvm_apply_rhs(fvm_ctx* h, double t, double* x, double* out);
 int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* out, bool add_b, bool scale);
-// part: 0 = everything, 1 = independent tiles only, 2 = halo-dependent tiles + boundary/interface/tail kernels
+// part: 0 = everything, 1 = independent tiles only, 2 = halo-dependent tiles (+ boundary-edge kernel),
+// 3 = the kernels that need every tile (interface / tail rows)
 int32_t fvm_launch_rhs_part(fvm_ctx* h, double t, const double* u, double* du, int part);
 int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part);
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);

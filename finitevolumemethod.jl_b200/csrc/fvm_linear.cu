@@ -413,17 +413,18 @@ static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part) {
             off = h->n_tiles_indep;
             grid = h->dm.n_tiles - h->n_tiles_indep;
         }
-        if (grid > 0) {
-            fvm_prof_begin(h);
-            spmv_tile_kernel<ADD_B, SCALE><<<grid, SPMV_BLOCK, c.tile_smem, h->stream>>>(
+        cudaStream_t st = h->launch_stream;
+        if (grid > 0 && part != 3) {
+            if (st == h->stream) fvm_prof_begin(h);
+            spmv_tile_kernel<ADD_B, SCALE><<<grid, SPMV_BLOCK, c.tile_smem, st>>>(
                 h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale, x, y, list, off);
-            fvm_prof_end(h);
+            if (st == h->stream) fvm_prof_end(h);
         }
-        if (c.n_tail > 0 && part != 1)
-            spmv_rows_kernel<ADD_B, SCALE><<<(c.n_tslices * 32 + 127) / 128, 128, 0, h->stream>>>(
+        if (c.n_tail > 0 && (part == 0 || part == 3))
+            spmv_rows_kernel<ADD_B, SCALE><<<(c.n_tslices * 32 + 127) / 128, 128, 0, st>>>(
                 c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b, c.rowscale, x, y);
-    } else if (part == 1) {
-        return FVM_OK;  // the generic kernels have no tile split: everything runs in part 2
+    } else if (part == 1 || part == 2) {
+        return FVM_OK;  // the generic kernels have no tile split: everything runs in part 3
     } else if (c.use_tile_spmv == 0 && c.chunk_rows > 0 && getenv("FVM_SPMV_BLOCK")) {
         const int grid = (c.n + SPMV_ROWS - 1) / SPMV_ROWS;
         fvm_prof_begin(h);
@@ -460,9 +461,14 @@ int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* y, bool add_b, bool scale)
         return fvm_launch_spmv_part(h, x, y, add_b, scale, 0);
     }
     if ((rc = fvm_halo_begin(h, x))) return rc;
+    h->launch_stream = h->comm_stream;  // halo-dependent tiles right behind the unpack, on the communication stream
+    rc = fvm_launch_spmv_part(h, x, y, add_b, scale, 2);
+    h->launch_stream = h->stream;
+    if (rc) return rc;
+    if ((rc = fvm_halo_done(h))) return rc;
     if ((rc = fvm_launch_spmv_part(h, x, y, add_b, scale, 1))) return rc;
     if ((rc = fvm_halo_wait(h))) return rc;
-    return fvm_launch_spmv_part(h, x, y, add_b, scale, 2);
+    return fvm_launch_spmv_part(h, x, y, add_b, scale, 3);
 }
 
 // ---- host side -------------------------------------------------------------------------------

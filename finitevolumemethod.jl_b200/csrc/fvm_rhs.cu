@@ -446,9 +446,10 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
         grid = h->dm.n_tiles - h->n_tiles_indep;
     }
     if (grid == 0) return FVM_OK;
-    fvm_prof_begin(h);
-    kern<<<grid, RHS_BLOCK, smem, h->stream>>>(h->dm, h->flux, h->source, t, u, du, h->max_nloc, list, off);
-    fvm_prof_end(h);
+    cudaStream_t st = h->launch_stream;
+    if (st == h->stream) fvm_prof_begin(h);
+    kern<<<grid, RHS_BLOCK, smem, st>>>(h->dm, h->flux, h->source, t, u, du, h->max_nloc, list, off);
+    if (st == h->stream) fvm_prof_end(h);
     FVM_CUDA(h, cudaGetLastError());
     return FVM_OK;
 }
@@ -456,10 +457,18 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
 template <int NEQ>
 static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du, int part) {
     int32_t rc = FVM_OK;
-    if (h->n_bnd_live > 0 && part != 1) {
-        rhs_boundary_kernel<NEQ><<<(h->n_bnd_live + 127) / 128, 128, 0, h->stream>>>(h->dm, h->flux, t, h->d_bnd, h->d_dbnd,
-                                                                                     h->n_bnd_live, u);
+    if (h->n_bnd_live > 0 && (part == 0 || part == 2)) {
+        rhs_boundary_kernel<NEQ><<<(h->n_bnd_live + 127) / 128, 128, 0, h->launch_stream>>>(h->dm, h->flux, t, h->d_bnd, h->d_dbnd,
+                                                                                            h->n_bnd_live, u);
         FVM_CUDA(h, cudaGetLastError());
+    }
+    if (part == 3) {
+        const int n_tail3 = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
+        if (n_tail3 > 0) {
+            rhs_interface_kernel<NEQ, false><<<(n_tail3 + 255) / 256, 256, 0, h->launch_stream>>>(h->dm, h->source, t, u, du);
+            FVM_CUDA(h, cudaGetLastError());
+        }
+        return FVM_OK;
     }
     const int model = h->flux.model;
     const int geom = h->geometry_mode;
@@ -485,8 +494,8 @@ static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du,
 #undef TILE_CASE
     if (rc) return rc;
     const int n_tail = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
-    if (n_tail > 0 && part != 1) {
-        rhs_interface_kernel<NEQ, false><<<(n_tail + 255) / 256, 256, 0, h->stream>>>(h->dm, h->source, t, u, du);
+    if (n_tail > 0 && part == 0) {
+        rhs_interface_kernel<NEQ, false><<<(n_tail + 255) / 256, 256, 0, h->launch_stream>>>(h->dm, h->source, t, u, du);
         FVM_CUDA(h, cudaGetLastError());
     }
     return FVM_OK;
@@ -512,10 +521,17 @@ int32_t fvm_apply_rhs(fvm_ctx* h, double t, double* x, double* out) {
         if ((rc = fvm_halo_exchange(h, x))) return rc;
         return fvm_launch_rhs_part(h, t, x, out, 0);
     }
+    // communication stream: exchange -> unpack -> halo-dependent tiles + boundary edges, concurrently with
+    // the independent tiles on the compute stream (they fill its tail wave); then the interface kernel
     if ((rc = fvm_halo_begin(h, x))) return rc;
+    h->launch_stream = h->comm_stream;
+    rc = fvm_launch_rhs_part(h, t, x, out, 2);
+    h->launch_stream = h->stream;
+    if (rc) return rc;
+    if ((rc = fvm_halo_done(h))) return rc;
     if ((rc = fvm_launch_rhs_part(h, t, x, out, 1))) return rc;
     if ((rc = fvm_halo_wait(h))) return rc;
-    return fvm_launch_rhs_part(h, t, x, out, 2);
+    return fvm_launch_rhs_part(h, t, x, out, 3);
 }
 
 int32_t fvm_launch_geometry(fvm_ctx* h, const int32_t* d_tri_native) {

@@ -64,6 +64,7 @@ extern "C" int32_t fvm_create(const double* xy, int64_t N, const int32_t* tri, i
         delete h;
         return bad(FVM_ERR_CUDA, "fvm_create: cannot create stream");
     }
+    h->launch_stream = h->stream;
     h->h_xy.assign(xy, xy + 2 * N);
     h->h_tri.resize(3 * T);
     for (int64_t i = 0; i < 3 * T; ++i) {

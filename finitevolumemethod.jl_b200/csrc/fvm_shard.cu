@@ -103,6 +103,7 @@ extern "C" int32_t fvm_set_halo(fvm_handle h, int32_t n_neigh, const int32_t* ne
         FVM_CUDA(h, cudaEventCreateWithFlags(&s->ev_packed, cudaEventDisableTiming));
         FVM_CUDA(h, cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
     }
+    h->comm_stream = s->comm_stream;
     // tiles whose local nodes (own range or external interface nodes) contain no received ghost node
     // can run while the exchange is in flight
     {
@@ -121,9 +122,10 @@ extern "C" int32_t fvm_set_halo(fvm_handle h, int32_t n_neigh, const int32_t* ne
         h->n_tiles_indep = (int32_t)indep.size();
         indep.insert(indep.end(), dep.begin(), dep.end());
         if ((rc = fvm_dev_upload(h, &h->d_tile_order, indep))) return rc;
-        // measured on 2 B200s at 16.7M nodes per GPU: overlapped 1.133 ms/step vs serialised 1.121 ms/step (the
-        // exchange is ~20 us; a second tile launch and two event waits cost more than they hide), so the
-        // overlapped schedule is opt-in
+        // measured on 2 B200s at 16.7M nodes per GPU (general kernel): 1 GPU 1.072 ms/step, serialised exchange
+        // 1.079 ms, overlapped schedule 1.086 ms.  The 32 KB exchange costs ~7 us over NVLink, so there is
+        // nothing left to hide and the extra launches/event waits of the overlapped schedule do not pay:
+        // it is opt-in (it matters for small subdomains or many neighbours)
         const char* ov = getenv("FVM_HALO_OVERLAP");
         h->overlap = n_neigh > 0 && ov && ov[0] == '1';
         h->stats[13] = h->n_tiles_indep;
@@ -202,6 +204,12 @@ int32_t fvm_halo_begin(fvm_ctx* h, double* u_native) {
                                                                                                   s->d_recv_buf, u_native);
         FVM_CUDA(h, cudaGetLastError());
     }
+    return FVM_OK;
+}
+
+int32_t fvm_halo_done(fvm_ctx* h) {
+    ShardState* s = (ShardState*)h->shard;
+    if (!s || !h->halo_ready || s->n_neigh == 0) return FVM_OK;
     FVM_CUDA(h, cudaEventRecord(s->ev_done, s->comm_stream));
     return FVM_OK;
 }

@@ -308,3 +308,54 @@ def test_pl_interpolate_and_compute_flux():
     got = G.compute_flux(ps, E[:50, 0], E[:50, 1], U, 0.0)
     ref = np.array([O.compute_flux(O.FVMSystem(o1, o2), int(a), int(b), U, 0.0) for a, b in E[:50]])
     assert got.shape == (50, 2) and rel_err(got, ref) <= 1e-12
+
+
+def test_abi_index_base_one_and_native_entry_points():
+    """Julia passes 1-based triangles / edges (index_base = 1): same result as 0-based.  Device-pointer
+    entry points: fvm_to_native -> fvm_rhs_native -> fvm_from_native equals fvm_rhs (caller order)."""
+    import ctypes as C
+    import torch
+    from fvm_b200 import _lib as L
+    lib = L.lib()
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 1, 31, 17, single_boundary=False))
+    tri = pair.gtri
+    N = tri.num_points
+    gp, op = pair.problem((G.Const(0.1), G.Const(0.0), G.AffineU(0.2, -0.3), G.Const(0.0)),
+                          (G.Neumann, G.Dirichlet, G.Neumann, G.Dudt), G.ConstantDiffusion(0.4))
+    u = np.random.default_rng(31).random(N)
+    ref = G.fvm_eqs(np.zeros(N), u, G.get_cuda_parameters(gp), 0.0)
+    c = gp.conditions
+    h = L.H()
+    pts, tr1 = L.f64(tri.points), L.i32(tri.triangles + 1)
+    assert lib.fvm_create(L.dp(pts), N, L.ip(tr1), tri.num_triangles, 1, 1, 0, C.byref(h)) == L.OK
+    uv1 = L.i32(c.boundary_edges + 1)
+    L.check(h, lib.fvm_set_boundary_edges(h, L.ip(uv1), len(uv1)))
+    ek, ef = np.ascontiguousarray(c.edge_kind), L.i32(c.edge_fidx)
+    nk, nf = np.ascontiguousarray(c.node_kind), L.i32(c.node_fidx)
+    L.check(h, lib.fvm_set_edge_conditions(h, 0, L.bp(ek), L.ip(ef)))
+    L.check(h, lib.fvm_set_node_conditions(h, 0, L.bp(nk), L.ip(nf)))
+    for fidx, spec in enumerate(c.functions):
+        fid, params = G.functors.cond_spec(spec)
+        pp = L.f64(params)
+        L.check(h, lib.fvm_set_condition_fn(h, 0, fidx, fid, L.dp(pp), len(pp)))
+    d = L.f64([0.4])
+    L.check(h, lib.fvm_set_flux(h, G.FLUX_DIFF_CONST, L.dp(d), 1))
+    L.check(h, lib.fvm_finalize(h, 128, 0))
+    du = np.zeros(N)
+    L.check(h, lib.fvm_rhs(h, 0.0, u.ctypes.data, du.ctypes.data, 0))
+    assert np.array_equal(du, ref)
+    # device pointers, native order
+    ud = torch.from_numpy(u).cuda()
+    un, dn, dc = torch.empty_like(ud), torch.empty_like(ud), torch.empty_like(ud)
+    L.check(h, lib.fvm_to_native(h, ud.data_ptr(), un.data_ptr()))
+    L.check(h, lib.fvm_rhs_native(h, 0.0, un.data_ptr(), dn.data_ptr()))
+    L.check(h, lib.fvm_from_native(h, dn.data_ptr(), dc.data_ptr()))
+    L.check(h, lib.fvm_stream_synchronize(h))
+    assert np.array_equal(dc.cpu().numpy(), ref)
+    dd = torch.empty_like(ud)
+    L.check(h, lib.fvm_rhs(h, 0.0, ud.data_ptr(), dd.data_ptr(), 1))
+    assert np.array_equal(dd.cpu().numpy(), ref)
+    node_perm = np.empty(N, np.int32)
+    L.check(h, lib.fvm_get_permutation(h, L.ip(node_perm), None))
+    assert np.array_equal(un.cpu().numpy(), u[node_perm])
+    lib.fvm_destroy(h)
