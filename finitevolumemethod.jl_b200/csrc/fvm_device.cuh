@@ -263,6 +263,7 @@ __device__ __forceinline__ T cond_eval_t(const CondFn& c, double x, double y, do
         case FVM_COND_AFFINE_U: return c.p[1] * u + c.p[0];
         case FVM_COND_EXP_SAT: return T(c.p[0] * (1.0 - exp(-t / c.p[1])));
         case FVM_COND_LINEAR_XY: return T(c.p[0] + c.p[1] * x + c.p[2] * y);
+        case FVM_COND_EXP_XYT: return T(c.p[0] * exp(c.p[1] * x + c.p[2] * y + c.p[3] * t));
         default: return T(c.p[0]);
     }
 }
@@ -271,6 +272,7 @@ __device__ __forceinline__ double cond_eval(const CondFn& c, double x, double y,
         case FVM_COND_AFFINE_U: return c.p[0] + c.p[1] * u;
         case FVM_COND_EXP_SAT: return c.p[0] * (1.0 - exp(-t / c.p[1]));
         case FVM_COND_LINEAR_XY: return c.p[0] + c.p[1] * x + c.p[2] * y;
+        case FVM_COND_EXP_XYT: return c.p[0] * exp(c.p[1] * x + c.p[2] * y + c.p[3] * t);
         default: return c.p[0];
     }
 }

@@ -165,17 +165,18 @@ extern "C" int32_t fvm_set_condition_fn(fvm_handle h, int32_t var, int32_t fidx,
     if (!h) return FVM_ERR_ARG;
     FVM_REQUIRE(h, var >= 0 && var < h->neq, "fvm_set_condition_fn: bad species index");
     FVM_REQUIRE(h, fidx >= 0 && fidx < FVM_MAX_COND_FN, "fvm_set_condition_fn: fidx out of range");
-    if (fn_id < FVM_COND_CONST || fn_id > FVM_COND_LINEAR_XY)
+    if (fn_id < FVM_COND_CONST || fn_id > FVM_COND_EXP_XYT)
         return fvm_fail(h, FVM_ERR_UNSUPPORTED,
                         "fvm_set_condition_fn: condition function is not in the compiled registry "
                         "(arbitrary closures cannot run on the device)");
-    static const int need[] = {1, 2, 2, 3};
+    static const int need[] = {1, 2, 2, 3, 4};
     FVM_REQUIRE(h, nparams == need[fn_id] && params, "fvm_set_condition_fn: wrong parameter count");
     CondFn c{fn_id, {0, 0, 0, 0}};
     for (int i = 0; i < nparams; ++i) c.p[i] = params[i];
     h->h_cond[(size_t)var * FVM_MAX_COND_FN + fidx] = c;
     h->time_dependent = false;
-    for (const CondFn& q : h->h_cond) h->time_dependent = h->time_dependent || q.id == FVM_COND_EXP_SAT;
+    for (const CondFn& q : h->h_cond)
+        h->time_dependent = h->time_dependent || q.id == FVM_COND_EXP_SAT || (q.id == FVM_COND_EXP_XYT && q.p[3] != 0.0);
     if (h->finalized) {  // condition parameters may change between solves
         FVM_CUDA(h, cudaMemcpyAsync((void*)(h->dm.cond + (size_t)var * FVM_MAX_COND_FN + fidx), &c, sizeof(CondFn),
                                     cudaMemcpyHostToDevice, h->stream));

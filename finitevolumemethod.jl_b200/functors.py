@@ -10,7 +10,7 @@ from typing import Callable, Sequence
 # ids mirror include/fvmcuda.h
 FLUX_DIFF_CONST, FLUX_DIFF_TABLE, FLUX_DIFF_POWER, FLUX_ADVDIFF, FLUX_KELLER_SEGEL = range(5)
 SRC_ZERO, SRC_LINEAR, SRC_LOGISTIC, SRC_TABLE, SRC_GRAY_SCOTT, SRC_BRUSSELATOR, SRC_KELLER_SEGEL = range(7)
-COND_CONST, COND_AFFINE_U, COND_EXP_SAT, COND_LINEAR_XY = range(4)
+COND_CONST, COND_AFFINE_U, COND_EXP_SAT, COND_LINEAR_XY, COND_EXP_XYT = range(5)
 
 
 # ---- diffusion / flux functions: q(x,y,t,alpha,beta,gamma,p) or D(x,y,t,u,p) ------------------
@@ -121,6 +121,15 @@ class LinearXY:
     cy: float
 
 
+@dataclass(frozen=True)
+class ExpXYT:
+    """c0 * exp(cx * x + cy * y + ct * t)  (the Brusselator tutorial's boundary data)"""
+    c0: float
+    cx: float = 0.0
+    cy: float = 0.0
+    ct: float = 0.0
+
+
 def cond_spec(fn):
     from ._lib import ERR_UNSUPPORTED, UnsupportedClosureError
     if isinstance(fn, Const):
@@ -131,9 +140,11 @@ def cond_spec(fn):
         return COND_EXP_SAT, [fn.c0, fn.tau]
     if isinstance(fn, LinearXY):
         return COND_LINEAR_XY, [fn.c0, fn.cx, fn.cy]
+    if isinstance(fn, ExpXYT):
+        return COND_EXP_XYT, [fn.c0, fn.cx, fn.cy, fn.ct]
     if isinstance(fn, (int, float)):
         return COND_CONST, [float(fn)]
     raise UnsupportedClosureError(
         ERR_UNSUPPORTED,
-        "condition function %r is not in the compiled device registry (Const, AffineU, ExpSaturation, LinearXY); "
+        "condition function %r is not in the compiled device registry (Const, AffineU, ExpSaturation, LinearXY, ExpXYT); "
         "arbitrary closures cannot run on the GPU" % (fn,))

@@ -29,7 +29,9 @@ def _eval_cond(fn, x, y):
         return np.full(x.shape, fn.c)
     if isinstance(fn, F.LinearXY):
         return fn.c0 + fn.cx * x + fn.cy * np.asarray(y)
-    if isinstance(fn, (F.AffineU, F.ExpSaturation)):
+    if isinstance(fn, F.ExpXYT) and fn.ct == 0.0:
+        return fn.c0 * np.exp(fn.cx * x + fn.cy * np.asarray(y))
+    if isinstance(fn, (F.AffineU, F.ExpSaturation, F.ExpXYT)):
         raise TypeError("template conditions are evaluated with t = u = nothing; %r depends on t or u" % (fn,))
     return np.broadcast_to(np.asarray(fn(x, y, None, None, None), dtype=np.float64), x.shape)
 

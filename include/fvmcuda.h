@@ -72,7 +72,8 @@ enum fvm_cond_fn {
     FVM_COND_CONST = 0,    /* c0                                   */
     FVM_COND_AFFINE_U = 1, /* c0 + c1 * u_var                      */
     FVM_COND_EXP_SAT = 2,  /* c0 * (1 - exp(-t / c1))              */
-    FVM_COND_LINEAR_XY = 3 /* c0 + c1 x + c2 y                     */
+    FVM_COND_LINEAR_XY = 3, /* c0 + c1 x + c2 y                    */
+    FVM_COND_EXP_XYT = 4    /* c0 * exp(c1 x + c2 y + c3 t)        */
 };
 
 /* Linear templates: src/specific_problems/*.jl */

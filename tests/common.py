@@ -30,6 +30,8 @@ def cond_closure(spec):
         return lambda x, y, t, u, p: spec.c0 * (1.0 - math.exp(-t / spec.tau)) + 0.0 * x
     if isinstance(spec, G.LinearXY):
         return lambda x, y, t, u, p: spec.c0 + spec.cx * x + spec.cy * y
+    if isinstance(spec, G.ExpXYT):
+        return lambda x, y, t, u, p: spec.c0 * np.exp(spec.cx * x + spec.cy * y + spec.ct * t)
     raise TypeError(spec)
 
 

@@ -273,3 +273,32 @@ def test_annulus_two_boundary_loops():
     exact = np.log(rr / 1.0) / np.log(0.2 / 1.0)
     assert rel_err(s2.u, O.solve_steady(ref)) <= 1e-9
     assert np.abs(s2.u - exact).max() <= 5e-3
+
+
+def test_brusselator_tutorial_exact_solution():
+    """docs/src/literate_tutorials/reaction_diffusion_brusselator_system_of_pdes.jl:95-140: a 2-species
+    FVMSystem with per-species mixed, time-dependent Neumann / Dirichlet data and the exact solution
+    Phi = exp(-x-y-t/2), Psi = exp(x+y+t/2).  Device Tsit5 vs the oracle (1e-10) and vs the exact
+    solution (discretisation level)."""
+    n = 31
+    pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, n, n, single_boundary=False))
+    P = pair.gtri.points
+    E = G.ExpXYT
+    phi_bc = (E(-0.25, -1, 0, -0.5), E(0.25 * np.exp(-1), 0, -1, -0.5), E(np.exp(-1), -1, 0, -0.5), E(-0.25, 0, -1, -0.5))
+    psi_bc = (E(1.0, 1, 0, 0.5), E(-0.25 * np.exp(1), 0, 1, 0.5), E(-0.25 * np.exp(1), 1, 0, 0.5), E(1.0, 0, 1, 0.5))
+    phi_t, psi_t = (G.Neumann, G.Neumann, G.Dirichlet, G.Neumann), (G.Dirichlet, G.Neumann, G.Neumann, G.Dirichlet)
+    phi0, psi0 = np.exp(-P[:, 0] - P[:, 1]), np.exp(P[:, 0] + P[:, 1])
+    src = G.BrusselatorSource()
+    g1, o1 = pair.problem(phi_bc, phi_t, G.ConstantDiffusion(0.25), source=src, var=0, ic=phi0, final_time=0.5)
+    g2, o2 = pair.problem(psi_bc, psi_t, G.ConstantDiffusion(0.25), source=src, var=1, ic=psi0, final_time=0.5)
+    gs, os_ = G.FVMSystem(g1, g2), O.FVMSystem(o1, o2)
+    U0 = gs.initial_condition
+    du = G.fvm_eqs(np.zeros_like(U0), U0, G.get_cuda_parameters(gs, tile_triangles=256), 0.3)
+    assert rel_err(du, O.fvm_eqs_vec(np.zeros_like(U0), U0, os_, 0.3)) <= RTOL_RHS
+    dt = 1e-3
+    sol = G.solve(gs, G.Tsit5(dt), tile_triangles=256)
+    uref = O.tsit5_fixed(lambda d, x, t: O.fvm_eqs_vec(d, x, os_, t), U0, 0.0, 0.5, dt,
+                         callback=lambda x, t: (O.update_dirichlet_nodes(x, t, os_), True)[1])
+    assert rel_err(sol.u, uref) <= RTOL_TSIT5
+    exact = np.stack([np.exp(-P[:, 0] - P[:, 1] - 0.25), np.exp(P[:, 0] + P[:, 1] + 0.25)], axis=1)
+    assert np.abs(sol.u - exact).max() <= 2e-2 * np.abs(exact).max()

@@ -414,3 +414,53 @@ def test_c_oracle_matches_numpy_oracle():
     assert np.array_equal(co.fvm_eqs_serial(u), ref)
     assert isapprox(co.fvm_eqs_threaded(u), ref, rtol=1e-14)
     assert isapprox(co.fvm_eqs_flat(u), ref, rtol=1e-14)
+
+
+def test_readme_square_plate_series_solution():
+    """BASELINE configs[0] end to end on the oracle: README diffusion (50x50, D = 1/9, Dirichlet 0) integrated
+    with the fixed-step Tsit5 and the Dirichlet callback, against the separated-variables series of
+    docs/src/literate_tutorials/diffusion_equation_on_a_square_plate.jl:79-94 (discretisation-level agreement;
+    the tutorial only plots it)."""
+    tri = O.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: 0.0 * u, O.Dirichlet)
+    ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
+    prob = O.FVMProblem(mesh, BCs, diffusion_function=lambda x, y, t, u, p: 1 / 9 + 0 * u, initial_condition=ic, final_time=0.5)
+    u = O.tsit5_fixed(lambda d, x, t: O.fvm_eqs_vec(d, x, prob, t), ic, 0.0, 0.5, 0.0025,
+                      callback=lambda x, t: (O.update_dirichlet_nodes(x, t, prob), True)[1])
+    x, y = tri.points[:, 0], tri.points[:, 1]
+    s = np.zeros_like(x)
+    for m in range(1, 50, 2):
+        mterm = 2 / m * np.sin(m * np.pi * x / 2) * np.exp(-np.pi**2 * m**2 * 0.5 / 36)
+        for n in range(1, 50):
+            s += mterm * (1 - np.cos(n * np.pi / 2)) / n * np.sin(n * np.pi * y / 2) * np.exp(-np.pi**2 * n**2 * 0.5 / 36)
+    exact = 200 * s / np.pi**2
+    assert np.abs(u - exact).max() <= 0.02 * exact.max()  # O(h^2) discretisation error on a 50x50 mesh
+    assert 20.0 < exact.max() < 50.0
+
+
+def test_brusselator_exact_solution_pins_system_path():
+    """docs/src/literate_tutorials/reaction_diffusion_brusselator_system_of_pdes.jl:95-140,125-126: exact
+    solution Phi = exp(-x-y-t/2), Psi = exp(x+y+t/2) of a 2-species FVMSystem with mixed time-dependent
+    Neumann / Dirichlet data.  Pins the oracle's system RHS, Neumann edges, Dirichlet callback and sources."""
+    tri = O.triangulate_rectangle(0, 1, 0, 1, 21, 21, single_boundary=False)
+    mesh = O.FVMGeometry(tri)
+    P = tri.points
+    e = math.e
+    phi_bc = (lambda x, y, t, u, p: -1 / 4 * np.exp(-x - t / 2), lambda x, y, t, u, p: 1 / 4 * np.exp(-1 - y - t / 2),
+              lambda x, y, t, u, p: np.exp(-1 - x - t / 2), lambda x, y, t, u, p: -1 / 4 * np.exp(-y - t / 2))
+    psi_bc = (lambda x, y, t, u, p: np.exp(x + t / 2), lambda x, y, t, u, p: -1 / 4 * np.exp(1 + y + t / 2),
+              lambda x, y, t, u, p: -1 / 4 * np.exp(1 + x + t / 2), lambda x, y, t, u, p: np.exp(y + t / 2))
+    pb = O.BoundaryConditions(mesh, phi_bc, (O.Neumann, O.Neumann, O.Dirichlet, O.Neumann))
+    sb = O.BoundaryConditions(mesh, psi_bc, (O.Dirichlet, O.Neumann, O.Neumann, O.Dirichlet))
+    p1 = O.FVMProblem(mesh, pb, flux_function=lambda x, y, t, a, b, g, p: (-a[0] / 4, -b[0] / 4),
+                      source_function=lambda x, y, t, u, p: u[0] ** 2 * u[1] - 2 * u[0], initial_condition=np.exp(-P[:, 0] - P[:, 1]),
+                      final_time=0.5)
+    p2 = O.FVMProblem(mesh, sb, flux_function=lambda x, y, t, a, b, g, p: (-a[1] / 4, -b[1] / 4),
+                      source_function=lambda x, y, t, u, p: -u[0] ** 2 * u[1] + u[0], initial_condition=np.exp(P[:, 0] + P[:, 1]),
+                      final_time=0.5)
+    sys_ = O.FVMSystem(p1, p2)
+    u = O.tsit5_fixed(lambda d, x, t: O.fvm_eqs_vec(d, x, sys_, t), sys_.initial_condition, 0.0, 0.5, 2e-3,
+                      callback=lambda x, t: (O.update_dirichlet_nodes(x, t, sys_), True)[1])
+    exact = np.stack([np.exp(-P[:, 0] - P[:, 1] - 0.25), np.exp(P[:, 0] + P[:, 1] + 0.25)], axis=1)
+    assert np.abs(u - exact).max() <= 2e-3 * np.abs(exact).max()

@@ -343,7 +343,8 @@ def test_abi_index_base_one_and_native_entry_points():
     L.check(h, lib.fvm_finalize(h, 128, 0))
     du = np.zeros(N)
     L.check(h, lib.fvm_rhs(h, 0.0, u.ctypes.data, du.ctypes.data, 0))
-    assert np.array_equal(du, ref)
+    assert rel_err(du, ref) <= 1e-13  # another tile size: only the summation order differs
+    ref = du
     # device pointers, native order
     ud = torch.from_numpy(u).cuda()
     un, dn, dc = torch.empty_like(ud), torch.empty_like(ud), torch.empty_like(ud)
