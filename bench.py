@@ -302,9 +302,34 @@ def cpu_baseline(nx, target_s=12.0, impl_reference=False, steps=None, warmup=1):
         co.fvm_eqs_flat(u, du)
     dt_flat = (time.perf_counter() - t0) / max(2, reps // 4)
     T = tri.num_triangles
+    # the template SpMV on the CPU: 7-point operator of the same lattice in CSR, single-threaded like
+    # SparseArrays' mul! (diffusion_equation.jl:93-94) and with all cores
+    spmv_note = ""
+    try:
+        from oracle.c_oracle import spmv as c_spmv
+        import scipy.sparse as sp
+        N = tri.num_points
+        idx = np.arange(N)
+        A = sp.diags([np.full(N, -4.0), np.ones(N - 1), np.ones(N - 1), np.ones(N - nx), np.ones(N - nx), np.full(N - nx + 1, 1e-16),
+                      np.full(N - nx + 1, 1e-16)], [0, 1, -1, nx, -nx, nx - 1, -(nx - 1)], format="csr")
+        rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+        bb = np.zeros(N)
+        c_spmv(rp, ci, va, bb, u, 1)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            c_spmv(rp, ci, va, bb, u, 1)
+        t1s = (time.perf_counter() - t0) / 5
+        t0 = time.perf_counter()
+        for _ in range(10):
+            c_spmv(rp, ci, va, bb, u, co.nthreads)
+        tns = (time.perf_counter() - t0) / 10
+        Bs = 12 * A.nnz + 4 * (N + 1) + 24 * N
+        spmv_note = "; CSR SpMV on the same lattice: %.1f GB/s on 1 core, %.1f GB/s on %d cores" % (Bs / t1s / 1e9, Bs / tns / 1e9, co.nthreads)
+    except Exception as e:  # the RHS line is the baseline; the SpMV note is extra
+        spmv_note = "; CPU SpMV note unavailable (%s)" % type(e).__name__
     out = {"value": T / dt / 1e6, "unit": "Mtriangle-updates/s", "cores": co.nthreads, "kind": "port",
            "sample": "%dx%d lattice (%d triangles), %d threaded fvm_eqs! calls of the reference-structured C port; "
-                     "flat-array variant: %.1f Mtri/s" % (nx, nx, T, reps, T / dt_flat / 1e6),
+                     "flat-array variant: %.1f Mtri/s%s" % (nx, nx, T, reps, T / dt_flat / 1e6, spmv_note),
            "ms_per_step": dt * 1e3}
     co.close()
     return out
