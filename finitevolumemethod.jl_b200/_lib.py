@@ -8,7 +8,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfvmcuda.so")
 
-OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NCCL = range(6)
+OK, ERR_ARG, ERR_CUDA, ERR_UNSUPPORTED, ERR_STATE, ERR_NCCL, ERR_IO = range(7)
 
 
 class FVMCudaError(RuntimeError):
@@ -72,12 +72,22 @@ _SIGS = {
     "fvm_set_halo": [H, C.c_int32, c_ip, c_ip, c_ip, c_ip, c_ip],
     "fvm_halo_exchange_native": [H, C.c_void_p],
     "fvm_nccl_unique_id": [C.c_void_p],
+    # FVMWIRE containers (host only)
+    "fvm_wire_create": [C.c_char_p, C.POINTER(H)],
+    "fvm_wire_put": [H, C.c_char_p, C.c_int32, C.c_int32, c_lp, C.c_void_p],
+    "fvm_wire_open": [C.c_char_p, C.POINTER(H)],
+    "fvm_wire_count": [H, c_ip],
+    "fvm_wire_info": [H, C.c_int32, C.c_char_p, c_ip, c_ip, c_lp, c_lp],
+    "fvm_wire_find": [H, C.c_char_p, c_ip],
+    "fvm_wire_get": [H, C.c_int32, C.c_void_p, C.c_int64],
+    "fvm_wire_close": [H],
+    "fvm_create_from_wire": [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(H)],
 }
 
 
 def exported_symbols():
     """Every entry point include/fvmcuda.h declares (checked by the CPU test-suite)."""
-    return sorted(list(_SIGS) + ["fvm_last_error", "fvm_version"])
+    return sorted(list(_SIGS) + ["fvm_last_error", "fvm_version", "fvm_wire_last_error", "fvm_wire_crc32"])
 
 
 def lib():
@@ -95,6 +105,10 @@ def lib():
         L.fvm_last_error.restype = C.c_char_p
         L.fvm_version.argtypes = []
         L.fvm_version.restype = C.c_char_p
+        L.fvm_wire_last_error.argtypes = [H]
+        L.fvm_wire_last_error.restype = C.c_char_p
+        L.fvm_wire_crc32.argtypes = [C.c_void_p, C.c_int64]
+        L.fvm_wire_crc32.restype = C.c_uint32
         _lib = L
     return _lib
 

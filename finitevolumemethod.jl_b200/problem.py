@@ -66,10 +66,16 @@ class FVMGeometry:
         return np.stack([(p + mij) / 2, (q + mij) / 2], axis=1)
 
 
-def _create_handle(tri, neq, device=None):
+def _create_handle(tri, neq, device=None, mesh_file=None):
     if device is None:
         device = _current_device()
     h = L.H()
+    if mesh_file is not None:  # points / triangles come from an FVMWIRE container (wire.py)
+        rc = L.lib().fvm_create_from_wire(str(mesh_file).encode(), neq, device, C.byref(h))
+        if rc != L.OK:
+            msg = L.lib().fvm_wire_last_error(None) if rc == L.ERR_IO else L.lib().fvm_last_error(None)
+            raise L.FVMCudaError(rc, msg.decode())
+        return h
     pts = L.f64(tri.points)
     tr = L.i32(tri.triangles)
     rc = L.lib().fvm_create(L.dp(pts), tri.num_points, L.ip(tr), tri.num_triangles, 0, neq, device, C.byref(h))
@@ -180,12 +186,13 @@ class SteadyFVMProblem:
 class Engine:
     """Owns one libfvmcuda handle for a problem (RHS) or a template (linear operator)."""
 
-    def __init__(self, mesh, neq, conditions, flux=None, source=None, tile_triangles=0, geometry_mode=0, device=None, ghost=None):
+    def __init__(self, mesh, neq, conditions, flux=None, source=None, tile_triangles=0, geometry_mode=0, device=None, ghost=None,
+                 mesh_file=None):
         lib = L.lib()
         tri = mesh.triangulation
         self.mesh, self.neq = mesh, neq
         self.N, self.T = tri.num_points, tri.num_triangles
-        self.h = _create_handle(tri, neq, device)
+        self.h = _create_handle(tri, neq, device, mesh_file)
         self._keep = []
         try:
             uv = conditions[0].boundary_edges
@@ -364,15 +371,16 @@ class CudaParameters:
         self.engine = engine
 
 
-def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None, ghost=None):
-    """Sibling of get_multithreading_parameters (solve.jl:1-27): builds the device state once."""
+def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None, ghost=None, mesh_file=None):
+    """Sibling of get_multithreading_parameters (solve.jl:1-27): builds the device state once.
+    `mesh_file`: let the library read points / triangles from an FVMWIRE container of the same mesh."""
     if isinstance(prob, SteadyFVMProblem):
         prob = prob.problem
     probs = prob.problems
     neq = max(1, prob.neqs)
     conds = [p.conditions for p in probs]
     eng = Engine(prob.mesh, neq, conds, [p.flux_function for p in probs], [p.source_function for p in probs],
-                 tile_triangles, geometry_mode, device, ghost)
+                 tile_triangles, geometry_mode, device, ghost, mesh_file)
     return CudaParameters(prob, eng)
 
 

@@ -38,7 +38,8 @@ enum fvm_status {
     FVM_ERR_CUDA = 2,        /* CUDA runtime failure, including "no device" */
     FVM_ERR_UNSUPPORTED = 3, /* functor / closure outside the registry (north_star b) */
     FVM_ERR_STATE = 4,       /* call order violated (e.g. rhs before finalize) */
-    FVM_ERR_NCCL = 5
+    FVM_ERR_NCCL = 5,
+    FVM_ERR_IO = 6           /* FVMWIRE container: file missing, truncated, corrupt or checksum mismatch */
 };
 
 /* node condition kinds: src/conditions.jl:36-41, flattened per node / per boundary edge */
@@ -218,6 +219,38 @@ int32_t fvm_shard_init(fvm_handle h, const void* nccl_unique_id, int32_t rank, i
 int32_t fvm_set_halo(fvm_handle h, int32_t n_neighbours, const int32_t* neighbour_ranks, const int32_t* send_ptr,
                      const int32_t* send_nodes, const int32_t* recv_ptr, const int32_t* recv_nodes);
 int32_t fvm_halo_exchange_native(fvm_handle h, double* u_native);
+
+/* ---- FVMWIRE: flat binary SoA container for meshes and solutions ------------
+ * The reference has no file format: a mesh is the DelaunayTriangulation object FVMGeometry(tri) walks
+ * (src/geometry.jl:99-106) and a solution is sol.u / sol.t (src/solve.jl:197-208).  The container holds
+ * exactly those arrays, column-major (dims[0] fastest, i.e. Julia's size(A)), 64-byte aligned so a payload
+ * can be handed to cudaMemcpy / mmap as it lies: 64-byte header, a fixed table of FVM_WIRE_MAX_ARRAYS
+ * 96-byte entries {name[32], dtype, rank, dims[4], offset, nbytes, crc32}, then the payloads.  Every
+ * payload and the table carry a CRC-32 (zlib polynomial); fvm_wire_open / fvm_wire_get fail with
+ * FVM_ERR_IO on truncation or corruption.  Host-only calls: they need no CUDA device.
+ * Mesh schema: "points" f64 (2,N); "triangles" i32 (3,T); "index_base" i32 (1); "boundary_ptr" i32 (S+1)
+ * + "boundary_nodes" i32 (ccw node sequence of every boundary section, get_boundary_nodes(tri));
+ * optional "boundary_edges" i32 (2,Eb).  Solution schema: "t" f64 (nsave); "u" f64 (N,nsave) or
+ * (neq,N,nsave). */
+#define FVM_WIRE_MAX_ARRAYS 64
+enum fvm_wire_dtype { FVM_WIRE_F64 = 1, FVM_WIRE_I32 = 2, FVM_WIRE_U8 = 3, FVM_WIRE_I64 = 4 };
+typedef struct fvm_wire* fvm_wire_handle;
+
+int32_t fvm_wire_create(const char* path, fvm_wire_handle* out); /* write mode; arrays are streamed to disk */
+int32_t fvm_wire_put(fvm_wire_handle w, const char* name, int32_t dtype, int32_t rank, const int64_t* dims,
+                     const void* data);
+int32_t fvm_wire_open(const char* path, fvm_wire_handle* out);   /* read mode; validates header + table */
+int32_t fvm_wire_count(fvm_wire_handle w, int32_t* n_arrays);
+int32_t fvm_wire_info(fvm_wire_handle w, int32_t index, char* name32, int32_t* dtype, int32_t* rank,
+                      int64_t* dims4, int64_t* nbytes);
+int32_t fvm_wire_find(fvm_wire_handle w, const char* name, int32_t* index);
+int32_t fvm_wire_get(fvm_wire_handle w, int32_t index, void* out, int64_t nbytes); /* verifies the CRC */
+int32_t fvm_wire_close(fvm_wire_handle w);                       /* write mode: finishes header + table */
+const char* fvm_wire_last_error(fvm_wire_handle w);              /* w == NULL: last failing open/create */
+uint32_t fvm_wire_crc32(const void* data, int64_t nbytes);
+/* fvm_create + fvm_set_boundary_edges from a mesh container (replaces FVMGeometry(tri) for meshes that
+ * are produced elsewhere); continue with the setters and fvm_finalize. */
+int32_t fvm_create_from_wire(const char* path, int32_t neq, int32_t device, fvm_handle* out);
 
 #ifdef __cplusplus
 }

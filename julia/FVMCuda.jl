@@ -100,4 +100,49 @@ function tsit5!(u::Array{Float64}, h::Handle, t0, t1, dt; use_operator = false)
     return u
 end
 
+# ---- FVMWIRE containers: the importer/exporter for DelaunayTriangulation objects and solutions -------
+wire_check(w, rc) = rc == 0 || throw(FVMCudaError(rc, unsafe_string(ccall((:fvm_wire_last_error, LIB), Cstring, (Ptr{Cvoid},), w))))
+const WIRE_DTYPE = Dict(Float64 => Int32(1), Int32 => Int32(2), UInt8 => Int32(3), Int64 => Int32(4))
+
+function wire_put(w::Ptr{Cvoid}, name::String, A::Array{T}) where {T}
+    dims = collect(Int64, size(A))          # Julia's size(A) is already fastest-first
+    wire_check(w, ccall((:fvm_wire_put, LIB), Int32, (Ptr{Cvoid}, Cstring, Int32, Int32, Ptr{Int64}, Ptr{Cvoid}),
+        w, name, WIRE_DTYPE[T], length(dims), dims, A))
+end
+
+"Writes the arrays `FVMGeometry(tri)` reads (src/geometry.jl:99-106) plus the boundary description."
+function write_mesh(path::String, tri::Triangulation)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    wire_check(C_NULL, ccall((:fvm_wire_create, LIB), Int32, (Cstring, Ptr{Ptr{Cvoid}}), path, out))
+    w = out[]
+    pts = reshape(collect(Float64, Iterators.flatten(DelaunayTriangulation.each_point(tri))), 2, :)
+    T = reshape(collect(Int32, Iterators.flatten(triangle_vertices(t) for t in each_solid_triangle(tri))), 3, :)
+    edges = collect(keys(get_boundary_edge_map(tri)))
+    wire_put(w, "points", pts); wire_put(w, "triangles", T); wire_put(w, "index_base", Int32[1])
+    wire_put(w, "boundary_edges", reshape(collect(Int32, Iterators.flatten(edges)), 2, :))
+    # section of an edge (u, v): the ghost vertex on its other side is -section (src/conditions.jl:507-515)
+    wire_put(w, "boundary_edge_section", Int32[-get_adjacent(tri, v, u) - 1 for (u, v) in edges])
+    wire_put(w, "num_sections", Int32[length(DelaunayTriangulation.get_ghost_vertex_map(tri))])
+    wire_check(C_NULL, ccall((:fvm_wire_close, LIB), Int32, (Ptr{Cvoid},), w))
+    return path
+end
+
+"`sol.u` / `sol.t` of `solve(prob, alg; saveat)` (src/solve.jl:197-208) as one (N, nsave) or (neq, N, nsave) array."
+function write_solution(path::String, sol)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    wire_check(C_NULL, ccall((:fvm_wire_create, LIB), Int32, (Cstring, Ptr{Ptr{Cvoid}}), path, out))
+    w = out[]
+    wire_put(w, "u", cat(sol.u...; dims = ndims(sol.u[1]) + 1)); wire_put(w, "t", collect(Float64, sol.t))
+    wire_check(C_NULL, ccall((:fvm_wire_close, LIB), Int32, (Ptr{Cvoid},), w))
+    return path
+end
+
+"`Handle` straight from a mesh container (no Triangulation object on the Julia side)."
+function handle_from_wire(path::String, neq::Integer; device = 0)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:fvm_create_from_wire, LIB), Int32, (Cstring, Int32, Int32, Ptr{Ptr{Cvoid}}), path, neq, device, out)
+    rc == 0 || throw(FVMCudaError(rc, unsafe_string(ccall((:fvm_wire_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL))))
+    return out[]
+end
+
 end # module
