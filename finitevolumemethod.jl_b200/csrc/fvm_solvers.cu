@@ -714,8 +714,51 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
         FVM_CUDA(h, cudaStreamSynchronize(st));
         return FVM_OK;
     };
-    // Outer loop = residual replacement: every cycle starts from the TRUE residual b - A x, so the
-    // recurrence drift of CG / BiCGStab cannot hide a residual above the tolerance.
+    // The iteration body is a dozen short kernels whose scalars (alpha, beta, omega, the convergence flag)
+    // live on the device, so a block of `check_every` iterations is captured once into a CUDA graph and
+    // replayed between two polls of the flag: no launch gaps on launch-bound meshes.  Not used when sharded
+    // (NCCL inside the iteration) or while the per-kernel profiling events are armed.
+    struct Graphs {
+        cudaGraphExec_t exec[2] = {nullptr, nullptr};
+        ~Graphs() {
+            for (cudaGraphExec_t e : exec)
+                if (e) cudaGraphExecDestroy(e);
+        }
+    } graphs;
+    const bool graph_ok = h->nranks == 1 && !h->halo_ready && !h->profiling && !getenv("FVM_NO_GRAPH");
+    auto run_iterations = [&](auto& iteration, int budget, cudaGraphExec_t& exec) -> int32_t {
+        for (int it = 0; it < budget;) {
+            const int chunk = std::min(check_every, budget - it);
+            if (graph_ok && chunk == check_every) {
+                if (!exec) {
+                    cudaGraph_t graph = nullptr;
+                    FVM_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                    int32_t r = FVM_OK;
+                    for (int q = 0; q < chunk && !r; ++q) r = iteration();
+                    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+                    if (r) {
+                        if (graph) cudaGraphDestroy(graph);
+                        return r;
+                    }
+                    FVM_CUDA(h, ce);
+                    ce = cudaGraphInstantiate(&exec, graph, 0);
+                    cudaGraphDestroy(graph);
+                    FVM_CUDA(h, ce);
+                }
+                FVM_CUDA(h, cudaGraphLaunch(exec, st));
+            } else {
+                for (int q = 0; q < chunk; ++q) {
+                    int32_t r = iteration();
+                    if (r) return r;
+                }
+            }
+            it += chunk;
+            int32_t r = poll();
+            if (r) return r;
+            if (hsc[SC_DONE] != 0.0) break;
+        }
+        return FVM_OK;
+    };
     int32_t total_iters = 0;
     double last_rr = -1.0;
     for (int cycle = 0; cycle < 8 && total_iters < maxit; ++cycle) {
@@ -727,20 +770,19 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
             pcg_init2_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, Q, c.diag_inv, R, Z, P, partial);
             if ((rc = reduce(3, 0))) return rc;
             pcg_init3_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
-            for (int it = 0; it < budget; ++it) {
-                if ((rc = spmv(P, Q, true))) return rc;
+            auto iteration = [&]() -> int32_t {
+                int32_t r;
+                if ((r = spmv(P, Q, true))) return r;
                 dot_kernel<<<G, B, 0, st>>>(n, P, Q, partial, sc);
-                if ((rc = reduce(1, 1))) return rc;
+                if ((r = reduce(1, 1))) return r;
                 pcg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
                 pcg_update_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, c.rowscale, X, R, Z, partial, sc);
-                if ((rc = reduce(2, 1))) return rc;
+                if ((r = reduce(2, 1))) return r;
                 pcg_beta_kernel<<<1, B, 0, st>>>(partial, sc);
                 pcg_p_kernel<<<G, B, 0, st>>>(n, Z, P, sc);
-                if ((it + 1) % check_every == 0 || it + 1 == budget) {
-                    if ((rc = poll())) return rc;
-                    if (hsc[SC_DONE] != 0.0) break;
-                }
-            }
+                return FVM_OK;
+            };
+            if ((rc = run_iterations(iteration, budget, graphs.exec[0]))) return rc;
         } else {
             double *R = h->d_work[1], *RH = h->d_work[2], *P = h->d_work[3], *V = h->d_work[4], *Y = h->d_work[5],
                    *S = h->d_work[6], *Z = h->d_work[7], *T = h->d_work[8], *KI = h->d_work[9];
@@ -750,25 +792,24 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
             bicg_init_kernel<<<G, B, 0, st>>>(n, c.b, V, R, RH, P, V, partial);
             if ((rc = reduce(2, 0))) return rc;
             bicg_init2_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
-            for (int it = 0; it < budget; ++it) {
+            auto iteration = [&]() -> int32_t {
+                int32_t r;
                 bicg_p_kernel<<<G, B, 0, st>>>(n, R, V, KI, P, Y, RH, sc);
-                if ((rc = spmv(Y, V, false))) return rc;
+                if ((r = spmv(Y, V, false))) return r;
                 dot_kernel<<<G, B, 0, st>>>(n, RH, V, partial, sc);
-                if ((rc = reduce(1, 1))) return rc;
+                if ((r = reduce(1, 1))) return r;
                 bicg_alpha_kernel<<<1, B, 0, st>>>(partial, sc);
                 bicg_s_kernel<<<G, B, 0, st>>>(n, R, V, KI, S, Z, sc);
-                if ((rc = spmv(Z, T, false))) return rc;
+                if ((r = spmv(Z, T, false))) return r;
                 bicg_ts_kernel<<<G, B, 0, st>>>(n, T, S, partial, sc);
-                if ((rc = reduce(2, 1))) return rc;
+                if ((r = reduce(2, 1))) return r;
                 bicg_omega_kernel<<<1, B, 0, st>>>(partial, sc);
                 bicg_x_kernel<<<G, B, 0, st>>>(n, Y, Z, S, T, RH, X, R, partial, sc);
-                if ((rc = reduce(2, 1))) return rc;
+                if ((r = reduce(2, 1))) return r;
                 bicg_end_kernel<<<1, B, 0, st>>>(partial, sc);
-                if ((it + 1) % check_every == 0 || it + 1 == budget) {
-                    if ((rc = poll())) return rc;
-                    if (hsc[SC_DONE] != 0.0) break;
-                }
-            }
+                return FVM_OK;
+            };
+            if ((rc = run_iterations(iteration, budget, graphs.exec[1]))) return rc;
         }
         FVM_CUDA(h, cudaGetLastError());
         if ((rc = poll())) return rc;

@@ -2,14 +2,53 @@
 import numpy as np
 
 from . import _lib as L
-from .problem import FVMProblem, FVMSystem, SteadyFVMProblem, get_cuda_parameters
+from .problem import FVMProblem, FVMSystem, SteadyFVMProblem, fvm_eqs, get_cuda_parameters, jacobian, update_dirichlet_nodes
 from .templates import AbstractFVMTemplate, Solution, Tsit5, run_tsit5, solve_template
+
+
+class NewtonRaphson:
+    """`solve(SteadyFVMProblem(prob), NewtonRaphson())` (solve.jl:209-220; used by
+    docs/src/literate_tutorials/helmholtz_equation_with_inhomogeneous_boundary_conditions.jl:65).  The
+    nonlinear solver is a caller of the hot path, so it stays on the host like the reference's
+    NonlinearSolve + KLU: every iteration evaluates fvm_eqs! and its sparse Jacobian on the device and
+    solves the Newton system with a sparse direct factorisation."""
+
+    def __init__(self, abstol=1e-11, reltol=1e-11, maxiters=50):
+        self.abstol, self.reltol, self.maxiters = float(abstol), float(reltol), int(maxiters)
+
+
+def _solve_steady_newton(prob, alg, p):
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    t = prob.initial_time
+    u = np.ascontiguousarray(prob.initial_condition, dtype=np.float64).copy()
+    update_dirichlet_nodes(u, t, p)  # Dirichlet rows of fvm_eqs! are identically zero: fix the values first
+    du = np.zeros_like(u)
+    fvm_eqs(du, u, p, t)
+    r0 = np.abs(du).max()
+    retcode, it = "MaxIters", 0
+    for it in range(alg.maxiters + 1):
+        res = np.abs(du).max()
+        if res <= alg.abstol + alg.reltol * r0:
+            retcode = "Success"
+            break
+        if it == alg.maxiters or not np.isfinite(res):
+            break
+        J = jacobian(u, p, t).tocsr()
+        # rows without any entry (Dirichlet nodes, points that are not vertices): du = 0 there, keep u
+        empty = np.asarray(abs(J).sum(axis=1)).ravel() == 0.0
+        J = (J + sp.diags(empty.astype(np.float64))).tocsc()
+        delta = spla.splu(J).solve(-du.ravel())
+        u += delta.reshape(u.shape)
+        fvm_eqs(du, u, p, t)
+    return Solution(u, None, iters=it, relres=float(np.abs(du).max() / r0) if r0 > 0 else 0.0, retcode=retcode)
 
 
 def solve(prob, alg=None, *, saveat=None, parallel="cuda", p=None, **kw):
     """`solve(prob, alg; saveat, parallel)`.
 
     * templates: device Tsit5 (transient) or Jacobi-Krylov (steady);
+    * SteadyFVMProblem with `NewtonRaphson()`: host Newton iteration on the device RHS and device Jacobian;
     * FVMProblem / FVMSystem with `Tsit5(dt)`: device-resident fixed-step Tsit5 on `fvm_eqs!` with the
       Dirichlet callback after every step (solve.jl:133-165);
     * any other integrator stays on the host and calls `fvm_eqs(du, u, p, t)` through
@@ -17,8 +56,12 @@ def solve(prob, alg=None, *, saveat=None, parallel="cuda", p=None, **kw):
     if isinstance(prob, AbstractFVMTemplate):
         return solve_template(prob, alg, saveat=saveat, **kw)
     if isinstance(prob, SteadyFVMProblem):
-        raise NotImplementedError("SteadyFVMProblem is solved by a host nonlinear solver around fvm_eqs(du,u,p,t) "
-                                  "(solve.jl:209-220); use get_cuda_parameters(prob) and your solver of choice")
+        if not isinstance(alg, NewtonRaphson):
+            raise TypeError("SteadyFVMProblem: NewtonRaphson() is provided; any other nonlinear / DynamicSS solver stays on "
+                            "the host around fvm_eqs(du,u,p,t) and jacobian(u,p,t) (solve.jl:209-220)")
+        if parallel != "cuda":
+            raise ValueError("this package only provides the CUDA path (no CPU fallback)")
+        return _solve_steady_newton(prob.problem, alg, p or get_cuda_parameters(prob, **kw))
     if not isinstance(prob, (FVMProblem, FVMSystem)):
         raise TypeError("cannot solve %r" % (prob,))
     if parallel != "cuda":

@@ -302,3 +302,34 @@ def test_brusselator_tutorial_exact_solution():
     assert rel_err(sol.u, uref) <= RTOL_TSIT5
     exact = np.stack([np.exp(-P[:, 0] - P[:, 1] - 0.25), np.exp(P[:, 0] + P[:, 1] + 0.25)], axis=1)
     assert np.abs(sol.u - exact).max() <= 2e-2 * np.abs(exact).max()
+
+
+def test_steady_newton_raphson_linear_and_nonlinear():
+    """solve(SteadyFVMProblem(prob), NewtonRaphson()) (solve.jl:209-220): device RHS + device Jacobian, host
+    Newton.  Linear diffusion reaches the LaplacesEquation template solution (the reference's own cross-check,
+    docs/src/literate_wyos/laplaces_equation.jl:188-193) in one step; the porous-medium problem is checked
+    through the ORACLE's residual at the returned state."""
+    gtri = _split_loop(delaunay_mesh(500, 13, jitter=0.3), k=4)
+    pair = Pair(gtri)
+    specs = (G.LinearXY(0.5, 1.0, -2.0), G.Const(0.0), G.LinearXY(0.1, 0.2, 0.3), G.Const(0.0))
+    types = (G.Dirichlet, G.Neumann, G.Dirichlet, G.Neumann)
+    ic = np.random.default_rng(1).random(gtri.num_points)
+    gp, op = pair.problem(specs, types, G.ConstantDiffusion(0.8), ic=ic)
+    sol = G.solve(G.SteadyFVMProblem(gp), G.NewtonRaphson())
+    assert sol.retcode == "Success" and sol.iters <= 2
+    oBC = O.BoundaryConditions(pair.omesh, tuple(xy_cond(s) for s in specs), types)
+    ref = O.solve_steady(O.LaplacesEquation(pair.omesh, oBC, diffusion_function=lambda x, y, p: 0.8))
+    assert rel_err(sol.u, ref) <= 1e-9
+    # nonlinear: D = 0.3 u, source 0.5 - 0.2 u
+    gp, op = pair.problem(specs, types, G.PowerDiffusion(0.3, 2.0), source=G.LinearSource(-0.2, 0.5), ic=0.5 + ic)
+    sol = G.solve(G.SteadyFVMProblem(gp), G.NewtonRaphson(), tile_triangles=128)
+    assert sol.retcode == "Success" and 2 <= sol.iters <= 20
+    u0 = (0.5 + ic).copy()
+    O.update_dirichlet_nodes(u0, 0.0, op)
+    f0 = np.abs(O.fvm_eqs_vec(np.zeros_like(u0), u0, op, 0.0)).max()
+    fs = np.abs(O.fvm_eqs_vec(np.zeros_like(sol.u), sol.u, op, 0.0)).max()
+    assert fs <= 1e-9 * f0
+    dn = np.array(sorted(op.conditions.dirichlet_nodes))
+    assert np.array_equal(sol.u[dn], u0[dn]) and sol.u.min() > 0
+    with pytest.raises(TypeError):
+        G.solve(G.SteadyFVMProblem(gp), G.Tsit5(0.1))
