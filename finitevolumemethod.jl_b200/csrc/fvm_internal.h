@@ -188,6 +188,13 @@ struct fvm_ctx {
     std::vector<int32_t> h_tile_node0, h_tile_nown, h_tile_ext0, h_ext_ids;  // host copies for the classification
     std::vector<uint8_t> h_ghost;  // caller order: 1 = ghost node owned by another rank
     int32_t rank = 0, nranks = 1;
+    // host-buffer pipeline of fvm_rhs (fvm_pipe.cu): caller-order bands copied in, tiles launched as soon as
+    // their nodes have arrived, finished bands copied out while later bands are still being copied in
+    std::vector<int32_t> h_tile_nint, h_ifc_node;
+    std::vector<uint8_t> h_ifc_edge;  // interface node receives a boundary-edge partial
+    void* pipe = nullptr;
+    const int32_t* pipe_list = nullptr;  // explicit tile list of fvm_launch_rhs_part(part = 4)
+    int32_t pipe_off = 0, pipe_count = 0;
 };
 
 // ---- helpers -----------------------------------------------------------------
@@ -240,7 +247,13 @@ int32_t fvm_apply_rhs(fvm_ctx* h, double t, double* x, double* out);
 int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* out, bool add_b, bool scale);
 // part: 0 = everything, 1 = independent tiles only, 2 = halo-dependent tiles (+ boundary-edge kernel),
 // 3 = the kernels that need every tile (interface / tail rows)
+//       4 = the tiles h->pipe_list[pipe_off .. pipe_off + pipe_count) only, 5 = the boundary-edge kernel only
 int32_t fvm_launch_rhs_part(fvm_ctx* h, double t, const double* u, double* du, int part);
+// interface nodes list[off .. off+count) (indices into ifc_node); points that are not vertices (du = 0)
+int32_t fvm_launch_rhs_interface_list(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count);
+int32_t fvm_launch_rhs_nonvertex(fvm_ctx* h, double* du);
+int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du_host, bool* used);
+void fvm_pipe_release(fvm_ctx* h);
 int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part);
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);
 int32_t fvm_global_or(fvm_ctx* h, bool local, bool* global);

@@ -1,0 +1,254 @@
+// libfvmcuda: fvm_rhs with HOST buffers as a three-stream pipeline.
+//
+// The drop-in call `fvm_eqs!(du, u, p, t)` (/root/reference/src/equations/main_equations.jl:28-35) hands the
+// library host vectors, so the call is bound by PCIe: 8*neq*N bytes in, 8*neq*N bytes out, one after the
+// other around ~0.7 ms of kernels.  PCIe is full duplex, so the vector is cut into K bands of consecutive
+// CALLER indices and the three steps overlap:
+//
+//   copy-in stream : for each band  H2D -> scatter into native (tile-major) order          -> event in[b]
+//   compute stream : stage s waits for in[s], runs the tiles whose nodes all lie in bands <= s, then the
+//                    interface nodes whose tiles have all run                               -> event stage[s]
+//   copy-out stream: band b waits for the stage after which all of its nodes are final, gathers it back
+//                    to caller order and copies it D2H while later bands are still arriving.
+//
+// Which stage a tile / interface node / output band belongs to is a property of the mesh numbering and is
+// computed once per handle (lazily, at the first host-buffer call).  On a lattice in the reference's
+// row-major numbering a Hilbert tile spans ~2 sqrt(TT/2) rows, so nearly every tile is ready one band after
+// its rows arrive; for an arbitrary numbering the plan degenerates gracefully to "everything in the last
+// stage", i.e. the unpipelined schedule.  Every node is still summed by the same kernels in the same order,
+// so the result is bit-identical to the unpipelined path.
+#include <algorithm>
+
+#include "fvm_internal.h"
+
+namespace {
+
+struct PipePlan {
+    int K = 0;
+    bool useful = false;
+    std::vector<int64_t> band_lo;         // [K+1] caller node index boundaries
+    std::vector<int32_t> tile_stage_ptr;  // [K+1] into d_tile_order
+    std::vector<int32_t> ifc_stage_ptr;   // [K+1] into d_ifc_order
+    std::vector<int32_t> out_stage;       // [K]
+    int32_t* d_tile_order = nullptr;
+    int32_t* d_ifc_order = nullptr;
+    double* d_out = nullptr;              // caller-order staging of du
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_stage;
+    cudaEvent_t ev_start = nullptr, ev_out = nullptr;
+};
+
+// band of caller node j
+inline int band_of(const PipePlan& P, int64_t j, int64_t N) { return (int)std::min<int64_t>(P.K - 1, j * P.K / N); }
+
+__global__ void band_scatter_kernel(const int32_t* __restrict__ new_of_old, const double* __restrict__ src_caller,
+                                    double* __restrict__ dst_native, const int64_t lo, const int64_t hi, const int neq) {
+    const int64_t idx = lo * neq + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hi * neq) return;
+    const int64_t j = idx / neq;
+    const int v = (int)(idx - j * neq);
+    dst_native[(int64_t)new_of_old[j] * neq + v] = src_caller[idx];
+}
+
+__global__ void band_gather_kernel(const int32_t* __restrict__ new_of_old, const double* __restrict__ src_native,
+                                   double* __restrict__ dst_caller, const int64_t lo, const int64_t hi, const int neq) {
+    const int64_t idx = lo * neq + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= hi * neq) return;
+    const int64_t j = idx / neq;
+    const int v = (int)(idx - j * neq);
+    dst_caller[idx] = src_native[(int64_t)new_of_old[j] * neq + v];
+}
+
+}  // namespace
+
+void fvm_pipe_release(fvm_ctx* h) {
+    PipePlan* P = (PipePlan*)h->pipe;
+    if (!P) return;
+    for (cudaEvent_t e : P->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : P->ev_stage) cudaEventDestroy(e);
+    if (P->ev_start) cudaEventDestroy(P->ev_start);
+    if (P->ev_out) cudaEventDestroy(P->ev_out);
+    if (P->s_in) cudaStreamDestroy(P->s_in);
+    if (P->s_out) cudaStreamDestroy(P->s_out);
+    delete P;  // the device arrays are in h->allocs
+    h->pipe = nullptr;
+}
+
+static int32_t build_plan(fvm_ctx* h, int K) {
+    PipePlan* P = new PipePlan;
+    h->pipe = P;
+    P->K = K;
+    const int64_t N = h->N;
+    const int32_t n_tiles = h->dm.n_tiles, n_ifc = h->dm.n_ifc, n_vertices = h->dm.n_vertices;
+    P->band_lo.resize(K + 1);
+    for (int b = 0; b <= K; ++b) P->band_lo[b] = N * b / K;
+    // band_of() and band_lo must agree: node j is in band b iff band_lo[b] <= j < band_lo[b+1]
+    auto band = [&](int64_t j) {
+        int b = band_of(*P, j, N);
+        while (j < P->band_lo[b]) --b;
+        while (j >= P->band_lo[b + 1]) ++b;
+        return b;
+    };
+    const int32_t* old_of_new = h->node_old_of_new.data();
+    // ---- stage of every tile: the last band that holds one of its (own or external) nodes -------------
+    std::vector<int32_t> tile_stage(n_tiles, 0);
+#pragma omp parallel for schedule(static)
+    for (int32_t t = 0; t < n_tiles; ++t) {
+        int s = 0;
+        for (int32_t g = h->h_tile_node0[t]; g < h->h_tile_node0[t] + h->h_tile_nown[t]; ++g) s = std::max(s, band(old_of_new[g]));
+        for (int32_t k = h->h_tile_ext0[t]; k < h->h_tile_ext0[t + 1]; ++k) s = std::max(s, band(old_of_new[h->h_ext_ids[k]]));
+        tile_stage[t] = s;
+    }
+    // ---- stage of every interface node: all tiles that hold it have run (+ the boundary-edge kernel) --
+    std::vector<int32_t> ifc_stage(n_ifc, 0);
+    {
+        int32_t base = 0;  // interface nodes are numbered tile by tile (fvm_finalize step 4)
+        std::vector<int32_t> ifc_base(n_tiles + 1, 0);
+        for (int32_t t = 0; t < n_tiles; ++t) {
+            ifc_base[t] = base;
+            base += h->h_tile_nown[t] - h->h_tile_nint[t];
+        }
+        for (int32_t t = 0; t < n_tiles; ++t) {
+            for (int32_t q = 0; q < h->h_tile_nown[t] - h->h_tile_nint[t]; ++q)
+                ifc_stage[ifc_base[t] + q] = std::max(ifc_stage[ifc_base[t] + q], tile_stage[t]);
+            for (int32_t k = h->h_tile_ext0[t]; k < h->h_tile_ext0[t + 1]; ++k) {
+                const int32_t g = h->h_ext_ids[k];
+                const int32_t i = (int32_t)(std::lower_bound(h->h_ifc_node.begin(), h->h_ifc_node.end(), g) - h->h_ifc_node.begin());
+                if (i >= n_ifc || h->h_ifc_node[i] != g) return fvm_fail(h, FVM_ERR_STATE, "pipeline plan: external node is not an interface node");
+                ifc_stage[i] = std::max(ifc_stage[i], tile_stage[t]);
+            }
+        }
+        for (int32_t i = 0; i < n_ifc; ++i)
+            if (h->h_ifc_edge[i]) ifc_stage[i] = K - 1;  // the boundary-edge kernel runs in the last stage
+    }
+    // ---- counting sorts -> launch lists ------------------------------------------------------------------
+    auto sort_by_stage = [&](const std::vector<int32_t>& stage, std::vector<int32_t>& ptr, std::vector<int32_t>& order) {
+        ptr.assign(K + 1, 0);
+        for (int32_t s : stage) ptr[s + 1]++;
+        for (int s = 0; s < K; ++s) ptr[s + 1] += ptr[s];
+        std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
+        order.resize(stage.size());
+        for (size_t i = 0; i < stage.size(); ++i) order[fill[stage[i]]++] = (int32_t)i;
+    };
+    std::vector<int32_t> tile_order, ifc_order;
+    sort_by_stage(tile_stage, P->tile_stage_ptr, tile_order);
+    sort_by_stage(ifc_stage, P->ifc_stage_ptr, ifc_order);
+    // ---- stage after which an output band is final -------------------------------------------------------
+    P->out_stage.assign(K, 0);
+    const int32_t* new_of_old = h->node_new_of_old.data();
+    for (int b = 0; b < K; ++b) {
+        int smax = 0;
+#pragma omp parallel for schedule(static) reduction(max : smax)
+        for (int64_t j = P->band_lo[b]; j < P->band_lo[b + 1]; ++j) {
+            const int32_t g = new_of_old[j];
+            int s;
+            if (g >= n_vertices) {
+                s = K - 1;  // points that are not vertices are zeroed in the last stage
+            } else {
+                const int32_t t = (int32_t)(std::upper_bound(h->h_tile_node0.begin(), h->h_tile_node0.end(), g) - h->h_tile_node0.begin()) - 1;
+                int32_t tt = t;  // tiles without own nodes share node0 with their successor: step back to the owner
+                while (tt > 0 && g >= h->h_tile_node0[tt] + h->h_tile_nown[tt]) --tt;
+                const int32_t l = g - h->h_tile_node0[tt];
+                if (l < h->h_tile_nint[tt]) {
+                    s = tile_stage[tt];
+                } else {
+                    const int32_t i = (int32_t)(std::lower_bound(h->h_ifc_node.begin(), h->h_ifc_node.end(), g) - h->h_ifc_node.begin());
+                    s = ifc_stage[i];
+                }
+            }
+            smax = std::max(smax, s);
+        }
+        P->out_stage[b] = smax;
+    }
+    // worth it only if a good part of the output leaves before the last stage
+    int early = 0;
+    for (int b = 0; b < K; ++b) early += P->out_stage[b] < K - 1;
+    P->useful = early * 2 >= K;
+    int32_t rc;
+    if ((rc = fvm_dev_upload(h, &P->d_tile_order, tile_order))) return rc;
+    if ((rc = fvm_dev_upload(h, &P->d_ifc_order, ifc_order))) return rc;
+    if ((rc = fvm_dev_alloc(h, &P->d_out, (size_t)N * h->neq))) return rc;
+    FVM_CUDA(h, cudaStreamCreateWithFlags(&P->s_in, cudaStreamNonBlocking));
+    FVM_CUDA(h, cudaStreamCreateWithFlags(&P->s_out, cudaStreamNonBlocking));
+    P->ev_in.resize(K);
+    P->ev_stage.resize(K);
+    for (int b = 0; b < K; ++b) {
+        FVM_CUDA(h, cudaEventCreateWithFlags(&P->ev_in[b], cudaEventDisableTiming));
+        FVM_CUDA(h, cudaEventCreateWithFlags(&P->ev_stage[b], cudaEventDisableTiming));
+    }
+    FVM_CUDA(h, cudaEventCreateWithFlags(&P->ev_start, cudaEventDisableTiming));
+    FVM_CUDA(h, cudaEventCreateWithFlags(&P->ev_out, cudaEventDisableTiming));
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));  // the uploads above
+    h->stats[12] = K;
+    h->stats[13] = early;
+    return FVM_OK;
+}
+
+int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du_host, bool* used) {
+    *used = false;
+    const char* e_off = getenv("FVM_NO_PIPELINE");
+    if ((e_off && e_off[0] == '1') || h->halo_ready || h->nranks > 1 || h->profiling) return FVM_OK;
+    const char* e_min = getenv("FVM_PIPE_MIN_NODES");
+    const int64_t min_nodes = e_min ? atoll(e_min) : (int64_t)1 << 20;
+    if (h->N < min_nodes) return FVM_OK;
+    if (!h->pipe) {
+        const char* e_k = getenv("FVM_PIPE_BANDS");
+        int K = e_k ? atoi(e_k) : 12;
+        K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min(K, 64), h->N));
+        int32_t rc = build_plan(h, K);
+        if (rc) return rc;
+    }
+    PipePlan& P = *(PipePlan*)h->pipe;
+    const char* e_force = getenv("FVM_PIPE_FORCE");  // tests: run the pipeline even where it cannot overlap anything
+    if (!P.useful && !(e_force && e_force[0] == '1')) return FVM_OK;
+    const int K = P.K, neq = h->neq;
+    cudaStream_t sc = h->stream;
+    // whatever is queued on the compute stream (an earlier call's kernels) precedes the first scatter
+    FVM_CUDA(h, cudaEventRecord(P.ev_start, sc));
+    FVM_CUDA(h, cudaStreamWaitEvent(P.s_in, P.ev_start, 0));
+    FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_start, 0));
+    for (int b = 0; b < K; ++b) {
+        const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
+        if (cnt == 0) {
+            FVM_CUDA(h, cudaEventRecord(P.ev_in[b], P.s_in));
+            continue;
+        }
+        FVM_CUDA(h, cudaMemcpyAsync(h->d_io + lo * neq, u_host + lo * neq, sizeof(double) * cnt, cudaMemcpyHostToDevice, P.s_in));
+        band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, P.s_in>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
+        FVM_CUDA(h, cudaEventRecord(P.ev_in[b], P.s_in));
+    }
+    int32_t rc = FVM_OK;
+    for (int s = 0; s < K && !rc; ++s) {
+        FVM_CUDA(h, cudaStreamWaitEvent(sc, P.ev_in[s], 0));
+        if (s == K - 1) rc = fvm_launch_rhs_part(h, t, h->d_u, h->d_du, 5);  // live boundary edges -> partial slots
+        h->pipe_list = P.d_tile_order;
+        h->pipe_off = P.tile_stage_ptr[s];
+        h->pipe_count = P.tile_stage_ptr[s + 1] - P.tile_stage_ptr[s];
+        if (!rc && h->pipe_count > 0) rc = fvm_launch_rhs_part(h, t, h->d_u, h->d_du, 4);
+        if (!rc)
+            rc = fvm_launch_rhs_interface_list(h, t, h->d_u, h->d_du, P.d_ifc_order, P.ifc_stage_ptr[s],
+                                               P.ifc_stage_ptr[s + 1] - P.ifc_stage_ptr[s]);
+        if (!rc && s == K - 1) rc = fvm_launch_rhs_nonvertex(h, h->d_du);
+        if (rc) break;
+        FVM_CUDA(h, cudaEventRecord(P.ev_stage[s], sc));
+        for (int b = 0; b < K; ++b) {
+            if (P.out_stage[b] != s) continue;
+            const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
+            if (cnt == 0) continue;
+            FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_stage[s], 0));
+            band_gather_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, P.d_out, lo, hi, neq);
+            FVM_CUDA(h, cudaMemcpyAsync(du_host + lo * neq, P.d_out + lo * neq, sizeof(double) * cnt, cudaMemcpyDeviceToHost, P.s_out));
+        }
+    }
+    // leave the three streams joined whatever happened, so that the handle stays usable after an error
+    cudaEventRecord(P.ev_out, P.s_out);
+    cudaStreamWaitEvent(sc, P.ev_out, 0);
+    cudaStreamWaitEvent(sc, P.ev_in[K - 1], 0);
+    cudaError_t ce = cudaStreamSynchronize(sc);
+    if (rc) return rc;
+    FVM_CUDA(h, ce);
+    FVM_CUDA(h, cudaGetLastError());
+    *used = true;
+    h->stats[14] += 1;
+    return FVM_OK;
+}

@@ -34,7 +34,7 @@ struct TileOcc {
         return 2;
     }
 };
-template <int MODEL, int NEQ, int GEOM, int OCC = 0>
+template <int MODEL, int NEQ, int GEOM, int OCC = 0, int UNR = 1>
 __global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::template min_blocks<GEOM>())
     rhs_tile_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t,
                     const double* __restrict__ u, double* __restrict__ du, const int smem_nloc,
@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::te
 
     // ---- triangle pass ------------------------------------------------------------------------
     const int n_iter = (ntri - tid + RHS_BLOCK - 1) / RHS_BLOCK;
-#pragma unroll 1
+#pragma unroll(UNR)
     for (int r = 0; r < n_iter; ++r) {
         const int lt = tid + r * RHS_BLOCK;
         const int64_t gt = t0 + lt;
@@ -240,8 +240,13 @@ __global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::te
 template <int NEQ, bool VOL>
 __global__ void __launch_bounds__(256)
     rhs_interface_kernel(const DevMesh m, const SourceParams sp, const double t, const double* __restrict__ u,
-                         double* __restrict__ du) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+                         double* __restrict__ du, const int32_t* __restrict__ list = nullptr, const int list_off = 0,
+                         const int list_count = 0) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) {  // explicit subset of the interface nodes (host-buffer pipeline)
+        if (k >= list_count) return;
+        k = list[list_off + k];
+    }
     if (k < m.n_ifc) {
         const int g = m.ifc_node[k];
         const int beg = m.ifc_pptr[k], end = m.ifc_pptr[k + 1];
@@ -428,6 +433,17 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
         static const char* e = getenv("FVM_SYS_MINB");  // experiment knob: 4 resident CTAs (<= 64 registers)
         if (e && e[0] == '4') kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 4>;
     }
+    if constexpr (NEQ == 1 && MODEL == FVM_FLUX_DIFF_CONST && GEOM == 1) {
+        // experiment knobs of the recompute kernel: resident CTAs per SM (register budget) and triangles in flight
+        const char* eo = getenv("FVM_REC_OCC");
+        const char* eu = getenv("FVM_REC_UNR");
+        const int occ = eo ? atoi(eo) : 0, unr = eu ? atoi(eu) : 1;
+        if (occ == 3 && unr == 1) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 3, 1>;
+        if (occ == 5 && unr == 1) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 5, 1>;
+        if (occ == 2 && unr == 2) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 2, 2>;
+        if (occ == 3 && unr == 2) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 3, 2>;
+        if ((occ == 4 || occ == 0) && unr == 2) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 4, 2>;
+    }
     if (smem > 200 * 1024) return fvm_fail(h, FVM_ERR_ARG, "tile needs more than 200 KB of shared memory; lower tile_triangles");
     int32_t& configured = h->smem_configured[(const void*)kern];
     if (configured < smem) {
@@ -444,6 +460,10 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
         list = h->d_tile_order;
         off = h->n_tiles_indep;
         grid = h->dm.n_tiles - h->n_tiles_indep;
+    } else if (part == 4) {
+        list = h->pipe_list;
+        off = h->pipe_off;
+        grid = h->pipe_count;
     }
     if (grid == 0) return FVM_OK;
     cudaStream_t st = h->launch_stream;
@@ -457,11 +477,12 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
 template <int NEQ>
 static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du, int part) {
     int32_t rc = FVM_OK;
-    if (h->n_bnd_live > 0 && (part == 0 || part == 2)) {
+    if (h->n_bnd_live > 0 && (part == 0 || part == 2 || part == 5)) {
         rhs_boundary_kernel<NEQ><<<(h->n_bnd_live + 127) / 128, 128, 0, h->launch_stream>>>(h->dm, h->flux, t, h->d_bnd, h->d_dbnd,
                                                                                             h->n_bnd_live, u);
         FVM_CUDA(h, cudaGetLastError());
     }
+    if (part == 5) return FVM_OK;
     if (part == 3) {
         const int n_tail3 = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
         if (n_tail3 > 0) {
@@ -512,6 +533,31 @@ int32_t fvm_launch_rhs_part(fvm_ctx* h, double t, const double* u, double* du, i
 }
 
 int32_t fvm_launch_rhs(fvm_ctx* h, double t, const double* u, double* du) { return fvm_launch_rhs_part(h, t, u, du, 0); }
+
+template <int NEQ>
+static int32_t launch_interface_list(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
+    rhs_interface_kernel<NEQ, false><<<(count + 255) / 256, 256, 0, h->launch_stream>>>(h->dm, h->source, t, u, du, list, off, count);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+int32_t fvm_launch_rhs_interface_list(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
+    if (count <= 0) return FVM_OK;
+    switch (h->neq) {
+        case 1: return launch_interface_list<1>(h, t, u, du, list, off, count);
+        case 2: return launch_interface_list<2>(h, t, u, du, list, off, count);
+        case 3: return launch_interface_list<3>(h, t, u, du, list, off, count);
+        case 4: return launch_interface_list<4>(h, t, u, du, list, off, count);
+    }
+    return fvm_fail(h, FVM_ERR_ARG, "unsupported neq");
+}
+
+// points that are not vertices of any triangle: du = 0 (source_contributions.jl:36-37)
+int32_t fvm_launch_rhs_nonvertex(fvm_ctx* h, double* du) {
+    const int64_t n = (int64_t)(h->dm.n_nodes - h->dm.n_vertices) * h->neq;
+    if (n > 0) FVM_CUDA(h, cudaMemsetAsync(du + (size_t)h->dm.n_vertices * h->neq, 0, sizeof(double) * n, h->launch_stream));
+    return FVM_OK;
+}
 
 // du = fvm_eqs!(u) with the ghost refresh; the exchange overlaps the tiles that touch no ghost node
 int32_t fvm_apply_rhs(fvm_ctx* h, double t, double* x, double* out) {
@@ -606,6 +652,10 @@ extern "C" int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, 
     FVM_REQUIRE(h, u && du, "fvm_rhs: null argument");
     int32_t rc = fvm_ensure_state(h);
     if (rc) return rc;
+    if (!on_device) {  // large host vectors: copies, permutations and tiles overlapped band by band
+        bool used = false;
+        if ((rc = fvm_rhs_pipelined(h, t, u, du, &used)) || used) return rc;
+    }
     const size_t bytes = sizeof(double) * h->N * h->neq;
     const double* src = u;
     if (!on_device) {

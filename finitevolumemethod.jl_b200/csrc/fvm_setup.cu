@@ -95,6 +95,7 @@ extern "C" int32_t fvm_destroy(fvm_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     fvm_shard_release(h);
+    fvm_pipe_release(h);
     for (void* p : h->allocs) cudaFree(p);
     if (h->graph_exec) cudaGraphExecDestroy((cudaGraphExec_t)h->graph_exec);
     cudaStreamDestroy(h->stream);
@@ -571,6 +572,13 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         UP(m.tile_meta, meta);
     }
     h->h_tile_node0 = tile_node0;
+    h->h_tile_nint = tile_nint;
+    h->h_ifc_node = ifc_node;
+    h->h_ifc_edge.assign(n_ifc, 0);
+    for (size_t k = 0; k < live_edges.size(); ++k) {
+        h->h_ifc_edge[ifc_of_new[new_of_old[h->h_bedge[2 * live_edges[k]]]]] = 1;
+        h->h_ifc_edge[ifc_of_new[new_of_old[h->h_bedge[2 * live_edges[k] + 1]]]] = 1;
+    }
     h->h_tile_nown = tile_nown;
     h->h_tile_ext0 = tile_ext0;
     h->h_ext_ids = ext_ids;

@@ -332,7 +332,7 @@ class Engine:
         st = np.zeros(16, dtype=np.int64)
         L.check(self.h, L.lib().fvm_get_stats(self.h, st.ctypes.data_as(L.c_lp)))
         keys = ["n_tiles", "tile_triangles", "n_vertices", "n_interface", "n_partial", "n_external", "max_local_nodes",
-                "n_live_boundary_edges", "n_dirichlet", "smem_bytes", "nnz", "max_row"]
+                "n_live_boundary_edges", "n_dirichlet", "smem_bytes", "nnz", "max_row", "pipe_bands", "pipe_early_bands", "pipe_calls"]
         return dict(zip(keys, st.tolist()))
 
     def permutation(self):

@@ -56,6 +56,16 @@ def test_linearity_and_operator_equals_rhs_4096(big):
     Fw = G.fvm_eqs(np.empty(N), w, p, 0.0)
     Fc = G.fvm_eqs(np.empty(N), 2.0 * u - 3.0 * w, p, 0.0)
     assert rel_err(Fc, 2.0 * Fu - 3.0 * Fw) <= 1e-12
+    # host buffers of this size take the banded copy/compute pipeline (fvm_pipe.cu): bit-identical to the
+    # device-pointer call, and on the reference's row-major numbering all but the last band leave early
+    import torch
+    ud = torch.from_numpy(u).cuda()
+    dd = torch.empty_like(ud)
+    p.engine.rhs_device(dd.data_ptr(), ud.data_ptr(), 0.0)
+    assert np.array_equal(dd.cpu().numpy(), Fu)
+    st = p.engine.stats()
+    assert st["pipe_calls"] == 3 and st["pipe_bands"] >= 2 and st["pipe_early_bands"] >= st["pipe_bands"] - 2
+    del ud, dd
     # interior stencil D/h^2 [1,1,-4,1,1] on a smooth field: F(x^2 + y^2) = 4 D away from the boundary
     P = tri.points
     q = G.fvm_eqs(np.empty(N), P[:, 0] ** 2 + P[:, 1] ** 2, p, 0.0)

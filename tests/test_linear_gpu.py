@@ -330,6 +330,6 @@ def test_steady_newton_raphson_linear_and_nonlinear():
     fs = np.abs(O.fvm_eqs_vec(np.zeros_like(sol.u), sol.u, op, 0.0)).max()
     assert fs <= 1e-9 * f0
     dn = np.array(sorted(op.conditions.dirichlet_nodes))
-    assert np.array_equal(sol.u[dn], u0[dn]) and sol.u.min() > 0
+    assert rel_err(sol.u[dn], u0[dn]) <= 1e-15 and sol.u.min() > 0  # device FMA vs NumPy in c0 + cx x + cy y
     with pytest.raises(TypeError):
         G.solve(G.SteadyFVMProblem(gp), G.Tsit5(0.1))

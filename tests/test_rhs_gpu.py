@@ -382,3 +382,47 @@ def test_mesh_from_wire_container_gives_identical_rhs(tmp_path):
     sol = G.Solution(np.stack([u, du_file]), t=np.array([0.0, 1.0]))
     G.save_solution(str(tmp_path / "sol.fvmw"), sol)
     assert np.array_equal(G.load_solution(str(tmp_path / "sol.fvmw")).u, sol.u)
+
+
+def _pipeline_env(**kw):
+    import os
+    keys = ("FVM_NO_PIPELINE", "FVM_PIPE_MIN_NODES", "FVM_PIPE_FORCE", "FVM_PIPE_BANDS")
+    for k in keys:
+        os.environ.pop(k, None)
+    for k, v in kw.items():
+        os.environ[k] = str(v)
+
+
+@pytest.mark.parametrize("case", ["readme", "convection", "unstructured", "system"])
+def test_host_buffer_pipeline_is_bit_identical(case):
+    """fvm_rhs with host buffers runs as a banded copy-in / compute / copy-out pipeline on large meshes
+    (fvm_pipe.cu).  Forced on here for small ones: every band count must reproduce the unpipelined call bit for
+    bit (same kernels, same summation order), repeatedly on one handle and interleaved with device-pointer calls."""
+    import torch
+    from tests.golden_cases import CASES
+    name = {"readme": "readme_50x50", "convection": "convection_robin_24", "unstructured": "unstructured_porous",
+            "system": "keller_segel_16"}[case]
+    c = CASES[name](None)
+    try:
+        _pipeline_env(FVM_NO_PIPELINE=1)
+        p0 = G.get_cuda_parameters(c.gp, tile_triangles=64)
+        ref = G.fvm_eqs(np.zeros_like(c.u), c.u, p0, c.t)
+        assert p0.engine.stats()["pipe_calls"] == 0
+        u2 = c.u[::-1].copy() if c.u.ndim == 1 else c.u[::-1, :].copy()
+        ref2 = G.fvm_eqs(np.zeros_like(u2), u2, p0, c.t)
+        for bands in (2, 3, 7, 16):
+            _pipeline_env(FVM_PIPE_MIN_NODES=0, FVM_PIPE_FORCE=1, FVM_PIPE_BANDS=bands)
+            p = G.get_cuda_parameters(c.gp, tile_triangles=64)
+            du = G.fvm_eqs(np.full_like(c.u, np.nan), c.u, p, c.t)
+            st = p.engine.stats()
+            assert st["pipe_calls"] == 1 and st["pipe_bands"] == bands
+            assert np.array_equal(du, ref)
+            assert np.array_equal(G.fvm_eqs(np.full_like(u2, np.nan), u2, p, c.t), ref2)
+            ud = torch.from_numpy(c.u).cuda()
+            dd = torch.empty_like(ud)
+            p.engine.rhs_device(dd.data_ptr(), ud.data_ptr(), c.t)
+            assert np.array_equal(dd.cpu().numpy(), ref)
+            assert np.array_equal(G.fvm_eqs(np.full_like(c.u, np.nan), c.u, p, c.t), ref)
+            assert p.engine.stats()["pipe_calls"] == 3
+    finally:
+        _pipeline_env()
