@@ -392,7 +392,7 @@ def main():
     peak, peak_src = measured_peak()
     # default: the README problem as the engine runs it (reduced stream) plus the same mesh through the
     # general 21-component layout of north_star (a); --all-variants adds the recompute-geometry kernels
-    names = sorted(VARIANTS) if args.all_variants else sorted({args.variant, "general_stored"})
+    names = sorted(VARIANTS) if args.all_variants else sorted({args.variant, "general_stored", "const_recompute"})
     if args.variant in names:
         names.remove(args.variant)
         names.append(args.variant)  # headline variant last: its engine stays alive for e2e
@@ -455,6 +455,16 @@ def main():
     for _ in range(args.e2e_steps):
         G.fvm_eqs(dun, un, p, 0.0)  # synchronous: H2D, to-native, kernels, from-native, D2H
     e2e_ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
+    e2e_plain_ms = None
+    if dist is None:  # the same call without the banded copy/compute pipeline (fvm_pipe.cu), for reference
+        os.environ["FVM_NO_PIPELINE"] = "1"
+        G.fvm_eqs(dun, un, p, 0.0)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            G.fvm_eqs(dun, un, p, 0.0)
+        e2e_plain_ms = (time.perf_counter() - t0) / 3 * 1e3
+        del os.environ["FVM_NO_PIPELINE"]
+    e2e_stats = eng.stats()
     if dist is not None:
         tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -494,7 +504,10 @@ def main():
                      "bytes_formula": {"general": "180*T + 25*N", "reduced": "108*T + 25*N", "recompute": "12*T + 41*N"}[head["layout"]],
                      "alg_bytes_per_launch": head["alg_bytes"], "kernel_ms": head["kernel_ms"]},
         "e2e": {"value": world * T / e2e_ms / 1e3, "unit": "Mtriangle-updates/s", "h2d_bytes_per_step": 8 * N,
-                "d2h_bytes_per_step": 8 * N, "ms_per_step": e2e_ms},
+                "d2h_bytes_per_step": 8 * N, "ms_per_step": e2e_ms,
+                "schedule": ("banded pipeline, %d bands (copy-in / tiles / copy-out overlapped)" % e2e_stats["pipe_bands"])
+                if e2e_stats.get("pipe_calls", 0) > 0 else "H2D, kernels, D2H in sequence",
+                "unpipelined_ms_per_step": e2e_plain_ms},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "setup_s": head["setup_s"],

@@ -7,7 +7,7 @@ from .conditions import (BoundaryConditions, Conditions, Constrained, Dirichlet,
 from .functors import *  # noqa: F401,F403
 from .mesh import Triangulation, triangulate_rectangle  # noqa: F401
 from .problem import (CudaParameters, Engine, compute_flux, pl_interpolate, FVMGeometry, FVMProblem, FVMSystem,  # noqa: F401
-                      SteadyFVMProblem, fvm_eqs, get_cuda_parameters, jacobian, jacobian_sparsity,
+                      SteadyFVMProblem, fvm_eqs, get_cuda_parameters, jacobian, jacobian_sparsity, pinned,
                       update_dirichlet_nodes)
 from .templates import (DiffusionEquation, KrylovJacobi, LaplacesEquation,  # noqa: F401
                         LinearReactionDiffusionEquation, MeanExitTimeProblem, PoissonsEquation, Solution, Tsit5)

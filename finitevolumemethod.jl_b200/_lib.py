@@ -72,6 +72,8 @@ _SIGS = {
     "fvm_set_halo": [H, C.c_int32, c_ip, c_ip, c_ip, c_ip, c_ip],
     "fvm_halo_exchange_native": [H, C.c_void_p],
     "fvm_nccl_unique_id": [C.c_void_p],
+    "fvm_host_register": [C.c_void_p, C.c_int64],
+    "fvm_host_unregister": [C.c_void_p],
     # FVMWIRE containers (host only)
     "fvm_wire_create": [C.c_char_p, C.POINTER(H)],
     "fvm_wire_put": [H, C.c_char_p, C.c_int32, C.c_int32, c_lp, C.c_void_p],

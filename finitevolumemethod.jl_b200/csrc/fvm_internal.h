@@ -191,7 +191,7 @@ struct fvm_ctx {
     // host-buffer pipeline of fvm_rhs (fvm_pipe.cu): caller-order bands copied in, tiles launched as soon as
     // their nodes have arrived, finished bands copied out while later bands are still being copied in
     std::vector<int32_t> h_tile_nint, h_ifc_node;
-    std::vector<uint8_t> h_ifc_edge;  // interface node receives a boundary-edge partial
+    std::vector<BndEdge> h_bnd;       // host copy of the live boundary-edge records
     void* pipe = nullptr;
     const int32_t* pipe_list = nullptr;  // explicit tile list of fvm_launch_rhs_part(part = 4)
     int32_t pipe_off = 0, pipe_count = 0;
@@ -247,11 +247,13 @@ int32_t fvm_apply_rhs(fvm_ctx* h, double t, double* x, double* out);
 int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* out, bool add_b, bool scale);
 // part: 0 = everything, 1 = independent tiles only, 2 = halo-dependent tiles (+ boundary-edge kernel),
 // 3 = the kernels that need every tile (interface / tail rows)
-//       4 = the tiles h->pipe_list[pipe_off .. pipe_off + pipe_count) only, 5 = the boundary-edge kernel only
+//       4 = the tiles h->pipe_list[pipe_off .. pipe_off + pipe_count) only
 int32_t fvm_launch_rhs_part(fvm_ctx* h, double t, const double* u, double* du, int part);
 // interface nodes list[off .. off+count) (indices into ifc_node); points that are not vertices (du = 0)
 int32_t fvm_launch_rhs_interface_list(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count);
 int32_t fvm_launch_rhs_nonvertex(fvm_ctx* h, double* du);
+// live boundary edges list[off .. off+count) (indices into the live-edge records) -> partial slots
+int32_t fvm_launch_rhs_boundary_list(fvm_ctx* h, double t, const double* u, const int32_t* list, int off, int count);
 int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du_host, bool* used);
 void fvm_pipe_release(fvm_ctx* h);
 int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part);

@@ -297,9 +297,11 @@ __device__ __forceinline__ void flux_dispatch(const FluxParams& fp, double x, do
 template <int NEQ>
 __global__ void __launch_bounds__(128)
     rhs_boundary_kernel(const DevMesh m, const FluxParams fp, const double t, const BndEdge* __restrict__ edges,
-                        const double* __restrict__ dbnd, const int n_edges, const double* __restrict__ u) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+                        const double* __restrict__ dbnd, const int n_edges, const double* __restrict__ u,
+                        const int32_t* __restrict__ list = nullptr, const int list_off = 0) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_edges) return;
+    if (list) k = list[list_off + k];  // explicit subset (host-buffer pipeline); n_edges is then the subset size
     const BndEdge E = edges[k];
     TriGeom G;
     tri_geometry<true>(m.xy[2 * (size_t)E.v[0]], m.xy[2 * (size_t)E.v[0] + 1], m.xy[2 * (size_t)E.v[1]],
@@ -477,12 +479,11 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
 template <int NEQ>
 static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du, int part) {
     int32_t rc = FVM_OK;
-    if (h->n_bnd_live > 0 && (part == 0 || part == 2 || part == 5)) {
+    if (h->n_bnd_live > 0 && (part == 0 || part == 2)) {
         rhs_boundary_kernel<NEQ><<<(h->n_bnd_live + 127) / 128, 128, 0, h->launch_stream>>>(h->dm, h->flux, t, h->d_bnd, h->d_dbnd,
                                                                                             h->n_bnd_live, u);
         FVM_CUDA(h, cudaGetLastError());
     }
-    if (part == 5) return FVM_OK;
     if (part == 3) {
         const int n_tail3 = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
         if (n_tail3 > 0) {
@@ -548,6 +549,24 @@ int32_t fvm_launch_rhs_interface_list(fvm_ctx* h, double t, const double* u, dou
         case 2: return launch_interface_list<2>(h, t, u, du, list, off, count);
         case 3: return launch_interface_list<3>(h, t, u, du, list, off, count);
         case 4: return launch_interface_list<4>(h, t, u, du, list, off, count);
+    }
+    return fvm_fail(h, FVM_ERR_ARG, "unsupported neq");
+}
+
+template <int NEQ>
+static int32_t launch_boundary_list(fvm_ctx* h, double t, const double* u, const int32_t* list, int off, int count) {
+    rhs_boundary_kernel<NEQ><<<(count + 127) / 128, 128, 0, h->launch_stream>>>(h->dm, h->flux, t, h->d_bnd, h->d_dbnd, count, u, list, off);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+int32_t fvm_launch_rhs_boundary_list(fvm_ctx* h, double t, const double* u, const int32_t* list, int off, int count) {
+    if (count <= 0) return FVM_OK;
+    switch (h->neq) {
+        case 1: return launch_boundary_list<1>(h, t, u, list, off, count);
+        case 2: return launch_boundary_list<2>(h, t, u, list, off, count);
+        case 3: return launch_boundary_list<3>(h, t, u, list, off, count);
+        case 4: return launch_boundary_list<4>(h, t, u, list, off, count);
     }
     return fvm_fail(h, FVM_ERR_ARG, "unsupported neq");
 }

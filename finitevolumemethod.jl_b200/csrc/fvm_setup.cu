@@ -22,12 +22,35 @@
 
 #include "fvm_internal.h"
 
+static thread_local std::string g_create_err;
+
 int32_t fvm_fail(fvm_ctx* h, int32_t code, const std::string& msg) {
     if (h) h->err = msg;
+    else g_create_err = msg;
     return code;
 }
 
-static thread_local std::string g_create_err;
+// Page-locks a caller-owned host buffer (a Julia Vector / NumPy array passed to fvm_rhs, fvm_spmv, ...): the
+// host-buffer entry points then copy at full PCIe rate and overlap copy-in, kernels and copy-out; pageable
+// memory goes through the driver's staging buffer (measured 19 ms instead of 3.9 ms per fvm_rhs at 16.7M
+// nodes).  The caller unregisters before freeing the buffer.
+extern "C" int32_t fvm_host_register(void* ptr, int64_t nbytes) {
+    if (!ptr || nbytes <= 0) return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_host_register: bad arguments");
+    cudaError_t e = cudaHostRegister(ptr, (size_t)nbytes, cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) {
+        cudaGetLastError();
+        return FVM_OK;
+    }
+    if (e != cudaSuccess) return fvm_fail(nullptr, FVM_ERR_CUDA, std::string("fvm_host_register: ") + cudaGetErrorString(e));
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_host_unregister(void* ptr) {
+    if (!ptr) return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_host_unregister: null pointer");
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) return fvm_fail(nullptr, FVM_ERR_CUDA, std::string("fvm_host_unregister: ") + cudaGetErrorString(e));
+    return FVM_OK;
+}
 
 extern "C" const char* fvm_version(void) { return "fvmcuda 0.1 (sm_100a)"; }
 
@@ -574,11 +597,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     h->h_tile_node0 = tile_node0;
     h->h_tile_nint = tile_nint;
     h->h_ifc_node = ifc_node;
-    h->h_ifc_edge.assign(n_ifc, 0);
-    for (size_t k = 0; k < live_edges.size(); ++k) {
-        h->h_ifc_edge[ifc_of_new[new_of_old[h->h_bedge[2 * live_edges[k]]]]] = 1;
-        h->h_ifc_edge[ifc_of_new[new_of_old[h->h_bedge[2 * live_edges[k] + 1]]]] = 1;
-    }
+    h->h_bnd = bnd;
     h->h_tile_nown = tile_nown;
     h->h_tile_ext0 = tile_ext0;
     h->h_ext_ids = ext_ids;

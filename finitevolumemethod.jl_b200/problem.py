@@ -197,7 +197,12 @@ class Engine:
         try:
             uv = conditions[0].boundary_edges
             self.boundary_edges = uv
-            L.check(self.h, lib.fvm_set_boundary_edges(self.h, L.ip(L.i32(uv)), len(uv)))
+            base = 0
+            if mesh_file is not None:  # the handle indexes like the file does (1-based when Julia wrote it)
+                from .wire import WireReader
+                with WireReader(mesh_file) as r:
+                    base = int(r.get("index_base")[0]) if "index_base" in r else 1
+            L.check(self.h, lib.fvm_set_boundary_edges(self.h, L.ip(L.i32(uv + base)), len(uv)))
             for v, c in enumerate(conditions):
                 ek, ef = np.ascontiguousarray(c.edge_kind, np.uint8), L.i32(c.edge_fidx)
                 nk, nf = np.ascontiguousarray(c.node_kind, np.uint8), L.i32(c.node_fidx)
@@ -382,6 +387,32 @@ def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None, gh
     eng = Engine(prob.mesh, neq, conds, [p.flux_function for p in probs], [p.source_function for p in probs],
                  tile_triangles, geometry_mode, device, ghost, mesh_file)
     return CudaParameters(prob, eng)
+
+
+class pinned:
+    """Context manager / helper that page-locks NumPy arrays for the host-buffer calls (fvm_host_register):
+
+        with G.pinned(u, du):
+            G.fvm_eqs(du, u, p, t)      # full PCIe rate, copy-in / kernels / copy-out overlapped
+    """
+
+    def __init__(self, *arrays):
+        self.arrays = arrays
+        for a in arrays:
+            rc = L.lib().fvm_host_register(a.ctypes.data, a.nbytes)
+            if rc != L.OK:
+                raise L.FVMCudaError(rc, L.lib().fvm_last_error(None).decode())
+
+    def release(self):
+        for a in self.arrays:
+            L.lib().fvm_host_unregister(a.ctypes.data)
+        self.arrays = ()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
 
 
 def fvm_eqs(du, u, p, t):

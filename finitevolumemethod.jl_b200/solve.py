@@ -18,7 +18,6 @@ class NewtonRaphson:
 
 
 def _solve_steady_newton(prob, alg, p):
-    import scipy.sparse as sp
     import scipy.sparse.linalg as spla
     t = prob.initial_time
     u = np.ascontiguousarray(prob.initial_condition, dtype=np.float64).copy()
@@ -35,10 +34,11 @@ def _solve_steady_newton(prob, alg, p):
         if it == alg.maxiters or not np.isfinite(res):
             break
         J = jacobian(u, p, t).tocsr()
-        # rows without any entry (Dirichlet nodes, points that are not vertices): du = 0 there, keep u
-        empty = np.asarray(abs(J).sum(axis=1)).ravel() == 0.0
-        J = (J + sp.diags(empty.astype(np.float64))).tocsc()
-        delta = spla.splu(J).solve(-du.ravel())
+        # rows without any entry (Dirichlet nodes, points that are not vertices) have du = 0 identically:
+        # those unknowns keep their value and the Newton system is solved on the remaining block
+        free = np.flatnonzero(np.asarray(abs(J).sum(axis=1)).ravel() != 0.0)
+        delta = np.zeros(J.shape[0])
+        delta[free] = spla.splu(J[free][:, free].tocsc()).solve(-du.ravel()[free])
         u += delta.reshape(u.shape)
         fvm_eqs(du, u, p, t)
     return Solution(u, None, iters=it, relres=float(np.abs(du).max() / r0) if r0 > 0 else 0.0, retcode=retcode)

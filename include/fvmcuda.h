@@ -137,6 +137,14 @@ int32_t fvm_apply_dirichlet(fvm_handle h, double t, double* u, int32_t on_device
 int32_t fvm_apply_dirichlet_native(fvm_handle h, double t, double* u_native);
 int32_t fvm_to_native(fvm_handle h, const double* v_caller_dev, double* v_native_dev);
 int32_t fvm_from_native(fvm_handle h, const double* v_native_dev, double* v_caller_dev);
+/* Host vectors of >= 2^20 nodes take a banded pipeline: the caller-order vector is cut into bands, each band is
+ * copied in and scattered to native order on a copy stream, the tiles (and boundary edges, interface nodes)
+ * whose inputs have arrived run on the compute stream, and finished bands are gathered and copied out on a
+ * third stream while later bands are still arriving (PCIe is full duplex).  Bit-identical to the plain
+ * schedule.  Page-lock the buffers once with fvm_host_register to get the full rate (a Julia Vector or NumPy
+ * array is pageable); unregister before freeing them.  Environment: FVM_NO_PIPELINE=1, FVM_PIPE_BANDS=K. */
+int32_t fvm_host_register(void* host_ptr, int64_t nbytes);
+int32_t fvm_host_unregister(void* host_ptr);
 /* the *_native calls are asynchronous on the handle's stream */
 int32_t fvm_stream_synchronize(fvm_handle h);
 int32_t fvm_get_stream(fvm_handle h, void** cuda_stream);
