@@ -192,7 +192,8 @@ struct fvm_ctx {
     // their nodes have arrived, finished bands copied out while later bands are still being copied in
     std::vector<int32_t> h_tile_nint, h_ifc_node;
     std::vector<BndEdge> h_bnd;       // host copy of the live boundary-edge records
-    void* pipe = nullptr;
+    void* pipe = nullptr;       // plan of fvm_rhs
+    void* pipe_spmv = nullptr;  // plan of fvm_spmv
     const int32_t* pipe_list = nullptr;  // explicit tile list of fvm_launch_rhs_part(part = 4)
     int32_t pipe_off = 0, pipe_count = 0;
 };
@@ -255,6 +256,8 @@ int32_t fvm_launch_rhs_nonvertex(fvm_ctx* h, double* du);
 // live boundary edges list[off .. off+count) (indices into the live-edge records) -> partial slots
 int32_t fvm_launch_rhs_boundary_list(fvm_ctx* h, double t, const double* u, const int32_t* list, int off, int count);
 int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du_host, bool* used);
+int32_t fvm_spmv_pipelined(fvm_ctx* h, const double* x_host, double* y_host, bool add_b, bool* used);
+int32_t fvm_launch_spmv_tail_list(fvm_ctx* h, const double* x, double* y, bool add_b, const int32_t* list, int off, int count);
 void fvm_pipe_release(fvm_ctx* h);
 int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part);
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);

@@ -345,8 +345,14 @@ template <bool ADD_B, bool SCALE>
 __global__ void __launch_bounds__(128)
     spmv_rows_kernel(const int n_rows, const int32_t* __restrict__ rows, const int32_t* __restrict__ sptr,
                      const int32_t* __restrict__ scol, const double* __restrict__ sval, const double* __restrict__ b,
-                     const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y) {
-    const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+                     const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y,
+                     const int32_t* __restrict__ slice_list = nullptr, const int list_off = 0, const int list_count = 0) {
+    int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (slice_list) {  // explicit subset of the slices (host-buffer pipeline)
+        if (sl >= list_count) return;
+        sl = slice_list[list_off + sl];
+    }
     if (sl * 32 >= n_rows) return;
     const int p0 = __ldg(sptr + sl), len = (__ldg(sptr + sl + 1) - p0) >> 5;
     const int k = sl * 32 + lane;
@@ -412,6 +418,10 @@ static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part) {
             list = h->d_tile_order;
             off = h->n_tiles_indep;
             grid = h->dm.n_tiles - h->n_tiles_indep;
+        } else if (part == 4) {  // explicit tile list (host-buffer pipeline)
+            list = h->pipe_list;
+            off = h->pipe_off;
+            grid = h->pipe_count;
         }
         cudaStream_t st = h->launch_stream;
         if (grid > 0 && part != 3) {
@@ -451,6 +461,21 @@ int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b,
 
 int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale) {
     return fvm_launch_spmv_part(h, x, y, add_b, scale, 0);
+}
+
+// tail-row slices list[off .. off+count) (interface rows and points that are not vertices)
+int32_t fvm_launch_spmv_tail_list(fvm_ctx* h, const double* x, double* y, bool add_b, const int32_t* list, int off, int count) {
+    Csr& c = h->csr;
+    if (count <= 0) return FVM_OK;
+    const int grid = (count * 32 + 127) / 128;
+    if (add_b)
+        spmv_rows_kernel<true, false><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
+                                                                          c.rowscale, x, y, list, off, count);
+    else
+        spmv_rows_kernel<false, false><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
+                                                                           c.rowscale, x, y, list, off, count);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
 }
 
 int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* y, bool add_b, bool scale) {
@@ -576,7 +601,7 @@ int32_t fvm_build_pattern(fvm_ctx* h) {
         if ((rc = fvm_dev_upload(h, &c.sell_ptr, sptr))) return rc;
         if ((rc = fvm_dev_alloc(h, &c.sell_val, (size_t)entries + 32))) return rc;
         if ((rc = fvm_dev_alloc(h, &c.sell_col, (size_t)entries + 32))) return rc;
-        h->stats[12] = entries;
+        h->stats[15] = entries;
         if ((rc = fvm_dev_upload(h, &c.tail_rows, tail))) return rc;
         {
             std::vector<int32_t> tp(1, 0);
@@ -825,6 +850,10 @@ extern "C" int32_t fvm_spmv(fvm_handle h, const double* x, double* y, int32_t ad
     FVM_REQUIRE(h, x && y, "fvm_spmv: null argument");
     int32_t rc = fvm_ensure_state(h);
     if (rc) return rc;
+    if (!on_device && x != y) {  // large host vectors: the banded copy / compute pipeline of fvm_pipe.cu
+        bool used = false;
+        if ((rc = fvm_spmv_pipelined(h, x, y, add_b != 0, &used)) || used) return rc;
+    }
     const size_t bytes = sizeof(double) * h->N;
     const double* src = x;
     if (!on_device) {

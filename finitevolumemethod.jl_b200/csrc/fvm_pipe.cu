@@ -25,6 +25,7 @@ namespace {
 
 struct PipePlan {
     int K = 0;
+    int mode = 0;  // 0: fvm_rhs (tiles, boundary edges, interface nodes)   1: fvm_spmv (tiles, tail-row slices)
     bool useful = false;
     std::vector<int64_t> band_lo;         // [K+1] caller node index boundaries
     std::vector<int32_t> tile_stage_ptr;  // [K+1] into d_tile_order
@@ -63,8 +64,8 @@ __global__ void band_gather_kernel(const int32_t* __restrict__ new_of_old, const
 
 }  // namespace
 
-void fvm_pipe_release(fvm_ctx* h) {
-    PipePlan* P = (PipePlan*)h->pipe;
+static void release_plan(void*& slot) {
+    PipePlan* P = (PipePlan*)slot;
     if (!P) return;
     for (cudaEvent_t e : P->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : P->ev_stage) cudaEventDestroy(e);
@@ -73,13 +74,19 @@ void fvm_pipe_release(fvm_ctx* h) {
     if (P->s_in) cudaStreamDestroy(P->s_in);
     if (P->s_out) cudaStreamDestroy(P->s_out);
     delete P;  // the device arrays are in h->allocs
-    h->pipe = nullptr;
+    slot = nullptr;
 }
 
-static int32_t build_plan(fvm_ctx* h, int K) {
+void fvm_pipe_release(fvm_ctx* h) {
+    release_plan(h->pipe);
+    release_plan(h->pipe_spmv);
+}
+
+static int32_t build_plan(fvm_ctx* h, int K, int mode, void*& slot) {
     PipePlan* P = new PipePlan;
-    h->pipe = P;
+    slot = P;
     P->K = K;
+    P->mode = mode;
     const int64_t N = h->N;
     const int32_t n_tiles = h->dm.n_tiles, n_ifc = h->dm.n_ifc, n_vertices = h->dm.n_vertices;
     P->band_lo.resize(K + 1);
@@ -102,7 +109,7 @@ static int32_t build_plan(fvm_ctx* h, int K) {
         tile_stage[t] = s;
     }
     // ---- stage of every live boundary edge: the three vertices of its triangle have arrived -----------
-    const int32_t n_edges = (int32_t)h->h_bnd.size();
+    const int32_t n_edges = mode == 0 ? (int32_t)h->h_bnd.size() : 0;  // the operator has no edge pass
     std::vector<int32_t> edge_stage(n_edges, 0);
     for (int32_t e = 0; e < n_edges; ++e)
         for (int q = 0; q < 3; ++q) edge_stage[e] = std::max(edge_stage[e], band(old_of_new[h->h_bnd[e].v[q]]));
@@ -142,9 +149,19 @@ static int32_t build_plan(fvm_ctx* h, int K) {
         order.resize(stage.size());
         for (size_t i = 0; i < stage.size(); ++i) order[fill[stage[i]]++] = (int32_t)i;
     };
+    // fvm_spmv: the interface rows (then the points that are not vertices) form the tail rows, 32 per sliced-ELL
+    // slice; the columns of an interface row are vertices of triangles that hold the node, i.e. local nodes of
+    // the tiles counted in ifc_stage, so the row can run in that stage; a slice runs when its 32 rows can
+    std::vector<int32_t> unit_stage = ifc_stage;  // what the third kernel of a stage iterates over
+    if (mode == 1) {
+        const int32_t n_tail = n_ifc + (int32_t)(N - n_vertices), n_slices = (n_tail + 31) / 32;
+        unit_stage.assign(n_slices, 0);
+        for (int32_t k = 0; k < n_tail; ++k) unit_stage[k / 32] = std::max(unit_stage[k / 32], k < n_ifc ? ifc_stage[k] : K - 1);
+        for (int32_t i = 0; i < n_ifc; ++i) ifc_stage[i] = unit_stage[i / 32];  // when the row's result is final
+    }
     std::vector<int32_t> tile_order, ifc_order, edge_order;
     sort_by_stage(tile_stage, P->tile_stage_ptr, tile_order);
-    sort_by_stage(ifc_stage, P->ifc_stage_ptr, ifc_order);
+    sort_by_stage(unit_stage, P->ifc_stage_ptr, ifc_order);
     sort_by_stage(edge_stage, P->edge_stage_ptr, edge_order);
     // ---- stage after which an output band is final -------------------------------------------------------
     P->out_stage.assign(K, 0);
@@ -198,23 +215,9 @@ static int32_t build_plan(fvm_ctx* h, int K) {
     return FVM_OK;
 }
 
-int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du_host, bool* used) {
-    *used = false;
-    const char* e_off = getenv("FVM_NO_PIPELINE");
-    if ((e_off && e_off[0] == '1') || h->halo_ready || h->nranks > 1 || h->profiling) return FVM_OK;
-    const char* e_min = getenv("FVM_PIPE_MIN_NODES");
-    const int64_t min_nodes = e_min ? atoll(e_min) : (int64_t)1 << 20;
-    if (h->N < min_nodes) return FVM_OK;
-    if (!h->pipe) {
-        const char* e_k = getenv("FVM_PIPE_BANDS");
-        int K = e_k ? atoi(e_k) : 8;  // measured at 16.7M nodes: 4.21 / 3.93 / 3.97 / 4.07 ms for 4 / 8 / 12 / 16 bands
-        K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min(K, 64), h->N));
-        int32_t rc = build_plan(h, K);
-        if (rc) return rc;
-    }
-    PipePlan& P = *(PipePlan*)h->pipe;
-    const char* e_force = getenv("FVM_PIPE_FORCE");  // tests: run the pipeline even where it cannot overlap anything
-    if (!P.useful && !(e_force && e_force[0] == '1')) return FVM_OK;
+// the schedule shared by fvm_rhs and fvm_spmv; stage(s) queues the kernels of stage s on the compute stream
+template <class StageFn>
+static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, double* out_host, StageFn stage) {
     const int K = P.K, neq = h->neq;
     cudaStream_t sc = h->stream;
     // whatever is queued on the compute stream (an earlier call's kernels) precedes the first scatter
@@ -223,27 +226,16 @@ int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du
     FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_start, 0));
     for (int b = 0; b < K; ++b) {
         const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
-        if (cnt == 0) {
-            FVM_CUDA(h, cudaEventRecord(P.ev_in[b], P.s_in));
-            continue;
+        if (cnt > 0) {
+            FVM_CUDA(h, cudaMemcpyAsync(h->d_io + lo * neq, in_host + lo * neq, sizeof(double) * cnt, cudaMemcpyHostToDevice, P.s_in));
+            band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, P.s_in>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
         }
-        FVM_CUDA(h, cudaMemcpyAsync(h->d_io + lo * neq, u_host + lo * neq, sizeof(double) * cnt, cudaMemcpyHostToDevice, P.s_in));
-        band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, P.s_in>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
         FVM_CUDA(h, cudaEventRecord(P.ev_in[b], P.s_in));
     }
     int32_t rc = FVM_OK;
     for (int s = 0; s < K && !rc; ++s) {
         FVM_CUDA(h, cudaStreamWaitEvent(sc, P.ev_in[s], 0));
-        rc = fvm_launch_rhs_boundary_list(h, t, h->d_u, P.d_edge_order, P.edge_stage_ptr[s], P.edge_stage_ptr[s + 1] - P.edge_stage_ptr[s]);
-        h->pipe_list = P.d_tile_order;
-        h->pipe_off = P.tile_stage_ptr[s];
-        h->pipe_count = P.tile_stage_ptr[s + 1] - P.tile_stage_ptr[s];
-        if (!rc && h->pipe_count > 0) rc = fvm_launch_rhs_part(h, t, h->d_u, h->d_du, 4);
-        if (!rc)
-            rc = fvm_launch_rhs_interface_list(h, t, h->d_u, h->d_du, P.d_ifc_order, P.ifc_stage_ptr[s],
-                                               P.ifc_stage_ptr[s + 1] - P.ifc_stage_ptr[s]);
-        if (!rc && s == K - 1) rc = fvm_launch_rhs_nonvertex(h, h->d_du);
-        if (rc) break;
+        if ((rc = stage(s))) break;
         FVM_CUDA(h, cudaEventRecord(P.ev_stage[s], sc));
         for (int b = 0; b < K; ++b) {
             if (P.out_stage[b] != s) continue;
@@ -251,7 +243,7 @@ int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du
             if (cnt == 0) continue;
             FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_stage[s], 0));
             band_gather_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, P.d_out, lo, hi, neq);
-            FVM_CUDA(h, cudaMemcpyAsync(du_host + lo * neq, P.d_out + lo * neq, sizeof(double) * cnt, cudaMemcpyDeviceToHost, P.s_out));
+            FVM_CUDA(h, cudaMemcpyAsync(out_host + lo * neq, P.d_out + lo * neq, sizeof(double) * cnt, cudaMemcpyDeviceToHost, P.s_out));
         }
     }
     // leave the three streams joined whatever happened, so that the handle stays usable after an error
@@ -262,7 +254,74 @@ int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du
     if (rc) return rc;
     FVM_CUDA(h, ce);
     FVM_CUDA(h, cudaGetLastError());
-    *used = true;
     h->stats[14] += 1;
+    return FVM_OK;
+}
+
+// common gate: returns the plan to use, or null for the plain schedule
+static int32_t pipeline_plan(fvm_ctx* h, int mode, void*& slot, PipePlan** out) {
+    *out = nullptr;
+    const char* e_off = getenv("FVM_NO_PIPELINE");
+    if ((e_off && e_off[0] == '1') || h->halo_ready || h->nranks > 1 || h->profiling) return FVM_OK;
+    const char* e_min = getenv("FVM_PIPE_MIN_NODES");
+    const int64_t min_nodes = e_min ? atoll(e_min) : (int64_t)1 << 20;
+    if (h->N < min_nodes) return FVM_OK;
+    if (!slot) {
+        const char* e_k = getenv("FVM_PIPE_BANDS");
+        int K = e_k ? atoi(e_k) : 8;  // measured at 16.7M nodes: 4.21 / 3.93 / 3.97 / 4.07 ms for 4 / 8 / 12 / 16 bands
+        K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min(K, 64), h->N));
+        int32_t rc = build_plan(h, K, mode, slot);
+        if (rc) return rc;
+    }
+    PipePlan* P = (PipePlan*)slot;
+    const char* e_force = getenv("FVM_PIPE_FORCE");  // tests: run the pipeline even where it cannot overlap anything
+    if (!P->useful && !(e_force && e_force[0] == '1')) return FVM_OK;
+    *out = P;
+    return FVM_OK;
+}
+
+int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du_host, bool* used) {
+    *used = false;
+    if (u_host == du_host) return FVM_OK;
+    PipePlan* Pp = nullptr;
+    int32_t rc = pipeline_plan(h, 0, h->pipe, &Pp);
+    if (rc || !Pp) return rc;
+    PipePlan& P = *Pp;
+    const int K = P.K;
+    rc = run_pipeline(h, P, u_host, du_host, [&](int s) -> int32_t {
+        int32_t r = fvm_launch_rhs_boundary_list(h, t, h->d_u, P.d_edge_order, P.edge_stage_ptr[s], P.edge_stage_ptr[s + 1] - P.edge_stage_ptr[s]);
+        if (r) return r;
+        h->pipe_list = P.d_tile_order;
+        h->pipe_off = P.tile_stage_ptr[s];
+        h->pipe_count = P.tile_stage_ptr[s + 1] - P.tile_stage_ptr[s];
+        if (h->pipe_count > 0 && (r = fvm_launch_rhs_part(h, t, h->d_u, h->d_du, 4))) return r;
+        if ((r = fvm_launch_rhs_interface_list(h, t, h->d_u, h->d_du, P.d_ifc_order, P.ifc_stage_ptr[s], P.ifc_stage_ptr[s + 1] - P.ifc_stage_ptr[s])))
+            return r;
+        return s == K - 1 ? fvm_launch_rhs_nonvertex(h, h->d_du) : FVM_OK;
+    });
+    if (rc) return rc;
+    *used = true;
+    return FVM_OK;
+}
+
+// y = A x (+ b) with host vectors: tiles own their interior rows; interface rows and points that are not
+// vertices are the sliced-ELL tail rows, run slice by slice as their columns arrive
+int32_t fvm_spmv_pipelined(fvm_ctx* h, const double* x_host, double* y_host, bool add_b, bool* used) {
+    *used = false;
+    if (x_host == y_host || !h->csr.use_tile_spmv || h->neq != 1) return FVM_OK;
+    PipePlan* Pp = nullptr;
+    int32_t rc = pipeline_plan(h, 1, h->pipe_spmv, &Pp);
+    if (rc || !Pp) return rc;
+    PipePlan& P = *Pp;
+    rc = run_pipeline(h, P, x_host, y_host, [&](int s) -> int32_t {
+        int32_t r;
+        h->pipe_list = P.d_tile_order;
+        h->pipe_off = P.tile_stage_ptr[s];
+        h->pipe_count = P.tile_stage_ptr[s + 1] - P.tile_stage_ptr[s];
+        if (h->pipe_count > 0 && (r = fvm_launch_spmv_part(h, h->d_u, h->d_du, add_b, false, 4))) return r;
+        return fvm_launch_spmv_tail_list(h, h->d_u, h->d_du, add_b, P.d_ifc_order, P.ifc_stage_ptr[s], P.ifc_stage_ptr[s + 1] - P.ifc_stage_ptr[s]);
+    });
+    if (rc) return rc;
+    *used = true;
     return FVM_OK;
 }

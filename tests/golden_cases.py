@@ -114,8 +114,8 @@ CASES = {f.__name__: f for f in (readme_50x50, convection_robin_24, keller_segel
 
 
 # ---- both sides of a template case ---------------------------------------------------------------
-def build_template(c, side):
-    """side 'oracle' -> oracle TemplateResult; side 'gpu' -> fvm_b200 template object."""
+def build_template(c, side, **kw):
+    """side 'oracle' -> oracle TemplateResult; side 'gpu' -> fvm_b200 template object (kw: engine options)."""
     const0 = lambda x, y, t, u, p: 0.0 * x
     if c.template == "diffusion":
         ic = np.where(c.pair.gtri.points[:, 1] <= 1.0, 50.0, 0.0)
@@ -123,14 +123,14 @@ def build_template(c, side):
             return O.DiffusionEquation(c.pair.omesh, O.BoundaryConditions(c.pair.omesh, const0, O.Dirichlet),
                                        diffusion_function=lambda x, y, p: 1 / 9, initial_condition=ic, final_time=0.1)
         return G.DiffusionEquation(c.pair.gmesh, G.BoundaryConditions(c.pair.gmesh, G.Const(0.0), G.Dirichlet),
-                                   diffusion_function=1 / 9, initial_condition=ic, final_time=0.1)
+                                   diffusion_function=1 / 9, initial_condition=ic, final_time=0.1, **kw)
     if c.template == "met":
         if side == "oracle":
             f99 = cond_closure(G.Const(99.0))
             bc = O.BoundaryConditions(c.pair.omesh, (lambda x, y, t, u, p: f99(x, y, 0.0, 0.0, p),) * 2, (O.Neumann, O.Dirichlet))
             return O.MeanExitTimeProblem(c.pair.omesh, bc, diffusion_function=lambda x, y, p: 2.5e-3)
         bc = G.BoundaryConditions(c.pair.gmesh, (G.Const(99.0), G.Const(99.0)), (G.Neumann, G.Dirichlet))
-        return G.MeanExitTimeProblem(c.pair.gmesh, bc, diffusion_function=2.5e-3)
+        return G.MeanExitTimeProblem(c.pair.gmesh, bc, diffusion_function=2.5e-3, **kw)
     raise KeyError(c.template)
 
 

@@ -333,3 +333,30 @@ def test_steady_newton_raphson_linear_and_nonlinear():
     assert rel_err(sol.u[dn], u0[dn]) <= 1e-15 and sol.u.min() > 0  # device FMA vs NumPy in c0 + cx x + cy y
     with pytest.raises(TypeError):
         G.solve(G.SteadyFVMProblem(gp), G.Tsit5(0.1))
+
+
+@pytest.mark.parametrize("case", ["readme_50x50", "mean_exit_time_unstructured"])
+def test_operator_host_buffer_pipeline_is_bit_identical(case):
+    """fvm_spmv with host vectors takes the same banded pipeline as fvm_rhs (tiles own the interior rows, the
+    sliced-ELL tail rows run slice by slice): forced on for small meshes, every band count must reproduce the
+    plain schedule bit for bit, with and without b."""
+    from tests.golden_cases import CASES, build_template
+    from tests.test_rhs_gpu import _pipeline_env
+    c = CASES[case](None)
+    rng = np.random.default_rng(5)
+    xs = [c.u, rng.random(len(c.u))]
+    try:
+        _pipeline_env(FVM_NO_PIPELINE=1)
+        tpl = build_template(c, "gpu", tile_triangles=128)
+        refs = [(tpl.mul(np.empty_like(x), x).copy(), tpl.mul(np.empty_like(x), x, add_b=False).copy()) for x in xs]
+        assert tpl.engine.stats()["pipe_calls"] == 0
+        for bands in (2, 5, 16):
+            _pipeline_env(FVM_PIPE_MIN_NODES=0, FVM_PIPE_FORCE=1, FVM_PIPE_BANDS=bands)
+            tpl = build_template(c, "gpu", tile_triangles=128)
+            for x, (yb, y0) in zip(xs, refs):
+                assert np.array_equal(tpl.mul(np.full_like(x, np.nan), x), yb)
+                assert np.array_equal(tpl.mul(np.full_like(x, np.nan), x, add_b=False), y0)
+            st = tpl.engine.stats()
+            assert st["pipe_calls"] == 4 and st["pipe_bands"] == bands
+    finally:
+        _pipeline_env()
