@@ -27,6 +27,7 @@ struct DevMesh {
     int32_t n_tris;
     int32_t n_tiles;
     int32_t tile_tris;     // TT
+    int32_t pf_ahead;      // recompute kernels prefetch the lists of tile + pf_ahead into L2 (0 = off)
     int64_t tpad;          // n_tiles * TT : stride between geometry components
     // per triangle (native order, padded to tpad)
     const ushort4* tri_loc;  // 3 tile-local vertex ids (+ spare)

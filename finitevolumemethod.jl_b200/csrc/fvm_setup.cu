@@ -578,6 +578,12 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     m.n_tiles = (int32_t)n_tiles;
     m.tile_tris = TT;
     m.tpad = tpad;
+    {   // distance (in tiles) between a running CTA and the CTAs about to be scheduled: SMs x resident CTAs
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+        const char* e = getenv("FVM_PF_AHEAD");
+        m.pf_ahead = e ? atoi(e) : 2 * sms;  // measured at 4096^2: 0.562 ms without, 0.533 at 148..296, 0.550 at 1184
+    }
     int32_t rc;
 #define UP(dst, vec)                                               \
     do {                                                           \
