@@ -84,6 +84,10 @@ function update_dirichlet_nodes!(integrator)
     return nothing
 end
 
+"Page-locks the arrays an integrator passes to `fvm_eqs!` / `mul!` (full PCIe rate, pipelined copies); undo with `unpin!`."
+pin!(a::Array{Float64}) = (ccall((:fvm_host_register, LIB), Int32, (Ptr{Cvoid}, Int64), a, sizeof(a)) == 0 || error("fvm_host_register failed"); a)
+unpin!(a::Array{Float64}) = (ccall((:fvm_host_unregister, LIB), Int32, (Ptr{Cvoid},), a); a)
+
 "Template operator: `mul!(du, A, u)` of the MatrixOperator (diffusion_equation.jl:93-94)."
 struct FVMCudaOperator; handle::Handle; n::Int; end
 function LinearAlgebra_mul!(du::Vector{Float64}, A::FVMCudaOperator, u::Vector{Float64})
