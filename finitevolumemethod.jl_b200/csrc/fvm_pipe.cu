@@ -5,11 +5,12 @@
 // other around ~0.7 ms of kernels.  PCIe is full duplex, so the vector is cut into K bands of consecutive
 // CALLER indices and the three steps overlap:
 //
-//   copy-in stream : for each band  H2D -> scatter into native (tile-major) order          -> event in[b]
-//   compute stream : stage s waits for in[s], runs the tiles and live boundary edges whose nodes all lie in
-//                    bands <= s, then the interface nodes whose tiles / edges have all run  -> event stage[s]
-//   copy-out stream: band b waits for the stage after which all of its nodes are final, gathers it back
-//                    to caller order and copies it D2H while later bands are still arriving.
+//   copy-in stream : the K bands H2D, back to back                                          -> event in[b]
+//   compute stream : stage s waits for in[s], scatters band s into native (tile-major) order, runs the tiles
+//                    and live boundary edges whose nodes all lie in bands <= s, then the interface nodes
+//                    whose tiles / edges have all run, then gathers the output bands that are now final
+//                    back to caller order                                                   -> event stage[s]
+//   copy-out stream: D2H of those bands, while later bands are still arriving.
 //
 // Which stage a tile / interface node / output band belongs to is a property of the mesh numbering and is
 // computed once per handle (lazily, at the first host-buffer call).  On a lattice in the reference's
@@ -40,9 +41,6 @@ struct PipePlan {
     std::vector<cudaEvent_t> ev_in, ev_stage;
     cudaEvent_t ev_start = nullptr, ev_out = nullptr;
 };
-
-// band of caller node j
-inline int band_of(const PipePlan& P, int64_t j, int64_t N) { return (int)std::min<int64_t>(P.K - 1, j * P.K / N); }
 
 __global__ void band_scatter_kernel(const int32_t* __restrict__ new_of_old, const double* __restrict__ src_caller,
                                     double* __restrict__ dst_native, const int64_t lo, const int64_t hi, const int neq) {
@@ -89,15 +87,25 @@ static int32_t build_plan(fvm_ctx* h, int K, int mode, void*& slot) {
     P->mode = mode;
     const int64_t N = h->N;
     const int32_t n_tiles = h->dm.n_tiles, n_ifc = h->dm.n_ifc, n_vertices = h->dm.n_vertices;
-    P->band_lo.resize(K + 1);
-    for (int b = 0; b <= K; ++b) P->band_lo[b] = N * b / K;
-    // band_of() and band_lo must agree: node j is in band b iff band_lo[b] <= j < band_lo[b+1]
-    auto band = [&](int64_t j) {
-        int b = band_of(*P, j, N);
-        while (j < P->band_lo[b]) --b;
-        while (j >= P->band_lo[b + 1]) ++b;
-        return b;
-    };
+    // Band borders.  The first output band can leave only after the second stage and the last two output bands
+    // only after the last input band, so the call costs about (first two bands) + max(copy-in, copy-out) of the
+    // rest + (last two bands): the first and last two bands get half the width of the others (FVM_PIPE_TAPER=0:
+    // uniform bands).
+    P->band_lo.assign(K + 1, 0);
+    {
+        const char* e = getenv("FVM_PIPE_TAPER");
+        const bool taper = K >= 6 && !(e && e[0] == '0');
+        std::vector<int64_t> w(K, 2);
+        if (taper) w[0] = w[1] = w[K - 2] = w[K - 1] = 1;
+        int64_t tot = 0, acc = 0;
+        for (int b = 0; b < K; ++b) tot += w[b];
+        for (int b = 0; b < K; ++b) {
+            acc += w[b];
+            P->band_lo[b + 1] = N * acc / tot;
+        }
+    }
+    // node j is in band b iff band_lo[b] <= j < band_lo[b+1]
+    auto band = [&](int64_t j) { return (int)(std::upper_bound(P->band_lo.begin() + 1, P->band_lo.end() - 1, j) - (P->band_lo.begin() + 1)); };
     const int32_t* old_of_new = h->node_old_of_new.data();
     // ---- stage of every tile: the last band that holds one of its (own or external) nodes -------------
     std::vector<int32_t> tile_stage(n_tiles, 0);
@@ -220,30 +228,43 @@ template <class StageFn>
 static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, double* out_host, StageFn stage) {
     const int K = P.K, neq = h->neq;
     cudaStream_t sc = h->stream;
-    // whatever is queued on the compute stream (an earlier call's kernels) precedes the first scatter
-    FVM_CUDA(h, cudaEventRecord(P.ev_start, sc));
+    // The copy streams carry nothing but copies, back to back, so that neither DMA engine ever waits for a
+    // kernel: the scatter of band s and the gathers of the bands that stage s completes run on the compute
+    // stream, which is idle most of the time (a stage is ~0.09 ms of kernels per ~0.3 ms of copy at 16.7M nodes).
+    FVM_CUDA(h, cudaEventRecord(P.ev_start, sc));  // an earlier call's kernels precede the first copy-in
     FVM_CUDA(h, cudaStreamWaitEvent(P.s_in, P.ev_start, 0));
     FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_start, 0));
     for (int b = 0; b < K; ++b) {
         const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
-        if (cnt > 0) {
+        if (cnt > 0)
             FVM_CUDA(h, cudaMemcpyAsync(h->d_io + lo * neq, in_host + lo * neq, sizeof(double) * cnt, cudaMemcpyHostToDevice, P.s_in));
-            band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, P.s_in>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
-        }
         FVM_CUDA(h, cudaEventRecord(P.ev_in[b], P.s_in));
     }
     int32_t rc = FVM_OK;
     for (int s = 0; s < K && !rc; ++s) {
         FVM_CUDA(h, cudaStreamWaitEvent(sc, P.ev_in[s], 0));
+        {
+            const int64_t lo = P.band_lo[s], hi = P.band_lo[s + 1], cnt = (hi - lo) * neq;
+            if (cnt > 0)
+                band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
+        }
         if ((rc = stage(s))) break;
-        FVM_CUDA(h, cudaEventRecord(P.ev_stage[s], sc));
+        bool any = false;
         for (int b = 0; b < K; ++b) {
             if (P.out_stage[b] != s) continue;
             const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
             if (cnt == 0) continue;
-            FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_stage[s], 0));
-            band_gather_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, P.d_out, lo, hi, neq);
-            FVM_CUDA(h, cudaMemcpyAsync(out_host + lo * neq, P.d_out + lo * neq, sizeof(double) * cnt, cudaMemcpyDeviceToHost, P.s_out));
+            band_gather_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_du, P.d_out, lo, hi, neq);
+            any = true;
+        }
+        if (!any) continue;
+        FVM_CUDA(h, cudaEventRecord(P.ev_stage[s], sc));
+        FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_stage[s], 0));
+        for (int b = 0; b < K; ++b) {
+            if (P.out_stage[b] != s) continue;
+            const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
+            if (cnt > 0)
+                FVM_CUDA(h, cudaMemcpyAsync(out_host + lo * neq, P.d_out + lo * neq, sizeof(double) * cnt, cudaMemcpyDeviceToHost, P.s_out));
         }
     }
     // leave the three streams joined whatever happened, so that the handle stays usable after an error
@@ -268,7 +289,7 @@ static int32_t pipeline_plan(fvm_ctx* h, int mode, void*& slot, PipePlan** out) 
     if (h->N < min_nodes) return FVM_OK;
     if (!slot) {
         const char* e_k = getenv("FVM_PIPE_BANDS");
-        int K = e_k ? atoi(e_k) : 8;  // measured at 16.7M nodes: 4.21 / 3.93 / 3.97 / 4.07 ms for 4 / 8 / 12 / 16 bands
+        int K = e_k ? atoi(e_k) : 10;
         K = (int)std::max<int64_t>(2, std::min<int64_t>(std::min(K, 64), h->N));
         int32_t rc = build_plan(h, K, mode, slot);
         if (rc) return rc;

@@ -34,7 +34,7 @@ struct TileOcc {
         return 2;
     }
 };
-template <int MODEL, int NEQ, int GEOM, int OCC = 0, int UNR = 1>
+template <int MODEL, int NEQ, int GEOM, int OCC = 0>
 __global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::template min_blocks<GEOM>())
     rhs_tile_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t,
                     const double* __restrict__ u, double* __restrict__ du, const int smem_nloc,
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::te
 
     // ---- triangle pass ------------------------------------------------------------------------
     const int n_iter = (ntri - tid + RHS_BLOCK - 1) / RHS_BLOCK;
-#pragma unroll(UNR)
+#pragma unroll 1
     for (int r = 0; r < n_iter; ++r) {
         const int lt = tid + r * RHS_BLOCK;
         const int64_t gt = t0 + lt;
@@ -454,17 +454,6 @@ static int32_t launch_tile(fvm_ctx* h, double t, const double* u, double* du, in
     if constexpr (NEQ == 2 && MODEL == FVM_FLUX_KELLER_SEGEL && GEOM == 0) {
         static const char* e = getenv("FVM_SYS_MINB");  // experiment knob: 4 resident CTAs (<= 64 registers)
         if (e && e[0] == '4') kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 4>;
-    }
-    if constexpr (NEQ == 1 && MODEL == FVM_FLUX_DIFF_CONST && GEOM == 1) {
-        // experiment knobs of the recompute kernel: resident CTAs per SM (register budget) and triangles in flight
-        const char* eo = getenv("FVM_REC_OCC");
-        const char* eu = getenv("FVM_REC_UNR");
-        const int occ = eo ? atoi(eo) : 0, unr = eu ? atoi(eu) : 1;
-        if (occ == 3 && unr == 1) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 3, 1>;
-        if (occ == 5 && unr == 1) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 5, 1>;
-        if (occ == 2 && unr == 2) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 2, 2>;
-        if (occ == 3 && unr == 2) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 3, 2>;
-        if ((occ == 4 || occ == 0) && unr == 2) kern = rhs_tile_kernel<MODEL, NEQ, GEOM, 4, 2>;
     }
     if (smem > 200 * 1024) return fvm_fail(h, FVM_ERR_ARG, "tile needs more than 200 KB of shared memory; lower tile_triangles");
     int32_t& configured = h->smem_configured[(const void*)kern];
