@@ -467,15 +467,15 @@ def main():
     for _ in range(args.e2e_steps):
         G.fvm_eqs(dun, un, p, 0.0)  # synchronous: H2D, to-native, kernels, from-native, D2H
     e2e_ms = (time.perf_counter() - t0) / args.e2e_steps * 1e3
-    e2e_plain_ms = None
-    if dist is None:  # the same call without the banded copy/compute pipeline (fvm_pipe.cu), for reference
-        os.environ["FVM_NO_PIPELINE"] = "1"
+    # the same call without the banded copy/compute pipeline (fvm_pipe.cu), for reference; every rank makes the
+    # same calls (sharded calls contain the NCCL halo exchange)
+    os.environ["FVM_NO_PIPELINE"] = "1"
+    G.fvm_eqs(dun, un, p, 0.0)
+    t0 = time.perf_counter()
+    for _ in range(3):
         G.fvm_eqs(dun, un, p, 0.0)
-        t0 = time.perf_counter()
-        for _ in range(3):
-            G.fvm_eqs(dun, un, p, 0.0)
-        e2e_plain_ms = (time.perf_counter() - t0) / 3 * 1e3
-        del os.environ["FVM_NO_PIPELINE"]
+    e2e_plain_ms = (time.perf_counter() - t0) / 3 * 1e3
+    del os.environ["FVM_NO_PIPELINE"]
     e2e_stats = eng.stats()
     if dist is not None:
         tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")

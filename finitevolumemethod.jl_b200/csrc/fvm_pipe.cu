@@ -116,11 +116,25 @@ static int32_t build_plan(fvm_ctx* h, int K, int mode, void*& slot) {
         for (int32_t k = h->h_tile_ext0[t]; k < h->h_tile_ext0[t + 1]; ++k) s = std::max(s, band(old_of_new[h->h_ext_ids[k]]));
         tile_stage[t] = s;
     }
+    // sharded: ghost entries are refreshed by the halo exchange, which needs the packed owned values of every
+    // band and therefore runs at the head of the last stage; whatever reads a ghost node runs after it
+    const bool sharded = h->halo_ready && !h->h_ghost.empty();
+    auto is_ghost = [&](int32_t g) { return sharded && h->h_ghost[old_of_new[g]] != 0; };
+    if (sharded) {
+#pragma omp parallel for schedule(static)
+        for (int32_t t = 0; t < n_tiles; ++t) {
+            bool d = false;
+            for (int32_t g = h->h_tile_node0[t]; !d && g < h->h_tile_node0[t] + h->h_tile_nown[t]; ++g) d = is_ghost(g);
+            for (int32_t k = h->h_tile_ext0[t]; !d && k < h->h_tile_ext0[t + 1]; ++k) d = is_ghost(h->h_ext_ids[k]);
+            if (d) tile_stage[t] = K - 1;
+        }
+    }
     // ---- stage of every live boundary edge: the three vertices of its triangle have arrived -----------
     const int32_t n_edges = mode == 0 ? (int32_t)h->h_bnd.size() : 0;  // the operator has no edge pass
     std::vector<int32_t> edge_stage(n_edges, 0);
     for (int32_t e = 0; e < n_edges; ++e)
-        for (int q = 0; q < 3; ++q) edge_stage[e] = std::max(edge_stage[e], band(old_of_new[h->h_bnd[e].v[q]]));
+        for (int q = 0; q < 3; ++q)
+            edge_stage[e] = std::max(edge_stage[e], is_ghost(h->h_bnd[e].v[q]) ? K - 1 : band(old_of_new[h->h_bnd[e].v[q]]));
     // ---- stage of every interface node: all tiles and boundary edges that feed it have run -----------
     std::vector<int32_t> ifc_stage(n_ifc, 0);
     {
@@ -283,7 +297,8 @@ static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, doub
 static int32_t pipeline_plan(fvm_ctx* h, int mode, void*& slot, PipePlan** out) {
     *out = nullptr;
     const char* e_off = getenv("FVM_NO_PIPELINE");
-    if ((e_off && e_off[0] == '1') || h->halo_ready || h->nranks > 1 || h->profiling) return FVM_OK;
+    if ((e_off && e_off[0] == '1') || h->profiling) return FVM_OK;
+    if (h->nranks > 1 && !h->halo_ready) return FVM_OK;  // sharded handle whose halo plan is not installed yet
     const char* e_min = getenv("FVM_PIPE_MIN_NODES");
     const int64_t min_nodes = e_min ? atoll(e_min) : (int64_t)1 << 20;
     if (h->N < min_nodes) return FVM_OK;
@@ -310,7 +325,9 @@ int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du
     PipePlan& P = *Pp;
     const int K = P.K;
     rc = run_pipeline(h, P, u_host, du_host, [&](int s) -> int32_t {
-        int32_t r = fvm_launch_rhs_boundary_list(h, t, h->d_u, P.d_edge_order, P.edge_stage_ptr[s], P.edge_stage_ptr[s + 1] - P.edge_stage_ptr[s]);
+        int32_t r;
+        if (s == K - 1 && (r = fvm_halo_exchange(h, h->d_u))) return r;  // no-op unless sharded
+        r = fvm_launch_rhs_boundary_list(h, t, h->d_u, P.d_edge_order, P.edge_stage_ptr[s], P.edge_stage_ptr[s + 1] - P.edge_stage_ptr[s]);
         if (r) return r;
         h->pipe_list = P.d_tile_order;
         h->pipe_off = P.tile_stage_ptr[s];
@@ -336,6 +353,7 @@ int32_t fvm_spmv_pipelined(fvm_ctx* h, const double* x_host, double* y_host, boo
     PipePlan& P = *Pp;
     rc = run_pipeline(h, P, x_host, y_host, [&](int s) -> int32_t {
         int32_t r;
+        if (s == P.K - 1 && (r = fvm_halo_exchange(h, h->d_u))) return r;  // no-op unless sharded
         h->pipe_list = P.d_tile_order;
         h->pipe_off = P.tile_stage_ptr[s];
         h->pipe_count = P.tile_stage_ptr[s + 1] - P.tile_stage_ptr[s];

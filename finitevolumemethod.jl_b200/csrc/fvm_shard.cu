@@ -128,10 +128,10 @@ extern "C" int32_t fvm_set_halo(fvm_handle h, int32_t n_neigh, const int32_t* ne
         // it is opt-in (it matters for small subdomains or many neighbours)
         const char* ov = getenv("FVM_HALO_OVERLAP");
         h->overlap = n_neigh > 0 && ov && ov[0] == '1';
-        h->stats[13] = h->n_tiles_indep;
     }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->halo_ready = true;
+    fvm_pipe_release(h);  // a host-buffer pipeline plan made before the halo existed is stale
     return FVM_OK;
 }
 

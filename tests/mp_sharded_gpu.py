@@ -46,6 +46,18 @@ def main():
         own = local.global_nodes[:local.n_owned]
         errs["rhs_" + kind] = rel_err(du[:local.n_owned], ref[own]) if np.abs(ref).max() > 0 else 0.0
         assert errs["rhs_" + kind] <= RTOL_RHS, errs
+        # the banded host-buffer pipeline (fvm_pipe.cu) with the halo exchange at the head of its last stage:
+        # forced on for this small mesh, bit-identical to the plain schedule on every rank
+        for bands in (3, 6):
+            os.environ.update(FVM_PIPE_MIN_NODES="0", FVM_PIPE_FORCE="1", FVM_PIPE_BANDS=str(bands))
+            p2 = G.get_sharded_cuda_parameters(lp, local, dist, tile_triangles=128, device=local_rank)
+            du2 = G.fvm_eqs(np.full_like(ul, np.nan), ul, p2, 0.3)
+            assert p2.engine.stats()["pipe_calls"] == 1, p2.engine.stats()
+            assert np.array_equal(du2, du), (kind, bands, np.abs(du2 - du).max())
+            p2.engine.close()
+            for k in ("FVM_PIPE_MIN_NODES", "FVM_PIPE_FORCE", "FVM_PIPE_BANDS"):
+                del os.environ[k]
+        log("pipelined rhs identical")
         # device Tsit5 on the sharded RHS vs the single-domain oracle
         if kind == "delaunay":
             dt, t1 = 2e-5, 2e-4
@@ -80,6 +92,15 @@ def main():
     own = local.global_nodes[:local.n_owned]
     errs["spmv"] = rel_err(y[:local.n_owned], (ref.A @ x + ref.b)[own])
     assert errs["spmv"] <= RTOL_RHS, errs
+    os.environ.update(FVM_PIPE_MIN_NODES="0", FVM_PIPE_FORCE="1", FVM_PIPE_BANDS="4")
+    tpl2 = G.DiffusionEquation(lmesh, G.BoundaryConditions(lmesh, G.Const(0.0), G.Dirichlet), diffusion_function=1 / 9,
+                               initial_condition=ic[local.global_nodes], final_time=0.02, ghost=local.is_ghost, tile_triangles=128)
+    G.install_halo(tpl2.engine, local, dist)
+    y2 = tpl2.mul(np.full_like(xl, np.nan), xl)
+    assert tpl2.engine.stats()["pipe_calls"] == 1 and rel_err(y2[:local.n_owned], y[:local.n_owned]) <= 1e-14, np.abs(y2 - y).max()
+    tpl2.engine.close()
+    for k in ("FVM_PIPE_MIN_NODES", "FVM_PIPE_FORCE", "FVM_PIPE_BANDS"):
+        del os.environ[k]
     sol = G.solve(tpl, G.Tsit5(0.001))
     uref = O.tsit5_fixed(lambda d, v, t: d.__setitem__(Ellipsis, ref.A @ v + ref.b), ref.u0, 0.0, 0.02, 0.001)
     errs["tsit5_operator"] = rel_err(sol.u[:local.n_owned], uref[own])
