@@ -142,7 +142,8 @@ int32_t fvm_from_native(fvm_handle h, const double* v_native_dev, double* v_call
  * whose inputs have arrived run on the compute stream, and finished bands are gathered and copied out on a
  * third stream while later bands are still arriving (PCIe is full duplex).  Bit-identical to the plain
  * schedule.  Page-lock the buffers once with fvm_host_register to get the full rate (a Julia Vector or NumPy
- * array is pageable); unregister before freeing them.  Environment: FVM_NO_PIPELINE=1, FVM_PIPE_BANDS=K. */
+ * array is pageable); unregister before freeing them.  Sharded handles do their halo
+ * exchange at the head of the last stage.  Environment: FVM_NO_PIPELINE=1, FVM_PIPE_BANDS=K, FVM_PIPE_TAPER=0. */
 int32_t fvm_host_register(void* host_ptr, int64_t nbytes);
 int32_t fvm_host_unregister(void* host_ptr);
 /* the *_native calls are asynchronous on the handle's stream */
