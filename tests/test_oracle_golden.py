@@ -464,3 +464,58 @@ def test_brusselator_exact_solution_pins_system_path():
                       callback=lambda x, t: (O.update_dirichlet_nodes(x, t, sys_), True)[1])
     exact = np.stack([np.exp(-P[:, 0] - P[:, 1] - 0.25), np.exp(P[:, 0] + P[:, 1] + 0.25)], axis=1)
     assert np.abs(u - exact).max() <= 2e-3 * np.abs(exact).max()
+
+
+def test_helmholtz_inhomogeneous_neumann_closed_form():
+    """docs/src/literate_tutorials/helmholtz_equation_with_inhomogeneous_boundary_conditions.jl:20-45,82-84: the
+    steady state of u_t = lap(u) + u with q.n = -1 on [-1,1]^2 is u = -(cos(x+1)+cos(1-x)+cos(y+1)+cos(1-y))/sin(2).
+    The RHS is affine in u, so one Newton step from a Jacobian assembled column by column from the ORACLE's
+    fvm_eqs! is exact.  Pins the inhomogeneous Neumann edges and the u-dependent source (the tutorial only
+    compares images)."""
+    n = 25
+    tri = O.triangulate_rectangle(-1, 1, -1, 1, n, n, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: -1.0 + 0.0 * u, O.Neumann)
+    prob = O.FVMProblem(mesh, BCs, diffusion_function=lambda x, y, t, u, p: 1.0 + 0.0 * u, source_function=lambda x, y, t, u, p: u,
+                        initial_condition=np.zeros(n * n), final_time=np.inf)
+    N = n * n
+    f0 = O.fvm_eqs_vec(np.zeros(N), np.zeros(N), prob, 0.0).copy()
+    J = np.empty((N, N))
+    for j in range(N):
+        e = np.zeros(N)
+        e[j] = 1.0
+        J[:, j] = O.fvm_eqs_vec(np.zeros(N), e, prob, 0.0) - f0
+    u = np.linalg.solve(J, -f0)
+    assert np.abs(O.fvm_eqs_vec(np.zeros(N), u, prob, 0.0)).max() <= 1e-9 * np.abs(f0).max()
+    x, y = tri.points[:, 0], tri.points[:, 1]
+    exact = -(np.cos(x + 1) + np.cos(1 - x) + np.cos(y + 1) + np.cos(1 - y)) / math.sin(2)
+    assert np.abs(u - exact).max() <= 2e-3 * np.abs(exact).max()  # O(h^2) at h = 1/12: measured 1.03e-3
+    assert -2.6 < exact.min() < exact.max() < -0.9  # the level range the tutorial plots (-2.5:0.15:-1.0)
+
+
+def test_porous_medium_barenblatt_solution():
+    """docs/src/literate_tutorials/porous_medium_equation.jl:20-50,88-99: u_t = div(D u^(m-1) grad u) has the
+    Barenblatt similarity solution.  Started from the exact profile at t = 1 (instead of the tutorial's narrow
+    Gaussian, which needs an implicit integrator) and integrated to t = 2 with the fixed-step Tsit5: pins the
+    u-dependent diffusion path D(u) = D0 u^(m-1) of construct_flux_function (problem.jl:425-440)."""
+    m, M, D = 2, 0.37, 2.53
+    RmM = 4 * m / (m - 1) * (M / (4 * np.pi)) ** ((m - 1) / m)
+
+    def exact(x, y, t):
+        r2 = x * x + y * y
+        inner = (M / (4 * np.pi)) ** ((m - 1) / m) - (m - 1) / (4 * m) * r2 * (D * t) ** (-1 / m)
+        return np.where(r2 < RmM * (D * t) ** (1 / m), (D * t) ** (-1 / m) * np.maximum(inner, 0.0) ** (1 / (m - 1)), 0.0)
+
+    L = 3.0
+    tri = O.triangulate_rectangle(-L, L, -L, L, 61, 61, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    x, y = tri.points[:, 0], tri.points[:, 1]
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: 0.0 * u, O.Dirichlet)
+    prob = O.FVMProblem(mesh, BCs, diffusion_function=lambda x, y, t, u, p: p[0] * u ** (p[1] - 1), diffusion_parameters=(D, m),
+                        initial_condition=exact(x, y, 1.0), initial_time=1.0, final_time=2.0)
+    u = O.tsit5_fixed(lambda d, v, t: O.fvm_eqs_vec(d, v, prob, t), prob.initial_condition, 1.0, 2.0, 0.005,
+                      callback=lambda v, t: (O.update_dirichlet_nodes(v, t, prob), True)[1])
+    ref = exact(x, y, 2.0)
+    assert np.abs(u - ref).max() <= 0.03 * ref.max()  # the free boundary is resolved to O(h)
+    assert abs(u @ mesh.cv_volumes - M) <= 2e-3 * M  # mass M is conserved (zero flux through the support)
+    assert (ref > 0).sum() > 500 and ref[0] == 0.0
