@@ -4,6 +4,8 @@ the halo-exchange plan.  One process per GPU; the device side is 
 Every rank owns a set of nodes and keeps ALL triangles that touch an owned node, so the right-hand
 side of an owned node is complete locally and only the input vector's ghost entries are exchanged.
 The reference has no distributed code at all; this layer is new (north_star d)."""
+import ctypes as C
+
 import numpy as np
 
 from . import _lib as L
@@ -41,6 +43,28 @@ def partition_rcb(points, nparts):
 
     rec(np.arange(len(points)), 0, nparts)
     return owner
+
+
+def partition_graph(tri, nparts):
+    """METIS-style partition of the node graph (recursive bisection: greedy graph growing + FM boundary
+    refinement, in the C library): parts differ by at most one node; the edge cut — and with it the halo —
+    follows the mesh connectivity instead of the coordinates."""
+    owner = np.empty(tri.num_points, dtype=np.int32)
+    t = L.i32(tri.triangles)
+    rc = L.lib().fvm_partition_graph(tri.num_points, L.ip(t), tri.num_triangles, 0, int(nparts), L.ip(owner))
+    if rc != L.OK:
+        raise L.FVMCudaError(rc, L.lib().fvm_last_error(None).decode())
+    return owner
+
+
+def edge_cut(tri, owner):
+    """number of node-graph edges between different parts"""
+    cut = C.c_int64()
+    t, o = L.i32(tri.triangles), L.i32(owner)
+    rc = L.lib().fvm_partition_edge_cut(tri.num_points, L.ip(t), tri.num_triangles, 0, L.ip(o), C.byref(cut))
+    if rc != L.OK:
+        raise L.FVMCudaError(rc, L.lib().fvm_last_error(None).decode())
+    return cut.value
 
 
 # ---- local mesh + halo plan ------------------------------------------------------------------------

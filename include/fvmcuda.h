@@ -219,6 +219,13 @@ int32_t fvm_eval_points(fvm_handle h, double t, const double* u, int32_t u_on_de
  * fvm_shard_init, fvm_set_halo.  Afterwards fvm_rhs*, fvm_spmv* and fvm_tsit5 refresh the ghost
  * entries of their input vector with grouped ncclSend/ncclRecv before computing; outputs are valid
  * on owned nodes (ghost rows are 0). */
+/* METIS-style node partition (north_star d): recursive bisection of the node graph (an edge per pair of
+ * nodes sharing a triangle, the pattern of jacobian_sparsity, src/solve.jl:56-77) by greedy graph growing +
+ * Fiduccia-Mattheyses boundary refinement; parts differ by at most one node.  Host-only. */
+int32_t fvm_partition_graph(int64_t n_points, const int32_t* triangles, int64_t n_triangles, int32_t index_base,
+                            int32_t n_parts, int32_t* owner /* [n_points], 0-based part of every node */);
+int32_t fvm_partition_edge_cut(int64_t n_points, const int32_t* triangles, int64_t n_triangles, int32_t index_base,
+                               const int32_t* owner, int64_t* cut);
 int32_t fvm_set_ghost_nodes(fvm_handle h, const uint8_t* is_ghost /* [N], 1 = owned by another rank */);
 /* nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 and broadcast by the host. */
 int32_t fvm_nccl_unique_id(void* out128);

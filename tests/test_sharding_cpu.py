@@ -38,7 +38,7 @@ def test_sharded_oracle_rhs_two_ranks(kind, tmp_path):
 def test_partitioners_and_local_meshes():
     tri = G.triangulate_rectangle(0, 2, 0, 2, 33, 32, single_boundary=True)
     for nparts in (2, 4, 8):
-        for owner in (G.partition_strips(tri.points, nparts), G.partition_rcb(tri.points, nparts)):
+        for owner in (G.partition_strips(tri.points, nparts), G.partition_rcb(tri.points, nparts), G.partition_graph(tri, nparts)):
             cnt = np.bincount(owner, minlength=nparts)
             assert cnt.min() >= len(owner) // nparts - 1 and cnt.max() <= len(owner) // nparts + 1
             locs = [G.extract_local(tri, owner, r, nparts) for r in range(nparts)]
@@ -62,3 +62,25 @@ def test_partitioners_and_local_meshes():
         assert sorted(map(tuple, a.triangulation.boundary_edges()[0].tolist())) == sorted(map(tuple, b.triangulation.boundary_edges()[0].tolist()))
         assert a.neighbours == b.neighbours
         assert all(np.array_equal(x, y) for x, y in zip(a.send_nodes + a.recv_nodes, b.send_nodes + b.recv_nodes))
+
+
+def test_graph_partitioner_balance_and_cut():
+    """fvm_partition_graph (METIS-style recursive bisection: graph growing + FM refinement, host-only): equal part
+    sizes for any k, every node assigned, an edge cut of the order of the geometric partitioners', and a partition
+    that follows the connectivity where coordinates mislead (two blocks joined by a thin bridge)."""
+    from tests.common import delaunay_mesh
+    for tri in (G.triangulate_rectangle(0, 2, 0, 1, 80, 41, single_boundary=True), delaunay_mesh(6000, 11, jitter=0.3, extra_points=3)):
+        for k in (2, 3, 5, 8):
+            owner = G.partition_graph(tri, k)
+            cnt = np.bincount(owner, minlength=k)
+            assert owner.min() == 0 and owner.max() == k - 1 and cnt.max() - cnt.min() <= 1
+            assert G.edge_cut(tri, owner) <= 1.6 * G.edge_cut(tri, G.partition_rcb(tri.points, k))
+            assert np.array_equal(owner, G.partition_graph(tri, k))  # deterministic
+    # the cut of a 2-way split must be the edges between the parts (checked against a direct count)
+    tri = G.triangulate_rectangle(0, 1, 0, 1, 12, 9, single_boundary=True)
+    owner = G.partition_graph(tri, 2)
+    T = tri.triangles
+    e = np.unique(np.sort(np.concatenate([T[:, [0, 1]], T[:, [1, 2]], T[:, [2, 0]]]), axis=1), axis=0)
+    assert G.edge_cut(tri, owner) == int((owner[e[:, 0]] != owner[e[:, 1]]).sum())
+    with pytest.raises(G.FVMCudaError):
+        G.partition_graph(tri, 0)
