@@ -49,16 +49,18 @@ Graph build_graph(int64_t N, const int32_t* tri, int64_t T, int32_t base) {
 
 // BFS over the nodes of `part` (label[v] == lab) from `src`; returns the visiting order (only the component of src)
 void bfs(const Graph& g, const std::vector<int32_t>& label, int32_t lab, int32_t src, std::vector<int32_t>& order,
-         std::vector<int32_t>& mark, int32_t stamp) {
+         std::vector<int32_t>& mark, int32_t stamp, std::vector<int32_t>* dist = nullptr) {
     order.clear();
     order.push_back(src);
     mark[src] = stamp;
+    if (dist) (*dist)[src] = 0;
     for (size_t head = 0; head < order.size(); ++head) {
         const int32_t v = order[head];
         for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
             const int32_t w = g.adj[e];
             if (label[w] == lab && mark[w] != stamp) {
                 mark[w] = stamp;
+                if (dist) (*dist)[w] = (*dist)[v] + 1;
                 order.push_back(w);
             }
         }
@@ -68,28 +70,32 @@ void bfs(const Graph& g, const std::vector<int32_t>& label, int32_t lab, int32_t
 struct Bisector {
     const Graph& g;
     std::vector<int32_t>& label;  // current part of every node
-    std::vector<int32_t> mark, order;
+    std::vector<int32_t> mark, order, dp, dq;
     int32_t stamp = 0;
     int32_t next_label;
 
     Bisector(const Graph& g_, std::vector<int32_t>& l, int32_t first_free) : g(g_), label(l), mark(g_.n, 0), next_label(first_free) {}
 
-    // splits the nodes `nodes` (all labelled `lab`) into `lab` (n_left nodes) and a new label; returns the new label
-    int32_t bisect(std::vector<int32_t>& nodes, int32_t lab, int64_t n_left) {
-        const int32_t other = next_label++;
-        const int64_t n = (int64_t)nodes.size();
-        // everything starts on the right; graph growing moves n_left nodes back to `lab`
+    // grows `lab` from `seed` over the unassigned nodes (label == other) until n_left nodes are taken; further
+    // components are entered from their own pseudo-peripheral nodes
+    void grow(const std::vector<int32_t>& nodes, int32_t lab, int32_t other, int64_t n_left, int32_t seed) {
         for (int32_t v : nodes) label[v] = other;
         int64_t grown = 0;
         size_t scan = 0;
+        bool first = true;
         while (grown < n_left) {
-            while (scan < nodes.size() && label[nodes[scan]] != other) ++scan;  // next unassigned component
-            int32_t src = nodes[scan];
-            // pseudo-peripheral start: the last node of a BFS from an arbitrary node, twice
-            for (int sweep = 0; sweep < 2; ++sweep) {
-                bfs(g, label, other, src, order, mark, ++stamp);
-                src = order.back();
+            int32_t src;
+            if (first && seed >= 0) {
+                src = seed;
+            } else {
+                while (scan < nodes.size() && label[nodes[scan]] != other) ++scan;  // next unassigned component
+                src = nodes[scan];
+                for (int sweep = 0; sweep < 2; ++sweep) {
+                    bfs(g, label, other, src, order, mark, ++stamp);
+                    src = order.back();
+                }
             }
+            first = false;
             bfs(g, label, other, src, order, mark, ++stamp);
             for (int32_t v : order) {
                 if (grown == n_left) break;
@@ -97,7 +103,63 @@ struct Bisector {
                 ++grown;
             }
         }
-        refine(nodes, lab, other, n_left, n);
+    }
+
+    int64_t cut_between(const std::vector<int32_t>& nodes, int32_t a, int32_t b) const {
+        int64_t c = 0;
+        for (int32_t v : nodes)
+            if (label[v] == a)
+                for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) c += label[g.adj[e]] == b;
+        return c;
+    }
+
+    // splits the nodes `nodes` (all labelled `lab`) into `lab` (n_left nodes) and a new label; returns the new label.
+    // Like METIS's initial partitioner, several growing seeds are tried and the smallest refined cut is kept: a
+    // pseudo-peripheral node p, its antipode q, and the node farthest from both (a "third corner": its front
+    // runs across the one grown from p).
+    int32_t bisect(std::vector<int32_t>& nodes, int32_t lab, int64_t n_left) {
+        const int32_t other = next_label++;
+        const int64_t n = (int64_t)nodes.size();
+        for (int32_t v : nodes) label[v] = other;
+        int32_t seeds[3] = {-1, -1, -1};
+        {
+            int32_t src = nodes[0];
+            for (int sweep = 0; sweep < 2; ++sweep) {
+                bfs(g, label, other, src, order, mark, ++stamp);
+                src = order.back();
+            }
+            seeds[0] = src;
+            if (dp.size() < (size_t)g.n) {
+                dp.assign(g.n, 0);
+                dq.assign(g.n, 0);
+            }
+            bfs(g, label, other, seeds[0], order, mark, ++stamp, &dp);  // graph distances from p
+            seeds[1] = order.back();
+            const std::vector<int32_t> comp = order;                      // the component of p
+            bfs(g, label, other, seeds[1], order, mark, ++stamp, &dq);  // ... and from q
+            int32_t best_d = -1;
+            for (int32_t v : comp) {
+                const int32_t d = std::min(dp[v], dq[v]);
+                if (d > best_d) {
+                    best_d = d;
+                    seeds[2] = v;
+                }
+            }
+        }
+        std::vector<int32_t> best_label;
+        int64_t best_cut = INT64_MAX;
+        for (int trial = 0; trial < 3; ++trial) {
+            if (seeds[trial] < 0 || (trial > 0 && seeds[trial] == seeds[trial - 1])) continue;
+            grow(nodes, lab, other, n_left, seeds[trial]);
+            refine(nodes, lab, other, n_left, n);
+            const int64_t c = cut_between(nodes, lab, other);
+            if (c < best_cut) {
+                best_cut = c;
+                best_label.resize(nodes.size());
+                for (size_t i = 0; i < nodes.size(); ++i) best_label[i] = label[nodes[i]];
+            }
+        }
+        for (size_t i = 0; i < nodes.size(); ++i) label[nodes[i]] = best_label[i];
         return other;
     }
 
