@@ -426,3 +426,20 @@ def test_host_buffer_pipeline_is_bit_identical(case):
             assert p.engine.stats()["pipe_calls"] == 3
     finally:
         _pipeline_env()
+
+
+def test_host_register_round_trip():
+    """fvm_host_register / fvm_host_unregister (G.pinned): page-locked caller arrays give the same result; a
+    second registration of the same array is accepted, a bad pointer is an error."""
+    from fvm_b200 import _lib as L
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True))
+    gp, op = pair.problem(G.Const(0.0), G.Dirichlet, G.ConstantDiffusion(1 / 9))
+    p = G.get_cuda_parameters(gp)
+    u = np.random.default_rng(2).random(2500)
+    ref = G.fvm_eqs(np.zeros_like(u), u, p, 0.0)
+    du = np.zeros_like(u)
+    with G.pinned(u, du):
+        assert L.lib().fvm_host_register(u.ctypes.data, u.nbytes) == L.OK  # already registered: accepted
+        assert np.array_equal(G.fvm_eqs(du, u, p, 0.0), ref)
+    assert L.lib().fvm_host_unregister(u.ctypes.data) != L.OK  # no longer registered
+    assert L.lib().fvm_host_register(None, 8) == L.ERR_ARG
