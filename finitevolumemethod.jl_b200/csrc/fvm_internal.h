@@ -204,9 +204,11 @@ int32_t fvm_fail(fvm_ctx* h, int32_t code, const std::string& msg);
 #define FVM_CUDA(h, call)                                                                         \
     do {                                                                                          \
         cudaError_t e__ = (call);                                                                 \
-        if (e__ != cudaSuccess)                                                                   \
+        if (e__ != cudaSuccess) {                                                                 \
+            cudaGetLastError(); /* a reported error must not fail the next, unrelated call */     \
             return fvm_fail((h), FVM_ERR_CUDA,                                                    \
                             std::string(#call) + ": " + cudaGetErrorString(e__));                \
+        }                                                                                         \
     } while (0)
 #define FVM_REQUIRE(h, cond, msg)                                 \
     do {                                                          \

@@ -41,14 +41,20 @@ extern "C" int32_t fvm_host_register(void* ptr, int64_t nbytes) {
         cudaGetLastError();
         return FVM_OK;
     }
-    if (e != cudaSuccess) return fvm_fail(nullptr, FVM_ERR_CUDA, std::string("fvm_host_register: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // do not leave the error behind for an unrelated later call to pick up
+        return fvm_fail(nullptr, FVM_ERR_CUDA, std::string("fvm_host_register: ") + cudaGetErrorString(e));
+    }
     return FVM_OK;
 }
 
 extern "C" int32_t fvm_host_unregister(void* ptr) {
     if (!ptr) return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_host_unregister: null pointer");
     cudaError_t e = cudaHostUnregister(ptr);
-    if (e != cudaSuccess) return fvm_fail(nullptr, FVM_ERR_CUDA, std::string("fvm_host_unregister: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fvm_fail(nullptr, FVM_ERR_CUDA, std::string("fvm_host_unregister: ") + cudaGetErrorString(e));
+    }
     return FVM_OK;
 }
 
