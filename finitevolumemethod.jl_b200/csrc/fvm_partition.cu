@@ -1,11 +1,16 @@
 // libfvmcuda: METIS-style graph partitioning of the mesh's node graph for the multi-GPU path (SURVEY.md 8e,
-// north_star d).  No METIS header exists offline, so this is the classical recursive-bisection scheme METIS's
-// initial partitioner is built on: greedy graph growing (a BFS level structure from a pseudo-peripheral node
-// fills the first half) followed by Fiduccia-Mattheyses-style boundary refinement (boundary nodes with
-// positive gain change sides while the balance stays within tolerance), recursively for k parts with
-// proportional targets, so k need not be a power of two.  The node graph is the one `jacobian_sparsity`
-// walks (/root/reference/src/solve.jl:56-77): an edge for every pair of nodes sharing a triangle.
-// Host-only code: needs no CUDA device.
+// north_star d).  No METIS header exists offline, so the scheme is written out here: multilevel recursive
+// bisection.
+//   coarsening    heavy-edge matching (a node is merged with the unmatched neighbour it shares the heaviest edge
+//                 with) until a few thousand weighted nodes are left;
+//   initial cut   greedy graph growing on the coarsest graph from several seeds (a pseudo-peripheral node, its
+//                 antipode, the node farthest from both, and pseudo-random ones), the smallest refined cut wins;
+//   uncoarsening  the cut is projected level by level and improved by Fiduccia-Mattheyses-style boundary
+//                 refinement (boundary nodes with positive gain change sides within a balance tolerance);
+//   k parts       recursive bisection with proportional targets (k need not be a power of two); on the finest
+//                 level node counts are restored exactly, so parts differ by at most one node.
+// The node graph is the one `jacobian_sparsity` walks (/root/reference/src/solve.jl:56-77): an edge for every
+// pair of nodes sharing a triangle.  Deterministic.  Host-only code: needs no CUDA device.
 #include <algorithm>
 #include <numeric>
 #include <queue>
@@ -14,15 +19,16 @@
 
 namespace {
 
-struct Graph {
-    int64_t n = 0;
+struct WGraph {
+    int32_t n = 0;
     std::vector<int64_t> ptr;
-    std::vector<int32_t> adj;
+    std::vector<int32_t> adj, ew, vw;  // neighbours, edge weights, node weights
+    int64_t total_w = 0;
 };
 
-Graph build_graph(int64_t N, const int32_t* tri, int64_t T, int32_t base) {
-    Graph g;
-    g.n = N;
+WGraph graph_from_triangles(int64_t N, const int32_t* tri, int64_t T, int32_t base) {
+    WGraph g;
+    g.n = (int32_t)N;
     std::vector<int64_t> cnt(N + 1, 0);
     for (int64_t t = 0; t < T; ++t)
         for (int r = 0; r < 3; ++r) cnt[tri[3 * t + r] - base + 1] += 2;
@@ -44,12 +50,177 @@ Graph build_graph(int64_t N, const int32_t* tri, int64_t T, int32_t base) {
         g.adj.insert(g.adj.end(), raw.begin() + cnt[i], e);
         g.ptr[i + 1] = (int64_t)g.adj.size();
     }
+    g.ew.assign(g.adj.size(), 1);
+    g.vw.assign(N, 1);
+    g.total_w = N;
     return g;
 }
 
-// BFS over the nodes of `part` (label[v] == lab) from `src`; returns the visiting order (only the component of src)
-void bfs(const Graph& g, const std::vector<int32_t>& label, int32_t lab, int32_t src, std::vector<int32_t>& order,
-         std::vector<int32_t>& mark, int32_t stamp, std::vector<int32_t>* dist = nullptr) {
+int64_t cut_of(const WGraph& g, const std::vector<uint8_t>& side) {
+    int64_t c = 0;
+    for (int32_t v = 0; v < g.n; ++v)
+        for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
+            if (side[v] != side[g.adj[e]]) c += g.ew[e];
+    return c / 2;
+}
+
+// ---- coarsening: heavy-edge matching --------------------------------------------------------------------
+WGraph coarsen(const WGraph& g, std::vector<int32_t>& cmap, int64_t max_vw) {
+    const int32_t n = g.n;
+    std::vector<int32_t> match(n, -1);
+    cmap.assign(n, -1);
+    int32_t nc = 0;
+    // visit in a fixed pseudo-random order (a stride coprime to n) so that the matching does not follow the numbering
+    int64_t stride = (int64_t)(0.6180339887 * n) | 1;
+    while (std::gcd<int64_t, int64_t>(stride, n) != 1) stride += 2;
+    int64_t v64 = 0;
+    for (int32_t it = 0; it < n; ++it, v64 = (v64 + stride) % n) {
+        const int32_t v = (int32_t)v64;
+        if (match[v] >= 0) continue;
+        int32_t best = -1, best_w = -1;
+        for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
+            const int32_t u = g.adj[e];
+            if (match[u] < 0 && u != v && g.ew[e] > best_w && (int64_t)g.vw[v] + g.vw[u] <= max_vw) {
+                best_w = g.ew[e];
+                best = u;
+            }
+        }
+        match[v] = best >= 0 ? best : v;
+        if (best >= 0) match[best] = v;
+        cmap[v] = nc;
+        if (best >= 0) cmap[best] = nc;
+        ++nc;
+    }
+    WGraph c;
+    c.n = nc;
+    c.vw.assign(nc, 0);
+    c.ptr.assign(nc + 1, 0);
+    c.total_w = g.total_w;
+    std::vector<int32_t> first(nc, -1), second(nc, -1);
+    for (int32_t v = 0; v < n; ++v) {
+        c.vw[cmap[v]] += g.vw[v];
+        (first[cmap[v]] < 0 ? first : second)[cmap[v]] = v;
+    }
+    std::vector<int64_t> pos(nc, -1);  // position of a coarse neighbour inside the row being built
+    c.adj.reserve(g.adj.size() / 2);
+    c.ew.reserve(g.adj.size() / 2);
+    for (int32_t cv = 0; cv < nc; ++cv) {
+        const int64_t row0 = (int64_t)c.adj.size();
+        for (int32_t v : {first[cv], second[cv]}) {
+            if (v < 0) continue;
+            for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
+                const int32_t cu = cmap[g.adj[e]];
+                if (cu == cv) continue;
+                if (pos[cu] >= row0) {
+                    c.ew[pos[cu]] += g.ew[e];
+                } else {
+                    pos[cu] = (int64_t)c.adj.size();
+                    c.adj.push_back(cu);
+                    c.ew.push_back(g.ew[e]);
+                }
+            }
+        }
+        c.ptr[cv + 1] = (int64_t)c.adj.size();
+    }
+    return c;
+}
+
+// ---- Fiduccia-Mattheyses-style boundary refinement --------------------------------------------------------
+// side 0 should weigh target0.  `exact`: finish with |w0 - target0| minimal (node counts on the finest level).
+void refine(const WGraph& g, int64_t target0, std::vector<uint8_t>& side, bool exact) {
+    const int32_t n = g.n;
+    int32_t max_vw = 1;
+    for (int32_t v = 0; v < n; ++v) max_vw = std::max(max_vw, g.vw[v]);
+    const int64_t tol = std::max<int64_t>(max_vw, g.total_w / 200);  // 0.5 % while the cut is being improved
+    int64_t w0 = 0;
+    for (int32_t v = 0; v < n; ++v)
+        if (!side[v]) w0 += g.vw[v];
+    auto gain = [&](int32_t v) {
+        int64_t ext = 0, in = 0;
+        for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) (side[g.adj[e]] != side[v] ? ext : in) += g.ew[e];
+        return ext - in;
+    };
+    // FM passes: always move the unlocked boundary node with the largest gain (negative gains included, so the
+    // search can climb out of a local minimum and straighten a wiggly cut), remember the best prefix of the move
+    // sequence, undo the rest.  A pass ends after `patience` moves without a new best.
+    std::vector<uint8_t> locked(n);
+    std::vector<std::pair<int64_t, int32_t>> cand;
+    std::vector<int32_t> moves;
+    std::priority_queue<std::pair<int64_t, int32_t>> heap;
+    const int64_t patience = std::max<int64_t>(64, std::min<int64_t>(2000, n / 50));
+    for (int pass = 0; pass < 8; ++pass) {
+        std::fill(locked.begin(), locked.end(), 0);
+        while (!heap.empty()) heap.pop();
+        for (int32_t v = 0; v < n; ++v) {
+            bool boundary = false;
+            for (int64_t e = g.ptr[v]; e < g.ptr[v + 1] && !boundary; ++e) boundary = side[g.adj[e]] != side[v];
+            if (boundary) heap.emplace(gain(v), v);
+        }
+        moves.clear();
+        int64_t delta = 0, best_delta = 0, best_imb = std::llabs(w0 - target0);
+        size_t best_len = 0;
+        while (!heap.empty() && (int64_t)(moves.size() - best_len) < patience) {
+            const auto top = heap.top();
+            heap.pop();
+            const int32_t v = top.second;
+            if (locked[v]) continue;
+            const int64_t gv = gain(v);
+            if (gv != top.first) {  // stale entry: requeue with the current gain
+                heap.emplace(gv, v);
+                continue;
+            }
+            const int64_t new_w0 = w0 + (side[v] ? g.vw[v] : -g.vw[v]);
+            if (std::llabs(new_w0 - target0) > tol && std::llabs(new_w0 - target0) >= std::llabs(w0 - target0)) continue;
+            side[v] ^= 1;
+            w0 = new_w0;
+            locked[v] = 1;
+            delta -= gv;
+            moves.push_back(v);
+            const int64_t imb = std::llabs(w0 - target0);
+            if (delta < best_delta || (delta == best_delta && imb < best_imb)) {
+                best_delta = delta;
+                best_imb = imb;
+                best_len = moves.size();
+            }
+            for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
+                if (!locked[g.adj[e]]) heap.emplace(gain(g.adj[e]), g.adj[e]);
+        }
+        for (size_t q = moves.size(); q > best_len; --q) {  // undo the tail after the best prefix
+            const int32_t v = moves[q - 1];
+            side[v] ^= 1;
+            w0 += side[v] ? -g.vw[v] : g.vw[v];
+        }
+        if (best_len == 0) break;
+    }
+    // balance: move the boundary nodes that cost the least from the heavy side
+    const int64_t slack = exact ? 0 : max_vw;
+    for (int guard = 0; guard < 64 && std::llabs(w0 - target0) > slack; ++guard) {
+        const uint8_t from = w0 > target0 ? 0 : 1;
+        cand.clear();
+        for (int32_t v = 0; v < n; ++v) {
+            if (side[v] != from) continue;
+            bool boundary = g.ptr[v + 1] == g.ptr[v];  // isolated points can go anywhere
+            for (int64_t e = g.ptr[v]; e < g.ptr[v + 1] && !boundary; ++e) boundary = side[g.adj[e]] != from;
+            if (boundary) cand.emplace_back(-gain(v), v);
+        }
+        if (cand.empty())  // nothing touches the other side (a disconnected remainder): any node will do
+            for (int32_t v = 0; v < n; ++v)
+                if (side[v] == from) cand.emplace_back(0, v);
+        std::sort(cand.begin(), cand.end());
+        for (auto& c : cand) {
+            const int64_t diff = std::llabs(w0 - target0);
+            if (diff <= slack) break;
+            const int32_t v = c.second;
+            if (g.vw[v] > 2 * diff) continue;  // would overshoot by more than it repairs
+            side[v] ^= 1;
+            w0 += from == 0 ? -g.vw[v] : g.vw[v];
+        }
+    }
+}
+
+// ---- initial bisection of the coarsest graph: greedy graph growing from several seeds ----------------------
+void bfs_order(const WGraph& g, const std::vector<uint8_t>& taken, int32_t src, std::vector<int32_t>& order, std::vector<int32_t>& mark,
+               int32_t stamp, std::vector<int32_t>* dist = nullptr) {
     order.clear();
     order.push_back(src);
     mark[src] = stamp;
@@ -58,7 +229,7 @@ void bfs(const Graph& g, const std::vector<int32_t>& label, int32_t lab, int32_t
         const int32_t v = order[head];
         for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
             const int32_t w = g.adj[e];
-            if (label[w] == lab && mark[w] != stamp) {
+            if (!taken[w] && mark[w] != stamp) {
                 mark[w] = stamp;
                 if (dist) (*dist)[w] = (*dist)[v] + 1;
                 order.push_back(w);
@@ -67,186 +238,133 @@ void bfs(const Graph& g, const std::vector<int32_t>& label, int32_t lab, int32_t
     }
 }
 
-struct Bisector {
-    const Graph& g;
-    std::vector<int32_t>& label;  // current part of every node
-    std::vector<int32_t> mark, order, dp, dq;
+void initial_bisect(const WGraph& g, int64_t target0, std::vector<uint8_t>& side) {
+    const int32_t n = g.n;
+    std::vector<int32_t> mark(n, 0), order, dp(n, 0), dq(n, 0);
+    std::vector<uint8_t> taken(n, 0);
     int32_t stamp = 0;
-    int32_t next_label;
-
-    Bisector(const Graph& g_, std::vector<int32_t>& l, int32_t first_free) : g(g_), label(l), mark(g_.n, 0), next_label(first_free) {}
-
-    // grows `lab` from `seed` over the unassigned nodes (label == other) until n_left nodes are taken; further
-    // components are entered from their own pseudo-peripheral nodes
-    void grow(const std::vector<int32_t>& nodes, int32_t lab, int32_t other, int64_t n_left, int32_t seed) {
-        for (int32_t v : nodes) label[v] = other;
-        int64_t grown = 0;
-        size_t scan = 0;
+    auto peripheral = [&](int32_t src) {
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            bfs_order(g, taken, src, order, mark, ++stamp);
+            src = order.back();
+        }
+        return src;
+    };
+    std::vector<int32_t> seeds;
+    {
+        const int32_t p = peripheral(0);
+        bfs_order(g, taken, p, order, mark, ++stamp, &dp);
+        const int32_t q = order.back();
+        const std::vector<int32_t> comp = order;
+        bfs_order(g, taken, q, order, mark, ++stamp, &dq);
+        int32_t third = p, best_d = -1;
+        for (int32_t v : comp) {
+            const int32_t d = std::min(dp[v], dq[v]);
+            if (d > best_d) {
+                best_d = d;
+                third = v;
+            }
+        }
+        seeds = {p, q, third};
+        uint64_t s = 0x9E3779B97F4A7C15ull;  // a few fixed pseudo-random seeds as well
+        for (int k = 0; k < 5; ++k) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            seeds.push_back((int32_t)((s >> 33) % (uint64_t)n));
+        }
+    }
+    std::vector<uint8_t> trial(n);
+    int64_t best_cut = INT64_MAX;
+    for (size_t t = 0; t < seeds.size(); ++t) {
+        std::fill(taken.begin(), taken.end(), 0);
+        std::fill(trial.begin(), trial.end(), 1);
+        int64_t w0 = 0;
+        int32_t scan = 0;
         bool first = true;
-        while (grown < n_left) {
+        while (w0 < target0) {
             int32_t src;
-            if (first && seed >= 0) {
-                src = seed;
-            } else {
-                while (scan < nodes.size() && label[nodes[scan]] != other) ++scan;  // next unassigned component
-                src = nodes[scan];
-                for (int sweep = 0; sweep < 2; ++sweep) {
-                    bfs(g, label, other, src, order, mark, ++stamp);
-                    src = order.back();
-                }
+            if (first) {
+                src = seeds[t];
+            } else {  // the seed's component is exhausted: continue in the next untouched one
+                while (scan < n && taken[scan]) ++scan;
+                if (scan == n) break;
+                src = peripheral(scan);
             }
             first = false;
-            bfs(g, label, other, src, order, mark, ++stamp);
+            bfs_order(g, taken, src, order, mark, ++stamp);
             for (int32_t v : order) {
-                if (grown == n_left) break;
-                label[v] = lab;
-                ++grown;
+                if (w0 >= target0) break;
+                trial[v] = 0;
+                w0 += g.vw[v];
             }
+            for (int32_t v : order) taken[v] = 1;  // the rest of this component stays on side 1
+        }
+        refine(g, target0, trial, false);
+        const int64_t c = cut_of(g, trial);
+        if (c < best_cut) {
+            best_cut = c;
+            side = trial;
         }
     }
+}
 
-    int64_t cut_between(const std::vector<int32_t>& nodes, int32_t a, int32_t b) const {
-        int64_t c = 0;
-        for (int32_t v : nodes)
-            if (label[v] == a)
-                for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) c += label[g.adj[e]] == b;
-        return c;
-    }
-
-    // splits the nodes `nodes` (all labelled `lab`) into `lab` (n_left nodes) and a new label; returns the new label.
-    // Like METIS's initial partitioner, several growing seeds are tried and the smallest refined cut is kept: a
-    // pseudo-peripheral node p, its antipode q, and the node farthest from both (a "third corner": its front
-    // runs across the one grown from p).
-    int32_t bisect(std::vector<int32_t>& nodes, int32_t lab, int64_t n_left) {
-        const int32_t other = next_label++;
-        const int64_t n = (int64_t)nodes.size();
-        for (int32_t v : nodes) label[v] = other;
-        int32_t seeds[3] = {-1, -1, -1};
-        {
-            int32_t src = nodes[0];
-            for (int sweep = 0; sweep < 2; ++sweep) {
-                bfs(g, label, other, src, order, mark, ++stamp);
-                src = order.back();
-            }
-            seeds[0] = src;
-            if (dp.size() < (size_t)g.n) {
-                dp.assign(g.n, 0);
-                dq.assign(g.n, 0);
-            }
-            bfs(g, label, other, seeds[0], order, mark, ++stamp, &dp);  // graph distances from p
-            seeds[1] = order.back();
-            const std::vector<int32_t> comp = order;                      // the component of p
-            bfs(g, label, other, seeds[1], order, mark, ++stamp, &dq);  // ... and from q
-            int32_t best_d = -1;
-            for (int32_t v : comp) {
-                const int32_t d = std::min(dp[v], dq[v]);
-                if (d > best_d) {
-                    best_d = d;
-                    seeds[2] = v;
-                }
-            }
-        }
-        std::vector<int32_t> best_label;
-        int64_t best_cut = INT64_MAX;
-        for (int trial = 0; trial < 3; ++trial) {
-            if (seeds[trial] < 0 || (trial > 0 && seeds[trial] == seeds[trial - 1])) continue;
-            grow(nodes, lab, other, n_left, seeds[trial]);
-            refine(nodes, lab, other, n_left, n);
-            const int64_t c = cut_between(nodes, lab, other);
-            if (c < best_cut) {
-                best_cut = c;
-                best_label.resize(nodes.size());
-                for (size_t i = 0; i < nodes.size(); ++i) best_label[i] = label[nodes[i]];
-            }
-        }
-        for (size_t i = 0; i < nodes.size(); ++i) label[nodes[i]] = best_label[i];
-        return other;
-    }
-
-    // Fiduccia-Mattheyses flavoured boundary refinement: alternate sides, always move the boundary node with the
-    // largest positive gain (external - internal degree) that keeps |left| within the tolerance of its target
-    void refine(const std::vector<int32_t>& nodes, int32_t a, int32_t b, int64_t target_a, int64_t n) {
-        const int64_t tol = std::max<int64_t>(1, n / 200);  // 0.5 % imbalance
-        int64_t size_a = 0;
-        for (int32_t v : nodes) size_a += label[v] == a;
-        auto gain = [&](int32_t v) {
-            int ext = 0, in = 0;
-            const int32_t mine = label[v], oth = mine == a ? b : a;
-            for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
-                ext += label[g.adj[e]] == oth;
-                in += label[g.adj[e]] == mine;
-            }
-            return ext - in;
-        };
-        for (int pass = 0; pass < 8; ++pass) {
-            int64_t moved = 0;
-            // bucket the boundary nodes by gain once per pass; a moved node is locked for the rest of the pass
-            std::vector<std::pair<int, int32_t>> cand;
-            for (int32_t v : nodes) {
-                const int gv = gain(v);
-                if (gv > 0) cand.emplace_back(-gv, v);
-            }
-            if (cand.empty()) break;
-            std::sort(cand.begin(), cand.end());
-            ++stamp;
-            for (auto& c : cand) {
-                const int32_t v = c.second;
-                if (mark[v] == stamp) continue;
-                if (gain(v) <= 0) continue;  // a neighbour moved meanwhile
-                const bool from_a = label[v] == a;
-                const int64_t new_a = size_a + (from_a ? -1 : 1);
-                if (std::llabs(new_a - target_a) > tol) continue;
-                label[v] = from_a ? b : a;
-                size_a = new_a;
-                mark[v] = stamp;
-                ++moved;
-            }
-            if (moved == 0) break;
-        }
-        // restore the exact target (the tolerance above lets the cut improve; the caller wants equal counts):
-        // move the boundary nodes that cost the least, best gain first
-        while (size_a != target_a) {
-            const bool need_more_a = size_a < target_a;
-            const int32_t from = need_more_a ? b : a, to = need_more_a ? a : b;
-            const int64_t need = std::llabs(target_a - size_a);
-            std::vector<std::pair<int, int32_t>> cand;
-            for (int32_t v : nodes) {
-                if (label[v] != from) continue;
-                bool boundary = g.ptr[v + 1] == g.ptr[v];  // isolated points can go anywhere
-                for (int64_t e = g.ptr[v]; e < g.ptr[v + 1] && !boundary; ++e) boundary = label[g.adj[e]] == to;
-                if (boundary) cand.emplace_back(-gain(v), v);
-            }
-            if (cand.empty())  // nothing touches the other side (disconnected remainder): take any node
-                for (int32_t v : nodes)
-                    if (label[v] == from) {
-                        cand.emplace_back(0, v);
-                        if ((int64_t)cand.size() == need) break;
-                    }
-            std::sort(cand.begin(), cand.end());
-            const int64_t take = std::min<int64_t>(need, (int64_t)cand.size());
-            for (int64_t q = 0; q < take; ++q) label[cand[q].second] = to;
-            size_a += need_more_a ? take : -take;
-        }
-    }
-
-    // recursive k-way split of `nodes` (labelled lab) into labels written to `out` as part ids part0 .. part0+k-1
-    void split(std::vector<int32_t>& nodes, int32_t lab, int32_t k, int32_t part0, std::vector<int32_t>& out) {
-        if (k == 1) {
-            for (int32_t v : nodes) out[v] = part0;
+void multilevel_bisect(const WGraph& g, int64_t target0, std::vector<uint8_t>& side, bool finest) {
+    const int32_t coarse_enough = 4000;
+    if (g.n > coarse_enough) {
+        std::vector<int32_t> cmap;
+        const WGraph c = coarsen(g, cmap, std::max<int64_t>(2, g.total_w / (coarse_enough / 4)));
+        if (c.n < g.n - g.n / 10) {  // the matching still shrinks the graph
+            std::vector<uint8_t> cside;
+            multilevel_bisect(c, target0, cside, false);
+            side.resize(g.n);
+            for (int32_t v = 0; v < g.n; ++v) side[v] = cside[cmap[v]];
+            refine(g, target0, side, finest);
             return;
         }
-        const int32_t k_left = k / 2;
-        const int64_t n_left = (int64_t)nodes.size() * k_left / k;
-        const int32_t other = bisect(nodes, lab, n_left);
-        std::vector<int32_t> left, right;
-        left.reserve(n_left);
-        right.reserve(nodes.size() - n_left);
-        for (int32_t v : nodes) (label[v] == lab ? left : right).push_back(v);
-        std::vector<int32_t>().swap(nodes);
-        split(left, lab, k_left, part0, out);
-        split(right, other, k - k_left, part0 + k_left, out);
     }
-};
+    initial_bisect(g, target0, side);
+    if (finest) refine(g, target0, side, true);
+}
+
+// induced subgraph of the nodes with side == s
+WGraph subgraph(const WGraph& g, const std::vector<uint8_t>& side, uint8_t s, const std::vector<int32_t>& ids, std::vector<int32_t>& ids_out) {
+    std::vector<int32_t> local(g.n, -1);
+    WGraph h;
+    for (int32_t v = 0; v < g.n; ++v)
+        if (side[v] == s) {
+            local[v] = h.n++;
+            ids_out.push_back(ids[v]);
+        }
+    h.ptr.assign(h.n + 1, 0);
+    h.vw.resize(h.n);
+    for (int32_t v = 0; v < g.n; ++v) {
+        if (local[v] < 0) continue;
+        h.vw[local[v]] = g.vw[v];
+        h.total_w += g.vw[v];
+        for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
+            if (local[g.adj[e]] >= 0) {
+                h.adj.push_back(local[g.adj[e]]);
+                h.ew.push_back(g.ew[e]);
+            }
+        h.ptr[local[v] + 1] = (int64_t)h.adj.size();
+    }
+    return h;
+}
+
+void partition_rec(const WGraph& g, const std::vector<int32_t>& ids, int32_t k, int32_t part0, int32_t* owner) {
+    if (k == 1) {
+        for (int32_t v = 0; v < g.n; ++v) owner[ids[v]] = part0;
+        return;
+    }
+    const int32_t k_left = k / 2;
+    const int64_t target0 = g.total_w * k_left / k;
+    std::vector<uint8_t> side;
+    multilevel_bisect(g, target0, side, true);
+    for (uint8_t s = 0; s < 2; ++s) {
+        std::vector<int32_t> sub_ids;
+        const WGraph h = subgraph(g, side, s, ids, sub_ids);
+        partition_rec(h, sub_ids, s == 0 ? k_left : k - k_left, s == 0 ? part0 : part0 + k_left, owner);
+    }
+}
 
 }  // namespace
 
@@ -258,12 +376,10 @@ extern "C" int32_t fvm_partition_graph(int64_t n_points, const int32_t* triangle
     for (int64_t i = 0; i < 3 * n_triangles; ++i)
         if (triangles[i] - index_base < 0 || triangles[i] - index_base >= n_points)
             return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_partition_graph: triangle vertex out of range");
-    const Graph g = build_graph(n_points, triangles, n_triangles, index_base);
-    std::vector<int32_t> label(n_points, 0), out(n_points, 0), nodes(n_points);
-    std::iota(nodes.begin(), nodes.end(), 0);
-    Bisector B(g, label, 1);
-    B.split(nodes, 0, n_parts, 0, out);
-    std::copy(out.begin(), out.end(), owner);
+    const WGraph g = graph_from_triangles(n_points, triangles, n_triangles, index_base);
+    std::vector<int32_t> ids(n_points);
+    std::iota(ids.begin(), ids.end(), 0);
+    partition_rec(g, ids, n_parts, 0, owner);
     return FVM_OK;
 }
 
@@ -271,7 +387,7 @@ extern "C" int32_t fvm_partition_graph(int64_t n_points, const int32_t* triangle
 extern "C" int32_t fvm_partition_edge_cut(int64_t n_points, const int32_t* triangles, int64_t n_triangles, int32_t index_base,
                                           const int32_t* owner, int64_t* cut) {
     if (!triangles || !owner || !cut || n_points <= 0 || n_triangles <= 0) return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_partition_edge_cut: bad arguments");
-    const Graph g = build_graph(n_points, triangles, n_triangles, index_base);
+    const WGraph g = graph_from_triangles(n_points, triangles, n_triangles, index_base);
     int64_t c = 0;
     for (int64_t v = 0; v < n_points; ++v)
         for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) c += owner[v] != owner[g.adj[e]];

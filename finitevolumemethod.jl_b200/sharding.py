@@ -46,9 +46,9 @@ def partition_rcb(points, nparts):
 
 
 def partition_graph(tri, nparts):
-    """METIS-style partition of the node graph (recursive bisection: greedy graph growing + FM boundary
-    refinement, in the C library): parts differ by at most one node; the edge cut — and with it the halo —
-    follows the mesh connectivity instead of the coordinates."""
+    """METIS-style partition of the node graph (multilevel recursive bisection in the C library: heavy-edge
+    matching, greedy graph growing, FM refinement): parts differ by at most one node; the edge cut — and with
+    it the halo — follows the mesh connectivity instead of the coordinates."""
     owner = np.empty(tri.num_points, dtype=np.int32)
     t = L.i32(tri.triangles)
     rc = L.lib().fvm_partition_graph(tri.num_points, L.ip(t), tri.num_triangles, 0, int(nparts), L.ip(owner))

@@ -219,9 +219,10 @@ int32_t fvm_eval_points(fvm_handle h, double t, const double* u, int32_t u_on_de
  * fvm_shard_init, fvm_set_halo.  Afterwards fvm_rhs*, fvm_spmv* and fvm_tsit5 refresh the ghost
  * entries of their input vector with grouped ncclSend/ncclRecv before computing; outputs are valid
  * on owned nodes (ghost rows are 0). */
-/* METIS-style node partition (north_star d): recursive bisection of the node graph (an edge per pair of
- * nodes sharing a triangle, the pattern of jacobian_sparsity, src/solve.jl:56-77) by greedy graph growing +
- * Fiduccia-Mattheyses boundary refinement; parts differ by at most one node.  Host-only. */
+/* METIS-style node partition (north_star d): multilevel recursive bisection of the node graph (an edge per
+ * pair of nodes sharing a triangle, the pattern of jacobian_sparsity, src/solve.jl:56-77): heavy-edge matching,
+ * greedy graph growing on the coarsest graph, Fiduccia-Mattheyses refinement while uncoarsening; parts differ
+ * by at most one node.  Deterministic.  Host-only. */
 int32_t fvm_partition_graph(int64_t n_points, const int32_t* triangles, int64_t n_triangles, int32_t index_base,
                             int32_t n_parts, int32_t* owner /* [n_points], 0-based part of every node */);
 int32_t fvm_partition_edge_cut(int64_t n_points, const int32_t* triangles, int64_t n_triangles, int32_t index_base,
