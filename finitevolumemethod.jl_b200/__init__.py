@@ -6,7 +6,7 @@ from .conditions import (BoundaryConditions, Conditions, Constrained, Dirichlet,
                          InternalConditions, Neumann)
 from .functors import *  # noqa: F401,F403
 from .mesh import Triangulation, triangulate_rectangle  # noqa: F401
-from .problem import (CudaParameters, Engine, compute_flux, pl_interpolate, FVMGeometry, FVMProblem, FVMSystem,  # noqa: F401
+from .problem import (CudaParameters, Engine, InvalidFluxError, compute_flux, pl_interpolate, FVMGeometry, FVMProblem, FVMSystem,  # noqa: F401
                       SteadyFVMProblem, fvm_eqs, get_cuda_parameters, jacobian, jacobian_sparsity, pinned,
                       update_dirichlet_nodes)
 from .templates import (DiffusionEquation, KrylovJacobi, LaplacesEquation,  # noqa: F401

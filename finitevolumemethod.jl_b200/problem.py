@@ -105,6 +105,26 @@ _SRC_TYPES = (F.ZeroSource, F.LinearSource, F.LogisticSource, F.TabulatedSource,
               F.KellerSegelSource)
 
 
+FLUX_ERROR = """
+The flux function errored when evaluated. Please recheck your specification of the function.
+If any of your problems have been defined in terms of a diffusion function D(x, y, t, u, p)
+rather than a flux function, then you need to instead provide a flux function q(x, y, t, α, β, γ, p),
+recalling the relationship between the two:
+
+    q(x, y, t, α, β, γ, p) = -D(x, y, t, α*x + β*y + γ, p) .* (α, β)
+
+where p is the same argument for both functions.
+"""
+
+
+class InvalidFluxError(Exception):
+    """problem.jl:291-316: a member of an FVMSystem was defined through `diffusion_function`, whose scalar
+    flux cannot take the tuples (α, β, γ) of all species (test/equations.jl:108)."""
+
+    def __init__(self):
+        super().__init__(FLUX_ERROR)
+
+
 class FVMProblem:
     """problem.jl:96-163."""
 
@@ -123,6 +143,7 @@ class FVMProblem:
         else:
             self.conditions = Conditions(mesh, boundary_conditions, internal_conditions or InternalConditions())
         self.flux_function = construct_flux_function(flux_function, diffusion_function, diffusion_parameters)
+        self._flux_from_diffusion = flux_function is None  # problem.jl:425-440 wraps D into a SCALAR flux function
         self.flux_parameters = flux_parameters
         self.source_function = source_function if source_function is not None else F.ZeroSource()
         self.source_parameters = source_parameters
@@ -169,6 +190,8 @@ class FVMSystem:
         self.conditions = tuple(p.conditions for p in probs)
         nf = [len(p.conditions.functions) for p in probs]
         self.cnum_fncs = tuple(int(x) for x in np.concatenate([[0], np.cumsum(nf)[:-1]]))  # problem.jl:380-383
+        if any(getattr(p, "_flux_from_diffusion", False) for p in probs):  # _check_fvmsystem_flux_function, problem.jl:295-316
+            raise InvalidFluxError()
 
     def __repr__(self):
         return "FVMSystem with %d equations and time span (%s, %s)" % (self.neqs, self.initial_time, self.final_time)

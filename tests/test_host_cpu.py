@@ -117,7 +117,10 @@ def test_constructor_errors_mirror_the_reference():
         G.FVMSystem(p1, p2)
     with pytest.raises(AssertionError):
         G.FVMSystem()
-    sys_ = G.FVMSystem(p1, p1)
+    with pytest.raises(G.InvalidFluxError, match="flux function q"):  # test/equations.jl:108: FVMSystem(prob, prob)
+        G.FVMSystem(p1, p1)
+    q1 = G.FVMProblem(mesh, BCs, flux_function=G.ConstantDiffusion(1.0), initial_condition=np.zeros(25), final_time=1.0)
+    sys_ = G.FVMSystem(q1, q1)
     assert sys_.initial_condition.shape == (25, 2) and sys_.cnum_fncs == (0, 1)
     assert "FVMProblem with 25 nodes" in repr(p1)
 
