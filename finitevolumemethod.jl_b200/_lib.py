@@ -40,6 +40,7 @@ _SIGS = {
     "fvm_set_source": [H, C.c_int32, c_dp, C.c_int32],
     "fvm_set_source_table": [H, c_dp],
     "fvm_finalize": [H, C.c_int32, C.c_int32],
+    "fvm_plan_selftest": [c_dp, C.c_int64, c_ip, C.c_int64, C.c_int32, C.c_int32, c_ip, C.c_int64, c_bp, C.c_int32, c_lp],
     "fvm_destroy": [H],
     "fvm_rhs": [H, C.c_double, C.c_void_p, C.c_void_p, C.c_int32],
     "fvm_rhs_native": [H, C.c_double, C.c_void_p, C.c_void_p],

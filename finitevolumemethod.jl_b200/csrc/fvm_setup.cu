@@ -308,26 +308,26 @@ static inline uint32_t hilbert_xy2d(uint32_t x, uint32_t y) {
     return d;
 }
 
-extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t geometry_mode) {
-    NOT_FINAL(h);
-    FVM_CUDA(h, cudaSetDevice(h->device));
+// Everything fvm_finalize computes on the host before the first device call: the Hilbert tiling, the tile-major
+// node numbering, tile-local triangle indices, per-tile gather lists, the interface / partial-slot bookkeeping and
+// the live boundary-edge records.  Pure host code on the handle's h_* vectors (fvm_plan_selftest runs it, and
+// checks its invariants, without a CUDA device).
+struct HostPlan {
+    int64_t n_tiles = 0, tpad = 0, n_partial = 0;
+    int32_t n_vertices = 0, n_ifc = 0, max_nloc = 0;
+    std::vector<int32_t> tile_node0, tile_nint, tile_nown, tile_nloc, tile_ext0, tile_loc0, tile_pp0;
+    std::vector<ushort4> tri_loc;
+    std::vector<int32_t> tri_native, ext_ids, ifc_node, ifc_pptr, ppos, live_edges;
+    std::vector<uint16_t> inc_ptr, inc;
+    std::vector<BndEdge> bnd;
+    std::vector<double> dbnd_live;
+};
+
+static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     const int64_t N = h->N, T = h->T, Eb = h->Eb;
     const int neq = h->neq;
-    // default tile size (measured on B200, 4096^2): kernels that stream the full 21-component SoA are
-    // register-limited to 3 CTAs/SM and like big tiles; the reduced stream wants 8 small CTAs per SM
-    const bool full_flux = h->flux.model == FVM_FLUX_DIFF_POWER || h->flux.model == FVM_FLUX_ADVDIFF || h->flux.model == FVM_FLUX_KELLER_SEGEL;
-    // (systems: 768 measured best for the 2-species Keller-Segel kernel: 1.20 ms vs 1.45 ms at 1024)
-    int TT = tile_triangles > 0 ? tile_triangles : (neq >= 2 ? 768 : ((geometry_mode == 0 && !full_flux) ? 512 : 1024));
-    if (tile_triangles <= 0)
-        if (const char* e = getenv("FVM_TILE_TRIANGLES")) TT = atoi(e);
-    FVM_REQUIRE(h, TT >= 64 && TT <= 4096 && TT % 64 == 0, "fvm_finalize: tile_triangles must be a multiple of 64 in 64..4096");
-    FVM_REQUIRE(h, geometry_mode == 0 || geometry_mode == 1, "fvm_finalize: geometry_mode must be 0 or 1");
-    if (h->flux.model == FVM_FLUX_DIFF_TABLE && h->h_dtab.empty())
-        return fvm_fail(h, FVM_ERR_STATE, "fvm_finalize: table flux model without fvm_set_flux_table");
-    h->geometry_mode = geometry_mode;
     const double* xy = h->h_xy.data();
     const int32_t* tri = h->h_tri.data();
-
     // ---- 1. Hilbert sort of triangles by centroid ------------------------------------
     double minx = xy[0], maxx = xy[0], miny = xy[1], maxy = xy[1];
     for (int64_t i = 0; i < N; ++i) {
@@ -354,6 +354,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     std::vector<uint64_t>().swap(keys);
     const int32_t* told = h->tri_old_of_new.data();
     const int64_t n_tiles = (T + TT - 1) / TT;
+    P.n_tiles = n_tiles;
     FVM_REQUIRE(h, n_tiles < INT32_MAX, "too many tiles");
 
     if (!h->h_ghost.empty())  // ghost nodes are neither free nor Dirichlet
@@ -362,7 +363,8 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
                 if (h->h_ghost[i]) h->h_nkind[v][i] = FVM_NODE_GHOST;
     // ---- 2. boundary edges: adjacent triangle, live flag --------------------------------
     std::vector<uint8_t> forced(N, 0);  // nodes that must be finished by the interface kernel
-    std::vector<int32_t> live_edges;
+    std::vector<int32_t>& live_edges = P.live_edges;
+    live_edges.clear();
     for (int64_t e = 0; e < Eb; ++e) {
         const int32_t i = h->h_bedge[2 * e], j = h->h_bedge[2 * e + 1];
         bool live = false;
@@ -417,7 +419,11 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
             if (tile > max_tile[v[r]]) max_tile[v[r]] = tile;
         }
     }
-    std::vector<int32_t> tile_node0(n_tiles), tile_nint(n_tiles), tile_nown(n_tiles), tile_nloc(n_tiles);
+    std::vector<int32_t>&tile_node0 = P.tile_node0, &tile_nint = P.tile_nint, &tile_nown = P.tile_nown, &tile_nloc = P.tile_nloc;
+    tile_node0.assign(n_tiles, 0);
+    tile_nint.assign(n_tiles, 0);
+    tile_nown.assign(n_tiles, 0);
+    tile_nloc.assign(n_tiles, 0);
     h->node_new_of_old.assign(N, -1);
     h->node_old_of_new.assign(N, -1);
     int32_t* new_of_old = h->node_new_of_old.data();
@@ -451,24 +457,37 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     }
     for (int64_t g = 0; g < N; ++g) h->node_old_of_new[new_of_old[g]] = (int32_t)g;
     const int32_t n_vertices = h->dm.n_vertices;
+    P.n_vertices = n_vertices;
 
     // ---- 4. tile-local indices, gather lists, interface bookkeeping -----------------------
     const int64_t tpad = n_tiles * TT;
-    std::vector<ushort4> tri_loc(tpad, make_ushort4(0, 0, 0, 0));
-    std::vector<int32_t> tri_native(3 * T);  // native node ids per native triangle (geometry kernel input)
-    std::vector<int32_t> tile_ext0(n_tiles + 1), tile_loc0(n_tiles + 1), tile_pp0(n_tiles + 1);
-    std::vector<int32_t> ext_ids;
-    std::vector<uint16_t> inc_ptr, inc((size_t)3 * tpad, 0);
+    P.tpad = tpad;
+    std::vector<ushort4>& tri_loc = P.tri_loc;
+    tri_loc.assign(tpad, make_ushort4(0, 0, 0, 0));
+    std::vector<int32_t>& tri_native = P.tri_native;  // native node ids per native triangle (geometry kernel input)
+    tri_native.assign(3 * T, 0);
+    std::vector<int32_t>&tile_ext0 = P.tile_ext0, &tile_loc0 = P.tile_loc0, &tile_pp0 = P.tile_pp0;
+    tile_ext0.assign(n_tiles + 1, 0);
+    tile_loc0.assign(n_tiles + 1, 0);
+    tile_pp0.assign(n_tiles + 1, 0);
+    std::vector<int32_t>& ext_ids = P.ext_ids;
+    ext_ids.clear();
+    std::vector<uint16_t>&inc_ptr = P.inc_ptr, &inc = P.inc;
+    inc_ptr.clear();
+    inc.assign((size_t)3 * tpad, 0);
     std::vector<int32_t> ifc_of_new(N, -1);  // compact interface index by native id
-    std::vector<int32_t> ifc_node;
+    std::vector<int32_t>& ifc_node = P.ifc_node;
+    ifc_node.clear();
     for (int64_t b = 0; b < n_tiles; ++b)
         for (int32_t l = tile_nint[b]; l < tile_nown[b]; ++l) {
             ifc_of_new[tile_node0[b] + l] = (int32_t)ifc_node.size();
             ifc_node.push_back(tile_node0[b] + l);
         }
     const int32_t n_ifc = (int32_t)ifc_node.size();
+    P.n_ifc = n_ifc;
     std::vector<int32_t> ifc_cnt(n_ifc + 1, 0);
-    int32_t max_nloc = 0;
+    int32_t& max_nloc = P.max_nloc;
+    max_nloc = 0;
     {
         std::vector<int32_t> stamp(N, -1), loc(N, 0);
         std::vector<int32_t> cnt, fill;
@@ -537,11 +556,14 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         ifc_cnt[ifc_of_new[new_of_old[h->h_bedge[2 * e]]]]++;
         ifc_cnt[ifc_of_new[new_of_old[h->h_bedge[2 * e + 1]]]]++;
     }
-    std::vector<int32_t> ifc_pptr(n_ifc + 1, 0);
+    std::vector<int32_t>& ifc_pptr = P.ifc_pptr;
+    ifc_pptr.assign(n_ifc + 1, 0);
     for (int32_t k = 0; k < n_ifc; ++k) ifc_pptr[k + 1] = ifc_pptr[k] + ifc_cnt[k];
     const int64_t n_partial = ifc_pptr[n_ifc];
+    P.n_partial = n_partial;
     std::vector<int32_t> pfill(ifc_pptr.begin(), ifc_pptr.end() - 1);
-    std::vector<int32_t> ppos;
+    std::vector<int32_t>& ppos = P.ppos;
+    ppos.clear();
     for (int64_t b = 0; b < n_tiles; ++b) {  // ascending tile order = fixed summation order
         tile_pp0[b] = (int32_t)ppos.size();
         for (int32_t l = tile_nint[b]; l < tile_nown[b]; ++l) ppos.push_back(pfill[ifc_of_new[tile_node0[b] + l]]++);
@@ -550,8 +572,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     tile_pp0[n_tiles] = (int32_t)ppos.size();
 
     // ---- 5. live boundary-edge records ------------------------------------------------------
-    std::vector<BndEdge> bnd(live_edges.size());
-    std::vector<double> dbnd_live;
+    std::vector<BndEdge>& bnd = P.bnd;
+    bnd.assign(live_edges.size(), BndEdge{});
+    std::vector<double>& dbnd_live = P.dbnd_live;
+    dbnd_live.clear();
     for (size_t k = 0; k < live_edges.size(); ++k) {
         const int32_t e = live_edges[k];
         BndEdge& r = bnd[k];
@@ -576,6 +600,189 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
             dbnd_live.push_back(h->h_dbnd[2 * e + 1]);
         }
     }
+    return FVM_OK;
+}
+
+// Runs the host planning of fvm_finalize on a mesh WITHOUT a CUDA device and checks the invariants the kernels
+// rely on (tests/test_host_cpu.py).  stats: n_tiles, n_vertices, n_interface, n_partial, n_external, max_local_nodes,
+// n_live_boundary_edges, gather-list entries.
+extern "C" int32_t fvm_plan_selftest(const double* xy, int64_t N, const int32_t* tri, int64_t T, int32_t index_base, int32_t neq,
+                                     const int32_t* bedges, int64_t Eb, const uint8_t* node_kind, int32_t tile_triangles,
+                                     int64_t* stats) {
+    if (!xy || !tri || N <= 0 || T <= 0 || neq < 1 || neq > FVM_MAX_NEQ || (Eb > 0 && !bedges) || !stats)
+        return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_plan_selftest: bad arguments");
+    if (tile_triangles < 64 || tile_triangles > 4096 || tile_triangles % 64) return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_plan_selftest: bad tile size");
+    fvm_ctx ctx;
+    fvm_ctx* h = &ctx;
+    h->N = N;
+    h->T = T;
+    h->Eb = Eb;
+    h->neq = neq;
+    h->h_xy.assign(xy, xy + 2 * N);
+    h->h_tri.resize(3 * T);
+    for (int64_t i = 0; i < 3 * T; ++i) {
+        h->h_tri[i] = tri[i] - index_base;
+        if (h->h_tri[i] < 0 || h->h_tri[i] >= N) return fvm_fail(nullptr, FVM_ERR_ARG, "fvm_plan_selftest: triangle vertex out of range");
+    }
+    h->h_bedge.resize(2 * Eb);
+    for (int64_t i = 0; i < 2 * Eb; ++i) h->h_bedge[i] = bedges[i] - index_base;
+    for (int v = 0; v < neq; ++v) {
+        h->h_nkind[v].assign(N, 0);
+        if (node_kind) h->h_nkind[v].assign(node_kind + (size_t)v * N, node_kind + (size_t)(v + 1) * N);
+        h->h_nfidx[v].assign(N, 0);
+        h->h_ekind[v].assign(Eb, 0);
+        h->h_efidx[v].assign(Eb, 0);
+    }
+    const int TT = tile_triangles;
+    HostPlan P;
+    int32_t rc = plan_host(h, TT, P);
+    if (rc) return fvm_fail(nullptr, rc, h->err);
+    auto bad = [&](const std::string& what) { return fvm_fail(nullptr, FVM_ERR_STATE, "fvm_plan_selftest: " + what); };
+    // permutations
+    {
+        std::vector<uint8_t> seen(T, 0);
+        for (int64_t t = 0; t < T; ++t) {
+            const int32_t o = h->tri_old_of_new[t];
+            if (o < 0 || o >= T || seen[o]) return bad("triangle order is not a permutation");
+            seen[o] = 1;
+        }
+        std::vector<uint8_t> seen_n(N, 0);
+        for (int64_t g = 0; g < N; ++g) {
+            const int32_t o = h->node_old_of_new[g];
+            if (o < 0 || o >= N || seen_n[o] || h->node_new_of_old[o] != g) return bad("node renumbering is not a permutation");
+            seen_n[o] = 1;
+        }
+    }
+    // tile ranges tile the vertex range
+    int64_t cursor = 0, gather_entries = 0;
+    std::vector<int32_t> touch(N, 0);  // number of tiles that hold a native node as a local node
+    for (int64_t b = 0; b < P.n_tiles; ++b) {
+        const int32_t node0 = P.tile_node0[b], nint = P.tile_nint[b], nown = P.tile_nown[b], nloc = P.tile_nloc[b];
+        if (node0 != cursor || nint < 0 || nint > nown || nown > nloc || nloc > P.max_nloc || nloc >= 65535) return bad("tile node ranges are inconsistent");
+        cursor += nown;
+        if (P.tile_ext0[b + 1] - P.tile_ext0[b] != nloc - nown) return bad("external node count mismatch");
+        const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
+        auto native_of = [&](int32_t l) { return l < nown ? node0 + l : P.ext_ids[P.tile_ext0[b] + (l - nown)]; };
+        for (int32_t l = 0; l < nloc; ++l) {
+            const int32_t g = native_of(l);
+            if (g < 0 || g >= P.n_vertices) return bad("local node maps outside the vertex range");
+            if (l >= nown && g >= node0 && g < node0 + nown) return bad("an own node is listed as external");
+            touch[g]++;
+        }
+        // triangles: local ids decode to the triangle's native vertices
+        for (int64_t nt = t0; nt < t1; ++nt) {
+            const ushort4 q = P.tri_loc[nt];
+            const int32_t l3[3] = {q.x, q.y, q.z};
+            for (int r = 0; r < 3; ++r) {
+                if (l3[r] >= nloc) return bad("tile-local vertex id out of range");
+                const int32_t want = h->node_new_of_old[h->h_tri[3 * (int64_t)h->tri_old_of_new[nt] + r]];
+                if (native_of(l3[r]) != want || P.tri_native[3 * nt + r] != want) return bad("tile-local vertex id decodes to the wrong node");
+            }
+        }
+        // gather list: every (triangle, slot) exactly once, under the node it belongs to, ascending triangle order
+        const uint16_t* iptr = P.inc_ptr.data() + P.tile_loc0[b];
+        const uint16_t* inc = P.inc.data() + (size_t)3 * TT * b;
+        if (iptr[0] != 0 || iptr[nloc] != 3 * (t1 - t0)) return bad("gather list does not cover the tile");
+        std::vector<uint8_t> hit(3 * (t1 - t0), 0);
+        for (int32_t l = 0; l < nloc; ++l) {
+            int32_t prev = -1;
+            for (int32_t e = iptr[l]; e < iptr[l + 1]; ++e) {
+                const int32_t lt = inc[e] >> 2, slot = inc[e] & 3;
+                if (lt >= t1 - t0 || slot > 2 || lt <= prev) return bad("gather list entry out of range or out of order");
+                prev = lt;
+                const ushort4 q = P.tri_loc[t0 + lt];
+                if ((slot == 0 ? q.x : slot == 1 ? q.y : q.z) != l) return bad("gather list entry points at another node");
+                if (hit[3 * lt + slot]++) return bad("gather list entry repeated");
+                ++gather_entries;
+            }
+        }
+    }
+    if (cursor != P.n_vertices) return bad("tile ranges do not cover the vertices");
+    // interior nodes belong to one tile; interface nodes own one partial slot per touching tile and live edge end
+    std::vector<int32_t> edge_ends(N, 0);
+    for (const BndEdge& e : P.bnd) {
+        edge_ends[e.v[e.pi]]++;
+        edge_ends[e.v[e.pj]]++;
+    }
+    std::vector<uint8_t> slot_used(P.n_partial, 0);
+    int32_t ifc = 0;
+    for (int64_t b = 0; b < P.n_tiles; ++b) {
+        for (int32_t l = 0; l < P.tile_nown[b]; ++l) {
+            const int32_t g = P.tile_node0[b] + l;
+            if (l < P.tile_nint[b]) {
+                if (touch[g] != 1 || edge_ends[g] != 0) return bad("an interior node is shared or carries a live boundary edge");
+            } else {
+                if (ifc >= P.n_ifc || P.ifc_node[ifc] != g) return bad("interface list is not in tile order");
+                if (P.ifc_pptr[ifc + 1] - P.ifc_pptr[ifc] != touch[g] + edge_ends[g]) return bad("partial slots of an interface node do not match its tiles and edges");
+                ++ifc;
+            }
+        }
+        // the tile's partial positions: own interface nodes, then external nodes
+        const int32_t n_if_local = (P.tile_nown[b] - P.tile_nint[b]) + (P.tile_nloc[b] - P.tile_nown[b]);
+        if (P.tile_pp0[b + 1] - P.tile_pp0[b] != n_if_local) return bad("partial position list has the wrong length");
+        for (int32_t q = 0; q < n_if_local; ++q) {
+            const int32_t l = P.tile_nint[b] + q;
+            const int32_t g = l < P.tile_nown[b] ? P.tile_node0[b] + l : P.ext_ids[P.tile_ext0[b] + (l - P.tile_nown[b])];
+            const int32_t k = (int32_t)(std::lower_bound(P.ifc_node.begin(), P.ifc_node.end(), g) - P.ifc_node.begin());
+            if (k >= P.n_ifc || P.ifc_node[k] != g) return bad("a shared node is not an interface node");
+            const int32_t pos = P.ppos[P.tile_pp0[b] + q];
+            if (pos < P.ifc_pptr[k] || pos >= P.ifc_pptr[k + 1] || slot_used[pos]++) return bad("partial slot outside its node's range or used twice");
+        }
+    }
+    if (ifc != P.n_ifc) return bad("interface node count mismatch");
+    for (const BndEdge& e : P.bnd)
+        for (int q = 0; q < 2; ++q) {
+            const int32_t g = e.v[q == 0 ? e.pi : e.pj], pos = q == 0 ? e.slot_i : e.slot_j;
+            const int32_t k = (int32_t)(std::lower_bound(P.ifc_node.begin(), P.ifc_node.end(), g) - P.ifc_node.begin());
+            if (k >= P.n_ifc || P.ifc_node[k] != g) return bad("a live boundary edge ends at a node that is not an interface node");
+            if (pos < P.ifc_pptr[k] || pos >= P.ifc_pptr[k + 1] || slot_used[pos]++) return bad("boundary-edge partial slot outside its node's range or used twice");
+        }
+    for (int64_t s = 0; s < P.n_partial; ++s)
+        if (!slot_used[s]) return bad("an allocated partial slot has no writer");
+    stats[0] = P.n_tiles;
+    stats[1] = P.n_vertices;
+    stats[2] = P.n_ifc;
+    stats[3] = P.n_partial;
+    stats[4] = (int64_t)P.ext_ids.size();
+    stats[5] = P.max_nloc;
+    stats[6] = (int64_t)P.bnd.size();
+    stats[7] = gather_entries;
+    return FVM_OK;
+}
+
+extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t geometry_mode) {
+    NOT_FINAL(h);
+    FVM_CUDA(h, cudaSetDevice(h->device));
+    const int64_t N = h->N, T = h->T, Eb = h->Eb;
+    const int neq = h->neq;
+    // default tile size (measured on B200, 4096^2): kernels that stream the full 21-component SoA are
+    // register-limited to 3 CTAs/SM and like big tiles; the reduced stream wants 8 small CTAs per SM
+    const bool full_flux = h->flux.model == FVM_FLUX_DIFF_POWER || h->flux.model == FVM_FLUX_ADVDIFF || h->flux.model == FVM_FLUX_KELLER_SEGEL;
+    // (systems: 768 measured best for the 2-species Keller-Segel kernel: 1.20 ms vs 1.45 ms at 1024)
+    int TT = tile_triangles > 0 ? tile_triangles : (neq >= 2 ? 768 : ((geometry_mode == 0 && !full_flux) ? 512 : 1024));
+    if (tile_triangles <= 0)
+        if (const char* e = getenv("FVM_TILE_TRIANGLES")) TT = atoi(e);
+    FVM_REQUIRE(h, TT >= 64 && TT <= 4096 && TT % 64 == 0, "fvm_finalize: tile_triangles must be a multiple of 64 in 64..4096");
+    FVM_REQUIRE(h, geometry_mode == 0 || geometry_mode == 1, "fvm_finalize: geometry_mode must be 0 or 1");
+    if (h->flux.model == FVM_FLUX_DIFF_TABLE && h->h_dtab.empty())
+        return fvm_fail(h, FVM_ERR_STATE, "fvm_finalize: table flux model without fvm_set_flux_table");
+    h->geometry_mode = geometry_mode;
+    const double* xy = h->h_xy.data();
+    const int32_t* tri = h->h_tri.data();
+
+    HostPlan P;
+    int32_t rc_plan = plan_host(h, TT, P);
+    if (rc_plan) return rc_plan;
+    const int64_t n_tiles = P.n_tiles, tpad = P.tpad, n_partial = P.n_partial;
+    const int32_t n_vertices = P.n_vertices, n_ifc = P.n_ifc, max_nloc = P.max_nloc;
+    const int32_t* told = h->tri_old_of_new.data();
+    std::vector<int32_t>&tile_node0 = P.tile_node0, &tile_nint = P.tile_nint, &tile_nown = P.tile_nown, &tile_nloc = P.tile_nloc;
+    std::vector<int32_t>&tile_ext0 = P.tile_ext0, &tile_loc0 = P.tile_loc0, &tile_pp0 = P.tile_pp0;
+    std::vector<ushort4>& tri_loc = P.tri_loc;
+    std::vector<int32_t>&tri_native = P.tri_native, &ext_ids = P.ext_ids, &ifc_node = P.ifc_node, &ifc_pptr = P.ifc_pptr, &ppos = P.ppos;
+    std::vector<uint16_t>&inc_ptr = P.inc_ptr, &inc = P.inc;
+    std::vector<BndEdge>& bnd = P.bnd;
+    std::vector<double>& dbnd_live = P.dbnd_live;
     // ---- 6. upload --------------------------------------------------------------------------
     DevMesh& m = h->dm;
     m.neq = neq;

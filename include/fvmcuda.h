@@ -122,6 +122,14 @@ int32_t fvm_set_source_table(fvm_handle h, const double* s_node /* [N][neq] */);
  * geometry SoA on the device.  Options: tile_triangles (0 = default 1024),
  * geometry_mode 0 = stored SoA (north_star layout), 1 = recomputed from vertex coordinates. */
 int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t geometry_mode);
+/* Host-only self-check of the planning fvm_finalize does before its first device call (Hilbert tiling, tile-major
+ * renumbering, tile-local indices, gather lists, interface / partial-slot bookkeeping, live boundary edges): runs it
+ * on the given mesh without a CUDA device and verifies the invariants the kernels rely on.  node_kind: [neq][N]
+ * fvm_node_kind values or NULL (all free).  stats[8]: n_tiles, n_vertices, n_interface, n_partial, n_external,
+ * max_local_nodes, n_live_boundary_edges, gather-list entries (= 3 T). */
+int32_t fvm_plan_selftest(const double* xy, int64_t n_points, const int32_t* triangles, int64_t n_triangles,
+                          int32_t index_base, int32_t neq, const int32_t* boundary_edges, int64_t n_edges,
+                          const uint8_t* node_kind, int32_t tile_triangles, int64_t* stats);
 int32_t fvm_destroy(fvm_handle h);
 const char* fvm_last_error(fvm_handle h);
 const char* fvm_version(void);

@@ -142,3 +142,45 @@ def test_template_argument_errors_mirror_the_reference():
     with pytest.raises(ValueError):
         G.Tsit5(adaptive=False)
     assert G.Tsit5().adaptive and not G.Tsit5(0.1).adaptive
+
+
+@pytest.mark.parametrize("tile", [64, 256, 1024])
+def test_finalize_host_planning_invariants(tile):
+    """fvm_plan_selftest runs the host half of fvm_finalize (Hilbert tiling, tile-major renumbering, tile-local
+    ids, gather lists, interface / partial-slot bookkeeping, live boundary edges) WITHOUT a device and checks, in
+    the library, every invariant the kernels rely on; here its summary is checked against the mesh."""
+    import ctypes as C
+    from fvm_b200 import _lib as L
+    lib = L.lib()
+    cases = []
+    lat = G.triangulate_rectangle(0, 2, 0, 2, 50, 50, single_boundary=True)
+    kinds = np.zeros(2500, np.uint8)
+    kinds[np.unique(lat.boundary_edges()[0])] = 1  # README: all-Dirichlet boundary -> no live edge
+    cases.append((lat, 1, kinds, 0))
+    cases.append((lat, 2, None, 196))  # all-free boundary, 2 species: every boundary edge is live
+    un = delaunay_mesh(1500, 3, extra_points=5)
+    cases.append((un, 1, None, len(un.boundary_edges()[0])))
+    big = G.triangulate_rectangle(0, 1, 0, 3, 120, 333, single_boundary=False)
+    cases.append((big, 1, None, len(big.boundary_edges()[0])))
+    for tri, neq, kind, n_live in cases:
+        uv = L.i32(tri.boundary_edges()[0] + 1)  # 1-based, like the Julia side passes them
+        pts, t1 = L.f64(tri.points), L.i32(tri.triangles + 1)
+        kk = None if kind is None else np.ascontiguousarray(np.tile(kind, neq))
+        st = np.zeros(8, np.int64)
+        rc = lib.fvm_plan_selftest(L.dp(pts), tri.num_points, L.ip(t1), tri.num_triangles, 1, neq, L.ip(uv), len(uv), L.bp(kk), tile,
+                                   st.ctypes.data_as(L.c_lp))
+        assert rc == L.OK, lib.fvm_last_error(None).decode()
+        n_tiles, n_vert, n_ifc, n_partial, n_ext, max_nloc, live, gather = st.tolist()
+        assert n_tiles == -(-tri.num_triangles // tile) and gather == 3 * tri.num_triangles
+        assert n_vert == int(tri.solid_vertex_mask().sum()) and live == n_live
+        assert n_partial >= n_ifc + n_ext and max_nloc <= 3 * tile  # every interface node: own slot + one per foreign tile
+        if n_tiles == 1:
+            assert n_ext == 0 and n_ifc == len(np.unique(tri.boundary_edges()[0])) * (live > 0)
+    # argument errors
+    st = np.zeros(8, np.int64)
+    assert lib.fvm_plan_selftest(L.dp(pts), tri.num_points, L.ip(t1), tri.num_triangles, 1, 1, L.ip(uv), len(uv), None, 100,
+                                 st.ctypes.data_as(L.c_lp)) == L.ERR_ARG
+    bad_uv = L.i32(uv[:, ::-1].copy())  # clockwise edges are not edges of any triangle
+    assert lib.fvm_plan_selftest(L.dp(pts), tri.num_points, L.ip(t1), tri.num_triangles, 1, 1, L.ip(bad_uv), len(bad_uv), None, tile,
+                                 st.ctypes.data_as(L.c_lp)) == L.ERR_ARG
+    assert b"not a ccw edge" in lib.fvm_last_error(None)
