@@ -77,7 +77,7 @@ enum fvm_cond_fn {
     FVM_COND_EXP_XYT = 4    /* c0 * exp(c1 x + c2 y + c3 t)        */
 };
 
-/* Linear templates: src/specific_problems/*.jl */
+/* Linear templates: the constructors under src/specific_problems */
 enum fvm_template {
     FVM_TPL_DIFFUSION = 0,                 /* diffusion_equation.jl:69-101 */
     FVM_TPL_LINEAR_REACTION_DIFFUSION = 1, /* linear_reaction_diffusion_equations.jl:76-125 */

@@ -184,3 +184,27 @@ def test_finalize_host_planning_invariants(tile):
     assert lib.fvm_plan_selftest(L.dp(pts), tri.num_points, L.ip(t1), tri.num_triangles, 1, 1, L.ip(bad_uv), len(bad_uv), None, tile,
                                  st.ctypes.data_as(L.c_lp)) == L.ERR_ARG
     assert b"not a ccw edge" in lib.fvm_last_error(None)
+
+
+def test_header_is_plain_c_and_the_c_example_runs(tmp_path):
+    """include/fvmcuda.h must compile as strict C99 (it is what a Julia ccall / cgo / JNI binding reads), and
+    examples/readme_diffusion.c drives the ABI from plain C: the host-only entry points work anywhere, the compute
+    part ends with status 2 and the "no CPU fallback" message when there is no device (0 on a GPU box)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "readme_diffusion")
+    libdir = os.path.dirname(G.LIB_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "readme_diffusion.c"), "-L", libdir, "-lfvmcuda", "-Wl,-rpath," + libdir, "-lm",
+                        "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, cwd=str(tmp_path), timeout=300)
+    assert "plan: 19 tiles, 2500 vertices" in r.stdout and "0 live boundary edges" in r.stdout
+    assert "partition: 625 625 625 625 nodes" in r.stdout and "written and verified" in r.stdout
+    if _have_gpu():
+        assert r.returncode == 0 and "Tsit5 to t = 0.5" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
+    assert not os.path.exists(str(tmp_path / "readme_mesh.fvmw")) or r.returncode != 2
