@@ -45,7 +45,8 @@ def build_case(kind):
         types = (G.Dirichlet, G.Dudt, G.Neumann, G.Constrained)
         internal = ((G.Const(0.7),), {200: 0}, {300: 0})
         gp, op = pair.problem(specs, types, G.PowerDiffusion(0.3, 2.0), source=G.LogisticSource(1.3), internal=internal)
-        owner = G.partition_rcb(pair.gtri.points, 2)
+        # "graph": the METIS-style partitioner of the library (irregular interface); else coordinate bisection
+        owner = G.partition_graph(pair.gtri, 2) if kind == "graph" else G.partition_rcb(pair.gtri.points, 2)
     return pair, gp, op, owner
 
 

@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("kind", ["lattice", "delaunay"])
+@pytest.mark.parametrize("kind", ["lattice", "delaunay", "graph"])
 def test_sharded_oracle_rhs_two_ranks(kind, tmp_path):
     import torch.multiprocessing as mp
     mp.spawn(worker, args=(2, _free_port(), kind, str(tmp_path)), nprocs=2, join=True)
