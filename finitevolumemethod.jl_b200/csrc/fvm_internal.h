@@ -62,6 +62,17 @@ struct DevMesh {
     const CondFn* cond;          // [neq][FVM_MAX_COND_FN]
 };
 
+// Tile pack of the streaming (recompute-geometry) RHS kernel (fvm_rhs_stream.cu): everything static a tile
+// needs -- local vertex ids, vertex coordinates (own + external), 1/V, condition kinds, partial slots and the
+// node gather list -- as ONE 16-byte aligned record, fetched by a single bulk async copy (cp.async.bulk).
+struct TilePackHdr {  // 64 bytes, section offsets in bytes from the start of the pack
+    int32_t node0, nint, nown, nloc;
+    int32_t ntri, next, nslice, bytes;
+    int32_t off_tri, off_xy, off_vinv, off_kind;
+    int32_t off_ppos, off_srow, off_list, off_dtab;
+};
+#define FVM_STREAM_MAX_TT 2688  // gather codes are 16-bit byte offsets into the contribution planes: 3*TT*8 + 8 <= 65536
+
 struct BndEdge {  // one live boundary edge (native ids); tiny count, AoS is fine
     int32_t v[3];      // stored vertex triple of the adjacent triangle
     int32_t pi, pj;    // positions of i and j inside v
@@ -197,6 +208,15 @@ struct fvm_ctx {
     void* pipe_spmv = nullptr;  // plan of fvm_spmv
     const int32_t* pipe_list = nullptr;  // explicit tile list of fvm_launch_rhs_part(part = 4)
     int32_t pipe_off = 0, pipe_count = 0;
+    // streaming recompute kernel (fvm_rhs_stream.cu): per-tile packs + directory
+    uint8_t* d_packs = nullptr;
+    int4* d_pack_dir = nullptr;   // 2 x int4 per tile: {pack offset / 16, pack bytes, node0, nown}, {ext0, next, 0, 0}
+    int32_t pack_cap = 0;         // largest pack (bytes)
+    int64_t pack_bytes_total = 0;
+    bool packs_ready = false;
+    int32_t stream_threads = 256;  // consumer threads per CTA of the streaming kernel
+    std::map<const void*, int32_t> occ_cache;  // kernel -> resident CTAs per SM at the configured shared memory
+    int32_t sm_count = 148;
 };
 
 // ---- helpers -----------------------------------------------------------------
@@ -253,6 +273,9 @@ int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* out, bool add_b, bool scal
 // 3 = the kernels that need every tile (interface / tail rows)
 //       4 = the tiles h->pipe_list[pipe_off .. pipe_off + pipe_count) only
 int32_t fvm_launch_rhs_part(fvm_ctx* h, double t, const double* u, double* du, int part);
+// streaming recompute kernel over tiles list[off .. off+count) (list == nullptr: tiles 0 .. count)
+int32_t fvm_launch_rhs_stream(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count);
+int32_t fvm_stream_fill_vinv(fvm_ctx* h);  // after the control volumes exist: 1/V of every interior node into the packs
 // interface nodes list[off .. off+count) (indices into ifc_node); points that are not vertices (du = 0)
 int32_t fvm_launch_rhs_interface_list(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count);
 int32_t fvm_launch_rhs_nonvertex(fvm_ctx* h, double* du);

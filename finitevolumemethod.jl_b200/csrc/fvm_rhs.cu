@@ -503,6 +503,29 @@ static int32_t launch_rhs_neq(fvm_ctx* h, double t, const double* u, double* du,
     }
     const int model = h->flux.model;
     const int geom = h->geometry_mode;
+    if (geom == 1 && h->packs_ready) {  // persistent streaming kernel (fvm_rhs_stream.cu)
+        int count = h->dm.n_tiles, off = 0;
+        const int32_t* list = nullptr;
+        if (part == 1) {
+            list = h->d_tile_order;
+            count = h->n_tiles_indep;
+        } else if (part == 2) {
+            list = h->d_tile_order;
+            off = h->n_tiles_indep;
+            count = h->dm.n_tiles - h->n_tiles_indep;
+        } else if (part == 4) {
+            list = h->pipe_list;
+            off = h->pipe_off;
+            count = h->pipe_count;
+        }
+        if ((rc = fvm_launch_rhs_stream(h, t, u, du, list, off, count))) return rc;
+        const int n_tail_s = h->dm.n_ifc + (h->dm.n_nodes - h->dm.n_vertices);
+        if (n_tail_s > 0 && part == 0) {
+            rhs_interface_kernel<NEQ, false><<<(n_tail_s + 255) / 256, 256, 0, h->launch_stream>>>(h->dm, h->source, t, u, du);
+            FVM_CUDA(h, cudaGetLastError());
+        }
+        return FVM_OK;
+    }
 #define TILE_CASE(M)                                                        \
     case M:                                                                 \
         rc = geom ? launch_tile<M, NEQ, 1>(h, t, u, du, part) : launch_tile<M, NEQ, 0>(h, t, u, du, part); \

@@ -1,0 +1,350 @@
+// libfvmcuda: the streaming recompute-geometry RHS kernel (geometry_mode = 1).
+//
+//   du = fvm_eqs!(du, u, p, t)      /root/reference/src/equations/main_equations.jl:38-44
+//
+// Same mathematics and the same per-node summation order as rhs_tile_kernel (fvm_rhs.cu), but built as a
+// persistent, warp-specialised pipeline so that HBM, the fp64 pipe and the issue slots work at the same time:
+//
+//   * a CTA walks tiles  blockIdx.x, blockIdx.x + gridDim.x, ...  (grid = SMs x resident CTAs);
+//   * one PRODUCER warp runs ahead: per tile it issues ONE bulk async copy (cp.async.bulk, the TMA engine) of the
+//     tile's static pack (TilePackHdr: local vertex ids, vertex coordinates, 1/V, kinds, partial slots, gather
+//     rows), one bulk copy of the tile's own `u` range and 8-byte cp.async gathers of the external nodes' `u`,
+//     all completing on the stage's `full` mbarrier; two stages, so tile k+1 lands while tile k is computed;
+//   * the CONSUMER warps never touch global memory for inputs: triangle pass (one thread per triangle:
+//     geometry.jl:107-161 recomputed from the staged coordinates, shape functions, three control-volume-edge
+//     fluxes, triangle_contributions.jl:28-35) -> contribution planes in shared memory -> one named barrier ->
+//     node pass (a warp owns 32 consecutive local nodes and walks their gather rows: conflict-free 16-bit
+//     loads of byte offsets into the planes), node pass of source_contributions.jl:33-68 for interior nodes
+//     (coalesced `du` stores), one partial per interface node;
+//   * the contribution planes are double buffered, so one barrier per tile is enough.
+//
+// No atomics; every output word has one writer and a fixed summation order.
+#include <algorithm>
+
+#include "fvm_device.cuh"
+
+namespace {
+
+constexpr int SK_STAGES = 2;
+constexpr int SK_PROD = 32;  // producer threads (one warp)
+
+struct StreamArgs {
+    const uint8_t* packs;
+    const int4* dir;
+    const int32_t* list;  // explicit tile list (or null: tiles 0 .. count)
+    int32_t list_off, count;
+    int32_t pack_cap;  // bytes reserved per stage for the pack
+    int32_t u_cap;     // doubles reserved per stage for the tile's u values
+    int32_t plane;     // doubles per contribution plane: 3 * TT + 2 (the last two stay zero)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk async copy (TMA engine, no tensor map); 16-byte aligned addresses, size multiple of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(b))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// the mbarrier gets one arrival from this thread when all of its earlier cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* b) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <int MODEL, int NEQ, int NCONS>
+struct StreamOcc {
+    // resident CTAs the register budget is planned for (shared memory decides the rest at run time)
+    static constexpr int min_blocks = NCONS >= 512 ? 2 : (NCONS >= 384 ? 2 : 3);
+};
+
+template <int MODEL, int NEQ, int NCONS>
+__global__ void __launch_bounds__(NCONS + SK_PROD, StreamOcc<MODEL, NEQ, NCONS>::min_blocks)
+    rhs_stream_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t, const double* __restrict__ u,
+                      double* __restrict__ du, const StreamArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int TT = m.tile_tris;
+    const int cbuf = NEQ * a.plane;  // doubles per contribution buffer
+    double* c_s = reinterpret_cast<double*>(smem_raw);
+    unsigned char* stage0 = smem_raw + (size_t)2 * cbuf * sizeof(double);
+    const int stage_bytes = a.pack_cap + a.u_cap * (int)sizeof(double);
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)SK_STAGES * stage_bytes);
+    uint64_t* empty = full + SK_STAGES;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SK_STAGES; ++s) {
+            mbar_init(full + s, SK_PROD + 1);  // 32 cp.async arrivals + the expect_tx arrival
+            mbar_init(empty + s, NCONS / 32);  // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (tid < 2 * NEQ) {  // the zero words padded gather entries point at
+        c_s[(tid / NEQ) * cbuf + (tid % NEQ) * a.plane + 3 * TT] = 0.0;
+        c_s[(tid / NEQ) * cbuf + (tid % NEQ) * a.plane + 3 * TT + 1] = 0.0;
+    }
+    __syncthreads();
+    const int n_my = ((int)a.count - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (tid >= NCONS) {
+        // ================================ producer warp ================================================
+        const int lane = tid - NCONS;
+        for (int i = 0; i < n_my; ++i) {
+            const int s = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            const int pos = blockIdx.x + i * gridDim.x;
+            const int tile = a.list ? __ldg(a.list + a.list_off + pos) : pos;
+            const int4 d0 = __ldg(a.dir + 2 * tile), d1 = __ldg(a.dir + 2 * tile + 1);
+            const int node0 = d0.z, nown = d0.w, ext0 = d1.x, next = d1.y;
+            mbar_wait(empty + s, ph ^ 1u);  // stage free (passes at once the first time round)
+            unsigned char* st = stage0 + (size_t)s * stage_bytes;
+            double* us = reinterpret_cast<double*>(st + a.pack_cap);
+            const double* usrc = u + (size_t)node0 * NEQ;
+            const int n = nown * NEQ;
+            // bulk copies need 16-byte aligned addresses: element j of the own range sits at us[shift + j], so global
+            // and shared addresses agree mod 16; an odd head / tail element goes by 8-byte cp.async
+            const int shift = (int)((reinterpret_cast<uintptr_t>(usrc) >> 3) & 1);
+            const int nb = n > shift ? ((n - shift) & ~1) : 0;
+            if (lane == 0) {
+                mbar_expect_tx(full + s, (uint32_t)d0.y + (uint32_t)nb * 8u);
+                bulk_g2s(st, a.packs + ((size_t)(uint32_t)d0.x << 4), (uint32_t)d0.y, full + s);
+                if (nb > 0) bulk_g2s(us + 2 * shift, usrc + shift, (uint32_t)nb * 8u, full + s);
+            } else if (lane == 1) {
+                if (shift && n > 0) cp_async8(us + 1, usrc);
+            } else if (lane == 2) {
+                if (n > shift && ((n - shift) & 1)) cp_async8(us + shift + n - 1, usrc + n - 1);
+            }
+            for (int k = lane; k < next; k += 32) {
+                const int g = __ldg(m.ext_ids + ext0 + k);
+#pragma unroll
+                for (int v = 0; v < NEQ; ++v) cp_async8(us + shift + (nown + k) * NEQ + v, u + (size_t)g * NEQ + v);
+            }
+            cp_async_arrive_noinc(full + s);
+        }
+        return;
+    }
+
+    // ==================================== consumer warps ================================================
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr bool FULL = FluxTraits<MODEL>::full;
+    for (int i = 0; i < n_my; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+        mbar_wait(full + s, ph);
+        const unsigned char* st = stage0 + (size_t)s * stage_bytes;
+        const int4 h0 = reinterpret_cast<const int4*>(st)[0], h1 = reinterpret_cast<const int4*>(st)[1];
+        const int4 h2 = reinterpret_cast<const int4*>(st)[2], h3 = reinterpret_cast<const int4*>(st)[3];
+        const int node0 = h0.x, nint = h0.y, nloc = h0.w, ntri = h1.x, nslice = h1.z;
+        const ushort4* __restrict__ tri_s = reinterpret_cast<const ushort4*>(st + h2.x);
+        const double2* __restrict__ xy_s = reinterpret_cast<const double2*>(st + h2.y);
+        const double* __restrict__ us =
+            reinterpret_cast<const double*>(st + a.pack_cap) + ((reinterpret_cast<uintptr_t>(u + (size_t)node0 * NEQ) >> 3) & 1);
+        double* cb = c_s + (size_t)(i & 1) * cbuf;
+
+        // ---- triangle pass --------------------------------------------------------------------------
+#pragma unroll 1
+        for (int lt = tid; lt < ntri; lt += NCONS) {
+            const ushort4 vv = tri_s[lt];
+            const double2 P = xy_s[vv.x], Q = xy_s[vv.y], R = xy_s[vv.z];
+            TriGeom G;
+            tri_geometry<false>(P.x, P.y, Q.x, Q.y, R.x, R.y, G, nullptr);
+            double dt3[3] = {0, 0, 0};
+            if constexpr (FluxTraits<MODEL>::table) {
+                const double* dts = reinterpret_cast<const double*>(st + h3.w);
+                const int np = (ntri + 1) & ~1;
+#pragma unroll
+                for (int e = 0; e < 3; ++e) dt3[e] = dts[e * np + lt];
+            }
+            double al[NEQ], be[NEQ], ga[NEQ];  // shape_functions.jl:2-19
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) {
+                const double ui = us[vv.x * NEQ + v], uj = us[vv.y * NEQ + v], uk = us[vv.z * NEQ + v];
+                al[v] = G.s[0] * ui + G.s[1] * uj + G.s[2] * uk;
+                be[v] = G.s[3] * ui + G.s[4] * uj + G.s[5] * uk;
+                if constexpr (FULL) ga[v] = G.s[6] * ui + G.s[7] * uj + G.s[8] * uk;
+                else ga[v] = 0.0;
+            }
+            double Qe[3][NEQ];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                double qx[NEQ], qy[NEQ];
+                flux_eval<MODEL, NEQ>(fp, FULL ? G.mx[e] : 0.0, FULL ? G.my[e] : 0.0, t, al, be, ga, dt3[e], qx, qy);
+#pragma unroll
+                for (int v = 0; v < NEQ; ++v) Qe[e][v] = qx[v] * G.ey[e] - qy[v] * G.ex[e];  // q . (l n),  l n = (e_y, -e_x)
+            }
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) {  // triangle_contributions.jl:10-25
+                double* cp = cb + v * a.plane + lt;
+                cp[0] = Qe[2][v] - Qe[0][v];
+                cp[TT] = Qe[0][v] - Qe[1][v];
+                cp[2 * TT] = Qe[1][v] - Qe[2][v];
+            }
+        }
+        bar_sync(1, NCONS);
+
+        // ---- node pass: a warp owns 32 consecutive local nodes ----------------------------------------
+        const double* __restrict__ vinv_s = reinterpret_cast<const double*>(st + h2.z);
+        const uint8_t* __restrict__ kind_s = st + h2.w;
+        const int kstride = (nint + 15) & ~15;
+        const int32_t* __restrict__ ppos_s = reinterpret_cast<const int32_t*>(st + h3.x);
+        const uint16_t* __restrict__ srow = reinterpret_cast<const uint16_t*>(st + h3.y);
+        const uint16_t* __restrict__ lst = reinterpret_cast<const uint16_t*>(st + h3.z);
+        const unsigned char* cbytes = reinterpret_cast<const unsigned char*>(cb);
+#pragma unroll 1
+        for (int sl = warp; sl < nslice; sl += NCONS / 32) {
+            const int r0 = srow[sl], r1 = srow[sl + 1];
+            const uint16_t* lp = lst + r0 * 32 + lane;
+            double acc[NEQ];
+#pragma unroll
+            for (int v = 0; v < NEQ; ++v) acc[v] = 0.0;
+#pragma unroll 2
+            for (int r = r0; r < r1; ++r, lp += 32) {
+                const uint32_t code = *lp;
+#pragma unroll
+                for (int v = 0; v < NEQ; ++v)
+                    acc[v] += *reinterpret_cast<const double*>(cbytes + code + (size_t)v * a.plane * sizeof(double));
+            }
+            const int l = sl * 32 + lane;
+            if (l < nint) {  // source_contributions.jl:33-68, finished in place
+                const int g = node0 + l;
+                double tab[NEQ];
+                if (sp.model == FVM_SRC_TABLE) {
+#pragma unroll
+                    for (int v = 0; v < NEQ; ++v) tab[v] = m.src_tab[(size_t)g * NEQ + v];
+                }
+                const double vi = vinv_s[l];
+#pragma unroll
+                for (int v = 0; v < NEQ; ++v) {
+                    const uint8_t kind = kind_s[v * kstride + l];
+                    double out;
+                    if (kind == FVM_NODE_FREE) {
+                        out = acc[v] * vi + source_eval<NEQ>(sp, v, us + l * NEQ, tab);
+                    } else if (kind == FVM_NODE_DUDT) {
+                        const CondFn c = m.cond[v * FVM_MAX_COND_FN + m.fidx[(size_t)v * m.n_nodes + g]];
+                        const double2 X = xy_s[l];
+                        out = cond_eval(c, X.x, X.y, t, us[l * NEQ + v]);
+                    } else {
+                        out = 0.0;  // Dirichlet node, ghost node
+                    }
+                    du[(size_t)g * NEQ + v] = out;
+                }
+            } else if (l < nloc) {
+                const size_t p = (size_t)ppos_s[l - nint] * NEQ;
+#pragma unroll
+                for (int v = 0; v < NEQ; ++v) m.partial[p + v] = acc[v];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);  // this warp is done with the stage
+    }
+}
+
+__global__ void pack_vinv_kernel(uint8_t* __restrict__ packs, const int4* __restrict__ dir, const double* __restrict__ vol) {
+    const int4 d0 = dir[2 * blockIdx.x];
+    uint8_t* base = packs + ((size_t)(uint32_t)d0.x << 4);
+    const TilePackHdr H = *reinterpret_cast<const TilePackHdr*>(base);
+    double* vinv = reinterpret_cast<double*>(base + H.off_vinv);
+    for (int l = threadIdx.x; l < H.nint; l += blockDim.x) vinv[l] = 1.0 / vol[H.node0 + l];
+}
+
+template <int MODEL, int NEQ, int NCONS>
+int32_t launch_stream_t(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
+    auto kern = rhs_stream_kernel<MODEL, NEQ, NCONS>;
+    StreamArgs a;
+    a.packs = h->d_packs;
+    a.dir = h->d_pack_dir;
+    a.list = list;
+    a.list_off = off;
+    a.count = count;
+    a.pack_cap = h->pack_cap;
+    a.u_cap = (h->max_nloc * NEQ + 2 + 1) & ~1;
+    a.plane = 3 * h->dm.tile_tris + 2;
+    const int32_t smem = (int32_t)(2 * NEQ * a.plane * sizeof(double) + SK_STAGES * (a.pack_cap + a.u_cap * sizeof(double)) + 2 * SK_STAGES * sizeof(uint64_t));
+    if (smem > 227 * 1024) return fvm_fail(h, FVM_ERR_ARG, "streaming RHS kernel: tile needs more than 227 KB of shared memory; lower tile_triangles");
+    int32_t& configured = h->smem_configured[(const void*)kern];
+    int32_t& occ = h->occ_cache[(const void*)kern];
+    if (configured != smem) {
+        FVM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int nb = 0;
+        FVM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NCONS + SK_PROD, smem));
+        if (nb < 1) return fvm_fail(h, FVM_ERR_CUDA, "streaming RHS kernel does not fit on an SM");
+        configured = smem;
+        occ = nb;
+    }
+    h->smem_rhs = smem;
+    const int grid = std::min(count, h->sm_count * occ);
+    cudaStream_t st = h->launch_stream;
+    if (st == h->stream) fvm_prof_begin(h);
+    kern<<<grid, NCONS + SK_PROD, smem, st>>>(h->dm, h->flux, h->source, t, u, du, a);
+    if (st == h->stream) fvm_prof_end(h);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}
+
+template <int MODEL, int NEQ>
+int32_t launch_stream_threads(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
+    switch (h->stream_threads) {
+        case 512: return launch_stream_t<MODEL, NEQ, 512>(h, t, u, du, list, off, count);
+        case 384: return launch_stream_t<MODEL, NEQ, 384>(h, t, u, du, list, off, count);
+        default: return launch_stream_t<MODEL, NEQ, 256>(h, t, u, du, list, off, count);
+    }
+}
+
+template <int NEQ>
+int32_t launch_stream_neq(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
+    switch (h->flux.model) {
+        case FVM_FLUX_DIFF_CONST: return launch_stream_threads<FVM_FLUX_DIFF_CONST, NEQ>(h, t, u, du, list, off, count);
+        case FVM_FLUX_DIFF_TABLE: return launch_stream_threads<FVM_FLUX_DIFF_TABLE, NEQ>(h, t, u, du, list, off, count);
+        case FVM_FLUX_DIFF_POWER: return launch_stream_threads<FVM_FLUX_DIFF_POWER, NEQ>(h, t, u, du, list, off, count);
+        case FVM_FLUX_ADVDIFF: return launch_stream_threads<FVM_FLUX_ADVDIFF, NEQ>(h, t, u, du, list, off, count);
+        case FVM_FLUX_KELLER_SEGEL:
+            if constexpr (NEQ == 2) return launch_stream_threads<FVM_FLUX_KELLER_SEGEL, 2>(h, t, u, du, list, off, count);
+            return fvm_fail(h, FVM_ERR_ARG, "Keller-Segel flux needs neq == 2");
+    }
+    return fvm_fail(h, FVM_ERR_UNSUPPORTED, "flux model is not in the compiled registry");
+}
+
+}  // namespace
+
+int32_t fvm_launch_rhs_stream(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
+    if (count <= 0) return FVM_OK;
+    switch (h->neq) {
+        case 1: return launch_stream_neq<1>(h, t, u, du, list, off, count);
+        case 2: return launch_stream_neq<2>(h, t, u, du, list, off, count);
+        case 3: return launch_stream_neq<3>(h, t, u, du, list, off, count);
+        case 4: return launch_stream_neq<4>(h, t, u, du, list, off, count);
+    }
+    return fvm_fail(h, FVM_ERR_ARG, "unsupported neq");
+}
+
+int32_t fvm_stream_fill_vinv(fvm_ctx* h) {
+    pack_vinv_kernel<<<h->dm.n_tiles, 128, 0, h->stream>>>(h->d_packs, h->d_pack_dir, h->dm.vol);
+    FVM_CUDA(h, cudaGetLastError());
+    return FVM_OK;
+}

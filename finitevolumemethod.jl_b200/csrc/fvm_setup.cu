@@ -603,6 +603,130 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     return FVM_OK;
 }
 
+// ---- tile packs of the streaming recompute kernel (fvm_rhs_stream.cu) ---------------------------------------------
+// One 16-byte aligned record per tile (TilePackHdr + sections), built tile-parallel on the host.  The node gather
+// list is re-laid out for a warp-per-32-nodes pass: slice s covers local nodes 32 s .. 32 s + 31 and owns
+// srow[s+1] - srow[s] rows of 32 uint16 codes (entry j of lane l at row (srow[s] + j), column l), each code the BYTE
+// offset of a vertex contribution inside the tile's contribution plane ((slot * TT + local_triangle) * 8); padded
+// entries point at a zero word behind the plane.  Same per-node order as the CSR list (ascending triangle).
+static inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, const double* xyn, const uint8_t* kn,
+                                const double* dtab_native /* [3][tpad] or null */, std::vector<uint8_t>& packs,
+                                std::vector<int4>& dir, int32_t& pack_cap) {
+    const int64_t n_tiles = P.n_tiles, N = h->N, T = h->T;
+    const int neq = h->neq;
+    std::vector<int64_t> off(n_tiles + 1, 0);
+    std::vector<int32_t> nrows(n_tiles, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < n_tiles; ++b) {
+        const int32_t nint = P.tile_nint[b], nloc = P.tile_nloc[b];
+        const int32_t ntri = (int32_t)std::min<int64_t>(TT, T - b * TT);
+        const uint16_t* iptr = P.inc_ptr.data() + P.tile_loc0[b];
+        const int32_t nslice = (nloc + 31) / 32;
+        int32_t rows = 0;
+        for (int32_t s = 0; s < nslice; ++s) {
+            int32_t w = 0;
+            for (int32_t l = 32 * s; l < std::min(nloc, 32 * s + 32); ++l) w = std::max<int32_t>(w, iptr[l + 1] - iptr[l]);
+            rows += w;
+        }
+        nrows[b] = rows;
+        int64_t sz = sizeof(TilePackHdr);
+        sz = align16(sz + 8 * (int64_t)ntri);                  // tri: ushort4
+        sz = align16(sz + 16 * (int64_t)nloc);                 // xy: double2
+        sz = align16(sz + 8 * (int64_t)nint);                  // 1 / V
+        sz = align16(sz + (int64_t)neq * align16(nint));       // kind: [neq][align16(nint)]
+        sz = align16(sz + 4 * (int64_t)(nloc - nint));         // partial slots
+        sz = align16(sz + 2 * (int64_t)(nslice + 1));          // slice row offsets
+        sz = align16(sz + 64 * (int64_t)rows);                 // gather rows
+        if (dtab_native) sz = align16(sz + 24 * (int64_t)((ntri + 1) & ~1));
+        off[b + 1] = sz;
+    }
+    pack_cap = 0;
+    for (int64_t b = 0; b < n_tiles; ++b) {
+        pack_cap = std::max<int32_t>(pack_cap, (int32_t)off[b + 1]);
+        FVM_REQUIRE(h, nrows[b] < 65535, "fvm_finalize: tile gather list too long for the streaming kernel");
+        off[b + 1] += off[b];
+    }
+    FVM_REQUIRE(h, (off[n_tiles] >> 4) < (int64_t)UINT32_MAX, "fvm_finalize: tile packs exceed 64 GB");
+    packs.assign((size_t)off[n_tiles], 0);
+    dir.resize(2 * n_tiles);
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < n_tiles; ++b) {
+        uint8_t* base = packs.data() + off[b];
+        TilePackHdr H{};
+        H.node0 = P.tile_node0[b];
+        H.nint = P.tile_nint[b];
+        H.nown = P.tile_nown[b];
+        H.nloc = P.tile_nloc[b];
+        H.ntri = (int32_t)std::min<int64_t>(TT, T - b * TT);
+        H.next = H.nloc - H.nown;
+        H.nslice = (H.nloc + 31) / 32;
+        H.bytes = (int32_t)(off[b + 1] - off[b]);
+        int64_t o = sizeof(TilePackHdr);
+        H.off_tri = (int32_t)o;
+        o = align16(o + 8 * (int64_t)H.ntri);
+        H.off_xy = (int32_t)o;
+        o = align16(o + 16 * (int64_t)H.nloc);
+        H.off_vinv = (int32_t)o;
+        o = align16(o + 8 * (int64_t)H.nint);
+        H.off_kind = (int32_t)o;
+        const int32_t kstride = (int32_t)align16(H.nint);
+        o = align16(o + (int64_t)neq * kstride);
+        H.off_ppos = (int32_t)o;
+        o = align16(o + 4 * (int64_t)(H.nloc - H.nint));
+        H.off_srow = (int32_t)o;
+        o = align16(o + 2 * (int64_t)(H.nslice + 1));
+        H.off_list = (int32_t)o;
+        o = align16(o + 64 * (int64_t)nrows[b]);
+        H.off_dtab = dtab_native ? (int32_t)o : 0;
+        std::memcpy(base, &H, sizeof(H));
+        std::memcpy(base + H.off_tri, P.tri_loc.data() + b * TT, 8 * (size_t)H.ntri);
+        double* xy = reinterpret_cast<double*>(base + H.off_xy);
+        for (int32_t l = 0; l < H.nloc; ++l) {
+            const int32_t g = l < H.nown ? H.node0 + l : P.ext_ids[P.tile_ext0[b] + (l - H.nown)];
+            xy[2 * l] = xyn[2 * (size_t)g];
+            xy[2 * l + 1] = xyn[2 * (size_t)g + 1];
+        }
+        // 1/V is written on the device once the control volumes exist (fvm_stream_fill_vinv)
+        for (int v = 0; v < neq; ++v)
+            std::memcpy(base + H.off_kind + (size_t)v * kstride, kn + (size_t)v * N + H.node0, (size_t)H.nint);
+        std::memcpy(base + H.off_ppos, P.ppos.data() + P.tile_pp0[b], 4 * (size_t)(H.nloc - H.nint));
+        uint16_t* srow = reinterpret_cast<uint16_t*>(base + H.off_srow);
+        uint16_t* list = reinterpret_cast<uint16_t*>(base + H.off_list);
+        const uint16_t* iptr = P.inc_ptr.data() + P.tile_loc0[b];
+        const uint16_t* inc = P.inc.data() + (size_t)3 * TT * b;
+        const uint16_t zero_code = (uint16_t)(3 * TT * 8);
+        int32_t row = 0;
+        for (int32_t s = 0; s < H.nslice; ++s) {
+            srow[s] = (uint16_t)row;
+            int32_t w = 0;
+            for (int32_t l = 32 * s; l < std::min(H.nloc, 32 * s + 32); ++l) w = std::max<int32_t>(w, iptr[l + 1] - iptr[l]);
+            for (int32_t j = 0; j < w; ++j)
+                for (int32_t lane = 0; lane < 32; ++lane) {
+                    const int32_t l = 32 * s + lane;
+                    uint16_t code = zero_code;
+                    if (l < H.nloc && iptr[l] + j < iptr[l + 1]) {
+                        const uint16_t c = inc[iptr[l] + j];
+                        code = (uint16_t)((((c & 3) * TT) + (c >> 2)) * 8);
+                    }
+                    list[(size_t)(row + j) * 32 + lane] = code;
+                }
+            row += w;
+        }
+        srow[H.nslice] = (uint16_t)row;
+        if (dtab_native) {
+            double* dt = reinterpret_cast<double*>(base + H.off_dtab);
+            const int32_t np = (H.ntri + 1) & ~1;
+            for (int e = 0; e < 3; ++e)
+                for (int32_t lt = 0; lt < H.ntri; ++lt) dt[(size_t)e * np + lt] = dtab_native[(size_t)e * P.tpad + b * TT + lt];
+        }
+        dir[2 * b] = make_int4((int32_t)(uint32_t)(off[b] >> 4), H.bytes, H.node0, H.nown);
+        dir[2 * b + 1] = make_int4(P.tile_ext0[b], H.next, 0, 0);
+    }
+    return FVM_OK;
+}
+
 // Runs the host planning of fvm_finalize on a mesh WITHOUT a CUDA device and checks the invariants the kernels
 // rely on (tests/test_host_cpu.py).  stats: n_tiles, n_vertices, n_interface, n_partial, n_external, max_local_nodes,
 // n_live_boundary_edges, gather-list entries.
@@ -759,7 +883,9 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     // register-limited to 3 CTAs/SM and like big tiles; the reduced stream wants 8 small CTAs per SM
     const bool full_flux = h->flux.model == FVM_FLUX_DIFF_POWER || h->flux.model == FVM_FLUX_ADVDIFF || h->flux.model == FVM_FLUX_KELLER_SEGEL;
     // (systems: 768 measured best for the 2-species Keller-Segel kernel: 1.20 ms vs 1.45 ms at 1024)
-    int TT = tile_triangles > 0 ? tile_triangles : (neq >= 2 ? 768 : ((geometry_mode == 0 && !full_flux) ? 512 : 1024));
+    // recompute mode (streaming kernel, fvm_rhs_stream.cu): two stages + two contribution buffers per CTA want small tiles
+    int TT = tile_triangles > 0 ? tile_triangles
+                                : (geometry_mode == 1 ? 512 : (neq >= 2 ? 768 : (!full_flux ? 512 : 1024)));
     if (tile_triangles <= 0)
         if (const char* e = getenv("FVM_TILE_TRIANGLES")) TT = atoi(e);
     FVM_REQUIRE(h, TT >= 64 && TT <= 4096 && TT % 64 == 0, "fvm_finalize: tile_triangles must be a multiple of 64 in 64..4096");
@@ -767,6 +893,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     if (h->flux.model == FVM_FLUX_DIFF_TABLE && h->h_dtab.empty())
         return fvm_fail(h, FVM_ERR_STATE, "fvm_finalize: table flux model without fvm_set_flux_table");
     h->geometry_mode = geometry_mode;
+    if (const char* e = getenv("FVM_STREAM_THREADS")) {
+        const int v = atoi(e);
+        if (v == 256 || v == 384 || v == 512) h->stream_threads = v;
+    }
     const double* xy = h->h_xy.data();
     const int32_t* tri = h->h_tri.data();
 
@@ -837,9 +967,9 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     m.n_partial = n_partial;
     if ((rc = fvm_dev_alloc(h, &m.partial, (size_t)n_partial * neq))) return rc;
     // per-node arrays in native order
+    std::vector<double> xyn(2 * N);
+    std::vector<uint8_t> kn((size_t)neq * N);
     {
-        std::vector<double> xyn(2 * N);
-        std::vector<uint8_t> kn((size_t)neq * N);
         std::vector<int32_t> fn((size_t)neq * N);
         std::vector<int32_t> dir;
 #pragma omp parallel for schedule(static)
@@ -871,13 +1001,26 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
             UP(m.src_tab, sn);
         }
     }
+    std::vector<double> dt;
     if (!h->h_dtab.empty()) {
-        std::vector<double> dt((size_t)3 * tpad, 0.0);
+        dt.assign((size_t)3 * tpad, 0.0);
 #pragma omp parallel for schedule(static)
         for (int64_t nt = 0; nt < T; ++nt)
             for (int e = 0; e < 3; ++e) dt[(size_t)e * tpad + nt] = h->h_dtab[3 * (int64_t)told[nt] + e];
         UP(m.dtab, dt);
     }
+    // tile packs of the streaming recompute kernel (geometry_mode 1; big template tiles keep the plain tile kernel)
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (geometry_mode == 1 && TT <= FVM_STREAM_MAX_TT && !getenv("FVM_NO_STREAM")) {
+        std::vector<uint8_t> packs;
+        std::vector<int4> pdir;
+        if ((rc = build_tile_packs(h, P, TT, xyn.data(), kn.data(), dt.empty() ? nullptr : dt.data(), packs, pdir, h->pack_cap))) return rc;
+        if ((rc = fvm_dev_upload(h, &h->d_packs, packs))) return rc;
+        if ((rc = fvm_dev_upload(h, &h->d_pack_dir, pdir))) return rc;
+        h->pack_bytes_total = (int64_t)packs.size();
+        FVM_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vectors die at the end of this block
+    }
+    std::vector<double>().swap(dt);
     UP(m.cond, h->h_cond);
     if ((rc = fvm_dev_upload(h, &h->d_node_old_of_new, h->node_old_of_new))) return rc;
     if ((rc = fvm_dev_upload(h, &h->d_node_new_of_old, h->node_new_of_old))) return rc;
@@ -901,6 +1044,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     if (rc) return rc;
     rc = fvm_launch_volumes(h);
     if (rc) return rc;
+    if (h->d_packs) {
+        if ((rc = fvm_stream_fill_vinv(h))) return rc;
+        h->packs_ready = true;
+    }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
 
     h->stats[0] = n_tiles;

@@ -1,0 +1,44 @@
+"""Experiment driver: tile size x consumer threads of the streaming recompute kernel (fvm_rhs_stream.cu) at 4096^2.
+Checks every configuration against the stored-geometry kernel's du (1e-12) before timing it."""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import fvm_b200 as G
+import bench
+
+nx = int(os.environ.get("SWEEP_NX", "4096"))
+names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["const_recompute"]
+tiles = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "256,384,512,768,1024".split(","))]
+threads = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "256,384,512".split(","))]
+for name in names:
+    flux_f, gmode, layout = bench.VARIANTS[name]
+    prob, _ = bench.lattice_problem(G, nx, nx, flux_f(G))
+    torch.manual_seed(1)
+    u_d = 50.0 * torch.rand(prob.mesh.triangulation.num_points, dtype=torch.float64, device="cuda")
+    p = G.get_cuda_parameters(prob, geometry_mode=0)
+    du_ref = torch.empty_like(u_d)
+    ms, kms = bench.time_rhs(torch, p.engine, u_d, du_ref, 30, 3)
+    print("%-18s stored-geometry reference: %.3f ms/step" % (name, ms), flush=True)
+    # native orders differ between tile sizes: compare in caller order
+    p.engine.rhs_device(du_ref.data_ptr(), u_d.data_ptr(), 0.0, native=False)
+    p.engine.close()
+    for tt in tiles:
+        for th in threads:
+            os.environ["FVM_STREAM_THREADS"] = str(th)
+            try:
+                p = G.get_cuda_parameters(prob, tile_triangles=tt, geometry_mode=gmode)
+            except Exception as e:
+                print("%-18s TT %4d thr %3d  setup failed: %s" % (name, tt, th, e), flush=True)
+                continue
+            eng = p.engine
+            du_d = torch.empty_like(u_d)
+            try:
+                eng.rhs_device(du_d.data_ptr(), u_d.data_ptr(), 0.0, native=False)
+                err = float((du_d - du_ref).abs().max() / du_ref.abs().max())
+                ms, kms = bench.time_rhs(torch, eng, u_d, du_d, 60, 5)
+                print("%-18s TT %4d thr %3d  %.3f ms/step  kernel %.3f ms  rel err vs stored %.2e" % (name, tt, th, ms, kms, err), flush=True)
+            except Exception as e:
+                print("%-18s TT %4d thr %3d  failed: %s" % (name, tt, th, e), flush=True)
+            eng.close()
+            del du_d, p, eng
