@@ -67,9 +67,9 @@ struct DevMesh {
 // node gather list -- as ONE 16-byte aligned record, fetched by a single bulk async copy (cp.async.bulk).
 struct TilePackHdr {  // 64 bytes, section offsets in bytes from the start of the pack
     int32_t node0, nint, nown, nloc;
-    int32_t ntri, next, nslice, bytes;
+    int32_t ntri, flags, nunit, bytes;  // flags bit 0: every interior node is free in every species
     int32_t off_tri, off_xy, off_vinv, off_kind;
-    int32_t off_ppos, off_srow, off_list, off_dtab;
+    int32_t off_ppos, off_urow, off_list, off_dtab;
 };
 #define FVM_STREAM_MAX_TT 2688  // gather codes are 16-bit byte offsets into the contribution planes: 3*TT*8 + 8 <= 65536
 
@@ -215,6 +215,7 @@ struct fvm_ctx {
     int64_t pack_bytes_total = 0;
     bool packs_ready = false;
     int32_t stream_threads = 256;  // consumer threads per CTA of the streaming kernel
+    int32_t stream_occ = 3;        // resident CTAs per SM its register budget is planned for (256-thread variant)
     std::map<const void*, int32_t> occ_cache;  // kernel -> resident CTAs per SM at the configured shared memory
     int32_t sm_count = 148;
 };

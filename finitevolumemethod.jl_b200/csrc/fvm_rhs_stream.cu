@@ -13,9 +13,10 @@
 //   * the CONSUMER warps never touch global memory for inputs: triangle pass (one thread per triangle:
 //     geometry.jl:107-161 recomputed from the staged coordinates, shape functions, three control-volume-edge
 //     fluxes, triangle_contributions.jl:28-35) -> contribution planes in shared memory -> one named barrier ->
-//     node pass (a warp owns 32 consecutive local nodes and walks their gather rows: conflict-free 16-bit
-//     loads of byte offsets into the planes), node pass of source_contributions.jl:33-68 for interior nodes
-//     (coalesced `du` stores), one partial per interface node;
+//     node pass (a warp takes units of 32 consecutive local nodes and walks their gather rows:
+//     coalesced 16-bit loads of byte offsets into the planes; the slots are
+//     edge-coloured at setup so that neither the scatter nor the gather has a bank conflict), node pass of
+//     source_contributions.jl:33-68 for interior nodes (coalesced `du` stores), one partial per interface node;
 //   * the contribution planes are double buffered, so one barrier per tile is enough.
 //
 // No atomics; every output word has one writer and a fixed summation order.
@@ -35,7 +36,8 @@ struct StreamArgs {
     int32_t list_off, count;
     int32_t pack_cap;  // bytes reserved per stage for the pack
     int32_t u_cap;     // doubles reserved per stage for the tile's u values
-    int32_t plane;     // doubles per contribution plane: 3 * TT + 2 (the last two stay zero)
+    int32_t prefetch;  // producer pulls the next tile's pack / u range into L2 one tile ahead
+    int32_t plane;     // doubles per contribution plane: 3 * TT + 16 (the last 16 stay zero: one per bank pair)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,6 +69,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(b))
                  : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -76,14 +81,9 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* b) {
 }
 __device__ __forceinline__ void bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-template <int MODEL, int NEQ, int NCONS>
-struct StreamOcc {
-    // resident CTAs the register budget is planned for (shared memory decides the rest at run time)
-    static constexpr int min_blocks = NCONS >= 512 ? 2 : (NCONS >= 384 ? 2 : 3);
-};
-
-template <int MODEL, int NEQ, int NCONS>
-__global__ void __launch_bounds__(NCONS + SK_PROD, StreamOcc<MODEL, NEQ, NCONS>::min_blocks)
+// OCC = resident CTAs per SM the register budget is planned for (shared memory decides the rest at run time)
+template <int MODEL, int NEQ, int NCONS, int OCC>
+__global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
     rhs_stream_kernel(const DevMesh m, const FluxParams fp, const SourceParams sp, const double t, const double* __restrict__ u,
                       double* __restrict__ du, const StreamArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -105,10 +105,8 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, StreamOcc<MODEL, NEQ, NCONS>:
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (tid < 2 * NEQ) {  // the zero words padded gather entries point at
-        c_s[(tid / NEQ) * cbuf + (tid % NEQ) * a.plane + 3 * TT] = 0.0;
-        c_s[(tid / NEQ) * cbuf + (tid % NEQ) * a.plane + 3 * TT + 1] = 0.0;
-    }
+    if (tid < 2 * NEQ * 16)  // the zero words padded gather entries point at (one per 8-byte bank pair)
+        c_s[(tid / (16 * NEQ)) * cbuf + ((tid / 16) % NEQ) * a.plane + 3 * TT + (tid & 15)] = 0.0;
     __syncthreads();
     const int n_my = ((int)a.count - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
@@ -140,6 +138,17 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, StreamOcc<MODEL, NEQ, NCONS>:
             } else if (lane == 2) {
                 if (n > shift && ((n - shift) & 1)) cp_async8(us + shift + n - 1, usrc + n - 1);
             }
+            if (lane == 3 && a.prefetch && i + 1 < n_my) {
+                // the pack and the u range of the NEXT tile of this CTA go to L2 now, one tile time before their bulk
+                // copies are issued: those then pay an L2 hit instead of the DRAM latency
+                const int npos = pos + gridDim.x;
+                const int ntile = a.list ? __ldg(a.list + a.list_off + npos) : npos;
+                const int4 p0 = __ldg(a.dir + 2 * ntile);
+                bulk_prefetch_l2(a.packs + ((size_t)(uint32_t)p0.x << 4), (uint32_t)p0.y);
+                const uintptr_t ua = (reinterpret_cast<uintptr_t>(u + (size_t)p0.z * NEQ) + 15) & ~(uintptr_t)15;
+                const uintptr_t ue = reinterpret_cast<uintptr_t>(u + (size_t)(p0.z + p0.w) * NEQ) & ~(uintptr_t)15;
+                if (ue > ua) bulk_prefetch_l2(reinterpret_cast<const void*>(ua), (uint32_t)(ue - ua));
+            }
             for (int k = lane; k < next; k += 32) {
                 const int g = __ldg(m.ext_ids + ext0 + k);
 #pragma unroll
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, StreamOcc<MODEL, NEQ, NCONS>:
         const unsigned char* st = stage0 + (size_t)s * stage_bytes;
         const int4 h0 = reinterpret_cast<const int4*>(st)[0], h1 = reinterpret_cast<const int4*>(st)[1];
         const int4 h2 = reinterpret_cast<const int4*>(st)[2], h3 = reinterpret_cast<const int4*>(st)[3];
-        const int node0 = h0.x, nint = h0.y, nloc = h0.w, ntri = h1.x, nslice = h1.z;
+        const int node0 = h0.x, nint = h0.y, nloc = h0.w, ntri = h1.x, nunit = h1.z;
         const ushort4* __restrict__ tri_s = reinterpret_cast<const ushort4*>(st + h2.x);
         const double2* __restrict__ xy_s = reinterpret_cast<const double2*>(st + h2.y);
         const double* __restrict__ us =
@@ -199,26 +208,28 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, StreamOcc<MODEL, NEQ, NCONS>:
                 for (int v = 0; v < NEQ; ++v) Qe[e][v] = qx[v] * G.ey[e] - qy[v] * G.ex[e];  // q . (l n),  l n = (e_y, -e_x)
             }
 #pragma unroll
-            for (int v = 0; v < NEQ; ++v) {  // triangle_contributions.jl:10-25
-                double* cp = cb + v * a.plane + lt;
-                cp[0] = Qe[2][v] - Qe[0][v];
-                cp[TT] = Qe[0][v] - Qe[1][v];
-                cp[2 * TT] = Qe[1][v] - Qe[2][v];
+            for (int v = 0; v < NEQ; ++v) {  // triangle_contributions.jl:10-25; slot positions: see build_tile_packs
+                double* cp = cb + v * a.plane + (lt & ~15);
+                cp[vv.w & 15] = Qe[2][v] - Qe[0][v];
+                cp[TT + ((vv.w >> 4) & 15)] = Qe[0][v] - Qe[1][v];
+                cp[2 * TT + ((vv.w >> 8) & 15)] = Qe[1][v] - Qe[2][v];
             }
         }
         bar_sync(1, NCONS);
 
-        // ---- node pass: a warp owns 32 consecutive local nodes ----------------------------------------
+        // ---- node pass: a warp takes one unit of 32 consecutive local nodes at a time and walks their gather rows
+        // (coalesced 16-bit codes; conflict-free plane reads by the slot colouring) -----------------------------
         const double* __restrict__ vinv_s = reinterpret_cast<const double*>(st + h2.z);
         const uint8_t* __restrict__ kind_s = st + h2.w;
         const int kstride = (nint + 15) & ~15;
         const int32_t* __restrict__ ppos_s = reinterpret_cast<const int32_t*>(st + h3.x);
-        const uint16_t* __restrict__ srow = reinterpret_cast<const uint16_t*>(st + h3.y);
+        const uint16_t* __restrict__ urow = reinterpret_cast<const uint16_t*>(st + h3.y);
         const uint16_t* __restrict__ lst = reinterpret_cast<const uint16_t*>(st + h3.z);
         const unsigned char* cbytes = reinterpret_cast<const unsigned char*>(cb);
+        const bool simple = (h1.y & 1) && sp.model == FVM_SRC_ZERO;
 #pragma unroll 1
-        for (int sl = warp; sl < nslice; sl += NCONS / 32) {
-            const int r0 = srow[sl], r1 = srow[sl + 1];
+        for (int q = warp; q < nunit; q += NCONS / 32) {
+            const int r0 = urow[q], r1 = urow[q + 1];
             const uint16_t* lp = lst + r0 * 32 + lane;
             double acc[NEQ];
 #pragma unroll
@@ -230,29 +241,34 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, StreamOcc<MODEL, NEQ, NCONS>:
                 for (int v = 0; v < NEQ; ++v)
                     acc[v] += *reinterpret_cast<const double*>(cbytes + code + (size_t)v * a.plane * sizeof(double));
             }
-            const int l = sl * 32 + lane;
+            const int l = q * 32 + lane;
             if (l < nint) {  // source_contributions.jl:33-68, finished in place
                 const int g = node0 + l;
-                double tab[NEQ];
-                if (sp.model == FVM_SRC_TABLE) {
-#pragma unroll
-                    for (int v = 0; v < NEQ; ++v) tab[v] = m.src_tab[(size_t)g * NEQ + v];
-                }
                 const double vi = vinv_s[l];
+                if (simple) {  // every interior node of the tile is free and there is no source term
 #pragma unroll
-                for (int v = 0; v < NEQ; ++v) {
-                    const uint8_t kind = kind_s[v * kstride + l];
-                    double out;
-                    if (kind == FVM_NODE_FREE) {
-                        out = acc[v] * vi + source_eval<NEQ>(sp, v, us + l * NEQ, tab);
-                    } else if (kind == FVM_NODE_DUDT) {
-                        const CondFn c = m.cond[v * FVM_MAX_COND_FN + m.fidx[(size_t)v * m.n_nodes + g]];
-                        const double2 X = xy_s[l];
-                        out = cond_eval(c, X.x, X.y, t, us[l * NEQ + v]);
-                    } else {
-                        out = 0.0;  // Dirichlet node, ghost node
+                    for (int v = 0; v < NEQ; ++v) du[(size_t)g * NEQ + v] = acc[v] * vi;
+                } else {
+                    double tab[NEQ];
+                    if (sp.model == FVM_SRC_TABLE) {
+#pragma unroll
+                        for (int v = 0; v < NEQ; ++v) tab[v] = m.src_tab[(size_t)g * NEQ + v];
                     }
-                    du[(size_t)g * NEQ + v] = out;
+#pragma unroll
+                    for (int v = 0; v < NEQ; ++v) {
+                        const uint8_t kind = kind_s[v * kstride + l];
+                        double out;
+                        if (kind == FVM_NODE_FREE) {
+                            out = acc[v] * vi + source_eval<NEQ>(sp, v, us + l * NEQ, tab);
+                        } else if (kind == FVM_NODE_DUDT) {
+                            const CondFn c = m.cond[v * FVM_MAX_COND_FN + m.fidx[(size_t)v * m.n_nodes + g]];
+                            const double2 X = xy_s[l];
+                            out = cond_eval(c, X.x, X.y, t, us[l * NEQ + v]);
+                        } else {
+                            out = 0.0;  // Dirichlet node, ghost node
+                        }
+                        du[(size_t)g * NEQ + v] = out;
+                    }
                 }
             } else if (l < nloc) {
                 const size_t p = (size_t)ppos_s[l - nint] * NEQ;
@@ -273,9 +289,9 @@ __global__ void pack_vinv_kernel(uint8_t* __restrict__ packs, const int4* __rest
     for (int l = threadIdx.x; l < H.nint; l += blockDim.x) vinv[l] = 1.0 / vol[H.node0 + l];
 }
 
-template <int MODEL, int NEQ, int NCONS>
+template <int MODEL, int NEQ, int NCONS, int OCC>
 int32_t launch_stream_t(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
-    auto kern = rhs_stream_kernel<MODEL, NEQ, NCONS>;
+    auto kern = rhs_stream_kernel<MODEL, NEQ, NCONS, OCC>;
     StreamArgs a;
     a.packs = h->d_packs;
     a.dir = h->d_pack_dir;
@@ -284,7 +300,9 @@ int32_t launch_stream_t(fvm_ctx* h, double t, const double* u, double* du, const
     a.count = count;
     a.pack_cap = h->pack_cap;
     a.u_cap = (h->max_nloc * NEQ + 2 + 1) & ~1;
-    a.plane = 3 * h->dm.tile_tris + 2;
+    a.plane = 3 * h->dm.tile_tris + 16;
+    static const bool pf = getenv("FVM_STREAM_PREFETCH") != nullptr;  // measured at 4096^2: no gain (0.349 vs 0.341 ms), off
+    a.prefetch = pf ? 1 : 0;
     const int32_t smem = (int32_t)(2 * NEQ * a.plane * sizeof(double) + SK_STAGES * (a.pack_cap + a.u_cap * sizeof(double)) + 2 * SK_STAGES * sizeof(uint64_t));
     if (smem > 227 * 1024) return fvm_fail(h, FVM_ERR_ARG, "streaming RHS kernel: tile needs more than 227 KB of shared memory; lower tile_triangles");
     int32_t& configured = h->smem_configured[(const void*)kern];
@@ -310,9 +328,11 @@ int32_t launch_stream_t(fvm_ctx* h, double t, const double* u, double* du, const
 template <int MODEL, int NEQ>
 int32_t launch_stream_threads(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
     switch (h->stream_threads) {
-        case 512: return launch_stream_t<MODEL, NEQ, 512>(h, t, u, du, list, off, count);
-        case 384: return launch_stream_t<MODEL, NEQ, 384>(h, t, u, du, list, off, count);
-        default: return launch_stream_t<MODEL, NEQ, 256>(h, t, u, du, list, off, count);
+        case 512: return launch_stream_t<MODEL, NEQ, 512, 2>(h, t, u, du, list, off, count);
+        case 384: return launch_stream_t<MODEL, NEQ, 384, 2>(h, t, u, du, list, off, count);
+        default:
+            if (h->stream_occ == 4) return launch_stream_t<MODEL, NEQ, 256, 4>(h, t, u, du, list, off, count);
+            return launch_stream_t<MODEL, NEQ, 256, 3>(h, t, u, du, list, off, count);
     }
 }
 

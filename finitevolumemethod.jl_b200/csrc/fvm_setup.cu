@@ -24,6 +24,19 @@
 
 static thread_local std::string g_create_err;
 
+// FVM_TIMING=1: wall-clock of the phases of fvm_finalize on stderr
+#include <chrono>
+struct PhaseTimer {
+    bool on = getenv("FVM_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fvm_finalize] %-28s %8.3f s\n", what, std::chrono::duration<double>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 int32_t fvm_fail(fvm_ctx* h, int32_t code, const std::string& msg) {
     if (h) h->err = msg;
     else g_create_err = msg;
@@ -328,6 +341,7 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     const int neq = h->neq;
     const double* xy = h->h_xy.data();
     const int32_t* tri = h->h_tri.data();
+    PhaseTimer tm;
     // ---- 1. Hilbert sort of triangles by centroid ------------------------------------
     double minx = xy[0], maxx = xy[0], miny = xy[1], maxy = xy[1];
     for (int64_t i = 0; i < N; ++i) {
@@ -357,6 +371,7 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     P.n_tiles = n_tiles;
     FVM_REQUIRE(h, n_tiles < INT32_MAX, "too many tiles");
 
+    tm.lap("hilbert sort");
     if (!h->h_ghost.empty())  // ghost nodes are neither free nor Dirichlet
         for (int v = 0; v < neq; ++v)
             for (int64_t i = 0; i < N; ++i)
@@ -409,6 +424,7 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
         edge_rot[k] = all_rot[live_edges[k]];
     }
 
+    tm.lap("boundary edges");
     // ---- 3. node classification and tile-major renumbering -------------------------------
     std::vector<int32_t> min_tile(N, INT32_MAX), max_tile(N, -1);
     for (int64_t nt = 0; nt < T; ++nt) {
@@ -459,6 +475,7 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     const int32_t n_vertices = h->dm.n_vertices;
     P.n_vertices = n_vertices;
 
+    tm.lap("node renumbering");
     // ---- 4. tile-local indices, gather lists, interface bookkeeping -----------------------
     const int64_t tpad = n_tiles * TT;
     P.tpad = tpad;
@@ -571,6 +588,7 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     }
     tile_pp0[n_tiles] = (int32_t)ppos.size();
 
+    tm.lap("tile lists");
     // ---- 5. live boundary-edge records ------------------------------------------------------
     std::vector<BndEdge>& bnd = P.bnd;
     bnd.assign(live_edges.size(), BndEdge{});
@@ -605,11 +623,26 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
 
 // ---- tile packs of the streaming recompute kernel (fvm_rhs_stream.cu) ---------------------------------------------
 // One 16-byte aligned record per tile (TilePackHdr + sections), built tile-parallel on the host.  The node gather
-// list is re-laid out for a warp-per-32-nodes pass: slice s covers local nodes 32 s .. 32 s + 31 and owns
-// srow[s+1] - srow[s] rows of 32 uint16 codes (entry j of lane l at row (srow[s] + j), column l), each code the BYTE
-// offset of a vertex contribution inside the tile's contribution plane ((slot * TT + local_triangle) * 8); padded
-// entries point at a zero word behind the plane.  Same per-node order as the CSR list (ascending triangle).
+// list is re-laid out in UNITS of 32 consecutive local nodes (one warp of the node pass): unit q owns
+// urow[q+1] - urow[q] rows of 32 uint16 codes, entry j of node 32 q + i at row urow[q] + j, column i.
+// Each code is the BYTE offset of a vertex
+// contribution inside the tile's contribution plane; padded entries point at a zero word behind the plane.
+// Per-node order = the CSR list (ascending triangle).
+//
+// Bank-conflict-free by construction: the contribution of (triangle lt, slot s) lives in the 16-double block
+// s * TT + (lt & ~15) at position color(lt, s).  A half-warp of the triangle pass (16 consecutive lt, one slot) writes one
+// block; a half-warp of the node pass (half a unit, one gather row) reads 16 contributions.  Taking the
+// write groups and the read groups as the two sides of a bipartite multigraph (one edge per contribution, degree <= 16),
+// a proper edge colouring with 16 colours (Koenig) puts every group's 16 accesses in 16 different 8-byte bank pairs:
+// neither the scatter nor the gather has a shared-memory bank conflict.  The 4-bit colours travel in the spare 16 bits
+// of the triangle's ushort4 record.
 static inline int64_t align16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+static inline int32_t unit_rows(const uint16_t* iptr, int32_t nloc, int32_t q) {
+    int32_t w = 0;
+    for (int32_t l = 32 * q; l < std::min(nloc, 32 * q + 32); ++l) w = std::max<int32_t>(w, iptr[l + 1] - iptr[l]);
+    return w;
+}
 
 static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, const double* xyn, const uint8_t* kn,
                                 const double* dtab_native /* [3][tpad] or null */, std::vector<uint8_t>& packs,
@@ -623,13 +656,9 @@ static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, con
         const int32_t nint = P.tile_nint[b], nloc = P.tile_nloc[b];
         const int32_t ntri = (int32_t)std::min<int64_t>(TT, T - b * TT);
         const uint16_t* iptr = P.inc_ptr.data() + P.tile_loc0[b];
-        const int32_t nslice = (nloc + 31) / 32;
+        const int32_t nunit = (nloc + 31) / 32;
         int32_t rows = 0;
-        for (int32_t s = 0; s < nslice; ++s) {
-            int32_t w = 0;
-            for (int32_t l = 32 * s; l < std::min(nloc, 32 * s + 32); ++l) w = std::max<int32_t>(w, iptr[l + 1] - iptr[l]);
-            rows += w;
-        }
+        for (int32_t q = 0; q < nunit; ++q) rows += unit_rows(iptr, nloc, q);
         nrows[b] = rows;
         int64_t sz = sizeof(TilePackHdr);
         sz = align16(sz + 8 * (int64_t)ntri);                  // tri: ushort4
@@ -637,7 +666,7 @@ static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, con
         sz = align16(sz + 8 * (int64_t)nint);                  // 1 / V
         sz = align16(sz + (int64_t)neq * align16(nint));       // kind: [neq][align16(nint)]
         sz = align16(sz + 4 * (int64_t)(nloc - nint));         // partial slots
-        sz = align16(sz + 2 * (int64_t)(nslice + 1));          // slice row offsets
+        sz = align16(sz + 2 * (int64_t)(nunit + 1));           // unit row offsets
         sz = align16(sz + 64 * (int64_t)rows);                 // gather rows
         if (dtab_native) sz = align16(sz + 24 * (int64_t)((ntri + 1) & ~1));
         off[b + 1] = sz;
@@ -649,80 +678,159 @@ static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, con
         off[b + 1] += off[b];
     }
     FVM_REQUIRE(h, (off[n_tiles] >> 4) < (int64_t)UINT32_MAX, "fvm_finalize: tile packs exceed 64 GB");
-    packs.assign((size_t)off[n_tiles], 0);
+    packs.resize((size_t)off[n_tiles]);
     dir.resize(2 * n_tiles);
-#pragma omp parallel for schedule(static)
-    for (int64_t b = 0; b < n_tiles; ++b) {
-        uint8_t* base = packs.data() + off[b];
-        TilePackHdr H{};
-        H.node0 = P.tile_node0[b];
-        H.nint = P.tile_nint[b];
-        H.nown = P.tile_nown[b];
-        H.nloc = P.tile_nloc[b];
-        H.ntri = (int32_t)std::min<int64_t>(TT, T - b * TT);
-        H.next = H.nloc - H.nown;
-        H.nslice = (H.nloc + 31) / 32;
-        H.bytes = (int32_t)(off[b + 1] - off[b]);
-        int64_t o = sizeof(TilePackHdr);
-        H.off_tri = (int32_t)o;
-        o = align16(o + 8 * (int64_t)H.ntri);
-        H.off_xy = (int32_t)o;
-        o = align16(o + 16 * (int64_t)H.nloc);
-        H.off_vinv = (int32_t)o;
-        o = align16(o + 8 * (int64_t)H.nint);
-        H.off_kind = (int32_t)o;
-        const int32_t kstride = (int32_t)align16(H.nint);
-        o = align16(o + (int64_t)neq * kstride);
-        H.off_ppos = (int32_t)o;
-        o = align16(o + 4 * (int64_t)(H.nloc - H.nint));
-        H.off_srow = (int32_t)o;
-        o = align16(o + 2 * (int64_t)(H.nslice + 1));
-        H.off_list = (int32_t)o;
-        o = align16(o + 64 * (int64_t)nrows[b]);
-        H.off_dtab = dtab_native ? (int32_t)o : 0;
-        std::memcpy(base, &H, sizeof(H));
-        std::memcpy(base + H.off_tri, P.tri_loc.data() + b * TT, 8 * (size_t)H.ntri);
-        double* xy = reinterpret_cast<double*>(base + H.off_xy);
-        for (int32_t l = 0; l < H.nloc; ++l) {
-            const int32_t g = l < H.nown ? H.node0 + l : P.ext_ids[P.tile_ext0[b] + (l - H.nown)];
-            xy[2 * l] = xyn[2 * (size_t)g];
-            xy[2 * l + 1] = xyn[2 * (size_t)g + 1];
-        }
-        // 1/V is written on the device once the control volumes exist (fvm_stream_fill_vinv)
-        for (int v = 0; v < neq; ++v)
-            std::memcpy(base + H.off_kind + (size_t)v * kstride, kn + (size_t)v * N + H.node0, (size_t)H.nint);
-        std::memcpy(base + H.off_ppos, P.ppos.data() + P.tile_pp0[b], 4 * (size_t)(H.nloc - H.nint));
-        uint16_t* srow = reinterpret_cast<uint16_t*>(base + H.off_srow);
-        uint16_t* list = reinterpret_cast<uint16_t*>(base + H.off_list);
-        const uint16_t* iptr = P.inc_ptr.data() + P.tile_loc0[b];
-        const uint16_t* inc = P.inc.data() + (size_t)3 * TT * b;
-        const uint16_t zero_code = (uint16_t)(3 * TT * 8);
-        int32_t row = 0;
-        for (int32_t s = 0; s < H.nslice; ++s) {
-            srow[s] = (uint16_t)row;
-            int32_t w = 0;
-            for (int32_t l = 32 * s; l < std::min(H.nloc, 32 * s + 32); ++l) w = std::max<int32_t>(w, iptr[l + 1] - iptr[l]);
-            for (int32_t j = 0; j < w; ++j)
-                for (int32_t lane = 0; lane < 32; ++lane) {
-                    const int32_t l = 32 * s + lane;
-                    uint16_t code = zero_code;
-                    if (l < H.nloc && iptr[l] + j < iptr[l + 1]) {
-                        const uint16_t c = inc[iptr[l] + j];
-                        code = (uint16_t)((((c & 3) * TT) + (c >> 2)) * 8);
-                    }
-                    list[(size_t)(row + j) * 32 + lane] = code;
+#pragma omp parallel
+    {
+        // scratch of the edge colouring, reused from tile to tile
+        std::vector<int16_t> colL, colR;  // [vertex][colour] -> edge using that colour there (or -1)
+        std::vector<int32_t> eL, eR, path;
+        std::vector<int8_t> ecol;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            uint8_t* base = packs.data() + off[b];
+            std::memset(base, 0, (size_t)(off[b + 1] - off[b]));
+            TilePackHdr H{};
+            H.node0 = P.tile_node0[b];
+            H.nint = P.tile_nint[b];
+            H.nown = P.tile_nown[b];
+            H.nloc = P.tile_nloc[b];
+            H.ntri = (int32_t)std::min<int64_t>(TT, T - b * TT);
+            H.nunit = (H.nloc + 31) / 32;
+            H.bytes = (int32_t)(off[b + 1] - off[b]);
+            int64_t o = sizeof(TilePackHdr);
+            H.off_tri = (int32_t)o;
+            o = align16(o + 8 * (int64_t)H.ntri);
+            H.off_xy = (int32_t)o;
+            o = align16(o + 16 * (int64_t)H.nloc);
+            H.off_vinv = (int32_t)o;
+            o = align16(o + 8 * (int64_t)H.nint);
+            H.off_kind = (int32_t)o;
+            const int32_t kstride = (int32_t)align16(H.nint);
+            o = align16(o + (int64_t)neq * kstride);
+            H.off_ppos = (int32_t)o;
+            o = align16(o + 4 * (int64_t)(H.nloc - H.nint));
+            H.off_urow = (int32_t)o;
+            o = align16(o + 2 * (int64_t)(H.nunit + 1));
+            H.off_list = (int32_t)o;
+            o = align16(o + 64 * (int64_t)nrows[b]);
+            H.off_dtab = dtab_native ? (int32_t)o : 0;
+            std::memcpy(base, &H, sizeof(H));
+            ushort4* tri_out = reinterpret_cast<ushort4*>(base + H.off_tri);
+            std::memcpy(tri_out, P.tri_loc.data() + b * TT, 8 * (size_t)H.ntri);
+            double* xy = reinterpret_cast<double*>(base + H.off_xy);
+            for (int32_t l = 0; l < H.nloc; ++l) {
+                const int32_t g = l < H.nown ? H.node0 + l : P.ext_ids[P.tile_ext0[b] + (l - H.nown)];
+                xy[2 * l] = xyn[2 * (size_t)g];
+                xy[2 * l + 1] = xyn[2 * (size_t)g + 1];
+            }
+            // 1/V is written on the device once the control volumes exist (fvm_stream_fill_vinv)
+            bool all_free = true;
+            for (int v = 0; v < neq; ++v) {
+                std::memcpy(base + H.off_kind + (size_t)v * kstride, kn + (size_t)v * N + H.node0, (size_t)H.nint);
+                for (int32_t l = 0; l < H.nint; ++l) all_free = all_free && kn[(size_t)v * N + H.node0 + l] == FVM_NODE_FREE;
+            }
+            reinterpret_cast<TilePackHdr*>(base)->flags = all_free ? 1 : 0;
+            std::memcpy(base + H.off_ppos, P.ppos.data() + P.tile_pp0[b], 4 * (size_t)(H.nloc - H.nint));
+            uint16_t* urow = reinterpret_cast<uint16_t*>(base + H.off_urow);
+            uint16_t* list = reinterpret_cast<uint16_t*>(base + H.off_list);
+            const uint16_t* iptr = P.inc_ptr.data() + P.tile_loc0[b];
+            const uint16_t* inc = P.inc.data() + (size_t)3 * TT * b;
+            int32_t row = 0;
+            for (int32_t q = 0; q < H.nunit; ++q) {
+                urow[q] = (uint16_t)row;
+                row += unit_rows(iptr, H.nloc, q);
+            }
+            urow[H.nunit] = (uint16_t)row;
+            // ---- bipartite edge colouring: left = write groups (slot, lt / 16), right = read groups (gather rows) ----
+            const int32_t nG = TT / 16, nL = 3 * nG, nR = 2 * row, nE = 3 * H.ntri;
+            colL.assign((size_t)nL * 16, -1);
+            colR.assign((size_t)std::max(nR, 1) * 16, -1);
+            eL.resize(nE);
+            eR.resize(nE);
+            ecol.assign(nE, -1);
+            for (int32_t l = 0; l < H.nloc; ++l)
+                for (int32_t q = iptr[l]; q < iptr[l + 1]; ++q) {
+                    const uint16_t c = inc[q];
+                    const int32_t lt = c >> 2, slot = c & 3, e = 3 * lt + slot;
+                    eL[e] = slot * nG + (lt >> 4);
+                    eR[e] = 2 * (urow[l >> 5] + (q - iptr[l])) + ((l >> 4) & 1);
                 }
-            row += w;
+            for (int32_t e = 0; e < nE; ++e) {
+                int16_t* cl = colL.data() + (size_t)eL[e] * 16;
+                int16_t* cr = colR.data() + (size_t)eR[e] * 16;
+                int ca = -1, cbb = -1, both = -1;
+                for (int c = 0; c < 16; ++c) {
+                    const bool fl = cl[c] < 0, fr = cr[c] < 0;
+                    if (fl && fr) {
+                        both = c;
+                        break;
+                    }
+                    if (fl && ca < 0) ca = c;
+                    if (fr && cbb < 0) cbb = c;
+                }
+                if (both < 0) {  // ca free on the left, cbb free on the right: flip the ca/cbb path that starts at the right end
+                    path.clear();
+                    int32_t cur = eR[e];
+                    bool right = true;
+                    int want = ca;
+                    for (;;) {
+                        const int16_t e1 = right ? colR[(size_t)cur * 16 + want] : colL[(size_t)cur * 16 + want];
+                        if (e1 < 0) break;
+                        path.push_back(e1);
+                        cur = right ? eL[e1] : eR[e1];
+                        right = !right;
+                        want = want == ca ? cbb : ca;
+                    }
+                    for (int32_t e1 : path) {
+                        colL[(size_t)eL[e1] * 16 + ecol[e1]] = -1;
+                        colR[(size_t)eR[e1] * 16 + ecol[e1]] = -1;
+                    }
+                    for (int32_t e1 : path) {
+                        ecol[e1] = (int8_t)(ecol[e1] == ca ? cbb : ca);
+                        colL[(size_t)eL[e1] * 16 + ecol[e1]] = (int16_t)e1;
+                        colR[(size_t)eR[e1] * 16 + ecol[e1]] = (int16_t)e1;
+                    }
+                    both = ca;
+                }
+                ecol[e] = (int8_t)both;
+                cl[both] = (int16_t)e;
+                cr[both] = (int16_t)e;
+            }
+            for (int32_t lt = 0; lt < H.ntri; ++lt)
+                tri_out[lt].w = (uint16_t)(ecol[3 * lt] | (ecol[3 * lt + 1] << 4) | (ecol[3 * lt + 2] << 8));
+            for (int32_t q = 0; q < H.nunit; ++q)
+                for (int32_t r = urow[q]; r < urow[q + 1]; ++r)
+                    for (int32_t half = 0; half < 2; ++half) {
+                        // padded entries of this read group share a zero word in a bank pair no real entry of the group uses
+                        const int16_t* cr = colR.data() + (size_t)(2 * r + half) * 16;
+                        int freec = 0;
+                        for (int c = 0; c < 16; ++c)
+                            if (cr[c] < 0) {
+                                freec = c;
+                                break;
+                            }
+                        const int32_t j = r - urow[q];
+                        for (int32_t i = 16 * half; i < 16 * half + 16; ++i) {
+                            const int32_t l = 32 * q + i;
+                            uint16_t code = (uint16_t)((3 * TT + freec) * 8);
+                            if (l < H.nloc && iptr[l] + j < iptr[l + 1]) {
+                                const uint16_t c = inc[iptr[l] + j];
+                                const int32_t lt = c >> 2, slot = c & 3;
+                                code = (uint16_t)((slot * TT + (lt & ~15) + ecol[3 * lt + slot]) * 8);
+                            }
+                            list[(size_t)r * 32 + i] = code;
+                        }
+                    }
+            if (dtab_native) {
+                double* dt = reinterpret_cast<double*>(base + H.off_dtab);
+                const int32_t np = (H.ntri + 1) & ~1;
+                for (int e = 0; e < 3; ++e)
+                    for (int32_t lt = 0; lt < H.ntri; ++lt) dt[(size_t)e * np + lt] = dtab_native[(size_t)e * P.tpad + b * TT + lt];
+            }
+            dir[2 * b] = make_int4((int32_t)(uint32_t)(off[b] >> 4), H.bytes, H.node0, H.nown);
+            dir[2 * b + 1] = make_int4(P.tile_ext0[b], H.nloc - H.nown, 0, 0);
         }
-        srow[H.nslice] = (uint16_t)row;
-        if (dtab_native) {
-            double* dt = reinterpret_cast<double*>(base + H.off_dtab);
-            const int32_t np = (H.ntri + 1) & ~1;
-            for (int e = 0; e < 3; ++e)
-                for (int32_t lt = 0; lt < H.ntri; ++lt) dt[(size_t)e * np + lt] = dtab_native[(size_t)e * P.tpad + b * TT + lt];
-        }
-        dir[2 * b] = make_int4((int32_t)(uint32_t)(off[b] >> 4), H.bytes, H.node0, H.nown);
-        dir[2 * b + 1] = make_int4(P.tile_ext0[b], H.next, 0, 0);
     }
     return FVM_OK;
 }
@@ -863,6 +971,76 @@ extern "C" int32_t fvm_plan_selftest(const double* xy, int64_t N, const int32_t*
         }
     for (int64_t s = 0; s < P.n_partial; ++s)
         if (!slot_used[s]) return bad("an allocated partial slot has no writer");
+    // tile packs of the streaming kernel: every contribution is gathered exactly once by the node it belongs to, and
+    // neither the write groups (16 consecutive triangles, one slot) nor the read groups (16 consecutive local nodes,
+    // one gather row) touch an 8-byte bank pair twice
+    if (TT <= FVM_STREAM_MAX_TT) {
+        std::vector<double> xyn(2 * N);
+        std::vector<uint8_t> kn((size_t)neq * N, 0);
+        for (int64_t g = 0; g < N; ++g) {
+            xyn[2 * g] = xy[2 * (int64_t)h->node_old_of_new[g]];
+            xyn[2 * g + 1] = xy[2 * (int64_t)h->node_old_of_new[g] + 1];
+        }
+        std::vector<uint8_t> packs;
+        std::vector<int4> pdir;
+        int32_t cap = 0;
+        rc = build_tile_packs(h, P, TT, xyn.data(), kn.data(), nullptr, packs, pdir, cap);
+        if (rc) return fvm_fail(nullptr, rc, h->err);
+        for (int64_t b = 0; b < P.n_tiles; ++b) {
+            const uint8_t* base = packs.data() + ((size_t)(uint32_t)pdir[2 * b].x << 4);
+            TilePackHdr H;
+            std::memcpy(&H, base, sizeof(H));
+            const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
+            if (H.node0 != P.tile_node0[b] || H.nint != P.tile_nint[b] || H.nown != P.tile_nown[b] || H.nloc != P.tile_nloc[b] ||
+                H.ntri != t1 - t0 || H.bytes != pdir[2 * b].y || H.bytes > cap || (H.bytes & 15) || pdir[2 * b].z != H.node0 ||
+                pdir[2 * b].w != H.nown || pdir[2 * b + 1].y != H.nloc - H.nown)
+                return bad("tile pack header does not match the plan");
+            const ushort4* tq = reinterpret_cast<const ushort4*>(base + H.off_tri);
+            const double* pxy = reinterpret_cast<const double*>(base + H.off_xy);
+            const uint16_t* urow = reinterpret_cast<const uint16_t*>(base + H.off_urow);
+            const uint16_t* list = reinterpret_cast<const uint16_t*>(base + H.off_list);
+            for (int32_t l = 0; l < H.nloc; ++l) {
+                const int32_t g = l < H.nown ? H.node0 + l : P.ext_ids[P.tile_ext0[b] + (l - H.nown)];
+                if (pxy[2 * l] != xyn[2 * (size_t)g] || pxy[2 * l + 1] != xyn[2 * (size_t)g + 1]) return bad("tile pack coordinates are wrong");
+            }
+            // write groups
+            std::vector<int32_t> owner((size_t)3 * TT, -1);  // contribution slot -> 3 * lt + slot
+            for (int32_t lt = 0; lt < H.ntri; ++lt) {
+                if (tq[lt].x != P.tri_loc[t0 + lt].x || tq[lt].y != P.tri_loc[t0 + lt].y || tq[lt].z != P.tri_loc[t0 + lt].z) return bad("tile pack triangle ids are wrong");
+                for (int sl = 0; sl < 3; ++sl) {
+                    const int32_t pos = sl * TT + (lt & ~15) + ((tq[lt].w >> (4 * sl)) & 15);
+                    if (owner[pos] >= 0) return bad("two contributions of a write group share a slot (bank conflict)");
+                    owner[pos] = 3 * lt + sl;
+                }
+            }
+            // read groups: one gather row of half a 32-node unit
+            std::vector<uint8_t> got((size_t)3 * TT, 0);
+            if (H.nunit != (H.nloc + 31) / 32 || urow[0] != 0) return bad("tile pack unit table is wrong");
+            for (int32_t q = 0; q < H.nunit; ++q)
+                for (int32_t r = urow[q]; r < urow[q + 1]; ++r)
+                    for (int half = 0; half < 2; ++half) {
+                        int used[16] = {0}, padcode = -1;
+                        for (int i = 16 * half; i < 16 * half + 16; ++i) {
+                            const int32_t code = list[(size_t)r * 32 + i];
+                            if (code & 7) return bad("gather code is not a multiple of 8");
+                            const int32_t pos = code >> 3, l = 32 * q + i;
+                            if (pos >= 3 * TT) {  // padded entry: one of the 16 zero words
+                                if (pos >= 3 * TT + 16 || (padcode >= 0 && padcode != code)) return bad("bad padded gather entry");
+                                padcode = code;
+                                continue;
+                            }
+                            if (l >= H.nloc || owner[pos] < 0 || got[pos]++) return bad("gather entry points at no contribution or at one already gathered");
+                            const int32_t lt = owner[pos] / 3, slot = owner[pos] % 3;
+                            if ((slot == 0 ? tq[lt].x : slot == 1 ? tq[lt].y : tq[lt].z) != l) return bad("gather entry belongs to another node");
+                            if (used[pos & 15]++) return bad("two entries of a read group share a bank pair");
+                        }
+                        if (padcode >= 0 && used[(padcode >> 3) & 15]) return bad("padded entries share a bank pair with a real entry");
+                    }
+            for (int32_t lt = 0; lt < H.ntri; ++lt)
+                for (int sl = 0; sl < 3; ++sl)
+                    if (!got[sl * TT + (lt & ~15) + ((tq[lt].w >> (4 * sl)) & 15)]) return bad("a contribution is never gathered");
+        }
+    }
     stats[0] = P.n_tiles;
     stats[1] = P.n_vertices;
     stats[2] = P.n_ifc;
@@ -897,12 +1075,15 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         const int v = atoi(e);
         if (v == 256 || v == 384 || v == 512) h->stream_threads = v;
     }
+    if (const char* e = getenv("FVM_STREAM_OCC")) h->stream_occ = atoi(e) == 4 ? 4 : 3;
     const double* xy = h->h_xy.data();
     const int32_t* tri = h->h_tri.data();
 
     HostPlan P;
+    PhaseTimer tm;
     int32_t rc_plan = plan_host(h, TT, P);
     if (rc_plan) return rc_plan;
+    tm.lap("plan_host total");
     const int64_t n_tiles = P.n_tiles, tpad = P.tpad, n_partial = P.n_partial;
     const int32_t n_vertices = P.n_vertices, n_ifc = P.n_ifc, max_nloc = P.max_nloc;
     const int32_t* told = h->tri_old_of_new.data();
@@ -1009,6 +1190,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
             for (int e = 0; e < 3; ++e) dt[(size_t)e * tpad + nt] = h->h_dtab[3 * (int64_t)told[nt] + e];
         UP(m.dtab, dt);
     }
+    tm.lap("upload + node arrays");
     // tile packs of the streaming recompute kernel (geometry_mode 1; big template tiles keep the plain tile kernel)
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (geometry_mode == 1 && TT <= FVM_STREAM_MAX_TT && !getenv("FVM_NO_STREAM")) {
@@ -1021,6 +1203,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         FVM_CUDA(h, cudaStreamSynchronize(h->stream));  // the host vectors die at the end of this block
     }
     std::vector<double>().swap(dt);
+    tm.lap("tile packs");
     UP(m.cond, h->h_cond);
     if ((rc = fvm_dev_upload(h, &h->d_node_old_of_new, h->node_old_of_new))) return rc;
     if ((rc = fvm_dev_upload(h, &h->d_node_new_of_old, h->node_new_of_old))) return rc;
@@ -1049,6 +1232,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         h->packs_ready = true;
     }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    tm.lap("device geometry + volumes");
 
     h->stats[0] = n_tiles;
     h->stats[1] = TT;

@@ -119,11 +119,12 @@ int32_t fvm_set_source_table(fvm_handle h, const double* s_node /* [N][neq] */);
 
 /* Freezes the mesh: Hilbert-sorts triangles into tiles, renumbers nodes tile-major, builds the
  * per-tile gather lists that make the scatter deterministic (no fp64 atomics), computes the
- * geometry SoA on the device.  Options: tile_triangles (0 = default 1024),
+ * geometry SoA on the device.  Options: tile_triangles (0 = measured default per kernel),
  * geometry_mode 0 = stored SoA (north_star layout), 1 = recomputed from vertex coordinates. */
 int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t geometry_mode);
 /* Host-only self-check of the planning fvm_finalize does before its first device call (Hilbert tiling, tile-major
- * renumbering, tile-local indices, gather lists, interface / partial-slot bookkeeping, live boundary edges): runs it
+ * renumbering, tile-local indices, gather lists, interface / partial-slot bookkeeping, live boundary edges, and the
+ * tile packs of the streaming recompute kernel incl. their bank-conflict-free slot colouring): runs it
  * on the given mesh without a CUDA device and verifies the invariants the kernels rely on.  node_kind: [neq][N]
  * fvm_node_kind values or NULL (all free).  stats[8]: n_tiles, n_vertices, n_interface, n_partial, n_external,
  * max_local_nodes, n_live_boundary_edges, gather-list entries (= 3 T). */

@@ -10,12 +10,28 @@ import bench
 nx = int(os.environ.get("SWEEP_NX", "4096"))
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["const_recompute"]
 tiles = [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "256,384,512,768,1024".split(","))]
-threads = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "256,384,512".split(","))]
+threads = [int(x) for x in (sys.argv[3].split(",") if len(sys.argv) > 3 else "256,384,512".split(","))]  # 2564 = 256 threads, 4 CTAs/SM register budget
+def system_problem():
+    """BASELINE config 4: 2-species Keller-Segel FVMSystem, all-Neumann zero flux."""
+    tri = G.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, nx, nx, single_boundary=True)
+    mesh = G.FVMGeometry(tri)
+    N = tri.num_points
+    ks, kss = G.KellerSegelFlux(4.0, 1.0), G.KellerSegelSource(0.1)
+    BC = G.BoundaryConditions(mesh, G.Const(0.0), G.Neumann)
+    pu = G.FVMProblem(mesh, BC, flux_function=ks, source_function=kss, initial_condition=np.zeros(N), final_time=1.0)
+    pv = G.FVMProblem(mesh, BC, flux_function=ks, source_function=kss, initial_condition=np.zeros(N), final_time=1.0)
+    return G.FVMSystem(pu, pv)
+
+
 for name in names:
-    flux_f, gmode, layout = bench.VARIANTS[name]
-    prob, _ = bench.lattice_problem(G, nx, nx, flux_f(G))
     torch.manual_seed(1)
-    u_d = 50.0 * torch.rand(prob.mesh.triangulation.num_points, dtype=torch.float64, device="cuda")
+    if name == "system":
+        prob, gmode = system_problem(), 1
+        u_d = 0.01 * torch.rand(2 * prob.mesh.triangulation.num_points, dtype=torch.float64, device="cuda")
+    else:
+        flux_f, gmode, layout = bench.VARIANTS[name]
+        prob, _ = bench.lattice_problem(G, nx, nx, flux_f(G))
+        u_d = 50.0 * torch.rand(prob.mesh.triangulation.num_points, dtype=torch.float64, device="cuda")
     p = G.get_cuda_parameters(prob, geometry_mode=0)
     du_ref = torch.empty_like(u_d)
     ms, kms = bench.time_rhs(torch, p.engine, u_d, du_ref, 30, 3)
@@ -25,7 +41,8 @@ for name in names:
     p.engine.close()
     for tt in tiles:
         for th in threads:
-            os.environ["FVM_STREAM_THREADS"] = str(th)
+            os.environ["FVM_STREAM_THREADS"] = str(th if th != 2564 else 256)
+            os.environ["FVM_STREAM_OCC"] = "4" if th == 2564 else "3"
             try:
                 p = G.get_cuda_parameters(prob, tile_triangles=tt, geometry_mode=gmode)
             except Exception as e:
