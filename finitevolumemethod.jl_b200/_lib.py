@@ -53,6 +53,7 @@ _SIGS = {
     "fvm_set_profiling": [H, C.c_int32],
     "fvm_get_profile": [H, c_dp, c_lp],
     "fvm_get_geometry": [H, c_dp, c_dp, c_dp, c_dp, c_dp],
+    "fvm_check_recompute_geometry": [H, c_lp],
     "fvm_get_permutation": [H, c_ip, c_ip],
     "fvm_get_stats": [H, c_lp],
     "fvm_assemble": [H, C.c_int32, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int32],

@@ -49,8 +49,10 @@ struct TriGeom {
     double ex[3], ey[3];  // centroid - edge midpoint; length-scaled normal is (ey, -ex)
 };
 
-// /root/reference/src/geometry.jl:107-161, same operation order.
-template <bool EXACT>
+// /root/reference/src/geometry.jl:107-161, same operation order.  EXACT: every operation individually rounded (IEEE
+// divisions).  !EXACT: contracted FMAs where the result is provably the same, a Newton reciprocal of Delta, and
+// EXACT_S selects how s1..s6 are formed from it (s7..s9 are always the correctly rounded quotients).
+template <bool EXACT, bool EXACT_S = EXACT>
 __device__ __forceinline__ void tri_geometry(double px, double py, double qx, double qy, double rx, double ry,
                                              TriGeom& G, double* S /* 3 sub-cv areas or nullptr */) {
     using A = Ar<EXACT>;
@@ -100,16 +102,33 @@ __device__ __forceinline__ void tri_geometry(double px, double py, double qx, do
         G.s[7] = A::div(n8, D);
         G.s[8] = A::div(n9, D);
     } else {
-        const double iD = rcp_newton(D);  // num * (1/D) differs from num / D by ~1 ulp (tolerance 1e-12)
-        G.s[0] = (qy - ry) * iD;
-        G.s[1] = (ry - py) * iD;
-        G.s[2] = (py - qy) * iD;
-        G.s[3] = (rx - qx) * iD;
-        G.s[4] = (px - rx) * iD;
-        G.s[5] = (qx - px) * iD;
-        G.s[6] = n7 * iD;
-        G.s[7] = n8 * iD;
-        G.s[8] = n9 * iD;
+        // s1..s6 = num * RN(1/D): within an ulp of the reference's quotient, harmless (6.5e-16 on du at 4096^2).
+        // s7..s9 ~ |x| / h are different: gamma = s7 u_i + s8 u_j + s9 u_k cancels from ~|u| |x| / h down to |u|, so an ulp
+        // there is 2e-12 in a u-dependent flux on the 4096^2 lattice.  They get the correctly rounded quotient without
+        // the IEEE division sequence (Markstein): with r = RN(1/D) and q0 = RN(n r), RN(q0 + r RN(n - D q0)) = RN(n / D)
+        const double iD = rcp_newton(D);
+        auto quot = [&](double n) {
+            const double q0 = n * iD;
+            return fma(fma(-D, q0, n), iD, q0);
+        };
+        if constexpr (EXACT_S) {  // u-dependent fluxes: alpha x + beta y + gamma cancels by |x| / h, every ulp of s counts
+            G.s[0] = quot(qy - ry);
+            G.s[1] = quot(ry - py);
+            G.s[2] = quot(py - qy);
+            G.s[3] = quot(rx - qx);
+            G.s[4] = quot(px - rx);
+            G.s[5] = quot(qx - px);
+        } else {
+            G.s[0] = (qy - ry) * iD;
+            G.s[1] = (ry - py) * iD;
+            G.s[2] = (py - qy) * iD;
+            G.s[3] = (rx - qx) * iD;
+            G.s[4] = (px - rx) * iD;
+            G.s[5] = (qx - px) * iD;
+        }
+        G.s[6] = quot(n7);
+        G.s[7] = quot(n8);
+        G.s[8] = quot(n9);
     }
     G.mx[0] = A::mul(A::add(m1x, cx), 0.5);
     G.my[0] = A::mul(A::add(m1y, cy), 0.5);
@@ -201,6 +220,21 @@ template <int K> __device__ __forceinline__ Dual<K> fast_rcp(const Dual<K>& a) {
     return r;
 }
 
+// u at a cv-edge midpoint, u = alpha x + beta y + gamma (src/problem.jl:428-434): the three terms are ~|u| |x| / h and
+// cancel to |u|, so the reference's individually rounded (alpha x + beta y) + gamma is kept -- a contracted FMA differs
+// by an ulp of the big terms, 1e-12 of u on the 4096^2 lattice
+__device__ __forceinline__ double shape_value(double a, double b, double g, double x, double y) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(a, x), __dmul_rn(b, y)), g);
+}
+template <int K>
+__device__ __forceinline__ Dual<K> shape_value(const Dual<K>& a, const Dual<K>& b, const Dual<K>& g, double x, double y) {
+    return a * x + b * y + g;
+}
+// s_a u_i + s_b u_j + s_c u_k (shape_functions.jl:2-19) with the reference's roundings, for the same reason
+__device__ __forceinline__ double shape_coeff(double sa, double sb, double sc, double ui, double uj, double uk) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(sa, ui), __dmul_rn(sb, uj)), __dmul_rn(sc, uk));
+}
+
 // ---- flux registry: q(x, y, t, alpha, beta, gamma, p), src/problem.jl:113-116, 425-440 ----
 template <int MODEL, int NEQ, class T>
 __device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double y, double t, const T* a, const T* b, const T* g,
@@ -220,7 +254,7 @@ __device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double
     } else if constexpr (MODEL == FVM_FLUX_DIFF_POWER) {
 #pragma unroll
         for (int v = 0; v < NEQ; ++v) {
-            const T u = a[v] * x + b[v] * y + g[v];
+            const T u = shape_value(a[v], b[v], g[v], x, y);
             const double D0 = fp.p[3 * v], mm = fp.p[3 * v + 1];
             const T base = fp.p[3 * v + 2] != 0.0 ? fabs_t(u) : u;
             T D;
@@ -234,7 +268,7 @@ __device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double
     } else if constexpr (MODEL == FVM_FLUX_ADVDIFF) {
 #pragma unroll
         for (int v = 0; v < NEQ; ++v) {
-            const T u = a[v] * x + b[v] * y + g[v];
+            const T u = shape_value(a[v], b[v], g[v], x, y);
             const double D = fp.p[3 * v];
             qx[v] = fp.p[3 * v + 1] * u - D * a[v];
             qy[v] = fp.p[3 * v + 2] * u - D * b[v];
@@ -242,7 +276,7 @@ __device__ __forceinline__ void flux_eval(const FluxParams& fp, double x, double
     } else if constexpr (MODEL == FVM_FLUX_KELLER_SEGEL) {
         // src/FiniteVolumeMethod.jl:98-110 : q_u = chi(u) grad v - grad u ; q_v = -D grad v
         static_assert(NEQ == 2 || MODEL != FVM_FLUX_KELLER_SEGEL, "Keller-Segel is a 2-species model");
-        const T u = a[0] * x + b[0] * y + g[0];
+        const T u = shape_value(a[0], b[0], g[0], x, y);
         const T chi = fp.p[0] * u * fast_rcp(u * u + 1.0);
         qx[0] = chi * a[1] - a[0];
         qy[0] = chi * b[1] - b[0];

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::te
                 }
             } else {
                 TriGeom G;
-                tri_geometry<false>(xy_s[2 * vv.x], xy_s[2 * vv.x + 1], xy_s[2 * vv.y], xy_s[2 * vv.y + 1],
-                                    xy_s[2 * vv.z], xy_s[2 * vv.z + 1], G, nullptr);
+                tri_geometry<false, FULL>(xy_s[2 * vv.x], xy_s[2 * vv.x + 1], xy_s[2 * vv.y], xy_s[2 * vv.y + 1],
+                                          xy_s[2 * vv.z], xy_s[2 * vv.z + 1], G, nullptr);
 #pragma unroll
                 for (int c = 0; c < 9; ++c) s[c] = G.s[c];
 #pragma unroll
@@ -197,10 +197,15 @@ __global__ void __launch_bounds__(RHS_BLOCK, OCC ? OCC : TileOcc<MODEL, NEQ>::te
 #pragma unroll
             for (int v = 0; v < NEQ; ++v) {
                 const double ui = u_s[vv.x * NEQ + v], uj = u_s[vv.y * NEQ + v], uk = u_s[vv.z * NEQ + v];
-                a[v] = s[0] * ui + s[1] * uj + s[2] * uk;
-                b[v] = s[3] * ui + s[4] * uj + s[5] * uk;
-                if constexpr (FULL) g[v] = s[6] * ui + s[7] * uj + s[8] * uk;
-                else g[v] = 0.0;
+                if constexpr (FULL) {  // fluxes that read u = alpha x + beta y + gamma: the reference's roundings throughout
+                    a[v] = shape_coeff(s[0], s[1], s[2], ui, uj, uk);
+                    b[v] = shape_coeff(s[3], s[4], s[5], ui, uj, uk);
+                    g[v] = shape_coeff(s[6], s[7], s[8], ui, uj, uk);
+                } else {
+                    a[v] = s[0] * ui + s[1] * uj + s[2] * uk;
+                    b[v] = s[3] * ui + s[4] * uj + s[5] * uk;
+                    g[v] = 0.0;
+                }
             }
             double Q[3][NEQ];
 #pragma unroll
@@ -330,9 +335,9 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
     for (int v = 0; v < NEQ; ++v) {
         const double ui = u[(size_t)E.v[0] * NEQ + v], uj = u[(size_t)E.v[1] * NEQ + v], uk = u[(size_t)E.v[2] * NEQ + v];
-        a[v] = G.s[0] * ui + G.s[1] * uj + G.s[2] * uk;
-        b[v] = G.s[3] * ui + G.s[4] * uj + G.s[5] * uk;
-        g[v] = G.s[6] * ui + G.s[7] * uj + G.s[8] * uk;
+        a[v] = shape_coeff(G.s[0], G.s[1], G.s[2], ui, uj, uk);
+        b[v] = shape_coeff(G.s[3], G.s[4], G.s[5], ui, uj, uk);
+        g[v] = shape_coeff(G.s[6], G.s[7], G.s[8], ui, uj, uk);
     }
     const double dx = E.qx - E.px, dy = E.qy - E.py;
     const double lij = sqrt(dx * dx + dy * dy);
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(128)
             double Q;
             if (E.kind[v] == FVM_EDGE_NEUMANN) {
                 const CondFn c = m.cond[v * FVM_MAX_COND_FN + E.fidx[v]];
-                const double ushape = a[v] * ptx[q] + b[v] * pty[q] + g[v];
+                const double ushape = shape_value(a[v], b[v], g[v], ptx[q], pty[q]);
                 Q = cond_eval(c, ptx[q], pty[q], t, ushape) * l;
             } else {
                 Q = (qx[v] * nx + qy[v] * ny) * l;
@@ -691,6 +696,45 @@ int32_t fvm_ensure_state(fvm_ctx* h) {
         if (!(h)->finalized) return fvm_fail((h), FVM_ERR_STATE, "call fvm_finalize first"); \
         FVM_CUDA(h, cudaSetDevice((h)->device));                                            \
     } while (0)
+
+// self-check of the recompute path's arithmetic: the contracted / division-free tri_geometry<false> the streaming kernel
+// runs must reproduce the individually rounded reference arithmetic (tri_geometry<true>): bit for bit in the variant of
+// the u-dependent fluxes; s7..s9, cv-edge midpoints and vectors bit for bit and s1..s6 to one ulp in the other
+__global__ void geometry_check_kernel(const DevMesh m, const int32_t* __restrict__ tri_native, unsigned long long* __restrict__ bad) {
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= m.n_tris) return;
+    const int i = tri_native[3 * gt], j = tri_native[3 * gt + 1], k = tri_native[3 * gt + 2];
+    TriGeom A, B, C;
+    const double px = m.xy[2 * (size_t)i], py = m.xy[2 * (size_t)i + 1], qx = m.xy[2 * (size_t)j], qy = m.xy[2 * (size_t)j + 1];
+    const double rx = m.xy[2 * (size_t)k], ry = m.xy[2 * (size_t)k + 1];
+    tri_geometry<true>(px, py, qx, qy, rx, ry, A, nullptr);          // the reference's arithmetic
+    tri_geometry<false, true>(px, py, qx, qy, rx, ry, B, nullptr);   // u-dependent fluxes
+    tri_geometry<false, false>(px, py, qx, qy, rx, ry, C, nullptr);  // fluxes that read alpha and beta only
+    bool same = true;
+    for (int c = 0; c < 9; ++c) same = same && A.s[c] == B.s[c];
+    for (int c = 6; c < 9; ++c) same = same && A.s[c] == C.s[c];
+    for (int c = 0; c < 6; ++c) same = same && fabs(A.s[c] - C.s[c]) <= 2.3e-16 * fabs(A.s[c]);  // num * RN(1/D): one ulp
+    for (int e = 0; e < 3; ++e)
+        same = same && A.mx[e] == B.mx[e] && A.my[e] == B.my[e] && A.ex[e] == B.ex[e] && A.ey[e] == B.ey[e] && A.mx[e] == C.mx[e] &&
+               A.my[e] == C.my[e] && A.ex[e] == C.ex[e] && A.ey[e] == C.ey[e];
+    if (!same) atomicAdd(bad, 1ULL);
+}
+
+extern "C" int32_t fvm_check_recompute_geometry(fvm_handle h, int64_t* n_mismatch) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, n_mismatch, "fvm_check_recompute_geometry: null argument");
+    unsigned long long* d = nullptr;
+    FVM_CUDA(h, cudaMalloc((void**)&d, sizeof(unsigned long long)));
+    cudaMemsetAsync(d, 0, sizeof(unsigned long long), h->stream);
+    geometry_check_kernel<<<(unsigned)((h->T + 255) / 256), 256, 0, h->stream>>>(h->dm, h->d_tri_native, d);
+    unsigned long long out = 0;
+    cudaError_t e = cudaMemcpyAsync(&out, d, sizeof(out), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d);
+    FVM_CUDA(h, e);
+    *n_mismatch = (int64_t)out;
+    return FVM_OK;
+}
 
 extern "C" int32_t fvm_rhs_native(fvm_handle h, double t, const double* u, double* du) {
     NEED_FINAL(h);

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
             const ushort4 vv = tri_s[lt];
             const double2 P = xy_s[vv.x], Q = xy_s[vv.y], R = xy_s[vv.z];
             TriGeom G;
-            tri_geometry<false>(P.x, P.y, Q.x, Q.y, R.x, R.y, G, nullptr);
+            tri_geometry<false, FULL>(P.x, P.y, Q.x, Q.y, R.x, R.y, G, nullptr);
             double dt3[3] = {0, 0, 0};
             if constexpr (FluxTraits<MODEL>::table) {
                 const double* dts = reinterpret_cast<const double*>(st + h3.w);
@@ -194,10 +194,15 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
 #pragma unroll
             for (int v = 0; v < NEQ; ++v) {
                 const double ui = us[vv.x * NEQ + v], uj = us[vv.y * NEQ + v], uk = us[vv.z * NEQ + v];
-                al[v] = G.s[0] * ui + G.s[1] * uj + G.s[2] * uk;
-                be[v] = G.s[3] * ui + G.s[4] * uj + G.s[5] * uk;
-                if constexpr (FULL) ga[v] = G.s[6] * ui + G.s[7] * uj + G.s[8] * uk;
-                else ga[v] = 0.0;
+                if constexpr (FULL) {  // fluxes that read u = alpha x + beta y + gamma: the reference's roundings throughout
+                    al[v] = shape_coeff(G.s[0], G.s[1], G.s[2], ui, uj, uk);
+                    be[v] = shape_coeff(G.s[3], G.s[4], G.s[5], ui, uj, uk);
+                    ga[v] = shape_coeff(G.s[6], G.s[7], G.s[8], ui, uj, uk);
+                } else {
+                    al[v] = G.s[0] * ui + G.s[1] * uj + G.s[2] * uk;
+                    be[v] = G.s[3] * ui + G.s[4] * uj + G.s[5] * uk;
+                    ga[v] = 0.0;
+                }
             }
             double Qe[3][NEQ];
 #pragma unroll

@@ -209,7 +209,7 @@ class SteadyFVMProblem:
 class Engine:
     """Owns one libfvmcuda handle for a problem (RHS) or a template (linear operator)."""
 
-    def __init__(self, mesh, neq, conditions, flux=None, source=None, tile_triangles=0, geometry_mode=0, device=None, ghost=None,
+    def __init__(self, mesh, neq, conditions, flux=None, source=None, tile_triangles=0, geometry_mode=1, device=None, ghost=None,
                  mesh_file=None):
         lib = L.lib()
         tri = mesh.triangulation
@@ -399,7 +399,7 @@ class CudaParameters:
         self.engine = engine
 
 
-def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=0, device=None, ghost=None, mesh_file=None):
+def get_cuda_parameters(prob, tile_triangles=0, geometry_mode=1, device=None, ghost=None, mesh_file=None):
     """Sibling of get_multithreading_parameters (solve.jl:1-27): builds the device state once.
     `mesh_file`: let the library read points / triangles from an FVMWIRE container of the same mesh."""
     if isinstance(prob, SteadyFVMProblem):

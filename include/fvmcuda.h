@@ -166,6 +166,11 @@ int32_t fvm_get_profile(fvm_handle h, double* total_ms, int64_t* launches);
 /* ---- geometry / connectivity read-back for parity (src/geometry.jl:21-49) ----------- */
 /* caller order; any pointer may be NULL.  V[N]; s9[T][9]; mid6[T][3][2]; nrm6[T][3][2]; len3[T][3] */
 int32_t fvm_get_geometry(fvm_handle h, double* V, double* s9, double* mid6, double* nrm6, double* len3);
+/* Self-check of geometry_mode 1: counts the triangles on which the division-free recomputed geometry of the
+ * streaming kernel differs from the individually rounded reference arithmetic (src/geometry.jl:107-161): any bit at all
+ * in the variant the u-dependent flux models run; any bit of s7..s9, the cv-edge midpoints or the cv-edge vectors, or
+ * more than one ulp of s1..s6, in the variant of the fluxes that read alpha and beta only.  0 on every mesh tested. */
+int32_t fvm_check_recompute_geometry(fvm_handle h, int64_t* n_mismatch);
 /* native permutations: node_perm[new] = old (N), tri_perm[new] = old (T); tile layout stats */
 int32_t fvm_get_permutation(fvm_handle h, int32_t* node_perm, int32_t* tri_perm);
 int32_t fvm_get_stats(fvm_handle h, int64_t* stats /* [16] */);

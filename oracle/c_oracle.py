@@ -28,6 +28,9 @@ def lib():
         L.oracle_spmv.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_spmv.restype = None
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_fvm_eqs_general.restype = C.c_int
+        L.oracle_fvm_eqs_general.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -83,3 +86,25 @@ def spmv(rowptr, col, val, b, x, nthreads=1):
     lib().oracle_spmv(len(y), rowptr.ctypes.data, col.ctypes.data, val.ctypes.data,
                       b.ctypes.data if b is not None else None, x.ctypes.data, y.ctypes.data, nthreads)
     return y
+
+
+def fvm_eqs_general(points, triangles, u, neq=1, flux_model=0, flux_params=(1.0,), src_model=0, src_params=(), dirichlet=None):
+    """Serial reference-order RHS for scalar problems / systems with the registered flux and source forms, geometry
+    recomputed per triangle (oracle_fvm_eqs_general).  `u`: (N,) or (N, neq); `dirichlet`: bool (neq, N) or (N,) or None.
+    Valid where the boundary-edge pass adds nothing (all-Dirichlet boundary or homogeneous Neumann)."""
+    xy = np.ascontiguousarray(points, dtype=np.float64)
+    tri = np.ascontiguousarray(triangles, dtype=np.int32)
+    N = len(xy)
+    uu = np.ascontiguousarray(u, dtype=np.float64)
+    assert uu.size == N * neq
+    du = np.empty_like(uu)
+    fp = np.ascontiguousarray(list(flux_params) + [0.0], dtype=np.float64)
+    sp = np.ascontiguousarray(list(src_params) + [0.0], dtype=np.float64)
+    dk = None
+    if dirichlet is not None:
+        dk = np.ascontiguousarray(np.broadcast_to(np.asarray(dirichlet, dtype=np.uint8).reshape(-1, N), (neq, N)))
+    rc = lib().oracle_fvm_eqs_general(xy.ctypes.data, N, tri.ctypes.data, len(tri), neq, flux_model, fp.ctypes.data, src_model,
+                                      sp.ctypes.data, None if dk is None else dk.ctypes.data, uu.ctypes.data, du.ctypes.data)
+    if rc:
+        raise ValueError("oracle_fvm_eqs_general: bad arguments")
+    return du

@@ -266,6 +266,108 @@ void oracle_fvm_eqs_flat(void* p, const double* u, double* du) {
     node_pass(o, du, 0);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * General stateless RHS for the full-size parity tests (BASELINE configs 2 and 4 at 4096^2): scalar problems and
+ * FVMSystems with the registered flux / source forms, geometry recomputed per triangle (no Dict: 33.5 M
+ * TriangleProperties would need 13 GB), serial, reference order:
+ *   zero du; triangles in the given order (fvm_eqs_single_triangle!, triangle_contributions.jl:10-35, with
+ *   get_shape_function_coefficients shape_functions.jl:2-19 and get_flux individual_flux_contributions.jl:27-50);
+ *   node pass (source_contributions.jl:33-68).
+ * The boundary-edge pass (boundary_edge_contributions.jl:77-86) is omitted: this entry point is only valid where it
+ * adds nothing -- boundary nodes all Dirichlet (their rows are overwritten in the node pass) or homogeneous Neumann
+ * edges (a = 0, so du[i] -= 0 exactly).  The caller states which nodes are Dirichlet per species.
+ * Flux forms (the tutorial closures the device registry mirrors; u = alpha x + beta y + gamma at the cv-edge midpoint):
+ *   0 constant D_v:            q_v = (-D_v alpha_v, -D_v beta_v)                          problem.jl:425-440
+ *   2 power law:               D = D0_v |u_v|^(m_v - 1) (|.| iff flag), q_v = (-D alpha_v, -D beta_v)
+ *   3 advection-diffusion:     q_v = (nux_v u_v - D_v alpha_v, nuy_v u_v - D_v beta_v)
+ *   4 Keller-Segel (2 species): chi = c u/(1 + u^2); q_u = (chi alpha_2 - alpha_1, chi beta_2 - beta_1); q_v = -D grad v
+ *                                                                          src/FiniteVolumeMethod.jl:98-110
+ * Sources: 0 zero; 1 lam_v u_v + mu_v; 2 lam_v u_v (1 - u_v); 4 Gray-Scott; 5 Brusselator; 6 Keller-Segel (u(1-u); u - a v).
+ * u and du are species-interleaved per node (Julia's column-major Matrix(neq, N)).
+ */
+static void general_flux(int model, const double* fp, int neq, double x, double y, const double* a, const double* b, const double* g,
+                         double* qx, double* qy) {
+    for (int v = 0; v < neq; ++v) {
+        if (model == 0) {
+            qx[v] = -fp[v] * a[v];
+            qy[v] = -fp[v] * b[v];
+        } else if (model == 2) {
+            double u = a[v] * x + b[v] * y + g[v];
+            double base = fp[3 * v + 2] != 0.0 ? fabs(u) : u;
+            double D = fp[3 * v] * pow(base, fp[3 * v + 1] - 1.0);
+            qx[v] = -D * a[v];
+            qy[v] = -D * b[v];
+        } else if (model == 3) {
+            double u = a[v] * x + b[v] * y + g[v];
+            qx[v] = fp[3 * v + 1] * u - fp[3 * v] * a[v];
+            qy[v] = fp[3 * v + 2] * u - fp[3 * v] * b[v];
+        }
+    }
+    if (model == 4) {
+        double u = a[0] * x + b[0] * y + g[0];
+        double chi = fp[0] * u / (1 + u * u);
+        qx[0] = chi * a[1] - a[0];
+        qy[0] = chi * b[1] - b[0];
+        qx[1] = -fp[1] * a[1];
+        qy[1] = -fp[1] * b[1];
+    }
+}
+
+static double general_source(int model, const double* sp, int v, const double* u) {
+    switch (model) {
+        case 1: return sp[2 * v] * u[v] + sp[2 * v + 1];
+        case 2: return sp[v] * u[v] * (1 - u[v]);
+        case 4: return v == 0 ? sp[0] * (1 - u[0]) - u[0] * (u[1] * u[1]) : -sp[1] * u[1] + u[0] * (u[1] * u[1]);
+        case 5: return v == 0 ? (u[0] * u[0]) * u[1] - 2 * u[0] : -((u[0] * u[0]) * u[1]) + u[0];
+        case 6: return v == 0 ? u[0] * (1 - u[0]) : u[0] - sp[0] * u[1];
+        default: return 0.0;
+    }
+}
+
+int oracle_fvm_eqs_general(const double* xy, int64_t N, const int32_t* tri, int64_t T, int neq, int flux_model, const double* fp,
+                           int src_model, const double* sp, const uint8_t* is_dirichlet /* [neq][N] */, const double* u, double* du) {
+    if (neq < 1 || neq > 4 || (flux_model == 4 && neq != 2)) return 1;
+    double* vol = (double*)calloc(N, sizeof(double));
+    uint8_t* is_vertex = (uint8_t*)calloc(N, 1);
+    memset(du, 0, sizeof(double) * N * neq);
+    for (int64_t t = 0; t < T; ++t) {
+        const int32_t i = tri[3 * t], j = tri[3 * t + 1], k = tri[3 * t + 2];
+        TriProps P;
+        double S[3];
+        tri_props(xy, i, j, k, &P, S);
+        vol[i] += S[0]; /* geometry.jl:126-135 */
+        vol[j] += S[1];
+        vol[k] += S[2];
+        is_vertex[i] = is_vertex[j] = is_vertex[k] = 1;
+        double a[4], b[4], g[4], Q[3][4];
+        for (int v = 0; v < neq; ++v) { /* shape_functions.jl:2-19 */
+            const double ui = u[(size_t)i * neq + v], uj = u[(size_t)j * neq + v], uk = u[(size_t)k * neq + v];
+            a[v] = P.s[0] * ui + P.s[1] * uj + P.s[2] * uk;
+            b[v] = P.s[3] * ui + P.s[4] * uj + P.s[5] * uk;
+            g[v] = P.s[6] * ui + P.s[7] * uj + P.s[8] * uk;
+        }
+        for (int e = 0; e < 3; ++e) { /* individual_flux_contributions.jl:21-50 */
+            double qx[4], qy[4];
+            general_flux(flux_model, fp, neq, P.mid[2 * e], P.mid[2 * e + 1], a, b, g, qx, qy);
+            for (int v = 0; v < neq; ++v) Q[e][v] = (qx[v] * P.nrm[2 * e] + qy[v] * P.nrm[2 * e + 1]) * P.len[e];
+        }
+        for (int v = 0; v < neq; ++v) { /* update_du!, triangle_contributions.jl:10-25 */
+            du[(size_t)i * neq + v] = du[(size_t)i * neq + v] + Q[2][v] - Q[0][v];
+            du[(size_t)j * neq + v] = du[(size_t)j * neq + v] + Q[0][v] - Q[1][v];
+            du[(size_t)k * neq + v] = du[(size_t)k * neq + v] + Q[1][v] - Q[2][v];
+        }
+    }
+    for (int64_t i = 0; i < N; ++i) /* source_contributions.jl:33-68 */
+        for (int v = 0; v < neq; ++v) {
+            double* d = du + (size_t)i * neq + v;
+            if (!is_vertex[i] || (is_dirichlet && is_dirichlet[(size_t)v * N + i])) *d = 0.0;
+            else *d = *d / vol[i] + general_source(src_model, sp, v, u + (size_t)i * neq);
+        }
+    free(vol);
+    free(is_vertex);
+    return 0;
+}
+
 /* CSC-free CSR y = A x + b, single-threaded like SparseArrays' mul! (diffusion_equation.jl:93-94) */
 void oracle_spmv(int64_t n, const int32_t* rowptr, const int32_t* col, const double* val, const double* b, const double* x,
                  double* y, int nthreads) {

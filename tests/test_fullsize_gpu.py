@@ -1,6 +1,7 @@
-"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot
-finish 16.7M nodes in seconds): conservation, linearity, operator == RHS, determinism, and a
-200k-point unstructured mesh against the vectorised oracle."""
+"""Parity at BASELINE.json's full sizes: DIRECT 1e-12 comparison of one fvm_eqs! at 4096^2 (configs 2 and 4, both
+geometry modes) with the serial C oracle (oracle_fvm_eqs_general, bitwise the NumPy oracle on small meshes),
+config 3 at 1024^2 against the SuperLU oracle, plus size-independent properties (conservation, linearity,
+operator == RHS, determinism) and a 200k-point unstructured mesh against the vectorised oracle."""
 import numpy as np
 import pytest
 
@@ -15,6 +16,66 @@ pytestmark = pytest.mark.gpu
 def big():
     tri = G.triangulate_rectangle(0, 2, 0, 2, 4096, 4096, single_boundary=True)
     return tri, G.FVMGeometry(tri)
+
+
+@pytest.mark.parametrize("flux,fm,fp", [(G.ConstantDiffusion(1 / 9), 0, [1 / 9]), (G.PowerDiffusion(1 / 9, 2.0), 2, [1 / 9, 2.0, 0.0])],
+                         ids=["const_D", "u_dependent_D"])
+def test_config2_rhs_4096_direct_parity(big, flux, fm, fp):
+    """BASELINE config 2 mesh (16.7M nodes, 33.5M triangles), README conditions (Dirichlet u = 0): one fvm_eqs! of
+    the streaming recompute kernel (the engine's default) and of the stored-geometry kernel against the serial
+    C oracle, 1e-12 relative -- the bar of /root/reference/test/test_functions.jl:645-657 at full size."""
+    from oracle import c_oracle
+    tri, mesh = big
+    N = tri.num_points
+    BC = G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet)
+    u = 50 * np.random.default_rng(20240517).random(N)
+    bnd = np.zeros(N, bool)
+    bnd[np.unique(tri.boundary_edges()[0])] = True
+    ref = c_oracle.fvm_eqs_general(tri.points, tri.triangles, u, 1, fm, fp, dirichlet=bnd)
+    prob = G.FVMProblem(mesh, BC, diffusion_function=flux, initial_condition=u, final_time=1.0)
+    for mode in (1, 0):
+        p = G.get_cuda_parameters(prob, geometry_mode=mode)
+        du = G.fvm_eqs(np.empty(N), u, p, 0.0)
+        assert rel_err(du, ref) <= RTOL_RHS, (mode, rel_err(du, ref))
+        p.engine.close()
+
+
+def test_config4_system_rhs_4096_direct_parity(big):
+    """BASELINE config 4: 2-species Keller-Segel FVMSystem (src/FiniteVolumeMethod.jl:92-138), all-Neumann zero flux,
+    4096^2, against the serial C oracle at 1e-12 per species."""
+    from oracle import c_oracle
+    tri, mesh = big
+    N = tri.num_points
+    rng = np.random.default_rng(20240517)
+    U = np.ascontiguousarray(np.stack([0.01 * rng.random(N), 0.005 * rng.random(N)], axis=1))
+    ks, kss = G.KellerSegelFlux(4.0, 1.0), G.KellerSegelSource(0.1)
+    BC = G.BoundaryConditions(mesh, G.Const(0.0), G.Neumann)
+    pu = G.FVMProblem(mesh, BC, flux_function=ks, source_function=kss, initial_condition=U[:, 0], final_time=1.0)
+    pv = G.FVMProblem(mesh, BC, flux_function=ks, source_function=kss, initial_condition=U[:, 1], final_time=1.0)
+    ref = c_oracle.fvm_eqs_general(tri.points, tri.triangles, U, 2, 4, [4.0, 1.0], 6, [0.1])
+    p = G.get_cuda_parameters(G.FVMSystem(pu, pv))
+    du = G.fvm_eqs(np.empty_like(U), U, p, 0.0)
+    assert rel_err(du[:, 0], ref[:, 0]) <= RTOL_RHS and rel_err(du[:, 1], ref[:, 1]) <= RTOL_RHS
+    p.engine.close()
+
+
+def test_config3_mean_exit_time_1024_vs_superlu_oracle():
+    """BASELINE config 3 at 1024^2 (1.05M unknowns): the assembled MeanExitTimeProblem matches the oracle's
+    (bitwise hand assembly in the reference: docs/src/literate_wyos/mean_exit_time.jl:206) to 1e-12 ||A||, and the
+    Jacobi-PCG solution agrees with the oracle's SuperLU solve to the solver tolerance."""
+    n = 1024
+    gtri = G.triangulate_rectangle(0, 2, 0, 2, n, n, single_boundary=True)
+    pair = Pair(gtri)
+    gBC = G.BoundaryConditions(pair.gmesh, G.Const(0.0), G.Dirichlet)
+    oBC = O.BoundaryConditions(pair.omesh, (lambda x, y, t, u, p: 0.0,), (O.Dirichlet,))
+    met = G.MeanExitTimeProblem(pair.gmesh, gBC, diffusion_function=1 / 9)
+    ref = O.MeanExitTimeProblem(pair.omesh, oBC, diffusion_function=lambda x, y, p: 1 / 9, vectorised=True)
+    assert abs(met.A - ref.A).max() <= 1e-12 * abs(ref.A).max()
+    assert rel_err(met.b, ref.b) <= 1e-12
+    sol = G.solve(met, G.KrylovJacobi("pcg", rtol=1e-12, maxiter=40000))
+    uo = O.solve_steady(ref)
+    assert rel_err(sol.u, uo) <= 1e-8
+    met.engine.close()
 
 
 def test_conservation_and_determinism_4096(big):

@@ -416,6 +416,58 @@ def test_c_oracle_matches_numpy_oracle():
     assert isapprox(co.fvm_eqs_flat(u), ref, rtol=1e-14)
 
 
+def test_general_c_oracle_matches_numpy_oracle():
+    """oracle_fvm_eqs_general (the checker of the full-size GPU parity tests: registered flux / source forms,
+    scalar problems and FVMSystems, geometry recomputed per triangle) is bitwise the NumPy oracle's serial
+    fvm_eqs! wherever the boundary-edge pass adds nothing (all-Dirichlet boundary, homogeneous Neumann)."""
+    import fvm_b200 as G
+    from oracle import c_oracle
+    from tests.common import Pair
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 23, 17, single_boundary=True))
+    tri = pair.gtri
+    N = tri.num_points
+    rng = np.random.default_rng(3)
+    u = 1 + rng.random(N)
+    bnd = np.zeros(N, bool)
+    bnd[np.unique(tri.boundary_edges()[0])] = True
+    scalar = ((G.ConstantDiffusion(1 / 9), None, 0, [1 / 9], 0, []),
+              (G.PowerDiffusion(0.3, 3.0), G.LogisticSource(1.3), 2, [0.3, 3.0, 0.0], 2, [1.3]),
+              (G.PowerDiffusion(0.3, 1.0), G.LinearSource(-0.4, 0.2), 2, [0.3, 1.0, 0.0], 1, [-0.4, 0.2]),
+              (G.AdvectionDiffusionFlux(0.05, 1.5, -0.7), None, 3, [0.05, 1.5, -0.7], 0, []))
+    for flux, src, fm, fp, sm, sp in scalar:
+        for bc, dirn in ((G.Dirichlet, bnd), (G.Neumann, None)):
+            if bc is G.Neumann and fm == 3:
+                continue  # advection through the boundary: the boundary-edge pass is not a no-op there
+            gp, op = pair.problem(G.Const(0.0), bc, flux, source=src, ic=u)
+            ref = O.fvm_eqs(np.zeros_like(u), u, op, 0.0)
+            out = c_oracle.fvm_eqs_general(tri.points, tri.triangles, u, 1, fm, fp, sm, sp, dirichlet=dirn)
+            assert np.array_equal(out, ref), (type(flux).__name__, bc)
+    # 2-species systems: Keller-Segel (BASELINE config 4) and Gray-Scott, zero-flux Neumann
+    U = np.ascontiguousarray(np.stack([0.5 + 0.5 * rng.random(N), 0.25 * rng.random(N)], axis=1))
+    for fluxes, src, fm, fp, sm, sp in (((G.KellerSegelFlux(4.0, 1.0),) * 2, G.KellerSegelSource(0.1), 4, [4.0, 1.0], 6, [0.1]),
+                                        ((G.ConstantDiffusion(2e-5), G.ConstantDiffusion(1e-5)), G.GrayScottSource(0.04, 0.1), 0,
+                                         [2e-5, 1e-5], 4, [0.04, 0.1])):
+        g1, o1 = pair.problem(G.Const(0.0), G.Neumann, fluxes[0], source=src, var=0, ic=U[:, 0])
+        g2, o2 = pair.problem(G.Const(0.0), G.Neumann, fluxes[1], source=src, var=1, ic=U[:, 1])
+        ref = O.fvm_eqs(np.zeros_like(U), U, O.FVMSystem(o1, o2), 0.0)
+        out = c_oracle.fvm_eqs_general(tri.points, tri.triangles, U, 2, fm, fp, sm, sp)
+        assert np.array_equal(out, ref)
+
+
+def test_vectorised_template_assembly_matches_the_loop():
+    """The vectorised MeanExitTimeProblem assembly (used only for the 10^6-unknown config-3 parity case) against the
+    loop restatement of abstract_templates.jl:73-99 / mean_exit_time.jl:57-94: same pattern, values to summation order."""
+    tri = O.triangulate_rectangle(0, 2, 0, 3, 31, 27, single_boundary=False)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, (lambda x, y, t, u, p: 0.0,) * 4, (O.Dirichlet, O.Neumann, O.Dirichlet, O.Neumann))
+    Dfn = lambda x, y, p: 0.3 + 0.1 * x * y
+    loop = O.MeanExitTimeProblem(mesh, BCs, diffusion_function=Dfn)
+    vec = O.MeanExitTimeProblem(mesh, BCs, diffusion_function=Dfn, vectorised=True)
+    assert np.array_equal(loop.b, vec.b)
+    assert np.array_equal(loop.A.indptr, vec.A.indptr) and np.array_equal(loop.A.indices, vec.A.indices)
+    assert np.abs(loop.A.data - vec.A.data).max() <= 4e-16 * np.abs(loop.A.data).max()
+
+
 def test_readme_square_plate_series_solution():
     """BASELINE configs[0] end to end on the oracle: README diffusion (50x50, D = 1/9, Dirichlet 0) integrated
     with the fixed-step Tsit5 and the Dirichlet callback, against the separated-variables series of

@@ -443,3 +443,25 @@ def test_host_register_round_trip():
         assert np.array_equal(G.fvm_eqs(du, u, p, 0.0), ref)
     assert L.lib().fvm_host_unregister(u.ctypes.data) != L.OK  # no longer registered
     assert L.lib().fvm_host_register(None, 8) == L.ERR_ARG
+
+
+def test_recompute_geometry_is_bit_identical_to_reference_arithmetic():
+    """geometry_mode 1 recomputes geometry.jl:107-161 per triangle with contracted FMAs, a Newton reciprocal and
+    Markstein-corrected quotients instead of IEEE divisions.  The variant the u-dependent fluxes run (they amplify an
+    ulp of s by |x|/h) must equal the individually rounded reference arithmetic in every bit; the variant of the
+    alpha/beta-only fluxes in every bit of s7..s9, cv-edge midpoints and vectors, and to one ulp in s1..s6 (lattices at h = 1.3e-3 where Delta cancels to 1e-10, a stretched lattice far
+    from the origin, a jittered Delaunay mesh)."""
+    import ctypes as C
+    from fvm_b200 import _lib as L
+    meshes = [G.triangulate_rectangle(0, 2, 0, 2, 1500, 1500, single_boundary=True),
+              G.triangulate_rectangle(-3, 40, 1e3, 1e3 + 1, 300, 700, single_boundary=True),
+              delaunay_mesh(60000, 5, jitter=0.35)]
+    for tri in meshes:
+        mesh = G.FVMGeometry(tri)
+        prob = G.FVMProblem(mesh, G.BoundaryConditions(mesh, G.Const(0.0), G.Neumann), diffusion_function=G.ConstantDiffusion(1.0),
+                            initial_condition=np.zeros(tri.num_points), final_time=1.0)
+        p = G.get_cuda_parameters(prob, geometry_mode=1)
+        bad = C.c_int64(-1)
+        L.check(p.engine.h, L.lib().fvm_check_recompute_geometry(p.engine.h, C.byref(bad)))
+        assert bad.value == 0, "%d of %d triangles differ" % (bad.value, tri.num_triangles)
+        p.engine.close()
