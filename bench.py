@@ -7,11 +7,14 @@
 A step = one pass of the hot path over the whole mesh: one `fvm_eqs!` evaluation (boundary-edge,
 tile and interface kernels) on the README diffusion problem scaled to BASELINE configs[1]'s mesh
 (triangulate_rectangle 4096x4096 on [0,2]^2, Dirichlet u=0, D=1/9).  The headline variant is the
-path the engine takes for that problem (constant D: the reduced s1..s6 + scaled-normal stream,
-108*T + 25*N bytes); the same mesh through the general 21-component layout (180*T + 25*N) is
-reported under "variants".  `value` times it with `u`
+path the engine takes by default (geometry_mode 1: the streaming kernel that recomputes the geometry
+from vertex coordinates, 12*T + 41*N algorithmic bytes); the stored-geometry layouts of north_star (a)
+(reduced 108*T + 25*N, general 180*T + 25*N) are reported under "variants", every variant also as a
+fraction of the roofline on the MINIMAL byte count (12*T + 41*N).  `value` times it with `u`
 resident in HBM (native order); `e2e` times the public `fvm_eqs(du,u,p,t)` call with pinned HOST
-buffers (H2D + permutation + kernels + D2H).  N>1: weak scaling, each rank owns a 4096-row strip.
+buffers (H2D + permutation + kernels + D2H).  N>1: weak scaling, each rank owns a 4096-row strip, plus
+`strong_8192` = BASELINE config 5 (the 8192x8192 lattice split over the N GPUs: RHS, template SpMV and
+Tsit5 step) and `parity_max_rel` (owned rows at the cuts against a single-domain evaluation).
 One JSON line on stdout (rank 0)."""
 import argparse
 import json
@@ -31,11 +34,14 @@ SEED = 20240517
 
 
 def profiled_traffic(key):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
-    try:
-        return int(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]["traffic_bytes"])
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel FROM THE COMMITTED ncu CAPTURE of the same command
+    (profiles/r02_traffic.json, falling back to round 1's) -- evidence of that capture, not of this run."""
+    for f in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            return int(json.load(open(os.path.join(ROOT, "profiles", f)))[key]["traffic_bytes"]), "profiles/" + f
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak():
@@ -144,7 +150,7 @@ def time_rhs(torch, eng, u_d, du_d, steps, warmup):
     return ms, (kms / steps if kn else float("nan"))  # per step (the overlapped sharded schedule launches it twice)
 
 
-def time_template(torch, G, prob, nx, steps, warmup, peak, lmesh=None, dist=None):
+def time_template(torch, G, prob, nx, steps, warmup, peak, lmesh=None, dist=None, e2e=True):
     """BASELINE configs[1]: DiffusionEquation template on the same mesh: y = A x + b SpMV and the
     device-resident fixed-step Tsit5 (6 SpMV + 6 stage combinations per step)."""
     mesh = prob.mesh
@@ -199,7 +205,7 @@ def time_template(torch, G, prob, nx, steps, warmup, peak, lmesh=None, dist=None
     ts_ms = (time.perf_counter() - t0) / nst * 1e3
     # the operator through the public call with pinned HOST vectors (mul!(du, A, u) of a host integrator)
     e2e_spmv_ms = None
-    if dist is None:
+    if dist is None and e2e:
         xh = torch.empty(N, dtype=torch.float64).pin_memory()
         yh = torch.empty(N, dtype=torch.float64).pin_memory()
         xh.copy_(x.cpu())
@@ -238,10 +244,11 @@ def time_extras(torch, G, nx, steps, warmup, peak):
     u_d = 0.01 * torch.rand(2 * N, dtype=torch.float64, device="cuda", generator=g)
     du_d = torch.empty_like(u_d)
     ms, kms = time_rhs(torch, eng, u_d, du_d, steps, warmup)
-    B = 180 * eng.T + (17 * 2 + 8) * N
+    B = rhs_bytes(eng.T, N, 2, "recompute")  # the engine's default path: geometry recomputed, 12*T + (24 + 17*2)*N
     out["system_rhs"] = {"config": "FVMSystem 2-species Keller-Segel (chi(u) grad v - grad u; -D grad v), all-Neumann, %dx%d" % (nx, nx),
-                         "mtri_s": eng.T / ms / 1e3, "ms_per_step": ms, "tile_kernel_ms": kms, "alg_bytes": B,
-                         "bytes_formula": "180*T + 42*N", "gbs": B / kms / 1e6, "frac": B / kms / 1e6 / peak,
+                         "mtri_s": eng.T / ms / 1e3, "ms_per_step": ms, "tile_kernel_ms": kms, "alg_bytes": B, "kernel": "rhs_stream_kernel",
+                         "bytes_formula": "12*T + 58*N", "gbs": B / kms / 1e6, "frac": B / kms / 1e6 / peak,
+                         "stored_layout_equivalent_gbs": (180 * eng.T + 42 * N) / kms / 1e6,
                          "finite": bool(torch.isfinite(du_d).all().item())}
     eng.close()
     del u_d, du_d, p, eng
@@ -289,14 +296,35 @@ def time_extras(torch, G, nx, steps, warmup, peak):
     return out
 
 
-def cpu_baseline(nx, target_s=12.0, impl_reference=False, steps=None, warmup=1):
-    """The oracle port (oracle/fvm_oracle_c.c, reference-structured: hash-table triangle props,
-    per-thread du copies, serial combine) timed on the host cores on a bounded sample."""
+def host_threads():
+    """Threads the CPU arm uses: every core the process may run on.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers; a baseline on one core would be meaningless, so the count is set explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def julia_probe():
+    """SURVEY 8c / BASELINE.md 3.1: use the real reference if Julia exists on the bench host.  It never has so far."""
+    import shutil
+    exe = shutil.which("julia")
+    if not exe:
+        return {"found": False, "note": "`command -v julia` found nothing on this host: the CPU arm is the C port of the reference's structure (kind: port)"}
+    return {"found": True, "path": exe, "note": "julia is on PATH but FiniteVolumeMethod.jl's dependencies (DelaunayTriangulation, SciMLBase, ...) "
+                                                "are not vendored and there is no network: the CPU arm stays the C port"}
+
+
+def cpu_baseline(nx, steps=None, warmup=1, budget_s=25.0, extras=True):
+    """The oracle port (oracle/fvm_oracle_c.c, reference-structured: hash-table triangle props, per-thread du
+    copies, serial combine) timed on ALL host cores on the README problem of side nx; beside it the flat-array
+    variant, the CPU CSR SpMV (1 thread like SparseArrays' mul!, and all threads) and a SuperLU steady solve."""
     from oracle.c_oracle import COracle
     import fvm_b200 as G
+    nthreads = host_threads()
     tri = G.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, nx, nx, single_boundary=True)
     uv, _ = tri.boundary_edges()
-    co = COracle(tri.points, tri.triangles, np.unique(uv), 1 / 9)
+    co = COracle(tri.points, tri.triangles, np.unique(uv), 1 / 9, nthreads=nthreads)
     u = 50 * np.random.default_rng(SEED).random(tri.num_points)
     du = np.empty_like(u)
     for _ in range(max(1, warmup)):
@@ -304,62 +332,165 @@ def cpu_baseline(nx, target_s=12.0, impl_reference=False, steps=None, warmup=1):
     t0 = time.perf_counter()
     co.fvm_eqs_threaded(u, du)
     one = time.perf_counter() - t0
-    reps = steps if steps else max(3, min(200, int(target_s / max(one, 1e-4))))
+    reps = steps if steps else max(3, min(200, int(budget_s / max(one, 1e-4))))
     t0 = time.perf_counter()
     for _ in range(reps):
         co.fvm_eqs_threaded(u, du)
     dt = (time.perf_counter() - t0) / reps
-    t0 = time.perf_counter()
-    for _ in range(max(2, reps // 4)):
-        co.fvm_eqs_flat(u, du)
-    dt_flat = (time.perf_counter() - t0) / max(2, reps // 4)
     T = tri.num_triangles
-    # the template SpMV on the CPU: 7-point operator of the same lattice in CSR, single-threaded like
-    # SparseArrays' mul! (diffusion_equation.jl:93-94) and with all cores
-    spmv_note = ""
-    try:
-        from oracle.c_oracle import spmv as c_spmv
-        import scipy.sparse as sp
-        N = tri.num_points
-        idx = np.arange(N)
-        A = sp.diags([np.full(N, -4.0), np.ones(N - 1), np.ones(N - 1), np.ones(N - nx), np.ones(N - nx), np.full(N - nx + 1, 1e-16),
-                      np.full(N - nx + 1, 1e-16)], [0, 1, -1, nx, -nx, nx - 1, -(nx - 1)], format="csr")
-        rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
-        bb = np.zeros(N)
-        c_spmv(rp, ci, va, bb, u, 1)
+    out = {"value": T / dt / 1e6, "unit": "Mtriangle-updates/s", "cores": nthreads, "kind": "port",
+           "sample": "README diffusion fvm_eqs! on the %dx%d lattice (%d triangles), %d threaded calls of the reference-structured "
+                     "C port (Dict-style triangle props, per-thread du copies, serial combine)" % (nx, nx, T, reps),
+           "ms_per_step": dt * 1e3, "nx": nx, "julia": julia_probe()}
+    if extras:
+        nflat = max(2, min(reps, 10))
+        co.fvm_eqs_flat(u, du)
         t0 = time.perf_counter()
-        for _ in range(5):
-            c_spmv(rp, ci, va, bb, u, 1)
-        t1s = (time.perf_counter() - t0) / 5
-        t0 = time.perf_counter()
-        for _ in range(10):
-            c_spmv(rp, ci, va, bb, u, co.nthreads)
-        tns = (time.perf_counter() - t0) / 10
-        Bs = 12 * A.nnz + 4 * (N + 1) + 24 * N
-        spmv_note = "; CSR SpMV on the same lattice: %.1f GB/s on 1 core, %.1f GB/s on %d cores" % (Bs / t1s / 1e9, Bs / tns / 1e9, co.nthreads)
-    except Exception as e:  # the RHS line is the baseline; the SpMV note is extra
-        spmv_note = "; CPU SpMV note unavailable (%s)" % type(e).__name__
-    out = {"value": T / dt / 1e6, "unit": "Mtriangle-updates/s", "cores": co.nthreads, "kind": "port",
-           "sample": "%dx%d lattice (%d triangles), %d threaded fvm_eqs! calls of the reference-structured C port; "
-                     "flat-array variant: %.1f Mtri/s%s" % (nx, nx, T, reps, T / dt_flat / 1e6, spmv_note),
-           "ms_per_step": dt * 1e3}
+        for _ in range(nflat):
+            co.fvm_eqs_flat(u, du)
+        out["cpu_flat"] = {"value": T / ((time.perf_counter() - t0) / nflat) / 1e6, "unit": "Mtriangle-updates/s", "cores": nthreads,
+                           "note": "same arithmetic on flat arrays without the hash containers, parallel combine (BASELINE.md 3: fair CPU line)"}
+        try:  # the template SpMV on the CPU: 7-point operator of the same lattice in CSR
+            from oracle.c_oracle import spmv as c_spmv
+            import scipy.sparse as sp
+            N = tri.num_points
+            A = sp.diags([np.full(N, -4.0), np.ones(N - 1), np.ones(N - 1), np.ones(N - nx), np.ones(N - nx), np.full(N - nx + 1, 1e-16),
+                          np.full(N - nx + 1, 1e-16)], [0, 1, -1, nx, -nx, nx - 1, -(nx - 1)], format="csr")
+            rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+            bb = np.zeros(N)
+            Bs = 12 * A.nnz + 4 * (N + 1) + 24 * N
+            for nt, key in ((1, "cpu_spmv_1t"), (nthreads, "cpu_spmv_nt")):
+                c_spmv(rp, ci, va, bb, u, nt)
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    c_spmv(rp, ci, va, bb, u, nt)
+                ts = (time.perf_counter() - t0) / 5
+                out[key] = {"gbs": Bs / ts / 1e9, "ms": ts * 1e3, "threads": nt,
+                            "note": "CSR y = A x + b, %s" % ("single-threaded like SparseArrays' mul! (diffusion_equation.jl:93-94)" if nt == 1 else "all host threads")}
+            del A, rp, ci, va
+        except Exception as e:  # the RHS line is the baseline; the SpMV lines are extra
+            out["cpu_spmv_note"] = "unavailable (%s)" % type(e).__name__
     co.close()
     return out
+
+
+def cpu_steady_baseline(n=512):
+    """BASELINE config 3 beside the GPU Jacobi-PCG: sparse-direct solve (SciPy SuperLU standing in for the reference's
+    KLUFactorization, docs/src/literate_wyos/poissons_equation.jl:101) of the MeanExitTimeProblem on an n x n lattice,
+    assembled by the oracle (vectorised restatement of abstract_templates.jl:73-99)."""
+    from oracle import fvm_oracle as O
+    tri = O.triangulate_rectangle(0, 2, 0, 2, n, n, single_boundary=True)
+    mesh = O.FVMGeometry(tri)
+    BCs = O.BoundaryConditions(mesh, (lambda x, y, t, u, p: 0.0,), (O.Dirichlet,))
+    ref = O.MeanExitTimeProblem(mesh, BCs, diffusion_function=lambda x, y, p: 1 / 9, vectorised=True)
+    t0 = time.perf_counter()
+    x = O.solve_steady(ref)
+    return {"n": n, "unknowns": n * n, "superlu_s": time.perf_counter() - t0, "centre_value": float(x[(n // 2) * n + n // 2]), "threads": 1}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = cpu_baseline(args.ref_nx, impl_reference=True, steps=args.steps, warmup=args.warmup)
+    # the CPU arm runs the SAME mesh as the GPU arm when K steps of it fit in a few minutes (~1 s per 4096^2 call)
+    nx = args.ref_nx if args.ref_nx else (args.nx if (args.steps + args.warmup) <= 120 else max(1024, args.nx // 2))
+    cb = cpu_baseline(nx, steps=args.steps, warmup=args.warmup, extras=False)
+    same = nx == args.nx
     line = {"impl": "reference", "metric": "fvm_eqs! Mtriangle-updates/s", "value": cb["value"], "unit": cb["unit"],
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "README diffusion fvm_eqs! (D=1/9, Dirichlet u=0); CPU arm on a bounded %dx%d sample of "
-                                   "the 4096x4096 lattice" % (args.ref_nx, args.ref_nx)},
+            "config": {"workload": "README diffusion fvm_eqs! (D=1/9, Dirichlet u=0) on triangulate_rectangle %dx%d; CPU arm: C port of the "
+                                   "reference's threaded path on %d host threads%s" % (nx, nx, cb["cores"], "" if same else
+                                   " (bounded sample of the %dx%d lattice: the metric is per triangle)" % (args.nx, args.nx)),
+                       "same_mesh_as_gpu_arm": same, "julia": cb["julia"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def global_u(gids):
+    """u as a function of the GLOBAL node id (any rank can evaluate any node): 50 * frac(sin(g) * 43758.5453)."""
+    g = np.asarray(gids, dtype=np.float64)
+    v = np.sin(g * 12.9898 + 78.233) * 43758.5453
+    return 50.0 * (v - np.floor(v))
+
+
+def sharded_parity(torch, G, eng, lmesh, du_d, nx, ny_total, ymax, flux, rank, world, gmode):
+    """In-run parity of a sharded RHS: du of the first, a middle and the last OWNED row of this rank's strip (the rows
+    that read the ghost layer) against a single-domain evaluation of a 5-row patch of the global lattice on this GPU
+    (same coordinates, same u by global id).  Returns max relative difference (inf-norm per row)."""
+    owned_rows = lmesh.n_owned // nx
+    j0 = rank * owned_rows
+    du_caller = torch.empty_like(du_d)
+    from fvm_b200 import _lib as L
+    L.check(eng.h, L.lib().fvm_from_native(eng.h, du_d.data_ptr(), du_caller.data_ptr()))
+    eng.synchronize()
+    du_h = du_caller.cpu().numpy()
+    worst = 0.0
+    for j in sorted({j0, j0 + owned_rows // 2, j0 + owned_rows - 1}):
+        r0, r1 = max(0, j - 2), min(ny_total, j + 3)
+        tri = G.lattice_rows(0.0, 2.0, 0.0, ymax, nx, ny_total, r0, r1)
+        mesh = G.FVMGeometry(tri)
+        gid = (np.arange(r0, r1, dtype=np.int64)[:, None] * nx + np.arange(nx)[None, :]).ravel()
+        up = global_u(gid)
+        prob = G.FVMProblem(mesh, G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet), diffusion_function=flux,
+                            initial_condition=up, final_time=0.5)
+        pp = G.get_cuda_parameters(prob, geometry_mode=gmode)
+        ref = G.fvm_eqs(np.empty_like(up), up, pp, 0.0)[(j - r0) * nx:(j - r0 + 1) * nx]
+        pp.engine.close()
+        got = du_h[(j - j0) * nx:(j - j0 + 1) * nx]  # owned rows come first, in ascending global order
+        if j in (0, ny_total - 1):
+            continue  # a global boundary row is Dirichlet in both: du = 0
+        worst = max(worst, float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)))
+    return worst
+
+
+def strong_scaling_leg(torch, G, dist, rank, world, local, steps, warmup, peak, nxs=8192):
+    """BASELINE config 5 as written: the nxs x nxs lattice (67M nodes, 134M triangles at 8192) on [0,2]^2 split into
+    `world` row strips, README diffusion: fvm_eqs!, the DiffusionEquation template SpMV and a Tsit5 step, device-timed,
+    max over ranks.  world == 1 gives the 1-GPU leg the speed-ups are quoted against."""
+    t0 = time.perf_counter()
+    lmesh = G.lattice_strip_local(0.0, 2.0, 0.0, 2.0, nxs, nxs // world, rank, world)
+    tri = lmesh.triangulation
+    mesh = G.FVMGeometry(tri)
+    BCs = G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet)
+    u_h = global_u(lmesh.global_nodes)
+    prob = G.FVMProblem(mesh, BCs, diffusion_function=G.ConstantDiffusion(1 / 9), initial_condition=u_h, final_time=0.5)
+    if world == 1:
+        p = G.get_cuda_parameters(prob, device=local)
+    else:
+        p = G.get_sharded_cuda_parameters(prob, lmesh, dist, device=local)
+    eng = p.engine
+    setup_rhs = time.perf_counter() - t0
+    N = eng.N
+    Tg = 2 * (nxs - 1) * (nxs - 1)
+    u_c = torch.from_numpy(u_h).cuda()
+    u_d = torch.empty_like(u_c)
+    from fvm_b200 import _lib as L
+    L.check(eng.h, L.lib().fvm_to_native(eng.h, u_c.data_ptr(), u_d.data_ptr()))
+    du_d = torch.empty_like(u_d)
+    if dist is not None:
+        dist.barrier()
+    ms_rhs, kms = time_rhs(torch, eng, u_d, du_d, steps, warmup)
+    parity = None
+    if world > 1:
+        parity = sharded_parity(torch, G, eng, lmesh, du_d, nxs, nxs, 2.0, G.ConstantDiffusion(1 / 9), rank, world, 1)
+    eng.close()
+    del p, eng, u_d, du_d, u_c
+    torch.cuda.empty_cache()
+    tpl = time_template(torch, G, prob, nxs, steps, warmup, peak, lmesh if world > 1 else None, dist, e2e=False)
+    out = {"rhs_ms": ms_rhs, "spmv_ms": tpl["spmv_ms"], "tsit5_ms_per_step": tpl["tsit5_ms_per_step"], "setup_s": setup_rhs,
+           "assemble_setup_s": tpl["assemble_setup_s"], "nodes_per_gpu": N, "parity_max_rel": parity}
+    if dist is not None:
+        v = torch.tensor([out["rhs_ms"], out["tsit5_ms_per_step"], parity if parity is not None else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(v, op=dist.ReduceOp.MAX)
+        out["rhs_ms"], out["tsit5_ms_per_step"], out["parity_max_rel"] = float(v[0]), float(v[1]), float(v[2])
+    out["mesh"] = "%dx%d lattice on [0,2]^2, %d row strips, one ghost row per neighbour (%d nodes, %d triangles in total)" % (
+        nxs, nxs, world, nxs * nxs, Tg)
+    out["rhs_mtri_s"] = Tg / out["rhs_ms"] / 1e3
+    nnz = nxs * nxs + 2 * (nxs * nxs + Tg - 1)
+    out["spmv_gbs"] = (12 * nnz + 4 * (nxs * nxs + 1) + 24 * nxs * nxs) / out["spmv_ms"] / 1e6
+    return out
 
 
 def main():
@@ -369,9 +500,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nx", type=int, default=4096)
-    ap.add_argument("--ref-nx", type=int, default=1024)
-    ap.add_argument("--variant", default="const_stored", choices=sorted(VARIANTS),
-                    help="headline variant; const_stored is what the engine runs for the README problem (D = 1/9, a ConstantDiffusion)")
+    ap.add_argument("--ref-nx", type=int, default=0, help="side of the CPU arm's lattice (0: the GPU arm's mesh when the run stays within minutes)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the BASELINE config 5 leg (8192^2 lattice over the N GPUs)")
+    ap.add_argument("--strong-nx", type=int, default=8192)
+    ap.add_argument("--variant", default="const_recompute", choices=sorted(VARIANTS),
+                    help="headline variant; const_recompute is what the engine runs by default for the README problem "
+                         "(D = 1/9, a ConstantDiffusion, geometry_mode 1: streaming recompute kernel)")
     ap.add_argument("--all-variants", action="store_true")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -386,11 +520,23 @@ def main():
     json_fd = os.dup(1)
     os.dup2(2, 1)
 
-    import torch
-    import fvm_b200 as G
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # one process per GPU on ONE host: give every rank its own slice of the cores (host-side planning in fvm_finalize is
+    # OpenMP code and torchrun exports OMP_NUM_THREADS=1; pinned buffers are first-touched by the rank's own cores)
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            mine = cores[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            cores = mine
+        os.environ["OMP_NUM_THREADS"] = str(len(cores))
+    except Exception:
+        pass
+    import torch
+    import fvm_b200 as G
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libfvmcuda has no CPU fallback")
     torch.cuda.set_device(local)
@@ -404,12 +550,13 @@ def main():
     peak, peak_src = measured_peak()
     # default: the README problem as the engine runs it (reduced stream) plus the same mesh through the
     # general 21-component layout of north_star (a); --all-variants adds the recompute-geometry kernels
-    names = sorted(VARIANTS) if args.all_variants else sorted({args.variant, "general_stored", "const_recompute"})
+    names = sorted(VARIANTS) if args.all_variants or world == 1 else [args.variant]
     if args.variant in names:
         names.remove(args.variant)
         names.append(args.variant)  # headline variant last: its engine stays alive for e2e
     results = {}
     eng = p = None
+    parity_max_rel = None
     for name in names:
         flux_f, gmode, layout = VARIANTS[name]
         if eng is not None:
@@ -425,9 +572,17 @@ def main():
         N = eng.N
         # triangles per rank of the GLOBAL mesh (cut triangles, computed on both sides, count once)
         T = eng.T if world == 1 else 2 * (nx - 1) * (nx * world - 1) // world
-        g = torch.Generator(device="cuda")
-        g.manual_seed(SEED + rank)
-        u_d = 50.0 * torch.rand(N, dtype=torch.float64, device="cuda", generator=g)
+        if lmesh is None:
+            g = torch.Generator(device="cuda")
+            g.manual_seed(SEED + rank)
+            u_d = 50.0 * torch.rand(N, dtype=torch.float64, device="cuda", generator=g)
+        else:  # u is a function of the GLOBAL node id, so that any rank can evaluate any node (in-run parity check)
+            from fvm_b200 import _lib as L
+            u_c = torch.from_numpy(global_u(lmesh.global_nodes)).cuda()
+            u_d = torch.empty_like(u_c)
+            L.check(eng.h, L.lib().fvm_to_native(eng.h, u_c.data_ptr(), u_d.data_ptr()))
+            eng.synchronize()
+            del u_c
         du_d = torch.empty_like(u_d)
         if dist is not None:
             dist.barrier()
@@ -446,10 +601,17 @@ def main():
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             ms = float(tmax.item())
         clocks = sampler.stop() if sampler else None
+        if lmesh is not None and name == names[-1]:
+            parity = sharded_parity(torch, G, eng, lmesh, du_d, nx, nx * world, 2.0 * world, flux_f(G), rank, world, gmode)
+            pv = torch.tensor([parity], dtype=torch.float64, device="cuda")
+            dist.all_reduce(pv, op=dist.ReduceOp.MAX)
+            parity_max_rel = float(pv.item())
         B = rhs_bytes(T, N, 1, layout)
+        Bmin = rhs_bytes(T, N, 1, "recompute")
         results[name] = {"ms_per_step": ms, "mtri_s": world * T / ms / 1e3, "kernel_ms": kms, "layout": layout,
-                         "alg_bytes": B, "kernel_gbs": B / kms / 1e6, "frac": B / kms / 1e6 / peak, "setup_s": setup_s,
-                         "tiles": eng.stats()}
+                         "alg_bytes": B, "kernel_gbs": B / kms / 1e6, "frac": B / kms / 1e6 / peak,
+                         "frac_vs_minimal_bytes": Bmin / kms / 1e6 / peak, "step_frac_vs_minimal_bytes": Bmin / ms / 1e6 / peak,
+                         "setup_s": setup_s, "tiles": eng.stats()}
         if rank == 0:
             sys.stderr.write("[bench] %-18s %.3f ms/step  %.1f Mtri/s  tile-kernel %.3f ms  %.0f GB/s (%.2f of %s)\n"
                              % (name, ms, results[name]["mtri_s"], kms, results[name]["kernel_gbs"], results[name]["frac"], peak_src))
@@ -460,7 +622,8 @@ def main():
     du_h = torch.empty(N, dtype=torch.float64).pin_memory()
     u_h.copy_(u_d.cpu())
     un, dun = u_h.numpy(), du_h.numpy()
-    G.fvm_eqs(dun, un, p, 0.0)
+    for _ in range(3):  # warm-up, and the handle's one-off choice between the banded pipeline and the plain schedule
+        G.fvm_eqs(dun, un, p, 0.0)
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
@@ -477,6 +640,7 @@ def main():
     e2e_plain_ms = (time.perf_counter() - t0) / 3 * 1e3
     del os.environ["FVM_NO_PIPELINE"]
     e2e_stats = eng.stats()
+    e2e_sched = e2e_stats.get("host_schedule_rhs", "undecided")
     if dist is not None:
         tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -494,12 +658,27 @@ def main():
     if not args.no_extras and world == 1:
         extras = time_extras(torch, G, nx, max(10, args.steps // 4), args.warmup, peak)
         sys.stderr.write("[bench] extras: %s\n" % json.dumps(extras))
+    strong = None
+    if not args.no_strong:
+        if eng is not None:
+            eng.close()
+        del u_d, du_d
+        torch.cuda.empty_cache()
+        strong = strong_scaling_leg(torch, G, dist, rank, world, local, max(10, args.steps // 2), args.warmup, peak, args.strong_nx)
+        if rank == 0:
+            sys.stderr.write("[bench] strong %s: RHS %.3f ms  SpMV %.3f ms  Tsit5 %.3f ms/step  parity %s\n"
+                             % (strong["mesh"], strong["rhs_ms"], strong["spmv_ms"], strong["tsit5_ms_per_step"], strong["parity_max_rel"]))
     if rank != 0:
         dist.destroy_process_group()
         return
-    cb = None
+    cb = steady_cpu = None
     if not args.no_cpu_baseline and world == 1:
-        cb = cpu_baseline(args.ref_nx)
+        cb = cpu_baseline(args.ref_nx or nx)
+        try:
+            steady_cpu = cpu_steady_baseline(512)
+        except Exception as e:
+            steady_cpu = {"unavailable": type(e).__name__}
+    traffic, traffic_src = profiled_traffic(args.variant) if (nx == 4096 and world == 1) else (None, None)
     launches_per_step = 1 + (1 if st["n_interface"] + (N - st["n_vertices"]) > 0 else 0) + (1 if st["n_live_boundary_edges"] else 0)
     line = {
         "metric": "fvm_eqs! Mtriangle-updates/s", "value": head["mtri_s"], "unit": "Mtriangle-updates/s",
@@ -511,14 +690,18 @@ def main():
                                % (nx, nx, nx, nx * world, 2 * world, N, T),
                    "variant": args.variant, "l2": "inputs larger than L2 (%.2f GB streamed per step vs 126 MB L2)" % (head["alg_bytes"] / 1e9),
                    "tile_triangles": st["tile_triangles"], "n_tiles": st["n_tiles"]},
-        "roofline": {"bound": "hbm", "kernel": "rhs_tile_kernel", "achieved": head["kernel_gbs"], "peak": peak, "unit": "GB/s",
-                     "frac": head["frac"], "traffic": profiled_traffic(args.variant) if nx == 4096 else None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "rhs_stream_kernel" if head["layout"] == "recompute" else "rhs_tile_kernel",
+                     "achieved": head["kernel_gbs"], "peak": peak, "unit": "GB/s", "frac": head["frac"],
+                     "frac_vs_minimal_bytes": head["frac_vs_minimal_bytes"],
+                     "traffic": traffic, "traffic_source": ("from the committed ncu capture " + traffic_src + ", not measured in this run") if traffic else None,
+                     "peak_source": peak_src,
                      "bytes_formula": {"general": "180*T + 25*N", "reduced": "108*T + 25*N", "recompute": "12*T + 41*N"}[head["layout"]],
                      "alg_bytes_per_launch": head["alg_bytes"], "kernel_ms": head["kernel_ms"]},
         "e2e": {"value": world * T / e2e_ms / 1e3, "unit": "Mtriangle-updates/s", "h2d_bytes_per_step": 8 * N,
                 "d2h_bytes_per_step": 8 * N, "ms_per_step": e2e_ms,
                 "schedule": ("banded pipeline, %d bands (copy-in / tiles / copy-out overlapped)" % e2e_stats["pipe_bands"])
-                if e2e_stats.get("pipe_calls", 0) > 0 else "H2D, kernels, D2H in sequence",
+                if e2e_sched == "pipeline" else "H2D, kernels, D2H in sequence",
+                "schedule_choice": "one-off timing per handle (call 1 pipelined, call 2 plain, then the faster): " + e2e_sched,
                 "unpipelined_ms_per_step": e2e_plain_ms},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
@@ -527,7 +710,8 @@ def main():
     if tplres:
         line["spmv"] = {"metric": "DiffusionEquation template y = A x + b, fp64 CSR SpMV", "gbs": tplres["spmv_gbs"],
                         "frac": tplres["spmv_frac"], "tile_kernel_ms": tplres["spmv_kernel_ms"], "ms_per_step": tplres["spmv_ms"],
-                        "launches_per_spmv": 2, "traffic": profiled_traffic("spmv") if nx == 4096 else None, "format": "sliced ELL per tile, 16-bit tile-local columns, x staged in shared memory",
+                        "launches_per_spmv": 2, "traffic": profiled_traffic("spmv")[0] if (nx == 4096 and world == 1) else None,
+                        "traffic_source": "from the committed ncu capture, not measured in this run", "format": "sliced ELL per tile, 16-bit tile-local columns, x staged in shared memory",
                         "alg_bytes_per_launch": tplres["spmv_alg_bytes"], "bytes_formula": "12*nnz + 4*(N+1) + 24*N",
                         "nnz": tplres["nnz"], "assemble_setup_s": tplres["assemble_setup_s"],
                         "e2e_ms_host_vectors": tplres["spmv_e2e_ms"]}
@@ -537,9 +721,20 @@ def main():
     if extras:
         line["other_configs"] = extras
     if cb:
-        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "cpu_flat", "cpu_spmv_1t", "cpu_spmv_nt", "julia")
+                                if k in cb}
+        line["cpu_baseline"]["same_mesh_as_gpu_arm"] = cb["nx"] == nx
+        if steady_cpu:
+            line["cpu_baseline"]["cpu_steady_superlu"] = steady_cpu
+    if parity_max_rel is not None:
+        line["parity_max_rel"] = parity_max_rel
+        line["parity_note"] = ("first / middle / last owned row of every rank's strip (the rows that read the NCCL-exchanged ghost layer) against a "
+                               "single-domain evaluation of a 5-row patch of the global lattice on the same GPU; max over rows and ranks")
+    if strong:
+        line["strong_%d" % args.strong_nx] = strong
     if len(results) > 1:
-        line["variants"] = {k: {kk: v[kk] for kk in ("ms_per_step", "mtri_s", "kernel_ms", "kernel_gbs", "frac", "layout")}
+        line["variants"] = {k: {kk: v[kk] for kk in ("ms_per_step", "mtri_s", "kernel_ms", "kernel_gbs", "frac", "frac_vs_minimal_bytes",
+                                                     "step_frac_vs_minimal_bytes", "layout")}
                             for k, v in results.items()}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(line) + "\n").encode())

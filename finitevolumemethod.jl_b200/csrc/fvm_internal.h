@@ -208,6 +208,7 @@ struct fvm_ctx {
     void* pipe_spmv = nullptr;  // plan of fvm_spmv
     const int32_t* pipe_list = nullptr;  // explicit tile list of fvm_launch_rhs_part(part = 4)
     int32_t pipe_off = 0, pipe_count = 0;
+    int32_t pipe_choice[2] = {0, 0};  // schedule chosen by the one-off timing (fvm_rhs, fvm_spmv): 0 undecided, 1 pipeline, 2 plain
     // streaming recompute kernel (fvm_rhs_stream.cu): per-tile packs + directory
     uint8_t* d_packs = nullptr;
     int4* d_pack_dir = nullptr;   // 2 x int4 per tile: {pack offset / 16, pack bytes, node0, nown}, {ext0, next, 0, 0}
@@ -286,6 +287,7 @@ int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du
 int32_t fvm_spmv_pipelined(fvm_ctx* h, const double* x_host, double* y_host, bool add_b, bool* used);
 int32_t fvm_launch_spmv_tail_list(fvm_ctx* h, const double* x, double* y, bool add_b, const int32_t* list, int off, int count);
 void fvm_pipe_release(fvm_ctx* h);
+void fvm_pipe_report(fvm_ctx* h, int mode, double seconds);
 int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part);
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);
 int32_t fvm_global_or(fvm_ctx* h, bool local, bool* global);

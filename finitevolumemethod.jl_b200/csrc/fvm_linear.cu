@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <chrono>
+
 #include "fvm_device.cuh"
 
 #define MAX_ROW 64
@@ -601,7 +603,6 @@ int32_t fvm_build_pattern(fvm_ctx* h) {
         if ((rc = fvm_dev_upload(h, &c.sell_ptr, sptr))) return rc;
         if ((rc = fvm_dev_alloc(h, &c.sell_val, (size_t)entries + 32))) return rc;
         if ((rc = fvm_dev_alloc(h, &c.sell_col, (size_t)entries + 32))) return rc;
-        h->stats[15] = entries;
         if ((rc = fvm_dev_upload(h, &c.tail_rows, tail))) return rc;
         {
             std::vector<int32_t> tp(1, 0);
@@ -850,9 +851,14 @@ extern "C" int32_t fvm_spmv(fvm_handle h, const double* x, double* y, int32_t ad
     FVM_REQUIRE(h, x && y, "fvm_spmv: null argument");
     int32_t rc = fvm_ensure_state(h);
     if (rc) return rc;
+    const auto wall0 = std::chrono::steady_clock::now();
     if (!on_device && x != y) {  // large host vectors: the banded copy / compute pipeline of fvm_pipe.cu
         bool used = false;
-        if ((rc = fvm_spmv_pipelined(h, x, y, add_b != 0, &used)) || used) return rc;
+        rc = fvm_spmv_pipelined(h, x, y, add_b != 0, &used);
+        if (rc || used) {
+            if (!rc) fvm_pipe_report(h, 1, std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count());
+            return rc;
+        }
     }
     const size_t bytes = sizeof(double) * h->N;
     const double* src = x;
@@ -869,5 +875,6 @@ extern "C" int32_t fvm_spmv(fvm_handle h, const double* x, double* y, int32_t ad
         FVM_CUDA(h, cudaMemcpyAsync(y, h->d_io, bytes, cudaMemcpyDeviceToHost, h->stream));
     }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!on_device && x != y) fvm_pipe_report(h, 1, std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count());
     return FVM_OK;
 }

@@ -40,6 +40,13 @@ struct PipePlan {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_stage;
     cudaEvent_t ev_start = nullptr, ev_out = nullptr;
+    // one-off choice between the banded pipeline and the plain schedule (H2D, kernels, D2H in sequence): call 0 warms
+    // the pipeline up, call 1 times it, call 2 times the plain schedule, later calls take the faster one.  Several
+    // ranks sharing one host can saturate its memory system, where the three concurrent streams of the pipeline lose
+    // (measured at 8 ranks: 16.3 ms pipelined vs 15.0 ms plain).  Both schedules give bit-identical results and contain
+    // exactly one halo exchange, so ranks may choose differently.
+    int calls = 0;
+    double t_pipe = 0.0, t_plain = 0.0;
 };
 
 __global__ void band_scatter_kernel(const int32_t* __restrict__ new_of_old, const double* __restrict__ src_caller,
@@ -311,9 +318,25 @@ static int32_t pipeline_plan(fvm_ctx* h, int mode, void*& slot, PipePlan** out) 
     }
     PipePlan* P = (PipePlan*)slot;
     const char* e_force = getenv("FVM_PIPE_FORCE");  // tests: run the pipeline even where it cannot overlap anything
-    if (!P->useful && !(e_force && e_force[0] == '1')) return FVM_OK;
+    const bool force = e_force && e_force[0] == '1';
+    if (!P->useful && !force) return FVM_OK;
+    static const bool tune = !(getenv("FVM_PIPE_AUTOTUNE") && getenv("FVM_PIPE_AUTOTUNE")[0] == '0');
+    if (tune && !force) {
+        if (P->calls == 2) return FVM_OK;                               // the timed plain call
+        if (P->calls > 2 && P->t_plain < P->t_pipe) return FVM_OK;      // plain won
+    }
     *out = P;
     return FVM_OK;
+}
+
+// wall time of one host-buffer call, reported by fvm_rhs / fvm_spmv (mode 0 / 1) for the one-off schedule choice
+void fvm_pipe_report(fvm_ctx* h, int mode, double seconds) {
+    PipePlan* P = (PipePlan*)(mode == 0 ? h->pipe : h->pipe_spmv);
+    if (!P) return;
+    if (P->calls == 1) P->t_pipe = seconds;
+    else if (P->calls == 2) P->t_plain = seconds;
+    if (P->calls == 2) h->pipe_choice[mode] = P->t_plain < P->t_pipe ? 2 : 1;  // 1: pipeline kept, 2: plain schedule chosen
+    if (P->calls < 3) P->calls += 1;
 }
 
 int32_t fvm_rhs_pipelined(fvm_ctx* h, double t, const double* u_host, double* du_host, bool* used) {

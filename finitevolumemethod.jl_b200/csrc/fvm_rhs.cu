@@ -14,6 +14,8 @@
 // No atomics anywhere: every output word has exactly one writer and a fixed summation order.
 #include <cuda_pipeline.h>
 
+#include <chrono>
+
 #include "fvm_device.cuh"
 
 #define RHS_BLOCK 256
@@ -747,9 +749,14 @@ extern "C" int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, 
     FVM_REQUIRE(h, u && du, "fvm_rhs: null argument");
     int32_t rc = fvm_ensure_state(h);
     if (rc) return rc;
+    const auto wall0 = std::chrono::steady_clock::now();
     if (!on_device) {  // large host vectors: copies, permutations and tiles overlapped band by band
         bool used = false;
-        if ((rc = fvm_rhs_pipelined(h, t, u, du, &used)) || used) return rc;
+        rc = fvm_rhs_pipelined(h, t, u, du, &used);
+        if (rc || used) {
+            if (!rc) fvm_pipe_report(h, 0, std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count());
+            return rc;
+        }
     }
     const size_t bytes = sizeof(double) * h->N * h->neq;
     const double* src = u;
@@ -766,6 +773,7 @@ extern "C" int32_t fvm_rhs(fvm_handle h, double t, const double* u, double* du, 
         FVM_CUDA(h, cudaMemcpyAsync(du, h->d_io, bytes, cudaMemcpyDeviceToHost, h->stream));
     }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (!on_device) fvm_pipe_report(h, 0, std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count());
     return FVM_OK;
 }
 

@@ -1262,5 +1262,7 @@ extern "C" int32_t fvm_get_permutation(fvm_handle h, int32_t* node_perm, int32_t
 extern "C" int32_t fvm_get_stats(fvm_handle h, int64_t* stats) {
     if (!h || !stats) return FVM_ERR_ARG;
     for (int i = 0; i < 16; ++i) stats[i] = h->stats[i];
+    stats[9] = h->smem_rhs;
+    stats[15] = h->pipe_choice[0] + 4 * h->pipe_choice[1];  // host-buffer schedule chosen for fvm_rhs / fvm_spmv: 0 undecided, 1 pipeline, 2 plain
     return FVM_OK;
 }

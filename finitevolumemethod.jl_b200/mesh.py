@@ -57,7 +57,12 @@ def _chain_boundary(tris):
     key = e[:, 0] * n + e[:, 1]
     rkey = e[:, 1] * n + e[:, 0]
     bnd = e[~np.isin(key, rkey)]
-    nxt = dict(zip(bnd[:, 0].tolist(), bnd[:, 1].tolist()))
+    src = bnd[:, 0]
+    if len(np.unique(src)) != len(src):
+        # a vertex with two outgoing boundary edges (pinch point, or a hole touching the outer boundary): the loops are
+        # ambiguous and DelaunayTriangulation would keep such a vertex in two sections -- pass boundary_sections explicitly
+        raise ValueError("non-manifold boundary: a vertex has more than one outgoing boundary edge; give boundary_sections")
+    nxt = dict(zip(src.tolist(), bnd[:, 1].tolist()))
     sections, seen = [], set()
     for start in sorted(nxt):
         if start in seen:
@@ -66,6 +71,8 @@ def _chain_boundary(tris):
         seen.add(start)
         cur = nxt[start]
         while cur != start:
+            if cur in seen or cur not in nxt or len(loop) > len(bnd):
+                raise ValueError("boundary edges do not form closed loops")
             loop.append(cur)
             seen.add(cur)
             cur = nxt[cur]

@@ -361,7 +361,10 @@ class Engine:
         L.check(self.h, L.lib().fvm_get_stats(self.h, st.ctypes.data_as(L.c_lp)))
         keys = ["n_tiles", "tile_triangles", "n_vertices", "n_interface", "n_partial", "n_external", "max_local_nodes",
                 "n_live_boundary_edges", "n_dirichlet", "smem_bytes", "nnz", "max_row", "pipe_bands", "pipe_early_bands", "pipe_calls"]
-        return dict(zip(keys, st.tolist()))
+        out = dict(zip(keys, st.tolist()))
+        names = ("undecided", "pipeline", "plain")
+        out["host_schedule_rhs"], out["host_schedule_spmv"] = names[int(st[15]) & 3], names[(int(st[15]) >> 2) & 3]
+        return out
 
     def permutation(self):
         node = np.empty(self.N, dtype=np.int32)

@@ -197,6 +197,28 @@ def lattice_strip_local(a, b, c, d, nx, ny_per_rank, rank, nparts):
                      recv_nodes)
 
 
+def lattice_rows(a, b, c, d, nx, ny, row0, row1):
+    """Rows [row0, row1) of the nx x ny lattice on [a,b]x[c,d] as a mesh of their own, with the GLOBAL coordinates
+    (same doubles as triangulate_rectangle) and the same triangle pattern: du of an inner row of the patch equals du
+    of that row in the global problem (bench.py's in-run parity check of sharded runs).  One boundary section."""
+    dx = (b - a) / (nx - 1)
+    dy = (d - c) / (ny - 1)
+    rows = np.arange(row0, row1)
+    nr = len(rows)
+    pts = np.empty((nr * nx, 2))
+    pts[:, 0] = np.tile(a + np.arange(nx, dtype=np.float64) * dx, nr)
+    pts[:, 1] = np.repeat(c + rows.astype(np.float64) * dy, nx)
+    p00 = (np.arange(nx - 1, dtype=np.int32)[None, :] + (np.arange(nr - 1, dtype=np.int32) * nx)[:, None]).ravel()
+    tris = np.empty((2 * len(p00), 3), dtype=np.int32)
+    tris[0::2, 0], tris[0::2, 1], tris[0::2, 2] = p00, p00 + 1, p00 + nx
+    tris[1::2, 0], tris[1::2, 1], tris[1::2, 2] = p00 + nx, p00 + 1, p00 + nx + 1
+    bottom = np.arange(0, nx)
+    right = np.arange(nx - 1, nx * nr, nx)
+    top = np.arange(nx * nr - 1, nx * (nr - 1) - 1, -1)
+    left = np.arange(nx * (nr - 1), -1, -nx)
+    return Triangulation(pts, tris, [np.concatenate([bottom, right[1:], top[1:], left[1:]])])
+
+
 # ---- problems ---------------------------------------------------------------------------------------
 def shard_problem(prob, local):
     """The rank-local FVMProblem / FVMSystem of a global problem (same condition functions, sections

@@ -125,7 +125,8 @@ def test_linearity_and_operator_equals_rhs_4096(big):
     p.engine.rhs_device(dd.data_ptr(), ud.data_ptr(), 0.0)
     assert np.array_equal(dd.cpu().numpy(), Fu)
     st = p.engine.stats()
-    assert st["pipe_calls"] == 3 and st["pipe_bands"] >= 2 and st["pipe_early_bands"] >= st["pipe_bands"] - 2
+    # 4 host-buffer calls so far: pipeline warm-up, pipeline timed, plain timed, then the faster of the two
+    assert st["pipe_calls"] in (2, 3) and st["host_schedule_rhs"] in ("pipeline", "plain") and st["pipe_bands"] >= 2 and st["pipe_early_bands"] >= st["pipe_bands"] - 2
     del ud, dd
     # interior stencil D/h^2 [1,1,-4,1,1] on a smooth field: F(x^2 + y^2) = 4 D away from the boundary
     P = tri.points
