@@ -78,6 +78,22 @@ static int32_t launch_lincomb(fvm_ctx* h, int S, int64_t n, double* out, const d
     return FVM_OK;
 }
 
+// saveat times must be sorted, inside [t0, t1] and (fixed step) on the step grid: an entry the stepper never reaches
+// would block every later one and leave its rows of the output unwritten
+static int32_t check_saveat(fvm_ctx* h, const char* who, int64_t nsave, const double* tsave, double t0, double t1, double dt_grid) {
+    const double eps = 1e-9 * std::max(1.0, std::max(std::fabs(t0), std::fabs(t1)));
+    for (int64_t k = 0; k < nsave; ++k) {
+        if (!(tsave[k] >= t0 - eps && tsave[k] <= t1 + eps)) return fvm_fail(h, FVM_ERR_ARG, std::string(who) + ": a saveat time lies outside [t0, t1]");
+        if (k > 0 && !(tsave[k] >= tsave[k - 1])) return fvm_fail(h, FVM_ERR_ARG, std::string(who) + ": saveat times must be sorted");
+        if (dt_grid > 0) {
+            const double q = (tsave[k] - t0) / dt_grid;
+            if (std::fabs(q - std::round(q)) * dt_grid > 1e-6 * dt_grid + eps)
+                return fvm_fail(h, FVM_ERR_ARG, std::string(who) + ": a saveat time is not a multiple of dt after t0 (fixed-step integration)");
+        }
+    }
+    return FVM_OK;
+}
+
 extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, double t0, double t1, double dt, int64_t nsave,
                              const double* tsave, double* usave, int32_t on_device) {
     NEED_FINAL(h);
@@ -88,8 +104,9 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
     const int64_t nsteps = llround((t1 - t0) / dt);
     FVM_REQUIRE(h, std::fabs(t0 + nsteps * dt - t1) <= 1e-9 * std::max(1.0, std::fabs(t1)),
                 "fvm_tsit5: dt must divide the time span (fixed-step integration)");
-    int32_t rc = ensure_work(h, 9);
+    int32_t rc = check_saveat(h, "fvm_tsit5", nsave, tsave, t0, t1, dt);
     if (rc) return rc;
+    if ((rc = ensure_work(h, 9))) return rc;
     if ((rc = fvm_ensure_state(h))) return rc;
     const int64_t n = h->N * h->neq;
     const size_t bytes = sizeof(double) * n;
@@ -213,6 +230,7 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
         FVM_CUDA(h, cudaMemcpyAsync(u, h->d_io, bytes, cudaMemcpyDeviceToHost, h->stream));
     }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (next_save != nsave) return fvm_fail(h, FVM_ERR_ARG, "fvm_tsit5: not every saveat time was reached");
     return FVM_OK;
 }
 
@@ -287,8 +305,8 @@ struct ErrComb {
 
 __global__ void __launch_bounds__(RED_THREADS)
     tsit5_err_kernel(const int64_t n, const double* __restrict__ u, const double* __restrict__ unew, const double dt,
-                     const ErrComb ec, const double abstol, const double reltol, const uint8_t* __restrict__ skip,
-                     double* __restrict__ partial) {
+                     const ErrComb ec, const double abstol, const double reltol, const uint8_t* __restrict__ kind /* [neq][N] or null */,
+                     const int64_t n_nodes, const int neq, double* __restrict__ partial) {
     double v[1] = {0.0};
     GRID_STRIDE(i, n) {
         double e = ec.c[0] * ec.k[0][i];
@@ -297,15 +315,25 @@ __global__ void __launch_bounds__(RED_THREADS)
         e *= dt;
         const double sc = abstol + fmax(fabs(u[i]), fabs(unew[i])) * reltol;
         const double r = e / sc;
-        if (!skip || !skip[i]) v[0] += r * r;
+        // sharded: ghost entries belong to another rank's norm (their du is 0 here); the step size must not depend on the partition
+        if (!kind || kind[(i % neq) * n_nodes + i / neq] != FVM_NODE_GHOST) v[0] += r * r;
     }
     block_reduce_store<1>(v, partial);
 }
 
+__global__ void __launch_bounds__(RED_THREADS) count_owned_kernel(const int64_t n, const uint8_t* __restrict__ kind, const int64_t n_nodes,
+                                                                  const int neq, double* __restrict__ partial) {
+    double v[1] = {0.0};
+    GRID_STRIDE(i, n) v[0] += kind[(i % neq) * n_nodes + i / neq] != FVM_NODE_GHOST ? 1.0 : 0.0;
+    block_reduce_store<1>(v, partial);
+}
+
 __global__ void __launch_bounds__(RED_THREADS) initdt_kernel(const int64_t n, const double* __restrict__ u, const double* __restrict__ f0,
-                                                             const double abstol, const double reltol, double* __restrict__ partial) {
+                                                             const double abstol, const double reltol, const uint8_t* __restrict__ kind,
+                                                             const int64_t n_nodes, const int neq, double* __restrict__ partial) {
     double v[2] = {0.0, 0.0};
     GRID_STRIDE(i, n) {
+        if (kind && kind[(i % neq) * n_nodes + i / neq] == FVM_NODE_GHOST) continue;
         const double sc = abstol + fabs(u[i]) * reltol;
         v[0] += (u[i] / sc) * (u[i] / sc);
         v[1] += (f0[i] / sc) * (f0[i] / sc);
@@ -320,8 +348,9 @@ extern "C" int32_t fvm_tsit5_adaptive(fvm_handle h, int32_t use_operator, double
     FVM_REQUIRE(h, u && t1 >= t0 && abstol > 0 && reltol > 0, "fvm_tsit5_adaptive: bad arguments");
     FVM_REQUIRE(h, nsave == 0 || (tsave && usave), "fvm_tsit5_adaptive: save buffers missing");
     if (use_operator && !h->csr.assembled) return fvm_fail(h, FVM_ERR_STATE, "fvm_tsit5_adaptive: call fvm_assemble first");
-    int32_t rc = ensure_work(h, 10);
+    int32_t rc = check_saveat(h, "fvm_tsit5_adaptive", nsave, tsave, t0, t1, 0.0);
     if (rc) return rc;
+    if ((rc = ensure_work(h, 10))) return rc;
     if ((rc = fvm_ensure_state(h))) return rc;
     const int64_t n = h->N * h->neq;
     const size_t bytes = sizeof(double) * n;
@@ -367,21 +396,21 @@ extern "C" int32_t fvm_tsit5_adaptive(fvm_handle h, int32_t use_operator, double
     };
     bool has_callback = false;
     if ((rc = fvm_global_or(h, !use_operator && h->n_dir > 0, &has_callback))) return rc;
-    // sharded: every rank must see the same error norm -> global sums and a global entry count (ghost
-    // entries mirror owned values and are counted on both sides; the RMS weighting absorbs it)
+    // sharded: every rank must see the same error norm -> global sums over OWNED entries and a global owned-entry count
+    // (ghost entries are excluded, so accepted / rejected steps do not depend on the number of shards)
     double n_glob = (double)n;
-    if (h->nranks > 1) {
-        FVM_CUDA(h, cudaMemcpyAsync(sc + SC_SUM0, &n_glob, sizeof(double), cudaMemcpyHostToDevice, st));
-        if ((rc = fvm_allreduce_sum(h, sc + SC_SUM0, 1))) return rc;
-        FVM_CUDA(h, cudaMemcpyAsync(&n_glob, sc + SC_SUM0, sizeof(double), cudaMemcpyDeviceToHost, st));
-        FVM_CUDA(h, cudaStreamSynchronize(st));
+    const uint8_t* ghost_kind = h->halo_ready ? h->dm.kind : nullptr;
+    if (ghost_kind) {
+        count_owned_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, ghost_kind, h->N, h->neq, partial);
+        if ((rc = sums(1))) return rc;
+        n_glob = hs[SC_SUM0];
     }
     double t = t0;
     if ((rc = save(t))) return rc;
     if ((rc = f(K[0], U, t))) return rc;
     double dt = dt0;
     if (!(dt > 0)) {  // Hairer's initial step from |u0| and |f(u0)|
-        initdt_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, U, K[0], abstol, reltol, partial);
+        initdt_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, U, K[0], abstol, reltol, ghost_kind, h->N, h->neq, partial);
         if ((rc = sums(2))) return rc;
         const double d0 = std::sqrt(hs[SC_SUM0] / n_glob), d1 = std::sqrt(hs[SC_SUM1] / n_glob);
         dt = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
@@ -414,7 +443,7 @@ extern "C" int32_t fvm_tsit5_adaptive(fvm_handle h, int32_t use_operator, double
             ec.k[j] = K[j];
             ec.c[j] = TS_BT[j];
         }
-        tsit5_err_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, U, UNEW, dt_try, ec, abstol, reltol, nullptr, partial);
+        tsit5_err_kernel<<<RED_BLOCKS, RED_THREADS, 0, st>>>(n, U, UNEW, dt_try, ec, abstol, reltol, ghost_kind, h->N, h->neq, partial);
         if ((rc = sums(1))) return rc;
         const double EEst = std::sqrt(hs[SC_SUM0] / n_glob);
         if (!(EEst == EEst)) return fvm_fail(h, FVM_ERR_ARG, "fvm_tsit5_adaptive: the error estimate is NaN (unstable step)");
@@ -452,6 +481,7 @@ extern "C" int32_t fvm_tsit5_adaptive(fvm_handle h, int32_t use_operator, double
     FVM_CUDA(h, cudaStreamSynchronize(st));
     if (n_accept) *n_accept = nacc;
     if (n_reject) *n_reject = nrej;
+    if (next_save != nsave) return fvm_fail(h, FVM_ERR_ARG, "fvm_tsit5_adaptive: not every saveat time was reached");
     return FVM_OK;
 }
 

@@ -217,6 +217,7 @@ class Engine:
         self.N, self.T = tri.num_points, tri.num_triangles
         self.h = _create_handle(tri, neq, device, mesh_file)
         self._keep = []
+        self.validation_error = None  # sharded templates: rank-local verdict, combined over ranks by install_halo
         try:
             uv = conditions[0].boundary_edges
             self.boundary_edges = uv

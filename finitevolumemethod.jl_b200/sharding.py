@@ -253,14 +253,22 @@ def install_halo(engine, local, dist=None):
     lib = L.lib()
     if local.nparts > 1:
         import ctypes as C
+        if dist is None:
+            import torch.distributed as dist
+        # a problem one rank rejects (its local conditions hold e.g. a Dudt node a steady template does not support) is
+        # rejected by EVERY rank, before anyone enters a collective
+        verdicts = [None] * local.nparts
+        dist.all_gather_object(verdicts, getattr(engine, "validation_error", None))
+        bad = [(r, v) for r, v in enumerate(verdicts) if v]
+        if bad:
+            engine.close()
+            raise ValueError(bad[0][1] + (" (conditions of rank %d)" % bad[0][0] if bad[0][0] != local.rank else ""))
         uid = C.create_string_buffer(128)
         if local.rank == 0:
             rc = lib.fvm_nccl_unique_id(uid)
             if rc != L.OK:
                 raise L.FVMCudaError(rc, "ncclGetUniqueId failed")
         box = [uid.raw]
-        if dist is None:
-            import torch.distributed as dist
         dist.broadcast_object_list(box, src=0)
         uid = C.create_string_buffer(box[0], 128)
         L.check(engine.h, lib.fvm_shard_init(engine.h, uid, local.rank, local.nparts))

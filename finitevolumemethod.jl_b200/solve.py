@@ -71,7 +71,7 @@ def solve(prob, alg=None, *, saveat=None, parallel="cuda", p=None, **kw):
     p = p or get_cuda_parameters(prob, **kw)
     u = np.ascontiguousarray(prob.initial_condition, dtype=np.float64).copy()
     ts = np.ascontiguousarray([] if saveat is None else saveat, dtype=np.float64)
-    us = np.empty((len(ts),) + u.shape)
+    us = np.full((len(ts),) + u.shape, np.nan)  # a row the stepper never wrote must not look like data
     run_tsit5(p.engine.h, alg, False, u, prob.initial_time, prob.final_time, ts, us)
     if saveat is None:
         return Solution(u, prob.final_time)

@@ -94,11 +94,17 @@ class AbstractFVMTemplate:
         self.diffusion_function, self.diffusion_parameters = diffusion_function, diffusion_parameters
         self.source_function, self.source_parameters = source_function, source_parameters
         c = self.conditions
+        err = None
         if self.steady and c.has_dudt_nodes():  # poissons_equation.jl:69-70, mean_exit_time.jl:66-67
-            raise ValueError("%s does not support Dudt nodes." % ("MeanExitTimeProblem" if self.template_id == TPL_MEAN_EXIT_TIME
-                                                                  else "PoissonsEquation"))
-        if self.template_id == TPL_MEAN_EXIT_TIME and c.has_constrained_edges():  # mean_exit_time.jl:68-69
-            raise ValueError("MeanExitTimeProblem does not support Constrained edges.")
+            err = "%s does not support Dudt nodes." % ("MeanExitTimeProblem" if self.template_id == TPL_MEAN_EXIT_TIME else "PoissonsEquation")
+        elif self.template_id == TPL_MEAN_EXIT_TIME and c.has_constrained_edges():  # mean_exit_time.jl:68-69
+            err = "MeanExitTimeProblem does not support Constrained edges."
+        if err and ghost is None:
+            raise ValueError(err)
+        # sharded: these checks see the rank-LOCAL conditions only.  A rank that raised here while its peers went on
+        # into the NCCL calls of install_halo would hang them, so the verdict is deferred: install_halo combines it over
+        # all ranks and every rank raises the same ValueError
+        self._validation_error = err
         tri = mesh.triangulation
         P = tri.points
         N = tri.num_points
@@ -130,7 +136,11 @@ class AbstractFVMTemplate:
         # big tiles: the sliced-ELL SpMV keeps only x of a tile in shared memory, and fewer interface rows
         # (3 % at 4096 triangles per tile) mean less gather traffic in the tail kernel
         self.engine = Engine(mesh, 1, [c], tile_triangles=tile_triangles or 4096, geometry_mode=1, ghost=ghost)  # assembly recomputes geometry; no SoA kept
+        self.engine.validation_error = err
         self.node_value = node_value
+        self.N = N
+        if err:
+            return
         node_value, edge_value = L.f64(node_value), L.f64(edge_value)
         L.check(self.engine.h, L.lib().fvm_assemble(self.engine.h, self.template_id, d_const, L.dp(d_edge), L.dp(d_bnd),
                                                     L.dp(node_value), L.dp(edge_value), L.dp(source), 1 if reference_quirks else 0))
@@ -244,7 +254,7 @@ def solve_template(prob, alg=None, saveat=None, x0=None):
         raise TypeError("transient templates are integrated with the device-resident fixed-step Tsit5(dt)")
     u = prob.u0.copy()
     ts = np.ascontiguousarray([] if saveat is None else saveat, dtype=np.float64)
-    us = np.empty((len(ts), prob.N))
+    us = np.full((len(ts), prob.N), np.nan)  # a row the stepper never wrote must not look like data
     run_tsit5(h, alg, True, u, prob.initial_time, prob.final_time, ts, us)
     # the reference's state is augmented by a trailing 1 that carries b (diffusion_equation.jl:82-94)
     if saveat is None:

@@ -126,6 +126,41 @@ def main():
         errs["krylov_" + method] = rel_err(sol.u[:local.n_owned], uref[own])
         assert errs["krylov_" + method] <= 1e-9 and sol.relres <= 1e-11, (errs, sol.relres, sol.iters)
         tpl.engine.close()
+    # a problem only ONE rank can see is invalid (a Dudt node inside rank 0's subdomain, steady template) is rejected by
+    # every rank with the same error, before any collective of the solver is entered
+    log("rank-consistent validation")
+    far = int(np.argmin(np.abs(tri.points - np.array([0.5, 0.5])).sum(axis=1)))
+    dud = {int(np.nonzero(local.global_nodes == far)[0][0]): 0} if far in set(local.global_nodes[:local.n_owned].tolist()) else {}
+    ics = G.InternalConditions((G.Const(1.0),), dudt_nodes=dud)
+    try:
+        bad = G.PoissonsEquation(lmesh, G.BoundaryConditions(lmesh, G.Const(0.0), G.Dirichlet), ics, source_function=src,
+                                 ghost=local.is_ghost, tile_triangles=256)
+        G.install_halo(bad.engine, local, dist)
+        raise AssertionError("rank %d accepted a problem another rank rejects" % rank)
+    except ValueError as e:
+        assert "does not support Dudt nodes" in str(e), str(e)
+    # adaptive Tsit5: ghost entries are excluded from the error norm, so the accepted / rejected step counts of the
+    # sharded run equal those of a single-domain run
+    log("adaptive step counts")
+    tri = G.triangulate_rectangle(0, 2, 0, 2, 40, 32, single_boundary=True)
+    owner = G.partition_strips(tri.points, world)
+    local = G.extract_local(tri, owner, rank, world)
+    lmesh = G.FVMGeometry(local.triangulation)
+    ic = np.where(tri.points[:, 1] <= 1.0, 50.0, 0.0)
+    tpl = G.DiffusionEquation(lmesh, G.BoundaryConditions(lmesh, G.Const(0.0), G.Dirichlet), diffusion_function=1 / 9,
+                              initial_condition=ic[local.global_nodes], final_time=0.05, ghost=local.is_ghost)
+    G.install_halo(tpl.engine, local, dist)
+    a_sh, a_one = G.Tsit5(), G.Tsit5()
+    sol = G.solve(tpl, a_sh)
+    gmesh = G.FVMGeometry(tri)
+    one = G.DiffusionEquation(gmesh, G.BoundaryConditions(gmesh, G.Const(0.0), G.Dirichlet), diffusion_function=1 / 9,
+                              initial_condition=ic, final_time=0.05)
+    sol1 = G.solve(one, a_one)
+    assert (a_sh.naccept, a_sh.nreject) == (a_one.naccept, a_one.nreject), ((a_sh.naccept, a_sh.nreject), (a_one.naccept, a_one.nreject))
+    errs["adaptive_vs_single"] = rel_err(sol.u[:local.n_owned], sol1.u[local.global_nodes[:local.n_owned]])
+    assert errs["adaptive_vs_single"] <= 1e-10, errs
+    tpl.engine.close()
+    one.engine.close()
     dist.barrier()
     print("rank %d/%d sharded parity OK: %s" % (rank, world, {k: float("%.2e" % v) for k, v in errs.items()}), flush=True)
     dist.destroy_process_group()

@@ -360,3 +360,23 @@ def test_operator_host_buffer_pipeline_is_bit_identical(case):
             assert st["pipe_calls"] == 4 and st["pipe_bands"] == bands
     finally:
         _pipeline_env()
+
+
+def test_saveat_is_validated():
+    """saveat times that the stepper can never hit (unsorted, outside the time span, off the fixed-step grid) are
+    rejected up front instead of blocking every later save and returning unwritten rows."""
+    from fvm_b200 import _lib as L
+    pair = Pair(G.triangulate_rectangle(0, 2, 0, 2, 20, 20, single_boundary=True))
+    ic = np.where(pair.gtri.points[:, 1] <= 1.0, 50.0, 0.0)
+    gBC = G.BoundaryConditions(pair.gmesh, G.Const(0.0), G.Dirichlet)
+    tpl = G.DiffusionEquation(pair.gmesh, gBC, diffusion_function=1 / 9, initial_condition=ic, final_time=0.1)
+    ok = G.solve(tpl, G.Tsit5(0.01), saveat=[0.0, 0.05, 0.1])
+    assert len(ok.u) == 3 and all(np.isfinite(r).all() for r in ok.u)
+    for bad in ([0.05, 0.02], [-0.1, 0.05], [0.05, 0.2], [0.055]):
+        with pytest.raises(L.FVMCudaError, match="saveat"):
+            G.solve(tpl, G.Tsit5(0.01), saveat=bad)
+    for bad in ([0.05, 0.02], [0.05, 0.2]):  # the adaptive stepper stops at any time inside the span, in order
+        with pytest.raises(L.FVMCudaError, match="saveat"):
+            G.solve(tpl, G.Tsit5(), saveat=bad)
+    assert len(G.solve(tpl, G.Tsit5(), saveat=[0.013, 0.0777]).u) == 2
+    tpl.engine.close()
