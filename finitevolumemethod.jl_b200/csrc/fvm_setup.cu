@@ -350,22 +350,34 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
         miny = std::min(miny, xy[2 * i + 1]);
         maxy = std::max(maxy, xy[2 * i + 1]);
     }
-    const double ext = std::max(maxx - minx, maxy - miny);
-    const double scale = ext > 0 ? 65535.0 / ext : 0.0;
-    std::vector<uint64_t> keys(T);
+    // The curve runs over near-square BLOCKS laid along the longer side of the bounding box (a row strip of a sharded
+    // lattice is 2:1 ... 8:1).  A Hilbert curve enters a square at one corner and leaves at the adjacent one, so the
+    // blocks chain without a jump and every tile stays one compact patch; one curve over the bounding square instead
+    // leaves and re-enters an elongated domain, and the tiles that span a jump hold 1.6x the nodes (which sizes the
+    // shared memory of every CTA).
+    const double ex = maxx - minx, ey = maxy - miny;
+    const bool long_x = ex >= ey;
+    const double e_long = long_x ? ex : ey, e_short = long_x ? ey : ex;
+    const int64_t n_blocks = e_short > 0 ? std::max<int64_t>(1, std::min<int64_t>(1 << 20, (int64_t)std::floor(e_long / e_short + 0.5))) : 1;
+    const double bw = e_long / (double)n_blocks;
+    const double s_long = bw > 0 ? 65535.0 / bw : 0.0, s_short = e_short > 0 ? 65535.0 / e_short : 0.0;
+    std::vector<std::pair<uint64_t, uint32_t>> keys(T);
 #pragma omp parallel for schedule(static)
     for (int64_t t = 0; t < T; ++t) {
         const int32_t a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
-        double cx = (xy[2 * a] + xy[2 * b] + xy[2 * c]) / 3.0, cy = (xy[2 * a + 1] + xy[2 * b + 1] + xy[2 * c + 1]) / 3.0;
-        uint32_t ix = (uint32_t)std::min(65535.0, std::max(0.0, (cx - minx) * scale));
-        uint32_t iy = (uint32_t)std::min(65535.0, std::max(0.0, (cy - miny) * scale));
-        keys[t] = ((uint64_t)hilbert_xy2d(ix, iy) << 32) | (uint64_t)t;
+        const double cx = (xy[2 * a] + xy[2 * b] + xy[2 * c]) / 3.0, cy = (xy[2 * a + 1] + xy[2 * b + 1] + xy[2 * c + 1]) / 3.0;
+        const double l = long_x ? cx - minx : cy - miny, w = long_x ? cy - miny : cx - minx;
+        const int64_t blk = bw > 0 ? std::min<int64_t>(n_blocks - 1, std::max<int64_t>(0, (int64_t)(l / bw))) : 0;
+        const uint32_t il = (uint32_t)std::min(65535.0, std::max(0.0, (l - (double)blk * bw) * s_long));
+        const uint32_t iw = (uint32_t)std::min(65535.0, std::max(0.0, w * s_short));
+        // hilbert_xy2d starts at (0, 0) and ends at (65535, 0): its first argument is the direction the blocks advance in
+        keys[t] = {((uint64_t)blk << 32) | (uint64_t)hilbert_xy2d(il, iw), (uint32_t)t};
     }
     __gnu_parallel::sort(keys.begin(), keys.end());
     h->tri_old_of_new.resize(T);
 #pragma omp parallel for schedule(static)
-    for (int64_t t = 0; t < T; ++t) h->tri_old_of_new[t] = (int32_t)(keys[t] & 0xffffffffu);
-    std::vector<uint64_t>().swap(keys);
+    for (int64_t t = 0; t < T; ++t) h->tri_old_of_new[t] = (int32_t)keys[t].second;
+    std::vector<std::pair<uint64_t, uint32_t>>().swap(keys);
     const int32_t* told = h->tri_old_of_new.data();
     const int64_t n_tiles = (T + TT - 1) / TT;
     P.n_tiles = n_tiles;
