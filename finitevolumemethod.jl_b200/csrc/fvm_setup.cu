@@ -439,12 +439,15 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     tm.lap("boundary edges");
     // ---- 3. node classification and tile-major renumbering -------------------------------
     std::vector<int32_t> min_tile(N, INT32_MAX), max_tile(N, -1);
-    for (int64_t nt = 0; nt < T; ++nt) {
+#pragma omp parallel for schedule(static)
+    for (int64_t nt = 0; nt < T; ++nt) {  // first / last tile of every vertex: atomic min / max (any order gives the same result)
         const int32_t tile = (int32_t)(nt / TT);
         const int32_t* v = tri + 3 * (int64_t)told[nt];
         for (int r = 0; r < 3; ++r) {
-            if (tile < min_tile[v[r]]) min_tile[v[r]] = tile;
-            if (tile > max_tile[v[r]]) max_tile[v[r]] = tile;
+            int32_t cur = __atomic_load_n(&min_tile[v[r]], __ATOMIC_RELAXED);
+            while (tile < cur && !__atomic_compare_exchange_n(&min_tile[v[r]], &cur, tile, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+            cur = __atomic_load_n(&max_tile[v[r]], __ATOMIC_RELAXED);
+            while (tile > cur && !__atomic_compare_exchange_n(&max_tile[v[r]], &cur, tile, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
         }
     }
     std::vector<int32_t>&tile_node0 = P.tile_node0, &tile_nint = P.tile_nint, &tile_nown = P.tile_nown, &tile_nloc = P.tile_nloc;
@@ -456,33 +459,51 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     h->node_old_of_new.assign(N, -1);
     int32_t* new_of_old = h->node_new_of_old.data();
     {
-        std::vector<int32_t> ilist, flist;
-        int32_t cursor = 0;
+        // a vertex is numbered by the FIRST tile that touches it, so the tiles work independently: pass 1 counts the
+        // interior / owned-interface vertices of every tile, a prefix sum gives the tile's first id, pass 2 numbers them in
+        // order of first appearance in the tile's triangle list (stamp 1 / 2 marks "seen in pass 1 / 2")
         std::vector<uint8_t> seen(N, 0);
+#pragma omp parallel for schedule(dynamic, 64)
         for (int64_t b = 0; b < n_tiles; ++b) {
-            ilist.clear();
-            flist.clear();
             const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
+            int32_t ni = 0, nf = 0;
             for (int64_t nt = t0; nt < t1; ++nt) {
                 const int32_t* v = tri + 3 * (int64_t)told[nt];
                 for (int r = 0; r < 3; ++r) {
                     const int32_t g = v[r];
                     if (min_tile[g] != b || seen[g]) continue;
                     seen[g] = 1;
-                    if (max_tile[g] == b && !forced[g]) ilist.push_back(g);
-                    else flist.push_back(g);
+                    if (max_tile[g] == b && !forced[g]) ++ni;
+                    else ++nf;
                 }
             }
+            tile_nint[b] = ni;
+            tile_nown[b] = ni + nf;
+        }
+        int32_t cursor = 0;
+        for (int64_t b = 0; b < n_tiles; ++b) {
             tile_node0[b] = cursor;
-            tile_nint[b] = (int32_t)ilist.size();
-            tile_nown[b] = (int32_t)(ilist.size() + flist.size());
-            for (int32_t g : ilist) new_of_old[g] = cursor++;
-            for (int32_t g : flist) new_of_old[g] = cursor++;
+            cursor += tile_nown[b];
+        }
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
+            int32_t ci = tile_node0[b], cf = tile_node0[b] + tile_nint[b];
+            for (int64_t nt = t0; nt < t1; ++nt) {
+                const int32_t* v = tri + 3 * (int64_t)told[nt];
+                for (int r = 0; r < 3; ++r) {
+                    const int32_t g = v[r];
+                    if (min_tile[g] != b || seen[g] == 2) continue;
+                    seen[g] = 2;
+                    new_of_old[g] = (max_tile[g] == b && !forced[g]) ? ci++ : cf++;
+                }
+            }
         }
         h->dm.n_vertices = cursor;
         for (int64_t g = 0; g < N; ++g)
             if (new_of_old[g] < 0) new_of_old[g] = cursor++;  // points that are not vertices
     }
+#pragma omp parallel for schedule(static)
     for (int64_t g = 0; g < N; ++g) h->node_old_of_new[new_of_old[g]] = (int32_t)g;
     const int32_t n_vertices = h->dm.n_vertices;
     P.n_vertices = n_vertices;
@@ -518,12 +539,18 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     int32_t& max_nloc = P.max_nloc;
     max_nloc = 0;
     {
-        std::vector<int32_t> stamp(N, -1), loc(N, 0);
-        std::vector<int32_t> cnt, fill;
-        for (int64_t b = 0; b < n_tiles; ++b) {
+        // Tiles are independent: pass A counts every tile's external interface vertices (first-appearance order,
+        // deduplicated through a small per-thread hash table), prefix sums place the tile's slices of ext_ids / inc_ptr,
+        // pass B fills the tile-local vertex ids, the gather list and the interface counters.
+        int hbits = 10;
+        while ((1 << hbits) < 8 * TT) ++hbits;
+        const int32_t hcap = 1 << hbits, hmask = hcap - 1;
+        struct Slot {
+            int32_t key, val;
+        };
+        auto walk_tile = [&](int64_t b, std::vector<Slot>& tab, std::vector<int32_t>& used, bool fill, int32_t* ext_out) -> int32_t {
             const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
             const int32_t node0 = tile_node0[b], nown = tile_nown[b];
-            tile_ext0[b] = (int32_t)ext_ids.size();
             int32_t next = 0;
             for (int64_t nt = t0; nt < t1; ++nt) {
                 const int32_t* v = tri + 3 * (int64_t)told[nt];
@@ -531,54 +558,88 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
                 for (int r = 0; r < 3; ++r) {
                     const int32_t g = v[r];
                     const int32_t gn = new_of_old[g];
-                    tri_native[3 * nt + r] = gn;
                     int32_t l;
                     if (min_tile[g] == b) l = gn - node0;
                     else {
-                        if (stamp[g] != b) {
-                            stamp[g] = (int32_t)b;
-                            loc[g] = nown + next++;
-                            ext_ids.push_back(gn);
+                        uint32_t q = ((uint32_t)g * 2654435761u) >> (32 - hbits);
+                        while (tab[q].key != -1 && tab[q].key != g) q = (q + 1) & hmask;
+                        if (tab[q].key == -1) {
+                            tab[q].key = g;
+                            tab[q].val = nown + next;
+                            used.push_back((int32_t)q);
+                            if (fill) ext_out[next] = gn;
+                            ++next;
                         }
-                        l = loc[g];
+                        l = tab[q].val;
                     }
                     l3[r] = (uint16_t)l;
+                    if (fill) tri_native[3 * nt + r] = gn;
                 }
-                tri_loc[nt] = make_ushort4(l3[0], l3[1], l3[2], 0);
+                if (fill) tri_loc[nt] = make_ushort4(l3[0], l3[1], l3[2], 0);
             }
-            const int32_t nloc = nown + next;
+            for (int32_t q : used) tab[q].key = -1;
+            used.clear();
+            return next;
+        };
+        std::vector<int32_t> next_of(n_tiles, 0);
+#pragma omp parallel
+        {
+            std::vector<Slot> tab(hcap, Slot{-1, 0});
+            std::vector<int32_t> used;
+#pragma omp for schedule(dynamic, 64)
+            for (int64_t b = 0; b < n_tiles; ++b) next_of[b] = walk_tile(b, tab, used, false, nullptr);
+        }
+        int64_t ext_total = 0, loc_total = 0;
+        for (int64_t b = 0; b < n_tiles; ++b) {
+            const int32_t nloc = tile_nown[b] + next_of[b];
             FVM_REQUIRE(h, nloc < 65535, "fvm_finalize: tile has too many nodes for 16-bit local ids");
             tile_nloc[b] = nloc;
             max_nloc = std::max(max_nloc, nloc);
-            // gather list: local node -> (local triangle, slot), ascending triangle order
-            if (inc_ptr.size() & 1) inc_ptr.push_back(0);  // 4-byte aligned per tile (staged with cp.async)
-            tile_loc0[b] = (int32_t)inc_ptr.size();
-            cnt.assign(nloc + 1, 0);
-            for (int64_t nt = t0; nt < t1; ++nt) {
-                const ushort4 q = tri_loc[nt];
-                cnt[q.x + 1]++;
-                cnt[q.y + 1]++;
-                cnt[q.z + 1]++;
-            }
-            for (int32_t l = 0; l < nloc; ++l) cnt[l + 1] += cnt[l];
-            for (int32_t l = 0; l <= nloc; ++l) inc_ptr.push_back((uint16_t)cnt[l]);
-            fill.assign(cnt.begin(), cnt.end() - 1);
-            uint16_t* tinc = inc.data() + (size_t)3 * TT * b;
-            for (int64_t nt = t0; nt < t1; ++nt) {
-                const ushort4 q = tri_loc[nt];
-                const uint16_t lt = (uint16_t)(nt - t0);
-                tinc[fill[q.x]++] = (uint16_t)(lt << 2 | 0);
-                tinc[fill[q.y]++] = (uint16_t)(lt << 2 | 1);
-                tinc[fill[q.z]++] = (uint16_t)(lt << 2 | 2);
-            }
-            // interface locals of this tile contribute one partial each
-            for (int32_t l = tile_nint[b]; l < nown; ++l) ifc_cnt[ifc_of_new[node0 + l]]++;
-            for (int32_t k = 0; k < next; ++k) ifc_cnt[ifc_of_new[ext_ids[tile_ext0[b] + k]]]++;
+            tile_ext0[b] = (int32_t)ext_total;
+            ext_total += next_of[b];
+            loc_total += loc_total & 1;  // 4-byte aligned per tile (staged with cp.async)
+            tile_loc0[b] = (int32_t)loc_total;
+            loc_total += nloc + 1;
+            FVM_REQUIRE(h, ext_total < INT32_MAX && loc_total < INT32_MAX, "fvm_finalize: tile tables exceed int32");
         }
-        tile_ext0[n_tiles] = (int32_t)ext_ids.size();
-        tile_loc0[n_tiles] = (int32_t)inc_ptr.size();
-        inc_ptr.push_back(0);
-        inc_ptr.push_back(0);  // slack for the 4-byte granular copy of the last tile
+        tile_ext0[n_tiles] = (int32_t)ext_total;
+        tile_loc0[n_tiles] = (int32_t)loc_total;
+        ext_ids.assign((size_t)ext_total, 0);
+        inc_ptr.assign((size_t)loc_total + 2, 0);  // + slack for the 4-byte granular copy of the last tile
+#pragma omp parallel
+        {
+            std::vector<Slot> tab(hcap, Slot{-1, 0});
+            std::vector<int32_t> used, cnt, fill;
+#pragma omp for schedule(dynamic, 64)
+            for (int64_t b = 0; b < n_tiles; ++b) {
+                const int64_t t0 = b * TT, t1 = std::min<int64_t>(T, t0 + TT);
+                const int32_t node0 = tile_node0[b], nown = tile_nown[b], nloc = tile_nloc[b];
+                const int32_t next = walk_tile(b, tab, used, true, ext_ids.data() + tile_ext0[b]);
+                // gather list: local node -> (local triangle, slot), ascending triangle order
+                cnt.assign(nloc + 1, 0);
+                for (int64_t nt = t0; nt < t1; ++nt) {
+                    const ushort4 q = tri_loc[nt];
+                    cnt[q.x + 1]++;
+                    cnt[q.y + 1]++;
+                    cnt[q.z + 1]++;
+                }
+                for (int32_t l = 0; l < nloc; ++l) cnt[l + 1] += cnt[l];
+                uint16_t* ip = inc_ptr.data() + tile_loc0[b];
+                for (int32_t l = 0; l <= nloc; ++l) ip[l] = (uint16_t)cnt[l];
+                fill.assign(cnt.begin(), cnt.end() - 1);
+                uint16_t* tinc = inc.data() + (size_t)3 * TT * b;
+                for (int64_t nt = t0; nt < t1; ++nt) {
+                    const ushort4 q = tri_loc[nt];
+                    const uint16_t lt = (uint16_t)(nt - t0);
+                    tinc[fill[q.x]++] = (uint16_t)(lt << 2 | 0);
+                    tinc[fill[q.y]++] = (uint16_t)(lt << 2 | 1);
+                    tinc[fill[q.z]++] = (uint16_t)(lt << 2 | 2);
+                }
+                // interface locals of this tile contribute one partial each
+                for (int32_t l = tile_nint[b]; l < nown; ++l) __atomic_fetch_add(&ifc_cnt[ifc_of_new[node0 + l]], 1, __ATOMIC_RELAXED);
+                for (int32_t k = 0; k < next; ++k) __atomic_fetch_add(&ifc_cnt[ifc_of_new[ext_ids[tile_ext0[b] + k]]], 1, __ATOMIC_RELAXED);
+            }
+        }
     }
     for (size_t k = 0; k < live_edges.size(); ++k) {
         const int32_t e = live_edges[k];
