@@ -557,6 +557,7 @@ def main():
     results = {}
     eng = p = None
     parity_max_rel = None
+    halo_mode = None
     for name in names:
         flux_f, gmode, layout = VARIANTS[name]
         if eng is not None:
@@ -602,6 +603,7 @@ def main():
             ms = float(tmax.item())
         clocks = sampler.stop() if sampler else None
         if lmesh is not None and name == names[-1]:
+            halo_mode = eng.halo_mode()[0]
             parity = sharded_parity(torch, G, eng, lmesh, du_d, nx, nx * world, 2.0 * world, flux_f(G), rank, world, gmode)
             pv = torch.tensor([parity], dtype=torch.float64, device="cuda")
             dist.all_reduce(pv, op=dist.ReduceOp.MAX)
@@ -726,6 +728,10 @@ def main():
         line["cpu_baseline"]["same_mesh_as_gpu_arm"] = cb["nx"] == nx
         if steady_cpu:
             line["cpu_baseline"]["cpu_steady_superlu"] = steady_cpu
+    if halo_mode is not None:
+        line["halo_exchange"] = {0: "none", 1: "grouped ncclSend/ncclRecv (pack, exchange, unpack)",
+                                 2: "peer-mapped: one kernel stores the boundary values into the neighbours' slabs over NVLink "
+                                    "(CUDA IPC), one kernel waits for their epoch flags and scatters"}[halo_mode]
     if parity_max_rel is not None:
         line["parity_max_rel"] = parity_max_rel
         line["parity_note"] = ("first / middle / last owned row of every rank's strip (the rows that read the NCCL-exchanged ghost layer) against a "

@@ -73,6 +73,7 @@ _SIGS = {
     "fvm_set_ghost_nodes": [H, c_bp],
     "fvm_set_halo": [H, C.c_int32, c_ip, c_ip, c_ip, c_ip, c_ip],
     "fvm_halo_exchange_native": [H, C.c_void_p],
+    "fvm_halo_mode": [H, c_ip, c_ip],
     "fvm_nccl_unique_id": [C.c_void_p],
     "fvm_partition_graph": [C.c_int64, c_ip, C.c_int64, C.c_int32, C.c_int32, c_ip],
     "fvm_partition_edge_cut": [C.c_int64, c_ip, C.c_int64, C.c_int32, c_ip, c_lp],

@@ -5,6 +5,7 @@
 // ncclSend/ncclRecv over NVLink and scattered into the ghost slots.
 #include <nccl.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "fvm_internal.h"
@@ -21,6 +22,27 @@ struct ShardState {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_packed = nullptr, ev_done = nullptr;
     int64_t n_send = 0, n_recv = 0;
+    // ---- peer-mapped exchange (NVLink direct stores instead of pack -> ncclSend/ncclRecv -> unpack) ----------------
+    // Every rank owns a receive slab: two parities x n_recv x neq doubles, plus one 64-bit epoch flag per (parity,
+    // neighbour).  Neighbours map it through CUDA IPC.  An exchange is ONE kernel that gathers the owned boundary values
+    // and stores them straight into the neighbours' slabs (the last CTA to finish publishes the epoch to every neighbour
+    // with a system-scope release) and ONE kernel that waits for the neighbours' epochs and scatters the slab into the
+    // ghost slots.  Parities alternate, so a fast neighbour can already push exchange e+1 while this rank still unpacks e
+    // (it cannot get to e+2 before it has seen this rank's push of e+1, which is issued after this rank's unpack of e).
+    bool peer = false;
+    double* slab = nullptr;                   // [2][n_recv * neq]
+    unsigned long long* flags = nullptr;      // [2][n_neigh], in the same allocation as the slab
+    void* slab_base = nullptr;
+    std::vector<void*> peer_base;             // mapped slab of neighbour q
+    double** d_peer_data = nullptr;           // [n_neigh] where my segment starts in neighbour q's slab (parity 0)
+    unsigned long long** d_peer_flag = nullptr;  // [n_neigh] my flag in neighbour q's slab (parity 0)
+    int64_t* d_peer_stride = nullptr;         // [n_neigh] doubles between neighbour q's parities
+    int32_t* d_peer_nneigh = nullptr;         // [n_neigh] flags per parity in neighbour q's slab
+    int32_t* d_send_ptr = nullptr;            // [n_neigh + 1]
+    int32_t* d_recv_ptr = nullptr;
+    unsigned int* d_done_ctr = nullptr;       // CTA completion counter of the push kernel
+    int32_t* d_timeout = nullptr;             // set by the wait kernel if a neighbour never signals
+    unsigned long long epoch = 0;
 };
 
 #define FVM_NCCL(h, call)                                                                            \
@@ -30,9 +52,14 @@ struct ShardState {
             return fvm_fail((h), FVM_ERR_NCCL, std::string(#call) + ": " + ncclGetErrorString(r__)); \
     } while (0)
 
+static int32_t peer_setup(fvm_ctx* h, ShardState* s);
+
 void fvm_shard_release(fvm_ctx* h) {
     ShardState* s = (ShardState*)h->shard;
     if (!s) return;
+    for (void* p : s->peer_base)
+        if (p) cudaIpcCloseMemHandle(p);
+    if (s->slab_base) cudaFree(s->slab_base);
     if (s->comm) ncclCommDestroy(s->comm);
     if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->ev_packed) cudaEventDestroy(s->ev_packed);
@@ -104,6 +131,7 @@ extern "C" int32_t fvm_set_halo(fvm_handle h, int32_t n_neigh, const int32_t* ne
         FVM_CUDA(h, cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming));
     }
     h->comm_stream = s->comm_stream;
+    if ((rc = peer_setup(h, s))) return rc;
     // tiles whose local nodes (own range or external interface nodes) contain no received ghost node
     // can run while the exchange is in flight
     {
@@ -150,11 +178,210 @@ __global__ void halo_unpack_kernel(const int32_t* __restrict__ idx, const int64_
     u[(int64_t)idx[q] * neq + (k - q * neq)] = buf[k];
 }
 
+
+// ---- peer-mapped exchange ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    halo_push_kernel(const int32_t* __restrict__ send_idx, const int32_t* __restrict__ send_ptr, const int n_neigh, const int neq,
+                     const double* __restrict__ u, double* const* __restrict__ peer_data, unsigned long long* const* __restrict__ peer_flag,
+                     const int64_t* __restrict__ peer_stride, const int32_t* __restrict__ peer_nneigh, const int parity,
+                     const unsigned long long epoch, unsigned int* __restrict__ done_ctr) {
+    const int64_t n = (int64_t)send_ptr[n_neigh] * neq;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = k / neq;
+        const int v = (int)(k - e * neq);
+        int q = 0;
+        while (e >= send_ptr[q + 1]) ++q;  // a handful of neighbours
+        peer_data[q][(int64_t)parity * peer_stride[q] + (e - send_ptr[q]) * neq + v] = u[(int64_t)send_idx[e] * neq + v];
+    }
+    // the last CTA to get here publishes the epoch: every CTA's stores are fenced at system scope before it counts itself
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned int last;
+    if (threadIdx.x == 0) last = atomicAdd(done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        for (int q = threadIdx.x; q < n_neigh; q += blockDim.x) {
+            unsigned long long* f = peer_flag[q] + (int64_t)parity * peer_nneigh[q];
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+        }
+        if (threadIdx.x == 0) *done_ctr = 0;
+    }
+}
+
+// one or more CTAs per neighbour: wait for its epoch, then scatter its slab segment into the ghost slots
+__global__ void __launch_bounds__(256)
+    halo_wait_unpack_kernel(const int32_t* __restrict__ recv_idx, const int32_t* __restrict__ recv_ptr, const int n_neigh, const int neq,
+                            const double* __restrict__ slab, const unsigned long long* __restrict__ flags, const int64_t slab_stride,
+                            const int parity, const unsigned long long epoch, double* __restrict__ u, int32_t* __restrict__ timeout_flag) {
+    const int q = blockIdx.y;
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        const unsigned long long* f = flags + (int64_t)parity * n_neigh + q;
+        unsigned long long seen = 0;
+        const long long t0 = clock64();
+        ok = 1;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f) : "memory");
+            if (seen >= epoch) break;
+            if (clock64() - t0 > 20000000000LL) {  // ~10 s: a neighbour died; fail loudly instead of hanging the device
+                ok = 0;
+                atomicExch(timeout_flag, 1);
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int64_t lo = (int64_t)recv_ptr[q] * neq, hi = (int64_t)recv_ptr[q + 1] * neq;
+    const double* src = slab + (int64_t)parity * slab_stride;
+    for (int64_t k = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = k / neq;
+        u[(int64_t)recv_idx[e] * neq + (k - e * neq)] = __ldcg(src + k);
+    }
+}
+
+// maps the neighbours' receive slabs (CUDA IPC); on any failure the NCCL path stays in use
+static int32_t peer_setup(fvm_ctx* h, ShardState* s) {
+    s->peer = false;
+    const char* env = getenv("FVM_HALO_PEER");
+    int want = (env && env[0] == '0') ? 0 : 1;
+    if (!s->comm || h->nranks < 2) return FVM_OK;
+    const int neq = h->neq, nr = h->nranks;
+    const int64_t stride = std::max<int64_t>(2, (s->n_recv * neq + 1) & ~(int64_t)1);
+    struct Info {
+        cudaIpcMemHandle_t handle;
+        int64_t stride;
+        int32_t n_neigh, ok;
+    };
+    Info mine{};
+    mine.stride = stride;
+    mine.n_neigh = s->n_neigh;
+    mine.ok = 0;
+    void* base = nullptr;
+    const size_t bytes = sizeof(double) * 2 * stride + sizeof(unsigned long long) * 2 * std::max(1, s->n_neigh);
+    if (want && cudaMalloc(&base, bytes) == cudaSuccess && cudaMemset(base, 0, bytes) == cudaSuccess &&
+        cudaIpcGetMemHandle(&mine.handle, base) == cudaSuccess)
+        mine.ok = 1;
+    cudaGetLastError();
+    // everyone learns everyone's handle and, per pair, where the sender's segment and flag live in the receiver's slab
+    std::vector<Info> all(nr);
+    std::vector<int64_t> my_off(nr, -1), all_off((size_t)nr * nr, -1);  // my_off[q]: offset (doubles) of q's segment in MY slab
+    std::vector<int32_t> my_slot(nr, -1), all_slot((size_t)nr * nr, -1);
+    for (int q = 0; q < s->n_neigh; ++q) {
+        my_off[s->neigh[q]] = (int64_t)s->recv_ptr[q] * neq;
+        my_slot[s->neigh[q]] = q;
+    }
+    char* d_tmp = nullptr;
+    const size_t per = sizeof(Info) + sizeof(int64_t) * nr + sizeof(int32_t) * nr;
+    FVM_CUDA(h, cudaMalloc((void**)&d_tmp, per * (nr + 1)));
+    std::vector<char> pack(per), gathered(per * nr);
+    std::memcpy(pack.data(), &mine, sizeof(Info));
+    std::memcpy(pack.data() + sizeof(Info), my_off.data(), sizeof(int64_t) * nr);
+    std::memcpy(pack.data() + sizeof(Info) + sizeof(int64_t) * nr, my_slot.data(), sizeof(int32_t) * nr);
+    cudaMemcpyAsync(d_tmp, pack.data(), per, cudaMemcpyHostToDevice, h->stream);
+    ncclResult_t nres = ncclAllGather(d_tmp, d_tmp + per, per, ncclChar, s->comm, h->stream);
+    cudaMemcpyAsync(gathered.data(), d_tmp + per, per * nr, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t ce = cudaStreamSynchronize(h->stream);
+    cudaFree(d_tmp);
+    if (nres != ncclSuccess) return fvm_fail(h, FVM_ERR_NCCL, ncclGetErrorString(nres));
+    FVM_CUDA(h, ce);
+    bool all_ok = true;
+    for (int r = 0; r < nr; ++r) {
+        std::memcpy(&all[r], gathered.data() + per * r, sizeof(Info));
+        std::memcpy(all_off.data() + (size_t)r * nr, gathered.data() + per * r + sizeof(Info), sizeof(int64_t) * nr);
+        std::memcpy(all_slot.data() + (size_t)r * nr, gathered.data() + per * r + sizeof(Info) + sizeof(int64_t) * nr, sizeof(int32_t) * nr);
+        all_ok = all_ok && all[r].ok;
+    }
+    std::vector<void*> mapped(s->n_neigh, nullptr);
+    int my_ok = all_ok ? 1 : 0;
+    for (int q = 0; q < s->n_neigh && my_ok; ++q) {
+        const int r = s->neigh[q];
+        if (all_off[(size_t)r * nr + h->rank] < 0 || cudaIpcOpenMemHandle(&mapped[q], all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            my_ok = 0;
+        }
+    }
+    // the choice must be unanimous: a rank on the NCCL path cannot pair with one that pushes
+    double* d_flag = nullptr;
+    FVM_CUDA(h, cudaMalloc((void**)&d_flag, sizeof(double)));
+    const double fv = my_ok ? 0.0 : 1.0;
+    double bad = 0.0;
+    cudaMemcpyAsync(d_flag, &fv, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    nres = ncclAllReduce(d_flag, d_flag, 1, ncclDouble, ncclSum, s->comm, h->stream);
+    cudaMemcpyAsync(&bad, d_flag, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    ce = cudaStreamSynchronize(h->stream);
+    cudaFree(d_flag);
+    if (nres != ncclSuccess) return fvm_fail(h, FVM_ERR_NCCL, ncclGetErrorString(nres));
+    FVM_CUDA(h, ce);
+    if (bad > 0.5) {
+        for (void* p : mapped)
+            if (p) cudaIpcCloseMemHandle(p);
+        if (base) cudaFree(base);
+        cudaGetLastError();
+        return FVM_OK;  // NCCL send/recv stays
+    }
+    s->slab_base = base;
+    s->slab = (double*)base;
+    s->flags = (unsigned long long*)((char*)base + sizeof(double) * 2 * stride);
+    s->peer_base = mapped;
+    std::vector<double*> pd(s->n_neigh);
+    std::vector<unsigned long long*> pf(s->n_neigh);
+    std::vector<int64_t> ps(s->n_neigh);
+    std::vector<int32_t> pn(s->n_neigh);
+    for (int q = 0; q < s->n_neigh; ++q) {
+        const int r = s->neigh[q];
+        pd[q] = (double*)mapped[q] + all_off[(size_t)r * nr + h->rank];
+        pf[q] = (unsigned long long*)((char*)mapped[q] + sizeof(double) * 2 * all[r].stride) + all_slot[(size_t)r * nr + h->rank];
+        ps[q] = all[r].stride;
+        pn[q] = all[r].n_neigh;
+    }
+    int32_t rc;
+    if ((rc = fvm_dev_upload(h, &s->d_peer_data, pd))) return rc;
+    if ((rc = fvm_dev_upload(h, &s->d_peer_flag, pf))) return rc;
+    if ((rc = fvm_dev_upload(h, &s->d_peer_stride, ps))) return rc;
+    if ((rc = fvm_dev_upload(h, &s->d_peer_nneigh, pn))) return rc;
+    if ((rc = fvm_dev_upload(h, &s->d_send_ptr, s->send_ptr))) return rc;
+    if ((rc = fvm_dev_upload(h, &s->d_recv_ptr, s->recv_ptr))) return rc;
+    if ((rc = fvm_dev_alloc(h, &s->d_done_ctr, 1))) return rc;
+    if ((rc = fvm_dev_alloc(h, &s->d_timeout, 1))) return rc;
+    FVM_CUDA(h, cudaMemsetAsync(s->d_done_ctr, 0, sizeof(unsigned int), h->stream));
+    FVM_CUDA(h, cudaMemsetAsync(s->d_timeout, 0, sizeof(int32_t), h->stream));
+    FVM_CUDA(h, cudaStreamSynchronize(h->stream));
+    s->epoch = 0;
+    s->peer = true;
+    return FVM_OK;
+}
+
+// both halves of a peer exchange on the given streams (the same stream for the serialised schedule)
+static int32_t peer_exchange(fvm_ctx* h, ShardState* s, double* u_native, cudaStream_t push_stream, cudaStream_t wait_stream) {
+    const int neq = h->neq;
+    s->epoch += 1;
+    const int parity = (int)(s->epoch & 1);
+    const int64_t stride = std::max<int64_t>(2, (s->n_recv * neq + 1) & ~(int64_t)1);
+    if (s->n_neigh > 0) {
+        const int64_t n = s->n_send * neq;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(296, (n + 255) / 256));
+        halo_push_kernel<<<grid, 256, 0, push_stream>>>(s->d_send_idx, s->d_send_ptr, s->n_neigh, neq, u_native, s->d_peer_data, s->d_peer_flag,
+                                                        s->d_peer_stride, s->d_peer_nneigh, parity, s->epoch, s->d_done_ctr);
+        FVM_CUDA(h, cudaGetLastError());
+        int64_t longest = 1;
+        for (int q = 0; q < s->n_neigh; ++q) longest = std::max<int64_t>(longest, (int64_t)(s->recv_ptr[q + 1] - s->recv_ptr[q]) * neq);
+        dim3 g((unsigned)std::max<int64_t>(1, std::min<int64_t>(64, (longest + 255) / 256)), (unsigned)s->n_neigh);
+        halo_wait_unpack_kernel<<<g, 256, 0, wait_stream>>>(s->d_recv_idx, s->d_recv_ptr, s->n_neigh, neq, s->slab, s->flags, stride, parity,
+                                                            s->epoch, u_native, s->d_timeout);
+        FVM_CUDA(h, cudaGetLastError());
+    }
+    return FVM_OK;
+}
+
 // Refreshes the ghost entries of a native-order vector.  Runs on the handle's stream.
 int32_t fvm_halo_exchange(fvm_ctx* h, double* u_native) {
     ShardState* s = (ShardState*)h->shard;
     if (!s || !h->halo_ready || s->n_neigh == 0) return FVM_OK;
     if (!s->comm) return fvm_fail(h, FVM_ERR_STATE, "halo exchange needs fvm_shard_init");
+    if (s->peer) return peer_exchange(h, s, u_native, h->stream, h->stream);
     const int neq = h->neq;
     if (s->n_send) {
         halo_pack_kernel<<<(unsigned)((s->n_send * neq + 255) / 256), 256, 0, h->stream>>>(s->d_send_idx, s->n_send, neq, u_native,
@@ -184,6 +411,11 @@ int32_t fvm_halo_begin(fvm_ctx* h, double* u_native) {
     if (!s || !h->halo_ready || s->n_neigh == 0) return FVM_OK;
     if (!s->comm) return fvm_fail(h, FVM_ERR_STATE, "halo exchange needs fvm_shard_init");
     const int neq = h->neq;
+    if (s->peer) {  // push on the compute stream, wait + unpack on the communication stream
+        FVM_CUDA(h, cudaEventRecord(s->ev_packed, h->stream));
+        FVM_CUDA(h, cudaStreamWaitEvent(s->comm_stream, s->ev_packed, 0));  // u_native is complete
+        return peer_exchange(h, s, u_native, s->comm_stream, s->comm_stream);
+    }
     if (s->n_send) {
         halo_pack_kernel<<<(unsigned)((s->n_send * neq + 255) / 256), 256, 0, h->stream>>>(s->d_send_idx, s->n_send, neq, u_native,
                                                                                            s->d_send_buf);
@@ -218,6 +450,21 @@ int32_t fvm_halo_wait(fvm_ctx* h) {
     ShardState* s = (ShardState*)h->shard;
     if (!s || !h->halo_ready || s->n_neigh == 0) return FVM_OK;
     FVM_CUDA(h, cudaStreamWaitEvent(h->stream, s->ev_done, 0));
+    return FVM_OK;
+}
+
+// 0: no halo / single rank, 1: NCCL send/recv, 2: peer-mapped NVLink stores.  *timed_out != 0: a neighbour never signalled
+extern "C" int32_t fvm_halo_mode(fvm_handle h, int32_t* mode, int32_t* timed_out) {
+    if (!h || !mode) return FVM_ERR_ARG;
+    ShardState* s = (ShardState*)h->shard;
+    *mode = (!s || !h->halo_ready || s->n_neigh == 0) ? 0 : (s->peer ? 2 : 1);
+    if (timed_out) {
+        *timed_out = 0;
+        if (s && s->peer) {
+            FVM_CUDA(h, cudaSetDevice(h->device));
+            FVM_CUDA(h, cudaMemcpy(timed_out, s->d_timeout, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        }
+    }
     return FVM_OK;
 }
 

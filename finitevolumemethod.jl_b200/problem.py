@@ -367,6 +367,13 @@ class Engine:
         out["host_schedule_rhs"], out["host_schedule_spmv"] = names[int(st[15]) & 3], names[(int(st[15]) >> 2) & 3]
         return out
 
+    def halo_mode(self):
+        """(mode, timed_out): mode 0 no halo, 1 grouped ncclSend/ncclRecv, 2 peer-mapped NVLink stores (fvm_halo_mode)."""
+        import ctypes as C
+        mode, to = C.c_int32(), C.c_int32()
+        L.check(self.h, L.lib().fvm_halo_mode(self.h, C.byref(mode), C.byref(to)))
+        return mode.value, to.value
+
     def permutation(self):
         node = np.empty(self.N, dtype=np.int32)
         tri = np.empty(self.T, dtype=np.int32)

@@ -250,6 +250,12 @@ int32_t fvm_shard_init(fvm_handle h, const void* nccl_unique_id, int32_t rank, i
 int32_t fvm_set_halo(fvm_handle h, int32_t n_neighbours, const int32_t* neighbour_ranks, const int32_t* send_ptr,
                      const int32_t* send_nodes, const int32_t* recv_ptr, const int32_t* recv_nodes);
 int32_t fvm_halo_exchange_native(fvm_handle h, double* u_native);
+/* How the ghost refresh runs: 0 none (single rank / no neighbours), 1 grouped ncclSend/ncclRecv, 2 peer-mapped: the
+ * neighbours' receive slabs are mapped through CUDA IPC and ONE kernel stores the owned boundary values straight into
+ * them over NVLink (epoch flag with system-scope release), ONE kernel waits for the neighbours' epochs and scatters.
+ * Chosen at fvm_set_halo (unanimously over the ranks; FVM_HALO_PEER=0 forces NCCL).  *timed_out != 0: a neighbour
+ * never signalled within ~10 s and the waiting kernel gave up. */
+int32_t fvm_halo_mode(fvm_handle h, int32_t* mode, int32_t* timed_out);
 
 /* ---- FVMWIRE: flat binary SoA container for meshes and solutions ------------
  * The reference has no file format: a mesh is the DelaunayTriangulation object FVMGeometry(tri) walks

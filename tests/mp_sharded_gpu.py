@@ -46,6 +46,23 @@ def main():
         own = local.global_nodes[:local.n_owned]
         errs["rhs_" + kind] = rel_err(du[:local.n_owned], ref[own]) if np.abs(ref).max() > 0 else 0.0
         assert errs["rhs_" + kind] <= RTOL_RHS, errs
+        # the ghost refresh runs through peer-mapped NVLink stores when CUDA IPC is available, else through NCCL
+        # send/recv; both give the same bits
+        mode, timed_out = p.engine.halo_mode()
+        log("halo exchange mode %d (1 = NCCL send/recv, 2 = peer-mapped stores)" % mode)
+        assert mode in (1, 2) and timed_out == 0
+        os.environ["FVM_HALO_PEER"] = "0"
+        p3 = G.get_sharded_cuda_parameters(lp, local, dist, tile_triangles=128, device=local_rank)
+        del os.environ["FVM_HALO_PEER"]
+        assert p3.engine.halo_mode()[0] == 1
+        du3 = G.fvm_eqs(np.zeros_like(ul), ul, p3, 0.3)
+        assert np.array_equal(du3, du), np.abs(du3 - du).max()
+        for rep in range(20):  # many exchanges back to back: the two slab parities and the epoch flags
+            du4 = G.fvm_eqs(np.zeros_like(ul), ul * (1.0 + 0.01 * rep), p, 0.3)
+            du5 = G.fvm_eqs(np.zeros_like(ul), ul * (1.0 + 0.01 * rep), p3, 0.3)
+            assert np.array_equal(du4, du5), rep
+        p3.engine.close()
+        errs["halo_mode_" + kind] = float(mode)
         # the banded host-buffer pipeline (fvm_pipe.cu) with the halo exchange at the head of its last stage:
         # forced on for this small mesh, bit-identical to the plain schedule on every rank
         for bands in (3, 6):
