@@ -69,6 +69,7 @@ _SIGS = {
     "fvm_get_jacobian_csr": [H, c_ip, c_ip, c_dp],
     "fvm_eval_points": [H, C.c_double, C.c_void_p, C.c_int32, C.c_int64, c_ip, c_dp, c_dp, c_dp],
     "fvm_krylov": [H, C.c_int32, C.c_void_p, C.c_double, C.c_int32, c_ip, c_dp, C.c_int32],
+    "fvm_newton": [H, C.c_double, C.c_void_p, C.c_double, C.c_double, C.c_int32, C.c_double, C.c_int32, c_ip, c_dp, c_dp, c_lp, C.c_int32],
     "fvm_shard_init": [H, C.c_void_p, C.c_int32, C.c_int32],
     "fvm_set_ghost_nodes": [H, c_bp],
     "fvm_set_halo": [H, C.c_int32, c_ip, c_ip, c_ip, c_ip, c_ip],

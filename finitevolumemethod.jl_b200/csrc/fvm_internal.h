@@ -179,6 +179,8 @@ struct fvm_ctx {
     Csr csr;
     double* d_work[12] = {nullptr};
     double* d_red = nullptr;  // reduction scratch
+    double* d_dotpart = nullptr;  // per-CTA partial dot products of the fused PCG operator
+    int32_t dotpart_n = 0;
     int64_t stats[16] = {0};
     // optional per-kernel timing of the dominant kernels (bench.py's roofline leg)
     bool profiling = false;
@@ -289,9 +291,27 @@ int32_t fvm_launch_spmv_tail_list(fvm_ctx* h, const double* x, double* y, bool a
 void fvm_pipe_release(fvm_ctx* h);
 void fvm_pipe_report(fvm_ctx* h, int mode, double seconds);
 int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part);
+// Work fused into the tile / tail SpMV kernels by the Krylov solvers (fvm_solvers.cu):
+//   kind 2: sum_i x[i] * y[i] over the CTA's rows goes to dotpart[tile] / dotpart[n_tiles + blockIdx.x] (fixed-shape
+//           block reduction: deterministic) -- the p.(A p) of CG without a separate pass over p and q; nothing runs
+//           once sc[SC_DONE] is set.  Works sharded as well (ghost rows of A are zero: they add nothing).
+// Measured and NOT kept (r2q/r2r/r2s logs): forming the input (p = z + beta p, or a Tsit5 stage combination)
+// while x is staged, or the next stage input in the epilogue -- the tile kernel is latency-bound in its staging phase
+// and its epilogue, so the extra loads cost more there (64 -> 116 us at 2048^2) than the streaming kernels they replace.
+struct SpmvFuse {
+    int32_t kind = 0;
+    const double* sc = nullptr;
+    double* dotpart = nullptr;
+};
+bool fvm_spmv_fusable(fvm_ctx* h);            // the tile / sliced-ELL kernels are in use
+int32_t fvm_spmv_fused_partials(fvm_ctx* h);  // entries of dotpart a kind-2 application writes (tiles + tail CTAs)
+int32_t fvm_apply_spmv_fused(fvm_ctx* h, double* x, double* out, bool add_b, bool scale, const SpmvFuse& f);
+// device scalars of the Krylov solvers / adaptive stepper (d_red + 8 * 2048)
+enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_SUM0, SC_SUM1, SC_SUM2, SC_N };
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);
 int32_t fvm_global_or(fvm_ctx* h, bool local, bool* global);
 #define FVM_NODE_GHOST 4
 int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale);
+int32_t fvm_launch_jacobian(fvm_ctx* h, double t, const double* u_native);  // fvm_jacobian.cu: block values -> h->jac_val
 void fvm_prof_begin(fvm_ctx* h);
 void fvm_prof_end(fvm_ctx* h);

@@ -259,6 +259,31 @@ static int32_t jac_prepare(fvm_ctx* h) {
     return FVM_OK;
 }
 
+// block values of d(fvm_eqs!)/du at the native-order state `u_native` (ghost layer already refreshed) -> h->jac_val
+int32_t fvm_launch_jacobian(fvm_ctx* h, double t, const double* u_native) {
+    if (h->neq > 2) return fvm_fail(h, FVM_ERR_ARG, "fvm_jacobian: systems with more than 2 species are not compiled");
+    int32_t rc = jac_prepare(h);
+    if (rc) return rc;
+    JacArgs a{};
+    a.n2t_ptr = h->csr.n2t_ptr;
+    a.n2t = h->csr.n2t;
+    a.tri = h->d_tri_native;
+    a.rowptr = h->csr.rowptr;
+    a.col = h->csr.col;
+    a.dtab_native = h->dm.dtab;
+    a.val = h->jac_val;
+    a.edges = (const JacEdge*)h->jac_edges;
+    a.bn_of_node = h->jac_bn_of;
+    a.bn_ptr = h->jac_bn_ptr;
+    a.bn_items = h->jac_bn_items;
+    const unsigned grid = (unsigned)((h->N + 127) / 128);
+    if (h->neq == 1) jacobian_rows_kernel<1><<<grid, 128, 0, h->stream>>>(h->dm, h->flux, h->source, a, t, u_native);
+    else jacobian_rows_kernel<2><<<grid, 128, 0, h->stream>>>(h->dm, h->flux, h->source, a, t, u_native);
+    FVM_CUDA(h, cudaGetLastError());
+    h->jac_ready = true;
+    return FVM_OK;
+}
+
 extern "C" int32_t fvm_jacobian(fvm_handle h, double t, const double* u, int32_t on_device) {
     NEED_FINAL(h);
     FVM_REQUIRE(h, u, "fvm_jacobian: null state");
@@ -274,24 +299,8 @@ extern "C" int32_t fvm_jacobian(fvm_handle h, double t, const double* u, int32_t
     }
     if ((rc = fvm_launch_permute(h, src, h->d_u, true))) return rc;
     if ((rc = fvm_halo_exchange(h, h->d_u))) return rc;
-    JacArgs a{};
-    a.n2t_ptr = h->csr.n2t_ptr;
-    a.n2t = h->csr.n2t;
-    a.tri = h->d_tri_native;
-    a.rowptr = h->csr.rowptr;
-    a.col = h->csr.col;
-    a.dtab_native = h->dm.dtab;
-    a.val = h->jac_val;
-    a.edges = (const JacEdge*)h->jac_edges;
-    a.bn_of_node = h->jac_bn_of;
-    a.bn_ptr = h->jac_bn_ptr;
-    a.bn_items = h->jac_bn_items;
-    const unsigned grid = (unsigned)((h->N + 127) / 128);
-    if (h->neq == 1) jacobian_rows_kernel<1><<<grid, 128, 0, h->stream>>>(h->dm, h->flux, h->source, a, t, h->d_u);
-    else jacobian_rows_kernel<2><<<grid, 128, 0, h->stream>>>(h->dm, h->flux, h->source, a, t, h->d_u);
-    FVM_CUDA(h, cudaGetLastError());
+    if ((rc = fvm_launch_jacobian(h, t, h->d_u))) return rc;
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
-    h->jac_ready = true;
     return FVM_OK;
 }
 

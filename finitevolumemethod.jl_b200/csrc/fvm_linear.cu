@@ -266,22 +266,45 @@ __global__ void __launch_bounds__(SPMV_BLOCK)
 // Reuses the RHS tiling: a CTA owns the interior rows of one tile.  x of the tile's local nodes is
 // staged in shared memory (own range coalesced, external interface nodes gathered), columns are
 // 16-bit tile-local ids: 10 B per nonzero instead of 12, and no global gather of x at all.
-template <bool ADD_B, bool SCALE>
+// fixed-shape sum over the CTA (warp shuffles, then the warps in ascending order): deterministic
+template <int THREADS>
+__device__ __forceinline__ double cta_sum(double v) {
+    __shared__ double sh[THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; ++w) s += sh[w];
+    return s;
+}
+
+template <bool ADD_B, bool SCALE, int FUSE>
 __global__ void __launch_bounds__(SPMV_BLOCK)
     spmv_tile_kernel(const DevMesh m, const int32_t* __restrict__ tile_slice0, const int32_t* __restrict__ sell_ptr,
                      const uint16_t* __restrict__ sell_col, const double* __restrict__ sell_val, const double* __restrict__ b,
                      const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y,
-                     const int32_t* __restrict__ tile_list, const int tile_off) {
+                     const int32_t* __restrict__ tile_list, const int tile_off, const SpmvFuse f) {
     extern __shared__ double x_s[];  // [max_nloc]
     const int tile = tile_list ? tile_list[blockIdx.x + tile_off] : (int)blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int4 m0 = __ldg(m.tile_meta + 2 * tile), m1 = __ldg(m.tile_meta + 2 * tile + 1);
     const int node0 = m0.x, nint = m0.y, nown = m0.z, nloc = m0.w, ext0 = m1.x;
-    if (nint == 0) return;
+    if constexpr (FUSE == 2) {
+        if (f.sc[SC_DONE] != 0.0) return;
+        if (nint == 0) {  // uniform: no row of this tile is computed here; its partial still has to exist
+            if (tid == 0) f.dotpart[tile] = 0.0;
+            return;
+        }
+    } else {
+        if (nint == 0) return;
+    }
     for (int i = tid; i < nown; i += SPMV_BLOCK) x_s[i] = x[node0 + i];
     for (int k = tid; k < nloc - nown; k += SPMV_BLOCK) x_s[nown + k] = x[m.ext_ids[ext0 + k]];
     const int s0 = __ldg(tile_slice0 + tile), s1 = __ldg(tile_slice0 + tile + 1);
     __syncthreads();
+    double dot = 0.0;
     // sliced ELL: entry k of the 32 rows of a slice is contiguous -> every load below is coalesced,
     // all 2*len loads of a row are independent, and the row is summed in CSR order in a register
     for (int sl = s0 + warp; sl < s1; sl += SPMV_BLOCK / 32) {
@@ -319,7 +342,12 @@ __global__ void __launch_bounds__(SPMV_BLOCK)
             if (ADD_B) acc += b[node0 + l];
             if (SCALE) acc *= rowscale[node0 + l];
             y[node0 + l] = acc;
+            if constexpr (FUSE == 2) dot += x_s[l] * acc;
         }
+    }
+    if constexpr (FUSE == 2) {
+        const double tot = cta_sum<SPMV_BLOCK>(dot);
+        if (tid == 0) f.dotpart[tile] = tot;
     }
 }
 
@@ -343,29 +371,43 @@ __global__ void sell_pack_kernel(const DevMesh m, const int32_t* __restrict__ ti
 }
 
 // interface rows and points that are not vertices: sliced ELL with global columns, one lane per row
-template <bool ADD_B, bool SCALE>
+template <bool ADD_B, bool SCALE, int FUSE>
 __global__ void __launch_bounds__(128)
     spmv_rows_kernel(const int n_rows, const int32_t* __restrict__ rows, const int32_t* __restrict__ sptr,
                      const int32_t* __restrict__ scol, const double* __restrict__ sval, const double* __restrict__ b,
                      const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y,
-                     const int32_t* __restrict__ slice_list = nullptr, const int list_off = 0, const int list_count = 0) {
+                     const int32_t* __restrict__ slice_list, const int list_off, const int list_count, const SpmvFuse f,
+                     const int dot_off) {
     int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (slice_list) {  // explicit subset of the slices (host-buffer pipeline)
-        if (sl >= list_count) return;
-        sl = slice_list[list_off + sl];
+    double dot = 0.0;
+    bool live = true;
+    if constexpr (FUSE == 2) {
+        if (f.sc[SC_DONE] != 0.0) return;
     }
-    if (sl * 32 >= n_rows) return;
-    const int p0 = __ldg(sptr + sl), len = (__ldg(sptr + sl + 1) - p0) >> 5;
-    const int k = sl * 32 + lane;
-    double acc = 0.0;
+    if (slice_list) {  // explicit subset of the slices (host-buffer pipeline)
+        if (sl >= list_count) live = false;
+        else sl = slice_list[list_off + sl];
+    }
+    if (live && sl * 32 >= n_rows) live = false;
+    if (FUSE != 2 && !live) return;
+    if (live) {
+        const int p0 = __ldg(sptr + sl), len = (__ldg(sptr + sl + 1) - p0) >> 5;
+        const int k = sl * 32 + lane;
+        const int g = k < n_rows ? rows[k] : -1;
+        double acc = 0.0;
 #pragma unroll 4
-    for (int q = 0; q < len; ++q) acc += __ldg(sval + p0 + q * 32 + lane) * __ldg(x + __ldg(scol + p0 + q * 32 + lane));
-    if (k < n_rows) {
-        const int g = rows[k];
-        if (ADD_B) acc += b[g];
-        if (SCALE) acc *= rowscale[g];
-        y[g] = acc;
+        for (int q = 0; q < len; ++q) acc += __ldg(sval + p0 + q * 32 + lane) * x[__ldg(scol + p0 + q * 32 + lane)];
+        if (g >= 0) {
+            if (ADD_B) acc += b[g];
+            if (SCALE) acc *= rowscale[g];
+            y[g] = acc;
+            if constexpr (FUSE == 2) dot = x[g] * acc;
+        }
+    }
+    if constexpr (FUSE == 2) {
+        const double tot = cta_sum<128>(dot);
+        if (threadIdx.x == 0) f.dotpart[dot_off + blockIdx.x] = tot;
     }
 }
 
@@ -407,8 +449,10 @@ __global__ void col16_kernel(const DevMesh m, const int32_t* __restrict__ rowptr
     }
 }
 
-template <bool ADD_B, bool SCALE>
-static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part) {
+static const SpmvFuse kNoFuse{};
+
+template <bool ADD_B, bool SCALE, int FUSE>
+static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part, const SpmvFuse& f) {
     Csr& c = h->csr;
     if (c.use_tile_spmv) {
         int grid = h->dm.n_tiles, off = 0;
@@ -427,14 +471,23 @@ static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part) {
         }
         cudaStream_t st = h->launch_stream;
         if (grid > 0 && part != 3) {
+            auto kern = spmv_tile_kernel<ADD_B, SCALE, FUSE>;
+            // the opt-in is per function and per device, not per handle: always the largest size the tile path accepts
+            int32_t& configured = h->smem_configured[(const void*)kern];
+            if (c.tile_smem > 48 * 1024 && configured == 0) {
+                FVM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                configured = 1;
+            }
             if (st == h->stream) fvm_prof_begin(h);
-            spmv_tile_kernel<ADD_B, SCALE><<<grid, SPMV_BLOCK, c.tile_smem, st>>>(
-                h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale, x, y, list, off);
+            kern<<<grid, SPMV_BLOCK, c.tile_smem, st>>>(h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale, x, y,
+                                                        list, off, f);
             if (st == h->stream) fvm_prof_end(h);
         }
         if (c.n_tail > 0 && (part == 0 || part == 3))
-            spmv_rows_kernel<ADD_B, SCALE><<<(c.n_tslices * 32 + 127) / 128, 128, 0, st>>>(
-                c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b, c.rowscale, x, y);
+            spmv_rows_kernel<ADD_B, SCALE, FUSE><<<(c.n_tslices * 32 + 127) / 128, 128, 0, st>>>(
+                c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b, c.rowscale, x, y, nullptr, 0, 0, f, h->dm.n_tiles);
+    } else if (FUSE != 0) {
+        return fvm_fail(h, FVM_ERR_STATE, "fused SpMV needs the tile kernels");
     } else if (part == 1 || part == 2) {
         return FVM_OK;  // the generic kernels have no tile split: everything runs in part 3
     } else if (c.use_tile_spmv == 0 && c.chunk_rows > 0 && getenv("FVM_SPMV_BLOCK")) {
@@ -454,11 +507,21 @@ static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part) {
     return FVM_OK;
 }
 
+template <int FUSE>
+static int32_t launch_spmv_f(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part, const SpmvFuse& f) {
+    if (add_b && !scale) return launch_spmv_t<true, false, FUSE>(h, x, y, part, f);
+    if (!add_b && !scale) return launch_spmv_t<false, false, FUSE>(h, x, y, part, f);
+    if (add_b && scale) return launch_spmv_t<true, true, FUSE>(h, x, y, part, f);
+    return launch_spmv_t<false, true, FUSE>(h, x, y, part, f);
+}
+
+static int32_t launch_spmv_any(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part, const SpmvFuse& f) {
+    if (f.kind == 2) return launch_spmv_f<2>(h, x, y, add_b, scale, part, f);
+    return launch_spmv_f<0>(h, x, y, add_b, scale, part, f);
+}
+
 int32_t fvm_launch_spmv_part(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale, int part) {
-    if (add_b && !scale) return launch_spmv_t<true, false>(h, x, y, part);
-    if (!add_b && !scale) return launch_spmv_t<false, false>(h, x, y, part);
-    if (add_b && scale) return launch_spmv_t<true, true>(h, x, y, part);
-    return launch_spmv_t<false, true>(h, x, y, part);
+    return launch_spmv_any(h, x, y, add_b, scale, part, kNoFuse);
 }
 
 int32_t fvm_launch_spmv(fvm_ctx* h, const double* x, double* y, bool add_b, bool scale) {
@@ -471,31 +534,41 @@ int32_t fvm_launch_spmv_tail_list(fvm_ctx* h, const double* x, double* y, bool a
     if (count <= 0) return FVM_OK;
     const int grid = (count * 32 + 127) / 128;
     if (add_b)
-        spmv_rows_kernel<true, false><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
-                                                                          c.rowscale, x, y, list, off, count);
+        spmv_rows_kernel<true, false, 0><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
+                                                                             c.rowscale, x, y, list, off, count, kNoFuse, 0);
     else
-        spmv_rows_kernel<false, false><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
-                                                                           c.rowscale, x, y, list, off, count);
+        spmv_rows_kernel<false, false, 0><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
+                                                                              c.rowscale, x, y, list, off, count, kNoFuse, 0);
     FVM_CUDA(h, cudaGetLastError());
     return FVM_OK;
 }
 
-int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* y, bool add_b, bool scale) {
-    if (!h->halo_ready) return fvm_launch_spmv_part(h, x, y, add_b, scale, 0);
+bool fvm_spmv_fusable(fvm_ctx* h) { return h->csr.assembled && h->csr.use_tile_spmv != 0; }
+
+int32_t fvm_spmv_fused_partials(fvm_ctx* h) {
+    return h->dm.n_tiles + (h->csr.n_tail > 0 ? (h->csr.n_tslices * 32 + 127) / 128 : 0);
+}
+
+int32_t fvm_apply_spmv_fused(fvm_ctx* h, double* x, double* y, bool add_b, bool scale, const SpmvFuse& f) {
+    if (!h->halo_ready) return launch_spmv_any(h, x, y, add_b, scale, 0, f);
     int32_t rc;
     if (!h->overlap) {
         if ((rc = fvm_halo_exchange(h, x))) return rc;
-        return fvm_launch_spmv_part(h, x, y, add_b, scale, 0);
+        return launch_spmv_any(h, x, y, add_b, scale, 0, f);
     }
     if ((rc = fvm_halo_begin(h, x))) return rc;
     h->launch_stream = h->comm_stream;  // halo-dependent tiles right behind the unpack, on the communication stream
-    rc = fvm_launch_spmv_part(h, x, y, add_b, scale, 2);
+    rc = launch_spmv_any(h, x, y, add_b, scale, 2, f);
     h->launch_stream = h->stream;
     if (rc) return rc;
     if ((rc = fvm_halo_done(h))) return rc;
-    if ((rc = fvm_launch_spmv_part(h, x, y, add_b, scale, 1))) return rc;
+    if ((rc = launch_spmv_any(h, x, y, add_b, scale, 1, f))) return rc;
     if ((rc = fvm_halo_wait(h))) return rc;
-    return fvm_launch_spmv_part(h, x, y, add_b, scale, 3);
+    return launch_spmv_any(h, x, y, add_b, scale, 3, f);
+}
+
+int32_t fvm_apply_spmv(fvm_ctx* h, double* x, double* y, bool add_b, bool scale) {
+    return fvm_apply_spmv_fused(h, x, y, add_b, scale, kNoFuse);
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -627,13 +700,7 @@ int32_t fvm_build_pattern(fvm_ctx* h) {
             tsell_pack_kernel<<<(c.n_tslices * 32 + 127) / 128, 128, 0, h->stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.rowptr, c.col,
                                                                                       nullptr, c.tsell_col, nullptr);
         FVM_CUDA(h, cudaGetLastError());
-        if (c.tile_smem > 200 * 1024) c.use_tile_spmv = 0;
-        else if (c.tile_smem > 48 * 1024) {
-            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
-            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
-            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
-            FVM_CUDA(h, cudaFuncSetAttribute(spmv_tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c.tile_smem));
-        }
+        if (c.tile_smem > 200 * 1024) c.use_tile_spmv = 0;  // (the tile kernels opt in to large shared memory at first launch)
         if (const char* e = getenv("FVM_SPMV_GENERIC")) c.use_tile_spmv = (e[0] == '1') ? 0 : c.use_tile_spmv;
         if (sizeof(double) * 32 * maxrow * (SPMV_BLOCK / 32) > 48 * 1024) {
             const int wb = (int)(sizeof(double) * 32 * maxrow * (SPMV_BLOCK / 32));

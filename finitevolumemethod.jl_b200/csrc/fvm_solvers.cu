@@ -237,7 +237,6 @@ extern "C" int32_t fvm_tsit5(fvm_handle h, int32_t use_operator, double* u, doub
 // ---- deterministic reductions (shared by the adaptive stepper and the Krylov solvers) ----------
 #define RED_BLOCKS 1184  // 148 SMs x 8
 #define RED_THREADS 256
-enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_SUM0, SC_SUM1, SC_SUM2, SC_N };
 
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __restrict__ partial) {
@@ -563,6 +562,37 @@ __global__ void __launch_bounds__(RED_THREADS) pcg_beta_kernel(const double* par
         if (rr <= sc[SC_TOL2] || !(rr == rr)) sc[SC_DONE] = 1.0;
     }
 }
+// fused iteration (single GPU, tile kernels): p.q comes out of the SpMV as one partial per CTA; this kernel sums them in a
+// fixed order and forms alpha; pcg_beta_fused_kernel does the same for the two sums of the update kernel
+__global__ void __launch_bounds__(1024) pcg_alpha_fused_kernel(const double* __restrict__ dotpart, const int count, double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    __shared__ double sh[32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += 1024) s += dotpart[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double pq = 0.0;
+        for (int w = 0; w < 32; ++w) pq += sh[w];
+        sc[SC_PQ] = pq;
+        sc[SC_ALPHA] = sc[SC_RZ] / pq;
+    }
+}
+__global__ void __launch_bounds__(RED_THREADS) pcg_beta_fused_kernel(const double* partial, double* sc) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double rz = final_sum(partial, 0);
+    __syncthreads();
+    const double rr = final_sum(partial, 1);
+    if (threadIdx.x == 0) {
+        sc[SC_BETA] = rz / sc[SC_RZ];
+        sc[SC_RZ] = rz;
+        sc[SC_RR] = rr;
+        sc[SC_ITER] += 1.0;
+        if (rr <= sc[SC_TOL2] || !(rr == rr)) sc[SC_DONE] = 1.0;
+    }
+}
 __global__ void pcg_p_kernel(int64_t n, const double* z, double* p, const double* sc) {
     if (sc[SC_DONE] != 0.0) return;
     const double beta = sc[SC_BETA];
@@ -728,7 +758,16 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
     }
     if ((rc = fvm_launch_permute(h, src, X, true))) return rc;
     const int G = RED_BLOCKS, B = RED_THREADS;
+    // PCG on one GPU with the tile kernels runs the fused iteration (see below)
+    const bool fused_pcg = method == FVM_KRYLOV_PCG && !h->halo_ready && h->nranks == 1 && fvm_spmv_fusable(h) && !getenv("FVM_NO_FUSE");
     const int check_every = 25;
+    if (fused_pcg) {
+        const int32_t np = fvm_spmv_fused_partials(h);
+        if (h->dotpart_n < np) {
+            if ((rc = fvm_dev_alloc(h, &h->d_dotpart, (size_t)np))) return rc;
+            h->dotpart_n = np;
+        }
+    }
     // local block partials -> local sums -> (sharded) NCCL all-reduce; ghost rows of A, b are zero, so
     // r, z, q, v, t vanish on ghost nodes and the local dot products count every node exactly once
     auto reduce = [&](int nslots, int guard) -> int32_t {
@@ -800,6 +839,22 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
             pcg_init2_kernel<<<G, B, 0, st>>>(n, c.b, c.rowscale, Q, c.diag_inv, R, Z, P, partial);
             if ((rc = reduce(3, 0))) return rc;
             pcg_init3_kernel<<<1, B, 0, st>>>(partial, sc, rtol);
+            // Fused form (one GPU, tile kernels): p.q comes out of the SpMV's epilogue as one partial per CTA, and the
+            // kernels that finish the sums also form alpha / beta: 6 launches and 14 vector passes per iteration instead
+            // of 9 and 16
+            auto iteration_fused = [&]() -> int32_t {
+                SpmvFuse F;
+                F.kind = 2;
+                F.sc = sc;
+                F.dotpart = h->d_dotpart;
+                int32_t r;
+                if ((r = fvm_apply_spmv_fused(h, P, Q, false, true, F))) return r;
+                pcg_alpha_fused_kernel<<<1, 1024, 0, st>>>(h->d_dotpart, fvm_spmv_fused_partials(h), sc);
+                pcg_update_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, c.rowscale, X, R, Z, partial, sc);
+                pcg_beta_fused_kernel<<<1, B, 0, st>>>(partial, sc);
+                pcg_p_kernel<<<G, B, 0, st>>>(n, Z, P, sc);
+                return FVM_OK;
+            };
             auto iteration = [&]() -> int32_t {
                 int32_t r;
                 if ((r = spmv(P, Q, true))) return r;
@@ -812,7 +867,11 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
                 pcg_p_kernel<<<G, B, 0, st>>>(n, Z, P, sc);
                 return FVM_OK;
             };
-            if ((rc = run_iterations(iteration, budget, graphs.exec[0]))) return rc;
+            if (fused_pcg) {
+                if ((rc = run_iterations(iteration_fused, budget, graphs.exec[0]))) return rc;
+            } else if ((rc = run_iterations(iteration, budget, graphs.exec[0]))) {
+                return rc;
+            }
         } else {
             double *R = h->d_work[1], *RH = h->d_work[2], *P = h->d_work[3], *V = h->d_work[4], *Y = h->d_work[5],
                    *S = h->d_work[6], *Z = h->d_work[7], *T = h->d_work[8], *KI = h->d_work[9];
@@ -870,3 +929,177 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
     return FVM_OK;
 }
 
+
+// ---- Newton-Raphson for steady problems, entirely on the device --------------------------------------------
+// solve(SteadyFVMProblem(prob), NewtonRaphson()) (/root/reference/src/solve.jl:209-220).  Each iteration evaluates
+// F = fvm_eqs!(u) and its sparse Jacobian (fvm_jacobian.cu: dual numbers on the jacobian_sparsity pattern) and solves
+// J delta = -F with Jacobi-preconditioned BiCGStab on the block CSR -- nothing but the residual norm crosses PCIe.
+// Rows of J without any non-zero (Dirichlet nodes, points that are not vertices: their du is identically 0) act as
+// identity rows, so delta stays 0 there and their columns drop out: the system the reference's sparse-direct solver
+// sees on the remaining block.
+
+// y = J x on the block CSR (native order, species interleaved); all-zero rows act as identity rows
+template <int NEQ>
+__global__ void __launch_bounds__(128) jac_spmv_kernel(const int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                        const double* __restrict__ val, const double* __restrict__ x, double* __restrict__ y) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    double acc[NEQ], mag[NEQ];
+#pragma unroll
+    for (int l = 0; l < NEQ; ++l) acc[l] = mag[l] = 0.0;
+    for (int e = rowptr[g]; e < rowptr[g + 1]; ++e) {
+        const int c = col[e];
+#pragma unroll
+        for (int l = 0; l < NEQ; ++l)
+#pragma unroll
+            for (int lp = 0; lp < NEQ; ++lp) {
+                const double v = val[((size_t)e * NEQ + l) * NEQ + lp];
+                acc[l] += v * x[(size_t)c * NEQ + lp];
+                mag[l] += fabs(v);
+            }
+    }
+#pragma unroll
+    for (int l = 0; l < NEQ; ++l) y[(size_t)g * NEQ + l] = mag[l] == 0.0 ? x[(size_t)g * NEQ + l] : acc[l];
+}
+// Jacobi preconditioner 1 / J_ii (1 on identity rows and where the diagonal vanishes); b = -F
+template <int NEQ>
+__global__ void __launch_bounds__(128) jac_prec_kernel(const int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                        const double* __restrict__ val, const double* __restrict__ F, double* __restrict__ kinv,
+                                                        double* __restrict__ b, double* __restrict__ x0) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    double d[NEQ];
+#pragma unroll
+    for (int l = 0; l < NEQ; ++l) d[l] = 0.0;
+    for (int e = rowptr[g]; e < rowptr[g + 1]; ++e)
+        if (col[e] == g) {
+#pragma unroll
+            for (int l = 0; l < NEQ; ++l) d[l] = val[((size_t)e * NEQ + l) * NEQ + l];
+        }
+#pragma unroll
+    for (int l = 0; l < NEQ; ++l) {
+        kinv[(size_t)g * NEQ + l] = d[l] != 0.0 ? 1.0 / d[l] : 1.0;
+        b[(size_t)g * NEQ + l] = -F[(size_t)g * NEQ + l];
+        x0[(size_t)g * NEQ + l] = 0.0;
+    }
+}
+__global__ void __launch_bounds__(RED_THREADS) maxabs_kernel(const int64_t n, const double* __restrict__ v, double* __restrict__ partial) {
+    __shared__ double sh[RED_THREADS / 32];
+    double m = 0.0;
+    GRID_STRIDE(i, n) {
+        const double a = fabs(v[i]);
+        m = (a > m || a != a) ? a : m;  // NaN propagates
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, m, o);
+        m = (w > m || w != w) ? w : m;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < RED_THREADS / 32; ++w) m = (sh[w] > m || sh[w] != sh[w]) ? sh[w] : m;
+        partial[blockIdx.x] = m;
+    }
+}
+__global__ void axpy1_kernel(const int64_t n, double* __restrict__ u, const double* __restrict__ d) {
+    GRID_STRIDE(i, n) u[i] += d[i];
+}
+
+extern "C" int32_t fvm_newton(fvm_handle h, double t, double* u, double abstol, double reltol, int32_t maxiters, double lin_rtol,
+                              int32_t lin_maxit, int32_t* iters, double* resid, double* resid0, int64_t* lin_iters, int32_t on_device) {
+    NEED_FINAL(h);
+    FVM_REQUIRE(h, u && maxiters >= 0 && lin_rtol > 0 && lin_maxit > 0, "fvm_newton: bad arguments");
+    FVM_REQUIRE(h, h->neq <= 2, "fvm_newton: systems with more than 2 species are not compiled");
+    if (h->halo_ready) return fvm_fail(h, FVM_ERR_UNSUPPORTED, "fvm_newton: sharded handles are not supported");
+    int32_t rc = ensure_work(h, 12);
+    if (rc) return rc;
+    if ((rc = fvm_ensure_state(h))) return rc;
+    const int64_t n = h->N * h->neq;
+    const size_t bytes = sizeof(double) * n;
+    cudaStream_t st = h->stream;
+    double *U = h->d_work[0], *R = h->d_work[1], *RH = h->d_work[2], *P = h->d_work[3], *V = h->d_work[4], *Y = h->d_work[5],
+           *S = h->d_work[6], *Z = h->d_work[7], *T = h->d_work[8], *KI = h->d_work[9], *X = h->d_work[10], *F = h->d_work[11];
+    double* B = h->d_du;  // right-hand side -F of the Newton system
+    double* partial = h->d_red;
+    double* sc = h->d_red + 8 * 2048;
+    const int G = RED_BLOCKS, Bt = RED_THREADS;
+    const double* src = u;
+    if (!on_device) {
+        FVM_CUDA(h, cudaMemcpyAsync(h->d_io, u, bytes, cudaMemcpyHostToDevice, st));
+        src = h->d_io;
+    }
+    if ((rc = fvm_launch_permute(h, src, U, true))) return rc;
+    if ((rc = fvm_launch_dirichlet(h, t, U))) return rc;  // Dirichlet rows of fvm_eqs! are identically zero: fix the values first
+    double hsc[SC_N];
+    std::vector<double> hpart(G);
+    auto maxabs = [&](const double* v, double* out) -> int32_t {
+        maxabs_kernel<<<G, Bt, 0, st>>>(n, v, partial);
+        FVM_CUDA(h, cudaMemcpyAsync(hpart.data(), partial, sizeof(double) * G, cudaMemcpyDeviceToHost, st));
+        FVM_CUDA(h, cudaStreamSynchronize(st));
+        double m = 0.0;
+        for (double a : hpart) m = (a > m || a != a) ? a : m;
+        *out = m;
+        return FVM_OK;
+    };
+    auto reduce = [&](int nslots, int guard) { reduce_partials_kernel<<<1, Bt, 0, st>>>(partial, nslots, sc, guard); };
+    const unsigned jgrid = (unsigned)((h->N + 127) / 128);
+    auto J = [&](const double* x, double* y) {
+        if (h->neq == 1) jac_spmv_kernel<1><<<jgrid, 128, 0, st>>>((int)h->N, h->csr.rowptr, h->csr.col, h->jac_val, x, y);
+        else jac_spmv_kernel<2><<<jgrid, 128, 0, st>>>((int)h->N, h->csr.rowptr, h->csr.col, h->jac_val, x, y);
+    };
+    if ((rc = fvm_launch_rhs(h, t, U, F))) return rc;
+    double res = 0.0, r0 = 0.0;
+    if ((rc = maxabs(F, &r0))) return rc;
+    res = r0;
+    int32_t it = 0;
+    int64_t lin_total = 0;
+    for (;; ++it) {
+        if (res <= abstol + reltol * r0 || it == maxiters || !(res == res) || std::isinf(res)) break;
+        if ((rc = fvm_launch_jacobian(h, t, U))) return rc;
+        if (h->neq == 1) jac_prec_kernel<1><<<jgrid, 128, 0, st>>>((int)h->N, h->csr.rowptr, h->csr.col, h->jac_val, F, KI, B, X);
+        else jac_prec_kernel<2><<<jgrid, 128, 0, st>>>((int)h->N, h->csr.rowptr, h->csr.col, h->jac_val, F, KI, B, X);
+        // BiCGStab from x = 0: r = rhat = b
+        J(X, V);
+        bicg_init_kernel<<<G, Bt, 0, st>>>(n, B, V, R, RH, P, V, partial);
+        reduce(2, 0);
+        bicg_init2_kernel<<<1, Bt, 0, st>>>(partial, sc, lin_rtol);
+        int32_t lit = 0;
+        while (lit < lin_maxit) {
+            const int chunk = std::min(25, lin_maxit - lit);
+            for (int q = 0; q < chunk; ++q) {
+                bicg_p_kernel<<<G, Bt, 0, st>>>(n, R, V, KI, P, Y, RH, sc);
+                J(Y, V);
+                dot_kernel<<<G, Bt, 0, st>>>(n, RH, V, partial, sc);
+                reduce(1, 1);
+                bicg_alpha_kernel<<<1, Bt, 0, st>>>(partial, sc);
+                bicg_s_kernel<<<G, Bt, 0, st>>>(n, R, V, KI, S, Z, sc);
+                J(Z, T);
+                bicg_ts_kernel<<<G, Bt, 0, st>>>(n, T, S, partial, sc);
+                reduce(2, 1);
+                bicg_omega_kernel<<<1, Bt, 0, st>>>(partial, sc);
+                bicg_x_kernel<<<G, Bt, 0, st>>>(n, Y, Z, S, T, RH, X, R, partial, sc);
+                reduce(2, 1);
+                bicg_end_kernel<<<1, Bt, 0, st>>>(partial, sc);
+            }
+            lit += chunk;
+            FVM_CUDA(h, cudaGetLastError());
+            FVM_CUDA(h, cudaMemcpyAsync(hsc, sc, sizeof(double) * SC_N, cudaMemcpyDeviceToHost, st));
+            FVM_CUDA(h, cudaStreamSynchronize(st));
+            if (hsc[SC_DONE] != 0.0) break;
+        }
+        lin_total += (int64_t)hsc[SC_ITER];
+        if (!(hsc[SC_RR] == hsc[SC_RR])) return fvm_fail(h, FVM_ERR_ARG, "fvm_newton: the linear solve broke down (NaN residual)");
+        axpy1_kernel<<<G, Bt, 0, st>>>(n, U, X);
+        if ((rc = fvm_launch_rhs(h, t, U, F))) return rc;
+        if ((rc = maxabs(F, &res))) return rc;
+    }
+    if ((rc = fvm_launch_permute(h, U, on_device ? u : h->d_io, false))) return rc;
+    if (!on_device) FVM_CUDA(h, cudaMemcpyAsync(u, h->d_io, bytes, cudaMemcpyDeviceToHost, st));
+    FVM_CUDA(h, cudaStreamSynchronize(st));
+    if (iters) *iters = it;
+    if (resid) *resid = res;
+    if (resid0) *resid0 = r0;
+    if (lin_iters) *lin_iters = lin_total;
+    return FVM_OK;
+}

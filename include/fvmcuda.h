@@ -220,6 +220,15 @@ int32_t fvm_get_jacobian_size(fvm_handle h, int64_t* n_rows, int64_t* nnz);
 /* caller numbering; val may be NULL to fetch the pattern only (the jac_prototype of solve.jl:170) */
 int32_t fvm_get_jacobian_csr(fvm_handle h, int32_t* rowptr, int32_t* col, double* val);
 
+/* solve(SteadyFVMProblem(prob), NewtonRaphson()) (src/solve.jl:209-220) on the device: u <- u - J(u)^-1 F(u) with
+ * F = fvm_eqs!(u, t), J = fvm_jacobian and every Newton system solved by Jacobi-preconditioned BiCGStab on the block CSR
+ * (rows of J without a non-zero -- Dirichlet nodes, points that are not vertices -- keep their value).  Stops when
+ * max|F| <= abstol + reltol * max|F(u0)| or after maxiters iterations.  u: in the initial guess, out the iterate
+ * (caller order, host or device; Dirichlet nodes are set to their condition values first).  Outputs (each may be NULL):
+ * Newton iterations taken, final and initial max|F|, total BiCGStab iterations. */
+int32_t fvm_newton(fvm_handle h, double t, double* u, double abstol, double reltol, int32_t maxiters, double lin_rtol,
+                   int32_t lin_maxit, int32_t* iters, double* resid, double* resid0, int64_t* lin_iters, int32_t on_device);
+
 /* ---- post-processing (src/utils.jl:23-27 pl_interpolate, src/problem.jl:458-487 compute_flux) ---- */
 /* For n query points (x,y) lying in given triangles (caller triangle indices): the piecewise-linear
  * interpolant alpha*x + beta*y + gamma of u (nrm == NULL), or q(x,y,t,alpha,beta,gamma) . nrm.

@@ -305,8 +305,8 @@ def test_brusselator_tutorial_exact_solution():
 
 
 def test_steady_newton_raphson_linear_and_nonlinear():
-    """solve(SteadyFVMProblem(prob), NewtonRaphson()) (solve.jl:209-220): device RHS + device Jacobian, host
-    Newton.  Linear diffusion reaches the LaplacesEquation template solution (the reference's own cross-check,
+    """solve(SteadyFVMProblem(prob), NewtonRaphson()) (solve.jl:209-220): device RHS + device Jacobian + device
+    BiCGStab (fvm_newton); linsolve="direct" keeps the host sparse-direct solve.  Linear diffusion reaches the LaplacesEquation template solution (the reference's own cross-check,
     docs/src/literate_wyos/laplaces_equation.jl:188-193) in one step; the porous-medium problem is checked
     through the ORACLE's residual at the returned state."""
     gtri = _split_loop(delaunay_mesh(500, 13, jitter=0.3), k=4)
@@ -323,7 +323,9 @@ def test_steady_newton_raphson_linear_and_nonlinear():
     # nonlinear: D = 0.3 u, source 0.5 - 0.2 u
     gp, op = pair.problem(specs, types, G.PowerDiffusion(0.3, 2.0), source=G.LinearSource(-0.2, 0.5), ic=0.5 + ic)
     sol = G.solve(G.SteadyFVMProblem(gp), G.NewtonRaphson(), tile_triangles=128)
-    assert sol.retcode == "Success" and 2 <= sol.iters <= 20
+    assert sol.retcode == "Success" and 2 <= sol.iters <= 20 and sol.linear_iters > sol.iters  # device Newton + BiCGStab (fvm_newton)
+    direct = G.solve(G.SteadyFVMProblem(gp), G.NewtonRaphson(linsolve="direct"), tile_triangles=128)  # host SuperLU on the device Jacobian
+    assert direct.retcode == "Success" and direct.iters == sol.iters and rel_err(sol.u, direct.u) <= 1e-9
     u0 = (0.5 + ic).copy()
     O.update_dirichlet_nodes(u0, 0.0, op)
     f0 = np.abs(O.fvm_eqs_vec(np.zeros_like(u0), u0, op, 0.0)).max()
@@ -380,3 +382,25 @@ def test_saveat_is_validated():
             G.solve(tpl, G.Tsit5(), saveat=bad)
     assert len(G.solve(tpl, G.Tsit5(), saveat=[0.013, 0.0777]).u) == 2
     tpl.engine.close()
+
+
+def test_fused_pcg_matches_unfused(monkeypatch):
+    """PCG on one GPU takes p.(A p) from the SpMV kernels' epilogue (one partial per CTA, fixed-order final sum) instead
+    of a separate dot kernel, and alpha / beta from the kernels that finish the sums.  The unfused iteration
+    (FVM_NO_FUSE=1) is the same arithmetic up to summation order: same solution, iteration counts within 2."""
+    gtri = _split_loop(delaunay_mesh(4000, 5, extra_points=3, jitter=0.3), k=2)  # interface rows, tail rows, points that are not vertices
+    pair = Pair(gtri)
+    gBC = G.BoundaryConditions(pair.gmesh, (G.Const(1.0), G.Const(0.0)), (G.Dirichlet, G.Dirichlet))
+
+    def run_pcg():
+        tpl = G.MeanExitTimeProblem(pair.gmesh, gBC, diffusion_function=1e-3, tile_triangles=256)
+        out = G.solve(tpl, G.KrylovJacobi("pcg", rtol=1e-12))
+        tpl.engine.close()
+        return out
+
+    fused_cg = run_pcg()
+    monkeypatch.setenv("FVM_NO_FUSE", "1")
+    plain_cg = run_pcg()
+    assert fused_cg.relres <= 1e-11 and plain_cg.relres <= 1e-11
+    assert abs(fused_cg.iters - plain_cg.iters) <= 2
+    assert rel_err(fused_cg.u, plain_cg.u) <= 1e-9
