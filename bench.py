@@ -445,12 +445,51 @@ def sharded_parity(torch, G, eng, lmesh, du_d, nx, ny_total, ymax, flux, rank, w
     return worst
 
 
-def strong_scaling_leg(torch, G, dist, rank, world, local, steps, warmup, peak, nxs=8192):
-    """BASELINE config 5 as written: the nxs x nxs lattice (67M nodes, 134M triangles at 8192) on [0,2]^2 split into
-    `world` row strips, README diffusion: fvm_eqs!, the DiffusionEquation template SpMV and a Tsit5 step, device-timed,
-    max over ranks.  world == 1 gives the 1-GPU leg the speed-ups are quoted against."""
+def patch_parity(torch, G, eng, tri_g, lmesh, du_d, flux, gmode, rank, max_cut=3000, max_inner=1000):
+    """In-run parity of a run sharded by an ARBITRARY partition: du at this rank's owned nodes next to the cuts (the nodes
+    whose triangle fans read the exchanged ghost values; a sample of at most `max_cut`) and at random owned nodes, against a
+    single-domain evaluation on this GPU of the patch made of every triangle incident to those nodes (global coordinates,
+    same u by global id; patch rim = Dirichlet, ignored).  Returns max |difference| / max |reference| over the sample."""
+    from fvm_b200 import _lib as L
+    rng = np.random.default_rng(SEED + rank)
+    cut = np.unique(np.concatenate([np.asarray(x) for x in lmesh.send_nodes])) if lmesh.send_nodes else np.zeros(0, np.int64)
+    if len(cut) > max_cut:
+        cut = rng.choice(cut, max_cut, replace=False)
+    inner = rng.choice(lmesh.n_owned, min(max_inner, lmesh.n_owned), replace=False)
+    loc = np.unique(np.concatenate([cut, inner]).astype(np.int64))          # local ids, all owned
+    patch, verts, pl = G.patch_mesh(tri_g, lmesh.global_nodes[loc])
+    up = global_u(verts)
+    mesh = G.FVMGeometry(patch)
+    prob = G.FVMProblem(mesh, G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet), diffusion_function=flux, initial_condition=up, final_time=0.5)
+    pp = G.get_cuda_parameters(prob, geometry_mode=gmode)
+    ref = G.fvm_eqs(np.empty_like(up), up, pp, 0.0)[pl]
+    pp.engine.close()
+    du_caller = torch.empty_like(du_d)
+    L.check(eng.h, L.lib().fvm_from_native(eng.h, du_d.data_ptr(), du_caller.data_ptr()))
+    eng.synchronize()
+    got = du_caller[torch.from_numpy(loc).cuda()].cpu().numpy()
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-300)), len(loc)
+
+
+def strong_scaling_leg(torch, G, dist, rank, world, local, steps, warmup, peak, nxs=8192, partition="strips"):
+    """BASELINE config 5 as written: the nxs x nxs lattice (67M nodes, 134M triangles at 8192) on [0,2]^2 split over the
+    `world` GPUs, README diffusion: fvm_eqs!, the DiffusionEquation template SpMV and a Tsit5 step, device-timed, max over
+    ranks.  partition: "strips" (row strips, built without the global mesh), "rcb" (recursive coordinate bisection) or
+    "graph" (fvm_partition_graph, the METIS-style multilevel partitioner; every rank computes the same deterministic
+    partition of the global mesh and extracts its part).  world == 1 gives the 1-GPU leg the speed-ups are quoted against."""
     t0 = time.perf_counter()
-    lmesh = G.lattice_strip_local(0.0, 2.0, 0.0, 2.0, nxs, nxs // world, rank, world)
+    tri_g, part_s, cut_edges = None, 0.0, None
+    if partition == "strips" or world == 1:
+        lmesh = G.lattice_strip_local(0.0, 2.0, 0.0, 2.0, nxs, nxs // world, rank, world)
+    else:
+        tri_g = G.triangulate_rectangle(0.0, 2.0, 0.0, 2.0, nxs, nxs, single_boundary=True)
+        tp = time.perf_counter()
+        owner = G.partition_rcb(tri_g.points, world) if partition == "rcb" else G.partition_graph(tri_g, world)
+        part_s = time.perf_counter() - tp
+        if rank == 0:
+            cut_edges = G.edge_cut(tri_g, owner)
+        lmesh = G.extract_local(tri_g, owner, rank, world)
+        del owner
     tri = lmesh.triangulation
     mesh = G.FVMGeometry(tri)
     BCs = G.BoundaryConditions(mesh, G.Const(0.0), G.Dirichlet)
@@ -472,21 +511,34 @@ def strong_scaling_leg(torch, G, dist, rank, world, local, steps, warmup, peak, 
     if dist is not None:
         dist.barrier()
     ms_rhs, kms = time_rhs(torch, eng, u_d, du_d, steps, warmup)
-    parity = None
-    if world > 1:
+    parity, parity_nodes = None, None
+    if world > 1 and tri_g is None:
         parity = sharded_parity(torch, G, eng, lmesh, du_d, nxs, nxs, 2.0, G.ConstantDiffusion(1 / 9), rank, world, 1)
+    elif world > 1:
+        parity, parity_nodes = patch_parity(torch, G, eng, tri_g, lmesh, du_d, G.ConstantDiffusion(1 / 9), 1, rank)
+    halo_nodes = int(sum(len(x) for x in lmesh.recv_nodes))
+    n_neigh = len(lmesh.neighbours)
     eng.close()
-    del p, eng, u_d, du_d, u_c
+    del p, eng, u_d, du_d, u_c, tri_g
     torch.cuda.empty_cache()
     tpl = time_template(torch, G, prob, nxs, steps, warmup, peak, lmesh if world > 1 else None, dist, e2e=False)
-    out = {"rhs_ms": ms_rhs, "spmv_ms": tpl["spmv_ms"], "tsit5_ms_per_step": tpl["tsit5_ms_per_step"], "setup_s": setup_rhs,
-           "assemble_setup_s": tpl["assemble_setup_s"], "nodes_per_gpu": N, "parity_max_rel": parity}
+    out = {"partition": partition if world > 1 else "none", "rhs_ms": ms_rhs, "spmv_ms": tpl["spmv_ms"], "tsit5_ms_per_step": tpl["tsit5_ms_per_step"],
+           "setup_s": setup_rhs, "partition_s": part_s, "assemble_setup_s": tpl["assemble_setup_s"], "nodes_per_gpu": N, "ghost_nodes_per_gpu": halo_nodes,
+           "neighbours": n_neigh, "parity_max_rel": parity}
+    if cut_edges is not None:
+        out["edge_cut"] = int(cut_edges)
+    if parity_nodes is not None:
+        out["parity_nodes_per_rank"] = parity_nodes
     if dist is not None:
-        v = torch.tensor([out["rhs_ms"], out["tsit5_ms_per_step"], parity if parity is not None else 0.0], dtype=torch.float64, device="cuda")
+        v = torch.tensor([out["rhs_ms"], out["tsit5_ms_per_step"], parity if parity is not None else 0.0, float(halo_nodes), float(n_neigh)],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(v, op=dist.ReduceOp.MAX)
         out["rhs_ms"], out["tsit5_ms_per_step"], out["parity_max_rel"] = float(v[0]), float(v[1]), float(v[2])
-    out["mesh"] = "%dx%d lattice on [0,2]^2, %d row strips, one ghost row per neighbour (%d nodes, %d triangles in total)" % (
-        nxs, nxs, world, nxs * nxs, Tg)
+        out["ghost_nodes_per_gpu"], out["neighbours"] = int(v[3]), int(v[4])  # max over ranks
+    out["mesh"] = "%dx%d lattice on [0,2]^2 (%d nodes, %d triangles in total), %s" % (
+        nxs, nxs, nxs * nxs, Tg, "one GPU" if world == 1 else
+        {"strips": "%d row strips" % world, "rcb": "%d parts by recursive coordinate bisection" % world,
+         "graph": "%d parts by fvm_partition_graph (multilevel: heavy-edge matching, graph growing, FM)" % world}[partition] + ", one-layer node halo")
     out["rhs_mtri_s"] = Tg / out["rhs_ms"] / 1e3
     nnz = nxs * nxs + 2 * (nxs * nxs + Tg - 1)
     out["spmv_gbs"] = (12 * nnz + 4 * (nxs * nxs + 1) + 24 * nxs * nxs) / out["spmv_ms"] / 1e6
@@ -503,6 +555,9 @@ def main():
     ap.add_argument("--ref-nx", type=int, default=0, help="side of the CPU arm's lattice (0: the GPU arm's mesh when the run stays within minutes)")
     ap.add_argument("--no-strong", action="store_true", help="skip the BASELINE config 5 leg (8192^2 lattice over the N GPUs)")
     ap.add_argument("--strong-nx", type=int, default=8192)
+    ap.add_argument("--strong-partition", default="strips", choices=["strips", "rcb", "graph"],
+                    help="how the config-5 lattice is split over the GPUs (rcb / graph build the global mesh on every rank: "
+                         "about a minute of extra host time at 8192^2)")
     ap.add_argument("--variant", default="const_recompute", choices=sorted(VARIANTS),
                     help="headline variant; const_recompute is what the engine runs by default for the README problem "
                          "(D = 1/9, a ConstantDiffusion, geometry_mode 1: streaming recompute kernel)")
@@ -666,7 +721,8 @@ def main():
             eng.close()
         del u_d, du_d
         torch.cuda.empty_cache()
-        strong = strong_scaling_leg(torch, G, dist, rank, world, local, max(10, args.steps // 2), args.warmup, peak, args.strong_nx)
+        strong = strong_scaling_leg(torch, G, dist, rank, world, local, max(10, args.steps // 2), args.warmup, peak, args.strong_nx,
+                                    args.strong_partition)
         if rank == 0:
             sys.stderr.write("[bench] strong %s: RHS %.3f ms  SpMV %.3f ms  Tsit5 %.3f ms/step  parity %s\n"
                              % (strong["mesh"], strong["rhs_ms"], strong["spmv_ms"], strong["tsit5_ms_per_step"], strong["parity_max_rel"]))

@@ -13,5 +13,5 @@ from .templates import (DiffusionEquation, KrylovJacobi, LaplacesEquation,  # no
                         LinearReactionDiffusionEquation, MeanExitTimeProblem, PoissonsEquation, Solution, Tsit5)
 from .solve import NewtonRaphson, solve  # noqa: F401
 from .sharding import (LocalMesh, edge_cut, extract_local, partition_graph, get_sharded_cuda_parameters, install_halo,  # noqa: F401
-                       lattice_rows, lattice_strip_local, partition_rcb, partition_strips, shard_problem)
+                       lattice_rows, lattice_strip_local, patch_mesh, partition_rcb, partition_strips, shard_problem)
 from .wire import WireError, WireReader, WireWriter, load_mesh, load_solution, save_mesh, save_solution  # noqa: F401

@@ -12,12 +12,27 @@
 // The node graph is the one `jacobian_sparsity` walks (/root/reference/src/solve.jl:56-77): an edge for every
 // pair of nodes sharing a triangle.  Deterministic.  Host-only code: needs no CUDA device.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <queue>
 
 #include "fvm_internal.h"
 
 namespace {
+
+// FVM_PART_VERBOSE=1: wall time of every phase on stderr
+struct PhaseTimer {
+    const char* name;
+    int32_t n;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    PhaseTimer(const char* nm, int32_t nn) : name(nm), n(nn) {}
+    ~PhaseTimer() {
+        static const bool on = getenv("FVM_PART_VERBOSE") != nullptr;
+        if (on) fprintf(stderr, "[partition] %-10s n = %9d  %.3f s\n", name, n, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 struct WGraph {
     int32_t n = 0;
@@ -27,29 +42,45 @@ struct WGraph {
 };
 
 WGraph graph_from_triangles(int64_t N, const int32_t* tri, int64_t T, int32_t base) {
+    PhaseTimer pt("graph", (int32_t)N);
     WGraph g;
     g.n = (int32_t)N;
     std::vector<int64_t> cnt(N + 1, 0);
+#pragma omp parallel for schedule(static)
     for (int64_t t = 0; t < T; ++t)
-        for (int r = 0; r < 3; ++r) cnt[tri[3 * t + r] - base + 1] += 2;
+        for (int r = 0; r < 3; ++r) {
+#pragma omp atomic
+            cnt[tri[3 * t + r] - base + 1] += 2;
+        }
     for (int64_t i = 0; i < N; ++i) cnt[i + 1] += cnt[i];
     std::vector<int32_t> raw(cnt[N]);
     std::vector<int64_t> fill(cnt.begin(), cnt.end() - 1);
+#pragma omp parallel for schedule(static)
     for (int64_t t = 0; t < T; ++t) {
         const int32_t v[3] = {tri[3 * t] - base, tri[3 * t + 1] - base, tri[3 * t + 2] - base};
         for (int r = 0; r < 3; ++r) {
-            raw[fill[v[r]]++] = v[(r + 1) % 3];
-            raw[fill[v[r]]++] = v[(r + 2) % 3];
+            int64_t at;
+#pragma omp atomic capture
+            {
+                at = fill[v[r]];
+                fill[v[r]] += 2;
+            }
+            raw[at] = v[(r + 1) % 3];  // the order inside a row depends on the schedule; the rows are sorted below
+            raw[at + 1] = v[(r + 2) % 3];
         }
     }
-    g.ptr.assign(N + 1, 0);
-    g.adj.reserve(raw.size() / 2 + N);
-    for (int64_t i = 0; i < N; ++i) {  // unique neighbours
+    // unique neighbours per row: sort + unique in place, then compact
+    std::vector<int64_t> len(N + 1, 0);
+#pragma omp parallel for schedule(dynamic, 4096)
+    for (int64_t i = 0; i < N; ++i) {
         std::sort(raw.begin() + cnt[i], raw.begin() + cnt[i + 1]);
-        auto e = std::unique(raw.begin() + cnt[i], raw.begin() + cnt[i + 1]);
-        g.adj.insert(g.adj.end(), raw.begin() + cnt[i], e);
-        g.ptr[i + 1] = (int64_t)g.adj.size();
+        len[i + 1] = std::unique(raw.begin() + cnt[i], raw.begin() + cnt[i + 1]) - (raw.begin() + cnt[i]);
     }
+    for (int64_t i = 0; i < N; ++i) len[i + 1] += len[i];
+    g.ptr = len;
+    g.adj.resize(len[N]);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; ++i) std::copy(raw.begin() + cnt[i], raw.begin() + cnt[i] + (len[i + 1] - len[i]), g.adj.begin() + len[i]);
     g.ew.assign(g.adj.size(), 1);
     g.vw.assign(N, 1);
     g.total_w = N;
@@ -65,7 +96,112 @@ int64_t cut_of(const WGraph& g, const std::vector<uint8_t>& side) {
 }
 
 // ---- coarsening: heavy-edge matching --------------------------------------------------------------------
+// Large graphs: the nodes are cut into fixed chunks of consecutive ids (independent of the thread count, so the result
+// is too); every chunk is matched on its own (heavy edges to nodes of the same chunk only, ascending ids) and the coarse
+// rows are built chunk by chunk with a linear search instead of a node-indexed position table.  Mesh numberings have locality, so few heavy edges cross a chunk border; if the
+// numbering has none the graph barely shrinks, `ok` is false and the caller falls back to the global serial matching.
+WGraph coarsen_chunked(const WGraph& g, std::vector<int32_t>& cmap, int64_t max_vw, bool& ok) {
+    PhaseTimer pt("coarsen/omp", g.n);
+    const int32_t n = g.n;
+    const int32_t CH = std::max<int32_t>(1 << 15, (n + 63) / 64);  // at most 64 chunks: a 67M-node lattice loses 1 row in 128
+    const int32_t nch = (n + CH - 1) / CH;
+    std::vector<int32_t> match(n, -1);
+    cmap.assign(n, -1);
+    std::vector<int32_t> cbase(nch + 1, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int32_t c = 0; c < nch; ++c) {
+        const int32_t lo = c * CH, hi = std::min<int64_t>(n, (int64_t)lo + CH);
+        int32_t nc = 0;
+        // ascending ids: sequential memory traffic.  On a row-major lattice this pairs along the rows at one level and
+        // across them at the next (the merged pairs share the heavier edges), i.e. it halves the graph every level
+        for (int32_t v = lo; v < hi; ++v) {
+            if (match[v] >= 0) continue;
+            int32_t best = -1, best_w = -1;
+            for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
+                const int32_t u = g.adj[e];
+                if (u >= lo && u < hi && match[u] < 0 && u != v && g.ew[e] > best_w && (int64_t)g.vw[v] + g.vw[u] <= max_vw) {
+                    best_w = g.ew[e];
+                    best = u;
+                }
+            }
+            match[v] = best >= 0 ? best : v;
+            if (best >= 0) match[best] = v;
+            cmap[v] = nc;
+            if (best >= 0) cmap[best] = nc;
+            ++nc;
+        }
+        cbase[c + 1] = nc;
+    }
+    for (int32_t c = 0; c < nch; ++c) cbase[c + 1] += cbase[c];
+    const int32_t nc = cbase[nch];
+    WGraph c;
+    ok = nc < n - n / 5;
+    if (!ok) return c;
+    std::vector<int32_t> first(nc), second(nc, -1);
+#pragma omp parallel for schedule(static)
+    for (int32_t v = 0; v < n; ++v) {
+        cmap[v] += cbase[v / CH];
+        if (match[v] == v) first[cmap[v]] = v;
+        else if (v < match[v]) {
+            first[cmap[v]] = v;
+            second[cmap[v]] = match[v];
+        }
+    }
+    c.n = nc;
+    c.vw.resize(nc);
+    c.ptr.assign(nc + 1, 0);
+    c.total_w = g.total_w;
+    const int32_t RCH = 1 << 15;
+    const int32_t nrch = (nc + RCH - 1) / RCH;
+    std::vector<std::vector<int32_t>> ladj(nrch), lew(nrch);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int32_t rc = 0; rc < nrch; ++rc) {
+        const int32_t lo = rc * RCH, hi = std::min<int64_t>(nc, (int64_t)lo + RCH);
+        std::vector<int32_t>& A = ladj[rc];
+        std::vector<int32_t>& W = lew[rc];
+        A.reserve((size_t)(hi - lo) * 7);
+        W.reserve((size_t)(hi - lo) * 7);
+        for (int32_t cv = lo; cv < hi; ++cv) {
+            const size_t row0 = A.size();
+            int32_t w = 0;
+            for (int32_t v : {first[cv], second[cv]}) {
+                if (v < 0) continue;
+                w += g.vw[v];
+                for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) {
+                    const int32_t cu = cmap[g.adj[e]];
+                    if (cu == cv) continue;
+                    size_t k = row0;
+                    while (k < A.size() && A[k] != cu) ++k;
+                    if (k < A.size()) W[k] += g.ew[e];
+                    else {
+                        A.push_back(cu);
+                        W.push_back(g.ew[e]);
+                    }
+                }
+            }
+            c.vw[cv] = w;
+            c.ptr[cv + 1] = (int64_t)(A.size() - row0);
+        }
+    }
+    for (int32_t cv = 0; cv < nc; ++cv) c.ptr[cv + 1] += c.ptr[cv];
+    c.adj.resize(c.ptr[nc]);
+    c.ew.resize(c.ptr[nc]);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int32_t rc = 0; rc < nrch; ++rc) {
+        const int64_t at = c.ptr[(int64_t)rc * RCH];
+        std::copy(ladj[rc].begin(), ladj[rc].end(), c.adj.begin() + at);
+        std::copy(lew[rc].begin(), lew[rc].end(), c.ew.begin() + at);
+    }
+    return c;
+}
+
 WGraph coarsen(const WGraph& g, std::vector<int32_t>& cmap, int64_t max_vw) {
+    if (g.n >= (1 << 17)) {
+        bool ok = false;
+        WGraph c = coarsen_chunked(g, cmap, max_vw, ok);
+        if (ok) return c;
+    }
+    PhaseTimer pt("coarsen", g.n);
     const int32_t n = g.n;
     std::vector<int32_t> match(n, -1);
     cmap.assign(n, -1);
@@ -128,6 +264,7 @@ WGraph coarsen(const WGraph& g, std::vector<int32_t>& cmap, int64_t max_vw) {
 // ---- Fiduccia-Mattheyses-style boundary refinement --------------------------------------------------------
 // side 0 should weigh target0.  `exact`: finish with |w0 - target0| minimal (node counts on the finest level).
 void refine(const WGraph& g, int64_t target0, std::vector<uint8_t>& side, bool exact) {
+    PhaseTimer pt("refine", g.n);
     const int32_t n = g.n;
     int32_t max_vw = 1;
     for (int32_t v = 0; v < n; ++v) max_vw = std::max(max_vw, g.vw[v]);
@@ -316,6 +453,7 @@ void multilevel_bisect(const WGraph& g, int64_t target0, std::vector<uint8_t>& s
             std::vector<uint8_t> cside;
             multilevel_bisect(c, target0, cside, false);
             side.resize(g.n);
+#pragma omp parallel for schedule(static)
             for (int32_t v = 0; v < g.n; ++v) side[v] = cside[cmap[v]];
             refine(g, target0, side, finest);
             return;
@@ -327,25 +465,56 @@ void multilevel_bisect(const WGraph& g, int64_t target0, std::vector<uint8_t>& s
 
 // induced subgraph of the nodes with side == s
 WGraph subgraph(const WGraph& g, const std::vector<uint8_t>& side, uint8_t s, const std::vector<int32_t>& ids, std::vector<int32_t>& ids_out) {
-    std::vector<int32_t> local(g.n, -1);
+    PhaseTimer pt("subgraph", g.n);
+    const int32_t n = g.n;
+    const int32_t CH = 1 << 16, nch = (n + CH - 1) / CH;
+    std::vector<int32_t> local(n, -1), base(nch + 1, 0);
+#pragma omp parallel for schedule(static)
+    for (int32_t c = 0; c < nch; ++c) {
+        int32_t k = 0;
+        for (int32_t v = c * CH; v < std::min<int64_t>(n, (int64_t)(c + 1) * CH); ++v) k += side[v] == s;
+        base[c + 1] = k;
+    }
+    for (int32_t c = 0; c < nch; ++c) base[c + 1] += base[c];
     WGraph h;
-    for (int32_t v = 0; v < g.n; ++v)
-        if (side[v] == s) {
-            local[v] = h.n++;
-            ids_out.push_back(ids[v]);
-        }
-    h.ptr.assign(h.n + 1, 0);
+    h.n = base[nch];
+    ids_out.resize(h.n);
+    h.ptr.assign((size_t)h.n + 1, 0);
     h.vw.resize(h.n);
-    for (int32_t v = 0; v < g.n; ++v) {
+#pragma omp parallel for schedule(static)
+    for (int32_t c = 0; c < nch; ++c) {
+        int32_t k = base[c];
+        for (int32_t v = c * CH; v < std::min<int64_t>(n, (int64_t)(c + 1) * CH); ++v)
+            if (side[v] == s) {
+                local[v] = k;
+                ids_out[k] = ids[v];
+                h.vw[k] = g.vw[v];
+                ++k;
+            }
+    }
+    int64_t tw = 0;
+#pragma omp parallel for schedule(static) reduction(+ : tw)
+    for (int32_t v = 0; v < n; ++v) {
         if (local[v] < 0) continue;
-        h.vw[local[v]] = g.vw[v];
-        h.total_w += g.vw[v];
+        tw += g.vw[v];
+        int64_t d = 0;
+        for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e) d += local[g.adj[e]] >= 0;
+        h.ptr[local[v] + 1] = d;
+    }
+    h.total_w = tw;
+    for (int32_t k = 0; k < h.n; ++k) h.ptr[k + 1] += h.ptr[k];
+    h.adj.resize(h.ptr[h.n]);
+    h.ew.resize(h.ptr[h.n]);
+#pragma omp parallel for schedule(static)
+    for (int32_t v = 0; v < n; ++v) {
+        if (local[v] < 0) continue;
+        int64_t at = h.ptr[local[v]];
         for (int64_t e = g.ptr[v]; e < g.ptr[v + 1]; ++e)
             if (local[g.adj[e]] >= 0) {
-                h.adj.push_back(local[g.adj[e]]);
-                h.ew.push_back(g.ew[e]);
+                h.adj[at] = local[g.adj[e]];
+                h.ew[at] = g.ew[e];
+                ++at;
             }
-        h.ptr[local[v] + 1] = (int64_t)h.adj.size();
     }
     return h;
 }

@@ -219,6 +219,29 @@ def lattice_rows(a, b, c, d, nx, ny, row0, row1):
     return Triangulation(pts, tris, [np.concatenate([bottom, right[1:], top[1:], left[1:]])])
 
 
+def patch_mesh(tri, nodes):
+    """The sub-mesh of every triangle incident to one of `nodes` (global ids), as a mesh of its own with the global
+    coordinates: `nodes` keep their complete triangle fans, so du of the global problem at those nodes equals du of the
+    patch problem there (the patch's rim is a Dirichlet boundary whose values are ignored).  Used by bench.py's in-run
+    parity check of runs sharded by an arbitrary partition.  Returns (Triangulation, patch -> global ids, local ids of
+    `nodes`)."""
+    N = tri.num_points
+    nodes = np.asarray(nodes, dtype=np.int64)
+    mark = np.zeros(N, dtype=bool)
+    mark[nodes] = True
+    lt = tri.triangles[mark[tri.triangles].any(axis=1)]
+    verts = np.unique(lt)
+    g2l = np.full(N, -1, dtype=np.int32)
+    g2l[verts] = np.arange(len(verts), dtype=np.int32)
+    ltri = g2l[lt]
+    e = np.concatenate([ltri[:, [0, 1]], ltri[:, [1, 2]], ltri[:, [2, 0]]]).astype(np.int64)
+    n = len(verts)
+    bnd = e[~np.isin(e[:, 0] * n + e[:, 1], e[:, 1] * n + e[:, 0])]  # directed edges without a reversed partner
+    patch = Triangulation(tri.points[verts], ltri, boundary_sections=[], boundary_edge_list=(bnd, np.zeros(len(bnd), np.int32)),
+                          num_sections=1)
+    return patch, verts, g2l[nodes]
+
+
 # ---- problems ---------------------------------------------------------------------------------------
 def shard_problem(prob, local):
     """The rank-local FVMProblem / FVMSystem of a global problem (same condition functions, sections

@@ -84,3 +84,28 @@ def test_graph_partitioner_balance_and_cut():
     assert G.edge_cut(tri, owner) == int((owner[e[:, 0]] != owner[e[:, 1]]).sum())
     with pytest.raises(G.FVMCudaError):
         G.partition_graph(tri, 0)
+
+
+def test_patch_mesh_reproduces_du_at_its_nodes():
+    """bench.py's in-run parity check of runs sharded by an arbitrary partition evaluates a patch (every triangle
+    incident to the sampled nodes) as a mesh of its own: du at the sampled nodes must equal du of the global problem
+    there -- checked here with the C oracle on an unstructured mesh and a graph partition's cut nodes."""
+    from oracle.c_oracle import fvm_eqs_general
+    from tests.common import delaunay_mesh
+    tri = delaunay_mesh(3000, 4, jitter=0.3)
+    owner = G.partition_graph(tri, 3)
+    loc = G.extract_local(tri, owner, 1, 3)
+    nodes = loc.global_nodes[np.unique(np.concatenate(loc.send_nodes))]
+    patch, verts, pl = G.patch_mesh(tri, nodes)
+    assert np.array_equal(verts[pl], nodes) and patch.num_triangles < tri.num_triangles // 2
+    u = np.random.default_rng(3).random(tri.num_points)
+    uvg, _ = tri.boundary_edges()
+    dg = np.zeros(tri.num_points, bool)
+    dg[np.unique(uvg)] = True
+    full = fvm_eqs_general(tri.points, tri.triangles, u, flux_params=(0.7,), dirichlet=dg)
+    uvp, _ = patch.boundary_edges()
+    dp = np.zeros(patch.num_points, bool)
+    dp[np.unique(uvp)] = True
+    assert not dp[pl][~dg[nodes]].any()  # a sampled node keeps its complete triangle fan: it is interior to the patch
+    part = fvm_eqs_general(patch.points, patch.triangles, u[verts], flux_params=(0.7,), dirichlet=dp)
+    assert np.abs(part[pl] - full[nodes]).max() <= 1e-13 * np.abs(full).max()
