@@ -699,9 +699,9 @@ def main():
     e2e_stats = eng.stats()
     e2e_sched = e2e_stats.get("host_schedule_rhs", "undecided")
     if dist is not None:
-        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        tmax = torch.tensor([e2e_ms, e2e_plain_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tmax.item())
+        e2e_ms, e2e_plain_ms = float(tmax[0].item()), float(tmax[1].item())
 
     tplres = None
     st = eng.stats()

@@ -150,12 +150,13 @@ extern "C" int32_t fvm_set_halo(fvm_handle h, int32_t n_neigh, const int32_t* ne
         h->n_tiles_indep = (int32_t)indep.size();
         indep.insert(indep.end(), dep.begin(), dep.end());
         if ((rc = fvm_dev_upload(h, &h->d_tile_order, indep))) return rc;
-        // measured on 2 B200s at 16.7M nodes per GPU (general kernel): 1 GPU 1.072 ms/step, serialised exchange
-        // 1.079 ms, overlapped schedule 1.086 ms.  The 32 KB exchange costs ~7 us over NVLink, so there is
-        // nothing left to hide and the extra launches/event waits of the overlapped schedule do not pay:
-        // it is opt-in (it matters for small subdomains or many neighbours)
+        // Overlapped schedule (exchange + halo-dependent tiles on the communication stream, independent tiles on the
+        // compute stream).  With the NCCL exchange it did not pay at 16.7M nodes per GPU (round 1, general kernel: 1 GPU
+        // 1.072 ms/step, serialised 1.079 ms, overlapped 1.086 ms).  With the peer-mapped exchange it does (2 B200s,
+        // gpurun_out/r2w_overlap_ab.log: RHS 0.373 -> 0.364 ms, SpMV 0.294 -> 0.285 ms, Tsit5 2.43 -> 2.37 ms per step),
+        // so it is the default there; FVM_HALO_OVERLAP=0 / 1 overrides.
         const char* ov = getenv("FVM_HALO_OVERLAP");
-        h->overlap = n_neigh > 0 && ov && ov[0] == '1';
+        h->overlap = n_neigh > 0 && (ov ? ov[0] == '1' : s->peer);
     }
     FVM_CUDA(h, cudaStreamSynchronize(h->stream));
     h->halo_ready = true;
