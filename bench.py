@@ -696,12 +696,32 @@ def main():
         G.fvm_eqs(dun, un, p, 0.0)
     e2e_plain_ms = (time.perf_counter() - t0) / 3 * 1e3
     del os.environ["FVM_NO_PIPELINE"]
+    # the host link's own ceiling for this call: the same pinned buffers copied in and out on two streams with no kernel
+    # at all, every rank at once (on the 8-GPU VM all ranks share one 154 GB/s PCIe root: profiles/r02_host_link_probe_8gpu.log)
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    scratch = torch.empty_like(u_d)
+
+    def pure_copies(iters):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            with torch.cuda.stream(s_in):
+                scratch.copy_(u_h, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                du_h.copy_(du_d, non_blocking=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / iters * 1e3
+    pure_copies(2)
+    if dist is not None:
+        dist.barrier()
+    copy_ms = pure_copies(5)
+    del scratch
     e2e_stats = eng.stats()
     e2e_sched = e2e_stats.get("host_schedule_rhs", "undecided")
     if dist is not None:
-        tmax = torch.tensor([e2e_ms, e2e_plain_ms], dtype=torch.float64, device="cuda")
+        tmax = torch.tensor([e2e_ms, e2e_plain_ms, copy_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_ms, e2e_plain_ms = float(tmax[0].item()), float(tmax[1].item())
+        e2e_ms, e2e_plain_ms, copy_ms = float(tmax[0].item()), float(tmax[1].item()), float(tmax[2].item())
 
     tplres = None
     st = eng.stats()
@@ -760,7 +780,10 @@ def main():
                 "schedule": ("banded pipeline, %d bands (copy-in / tiles / copy-out overlapped)" % e2e_stats["pipe_bands"])
                 if e2e_sched == "pipeline" else "H2D, kernels, D2H in sequence",
                 "schedule_choice": "one-off timing per handle (call 1 pipelined, call 2 plain, then the faster): " + e2e_sched,
-                "unpipelined_ms_per_step": e2e_plain_ms},
+                "unpipelined_ms_per_step": e2e_plain_ms,
+                "host_link_copies_only_ms": copy_ms,
+                "host_link_note": "the same two pinned buffers copied H2D and D2H on two streams with no kernel, all ranks at once "
+                                  "(max over ranks): the floor this host's PCIe path sets for one call"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
         "setup_s": head["setup_s"],

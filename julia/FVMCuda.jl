@@ -430,6 +430,30 @@ function CommonSolve.solve(prob::Union{PoissonsEquation, LaplacesEquation, MeanE
 end
 
 # ---------------------------------------------------------------------------------------------------------
+# solve(SteadyFVMProblem(prob), alg) on the device                                        src/solve.jl:209-220
+# ---------------------------------------------------------------------------------------------------------
+"Newton-Raphson with the Newton systems solved by Jacobi-preconditioned BiCGStab on the device Jacobian (fvm_newton)."
+Base.@kwdef struct FVMCudaNewton
+    abstol::Float64 = 1e-11
+    reltol::Float64 = 1e-11
+    maxiters::Int = 50
+    lin_rtol::Float64 = 1e-13
+    lin_maxiters::Int = 20_000
+end
+
+function CommonSolve.solve(prob::SteadyFVMProblem, alg::FVMCudaNewton; p::CudaParams = get_cuda_parameters(prob.problem), kwargs...)
+    h = p.handle
+    u = collect(Float64, prob.problem.initial_condition)
+    iters = Ref{Int32}(0); lin = Ref{Int64}(0); res = Ref{Float64}(0.0); res0 = Ref{Float64}(0.0)
+    check(h.ptr, ccall((:fvm_newton, LIB), Int32,
+        (Ptr{Cvoid}, Float64, Ptr{Float64}, Float64, Float64, Int32, Float64, Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Int32),
+        h.ptr, Float64(prob.problem.initial_time), u, alg.abstol, alg.reltol, Int32(alg.maxiters), alg.lin_rtol, Int32(alg.lin_maxiters),
+        iters, res, res0, lin, 0))
+    ok = res[] <= alg.abstol + alg.reltol * res0[]
+    return (u = u, iters = Int(iters[]), linear_iters = Int(lin[]), resid = res[], retcode = ok ? :Success : :MaxIters)
+end
+
+# ---------------------------------------------------------------------------------------------------------
 # post-processing on the device (pl_interpolate src/utils.jl:23-27, compute_flux src/problem.jl:458-487)
 # ---------------------------------------------------------------------------------------------------------
 "u (or q . n when `normals` is given) at points lying in the given triangles (indices into the handle's triangle order)."

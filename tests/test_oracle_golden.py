@@ -1,6 +1,7 @@
 """Pins the CPU oracle against the reference's own numeric known-answer tests
 (SURVEY.md section 8c).  Every test cites the reference test it restates."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -370,6 +371,26 @@ def test_tsit5_tableau_order_conditions_and_convergence():
         u = O.tsit5_fixed(f, np.array([1.0]), 0.0, 1.0, 1.0 / n)
         errs.append(abs(u[0] - exact(1.0)))
     assert 4.5 < math.log2(errs[0] / errs[1]) < 6.5 and 4.5 < math.log2(errs[1] / errs[2]) < 6.5
+
+
+def test_tsit5_embedded_error_weights():
+    """The embedded estimator of the adaptive stepper (f3): btilde = b - bhat must annihilate every elementary weight up
+    to order 4 (so bhat is a 4th-order method and the estimate is O(h^5)) and must NOT annihilate the 5th-order one;
+    the same constants sit in fvm_solvers.cu (TS_BT).  Published values: Tsitouras 2011 / OrdinaryDiffEq's
+    Tsit5ConstantCache -- neither is under /root/reference, so these identities are the pin that exists."""
+    A, c = O.TSIT5_A, np.array(O.TSIT5_C)
+    Am = np.zeros((7, 7))
+    for s in range(1, 7):
+        Am[s, :s] = A[s]
+    bt = np.array(O.TSIT5_BTILDE)
+    weights = [np.ones(7), c, c**2, Am @ c, c**3, c * (Am @ c), Am @ c**2, Am @ (Am @ c)]
+    for w in weights:
+        assert abs(bt @ w) <= 2e-15
+    assert 1e-4 < abs(bt @ c**4) < 1e-3
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "finitevolumemethod.jl_b200", "csrc", "fvm_solvers.cu")).read()
+    m = re.search(r"TS_BT\[7\]\s*=\s*\{([^}]*)\}", src)
+    assert m and np.array_equal(np.array([float(x) for x in m.group(1).replace("\n", " ").split(",")]), bt)
 
 
 def test_system_equals_scalar():
