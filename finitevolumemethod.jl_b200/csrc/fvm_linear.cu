@@ -280,15 +280,63 @@ __device__ __forceinline__ double cta_sum(double v) {
     return s;
 }
 
+// interface rows and points that are not vertices: sliced ELL with global columns, one lane per row.  Slice `sl` of the
+// tail (or nothing when !live); with FUSE == 2 every thread of the CTA must call it (block reduction inside).
+struct TailArgs {
+    int32_t n_rows = 0;
+    const int32_t* rows = nullptr;
+    const int32_t* sptr = nullptr;
+    const int32_t* scol = nullptr;
+    const double* sval = nullptr;
+    int32_t n_blocks = 0;  // CTAs of a merged launch that work on tail slices (SPMV_BLOCK / 32 slices each)
+};
+template <bool ADD_B, bool SCALE, int FUSE, int THREADS>
+__device__ __forceinline__ void tail_slice(const TailArgs& ta, const int sl, const bool live, const double* __restrict__ b,
+                                           const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y,
+                                           const SpmvFuse& f, const int dot_slot) {
+    const int lane = threadIdx.x & 31;
+    double dot = 0.0;
+    if (live) {
+        const int p0 = __ldg(ta.sptr + sl), len = (__ldg(ta.sptr + sl + 1) - p0) >> 5;
+        const int k = sl * 32 + lane;
+        const int g = k < ta.n_rows ? ta.rows[k] : -1;
+        double acc = 0.0;
+#pragma unroll 4
+        for (int q = 0; q < len; ++q) acc += __ldg(ta.sval + p0 + q * 32 + lane) * x[__ldg(ta.scol + p0 + q * 32 + lane)];
+        if (g >= 0) {
+            if (ADD_B) acc += b[g];
+            if (SCALE) acc *= rowscale[g];
+            y[g] = acc;
+            if constexpr (FUSE == 2) dot = x[g] * acc;
+        }
+    }
+    if constexpr (FUSE == 2) {
+        const double tot = cta_sum<THREADS>(dot);
+        if (threadIdx.x == 0) f.dotpart[dot_slot] = tot;
+    }
+}
+
+// One launch applies the whole operator: the first ta.n_blocks CTAs take the tail slices (they are gather-latency bound and
+// independent of the tiles, so they start first and overlap with the bandwidth-bound tile CTAs that fill the other slots),
+// every other CTA owns the interior rows of one tile.
 template <bool ADD_B, bool SCALE, int FUSE>
 __global__ void __launch_bounds__(SPMV_BLOCK)
     spmv_tile_kernel(const DevMesh m, const int32_t* __restrict__ tile_slice0, const int32_t* __restrict__ sell_ptr,
                      const uint16_t* __restrict__ sell_col, const double* __restrict__ sell_val, const double* __restrict__ b,
                      const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y,
-                     const int32_t* __restrict__ tile_list, const int tile_off, const SpmvFuse f) {
+                     const int32_t* __restrict__ tile_list, const int tile_off, const SpmvFuse f, const TailArgs ta) {
     extern __shared__ double x_s[];  // [max_nloc]
-    const int tile = tile_list ? tile_list[blockIdx.x + tile_off] : (int)blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if ((int)blockIdx.x < ta.n_blocks) {
+        if constexpr (FUSE == 2) {
+            if (f.sc[SC_DONE] != 0.0) return;
+        }
+        const int sl = blockIdx.x * (SPMV_BLOCK / 32) + warp;
+        tail_slice<ADD_B, SCALE, FUSE, SPMV_BLOCK>(ta, sl, sl * 32 < ta.n_rows, b, rowscale, x, y, f, m.n_tiles + blockIdx.x);
+        return;
+    }
+    const int bid = blockIdx.x - ta.n_blocks;
+    const int tile = tile_list ? tile_list[bid + tile_off] : bid;
     const int4 m0 = __ldg(m.tile_meta + 2 * tile), m1 = __ldg(m.tile_meta + 2 * tile + 1);
     const int node0 = m0.x, nint = m0.y, nown = m0.z, nloc = m0.w, ext0 = m1.x;
     if constexpr (FUSE == 2) {
@@ -370,45 +418,19 @@ __global__ void sell_pack_kernel(const DevMesh m, const int32_t* __restrict__ ti
     }
 }
 
-// interface rows and points that are not vertices: sliced ELL with global columns, one lane per row
-template <bool ADD_B, bool SCALE, int FUSE>
+// the tail slices on their own (host-buffer pipeline: explicit slice lists; sharded runs without a tile path)
+template <bool ADD_B, bool SCALE>
 __global__ void __launch_bounds__(128)
-    spmv_rows_kernel(const int n_rows, const int32_t* __restrict__ rows, const int32_t* __restrict__ sptr,
-                     const int32_t* __restrict__ scol, const double* __restrict__ sval, const double* __restrict__ b,
-                     const double* __restrict__ rowscale, const double* __restrict__ x, double* __restrict__ y,
-                     const int32_t* __restrict__ slice_list, const int list_off, const int list_count, const SpmvFuse f,
-                     const int dot_off) {
+    spmv_rows_kernel(const TailArgs ta, const double* __restrict__ b, const double* __restrict__ rowscale, const double* __restrict__ x,
+                     double* __restrict__ y, const int32_t* __restrict__ slice_list, const int list_off, const int list_count) {
     int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    double dot = 0.0;
     bool live = true;
-    if constexpr (FUSE == 2) {
-        if (f.sc[SC_DONE] != 0.0) return;
-    }
-    if (slice_list) {  // explicit subset of the slices (host-buffer pipeline)
+    if (slice_list) {  // explicit subset of the slices
         if (sl >= list_count) live = false;
         else sl = slice_list[list_off + sl];
     }
-    if (live && sl * 32 >= n_rows) live = false;
-    if (FUSE != 2 && !live) return;
-    if (live) {
-        const int p0 = __ldg(sptr + sl), len = (__ldg(sptr + sl + 1) - p0) >> 5;
-        const int k = sl * 32 + lane;
-        const int g = k < n_rows ? rows[k] : -1;
-        double acc = 0.0;
-#pragma unroll 4
-        for (int q = 0; q < len; ++q) acc += __ldg(sval + p0 + q * 32 + lane) * x[__ldg(scol + p0 + q * 32 + lane)];
-        if (g >= 0) {
-            if (ADD_B) acc += b[g];
-            if (SCALE) acc *= rowscale[g];
-            y[g] = acc;
-            if constexpr (FUSE == 2) dot = x[g] * acc;
-        }
-    }
-    if constexpr (FUSE == 2) {
-        const double tot = cta_sum<128>(dot);
-        if (threadIdx.x == 0) f.dotpart[dot_off + blockIdx.x] = tot;
-    }
+    if (!live || sl * 32 >= ta.n_rows) return;
+    tail_slice<ADD_B, SCALE, 0, 128>(ta, sl, true, b, rowscale, x, y, SpmvFuse{}, 0);
 }
 
 __global__ void tsell_pack_kernel(const int n_rows, const int32_t* __restrict__ rows, const int32_t* __restrict__ sptr,
@@ -470,7 +492,15 @@ static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part, c
             grid = h->pipe_count;
         }
         cudaStream_t st = h->launch_stream;
-        if (grid > 0 && part != 3) {
+        // the tail slices ride in the launch that may read the whole input: everything (0) or the halo-dependent part (2)
+        TailArgs ta;
+        ta.n_rows = c.n_tail;
+        ta.rows = c.tail_rows;
+        ta.sptr = c.tsell_ptr;
+        ta.scol = c.tsell_col;
+        ta.sval = c.tsell_val;
+        ta.n_blocks = (c.n_tail > 0 && (part == 0 || part == 2)) ? (c.n_tslices + SPMV_BLOCK / 32 - 1) / (SPMV_BLOCK / 32) : 0;
+        if (grid + ta.n_blocks > 0 && part != 3) {
             auto kern = spmv_tile_kernel<ADD_B, SCALE, FUSE>;
             // the opt-in is per function and per device, not per handle: always the largest size the tile path accepts
             int32_t& configured = h->smem_configured[(const void*)kern];
@@ -479,13 +509,10 @@ static int32_t launch_spmv_t(fvm_ctx* h, const double* x, double* y, int part, c
                 configured = 1;
             }
             if (st == h->stream) fvm_prof_begin(h);
-            kern<<<grid, SPMV_BLOCK, c.tile_smem, st>>>(h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale, x, y,
-                                                        list, off, f);
+            kern<<<grid + ta.n_blocks, SPMV_BLOCK, c.tile_smem, st>>>(h->dm, c.tile_slice0, c.sell_ptr, c.sell_col, c.sell_val, c.b, c.rowscale,
+                                                                      x, y, list, off, f, ta);
             if (st == h->stream) fvm_prof_end(h);
         }
-        if (c.n_tail > 0 && (part == 0 || part == 3))
-            spmv_rows_kernel<ADD_B, SCALE, FUSE><<<(c.n_tslices * 32 + 127) / 128, 128, 0, st>>>(
-                c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b, c.rowscale, x, y, nullptr, 0, 0, f, h->dm.n_tiles);
     } else if (FUSE != 0) {
         return fvm_fail(h, FVM_ERR_STATE, "fused SpMV needs the tile kernels");
     } else if (part == 1 || part == 2) {
@@ -533,12 +560,14 @@ int32_t fvm_launch_spmv_tail_list(fvm_ctx* h, const double* x, double* y, bool a
     Csr& c = h->csr;
     if (count <= 0) return FVM_OK;
     const int grid = (count * 32 + 127) / 128;
-    if (add_b)
-        spmv_rows_kernel<true, false, 0><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
-                                                                             c.rowscale, x, y, list, off, count, kNoFuse, 0);
-    else
-        spmv_rows_kernel<false, false, 0><<<grid, 128, 0, h->launch_stream>>>(c.n_tail, c.tail_rows, c.tsell_ptr, c.tsell_col, c.tsell_val, c.b,
-                                                                              c.rowscale, x, y, list, off, count, kNoFuse, 0);
+    TailArgs ta;
+    ta.n_rows = c.n_tail;
+    ta.rows = c.tail_rows;
+    ta.sptr = c.tsell_ptr;
+    ta.scol = c.tsell_col;
+    ta.sval = c.tsell_val;
+    if (add_b) spmv_rows_kernel<true, false><<<grid, 128, 0, h->launch_stream>>>(ta, c.b, c.rowscale, x, y, list, off, count);
+    else spmv_rows_kernel<false, false><<<grid, 128, 0, h->launch_stream>>>(ta, c.b, c.rowscale, x, y, list, off, count);
     FVM_CUDA(h, cudaGetLastError());
     return FVM_OK;
 }
@@ -546,7 +575,7 @@ int32_t fvm_launch_spmv_tail_list(fvm_ctx* h, const double* x, double* y, bool a
 bool fvm_spmv_fusable(fvm_ctx* h) { return h->csr.assembled && h->csr.use_tile_spmv != 0; }
 
 int32_t fvm_spmv_fused_partials(fvm_ctx* h) {
-    return h->dm.n_tiles + (h->csr.n_tail > 0 ? (h->csr.n_tslices * 32 + 127) / 128 : 0);
+    return h->dm.n_tiles + (h->csr.n_tail > 0 ? (h->csr.n_tslices + SPMV_BLOCK / 32 - 1) / (SPMV_BLOCK / 32) : 0);
 }
 
 int32_t fvm_apply_spmv_fused(fvm_ctx* h, double* x, double* y, bool add_b, bool scale, const SpmvFuse& f) {
