@@ -38,6 +38,7 @@ struct StreamArgs {
     int32_t u_cap;     // doubles reserved per stage for the tile's u values
     int32_t prefetch;  // producer pulls the next tile's pack / u range into L2 one tile ahead
     int32_t plane;     // doubles per contribution plane: 3 * TT + 16 (the last 16 stay zero: one per bank pair)
+    int32_t nbuf;      // contribution buffers: 2 (one barrier per tile) or 1 (a second barrier after the node pass, half the planes)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
     const int TT = m.tile_tris;
     const int cbuf = NEQ * a.plane;  // doubles per contribution buffer
     double* c_s = reinterpret_cast<double*>(smem_raw);
-    unsigned char* stage0 = smem_raw + (size_t)2 * cbuf * sizeof(double);
+    unsigned char* stage0 = smem_raw + (size_t)a.nbuf * cbuf * sizeof(double);
     const int stage_bytes = a.pack_cap + a.u_cap * (int)sizeof(double);
     uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + (size_t)SK_STAGES * stage_bytes);
     uint64_t* empty = full + SK_STAGES;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (tid < 2 * NEQ * 16)  // the zero words padded gather entries point at (one per 8-byte bank pair)
+    if (tid < a.nbuf * NEQ * 16)  // the zero words padded gather entries point at (one per 8-byte bank pair)
         c_s[(tid / (16 * NEQ)) * cbuf + ((tid / 16) % NEQ) * a.plane + 3 * TT + (tid & 15)] = 0.0;
     __syncthreads();
     const int n_my = ((int)a.count - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
         const double2* __restrict__ xy_s = reinterpret_cast<const double2*>(st + h2.y);
         const double* __restrict__ us =
             reinterpret_cast<const double*>(st + a.pack_cap) + ((reinterpret_cast<uintptr_t>(u + (size_t)node0 * NEQ) >> 3) & 1);
-        double* cb = c_s + (size_t)(i & 1) * cbuf;
+        double* cb = c_s + (size_t)(a.nbuf == 2 ? (i & 1) : 0) * cbuf;
 
         // ---- triangle pass --------------------------------------------------------------------------
 #pragma unroll 1
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);  // this warp is done with the stage
+        if (a.nbuf == 1) bar_sync(2, NCONS);    // single contribution buffer: nobody scatters into it before every node is gathered
     }
 }
 
@@ -308,18 +310,31 @@ int32_t launch_stream_t(fvm_ctx* h, double t, const double* u, double* du, const
     a.plane = 3 * h->dm.tile_tris + 16;
     static const bool pf = getenv("FVM_STREAM_PREFETCH") != nullptr;  // measured at 4096^2: no gain (0.349 vs 0.341 ms), off
     a.prefetch = pf ? 1 : 0;
-    const int32_t smem = (int32_t)(2 * NEQ * a.plane * sizeof(double) + SK_STAGES * (a.pack_cap + a.u_cap * sizeof(double)) + 2 * SK_STAGES * sizeof(uint64_t));
-    if (smem > 227 * 1024) return fvm_fail(h, FVM_ERR_ARG, "streaming RHS kernel: tile needs more than 227 KB of shared memory; lower tile_triangles");
-    int32_t& configured = h->smem_configured[(const void*)kern];
+    // Two contribution buffers need one barrier per tile; ONE buffer needs a second barrier but halves the planes.  The
+    // second form is taken only where it buys a resident CTA (systems: 2 -> 3 CTAs/SM, 2-species kernel 0.750 -> 0.703 ms;
+    // scalar kernels sit at 3 either way and lose 3 % to the extra barrier, gpurun_out/r3c_planes_ab.log).
+    const int32_t stage_smem = (int32_t)(SK_STAGES * (a.pack_cap + a.u_cap * sizeof(double)) + 2 * SK_STAGES * sizeof(uint64_t));
+    const int32_t plane_smem = (int32_t)(NEQ * a.plane * sizeof(double));
+    int32_t& configured = h->smem_configured[(const void*)kern];  // dynamic shared memory the choice below was made for
     int32_t& occ = h->occ_cache[(const void*)kern];
-    if (configured != smem) {
-        FVM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int nb = 0;
-        FVM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NCONS + SK_PROD, smem));
-        if (nb < 1) return fvm_fail(h, FVM_ERR_CUDA, "streaming RHS kernel does not fit on an SM");
-        configured = smem;
-        occ = nb;
+    if (2 * plane_smem + stage_smem <= 227 * 1024 ? configured != 2 * plane_smem + stage_smem && configured != plane_smem + stage_smem
+                                                  : configured != plane_smem + stage_smem) {
+        if (plane_smem + stage_smem > 227 * 1024)
+            return fvm_fail(h, FVM_ERR_ARG, "streaming RHS kernel: tile needs more than 227 KB of shared memory; lower tile_triangles");
+        // the opt-in is per function and device, not per handle: always the hardware maximum
+        FVM_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        int nb1 = 0, nb2 = 0;
+        FVM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb1, kern, NCONS + SK_PROD, plane_smem + stage_smem));
+        if (2 * plane_smem + stage_smem <= 227 * 1024)
+            FVM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, kern, NCONS + SK_PROD, 2 * plane_smem + stage_smem));
+        if (nb1 < 1) return fvm_fail(h, FVM_ERR_CUDA, "streaming RHS kernel does not fit on an SM");
+        static const char* nb_env = getenv("FVM_STREAM_PLANES");  // experiment knob: force 1 or 2 buffers
+        const bool one = nb_env ? nb_env[0] == '1' : nb1 > nb2;
+        configured = (one || nb2 < 1 ? 1 : 2) * plane_smem + stage_smem;
+        occ = (one || nb2 < 1) ? nb1 : nb2;
     }
+    a.nbuf = configured == plane_smem + stage_smem ? 1 : 2;
+    const int32_t smem = configured;
     h->smem_rhs = smem;
     const int grid = std::min(count, h->sm_count * occ);
     cudaStream_t st = h->launch_stream;
