@@ -12,6 +12,7 @@ for r in rows[hdr + 1:]:
     a[0] += 1
     a[1] += v
 tot = sum(a[1] for a in agg.values())
-skip = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+import signal
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `| head` closes the pipe early
 for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print("%8d x %9.2f us = %10.1f us  %5.1f%%  %s" % (n, t / n, t, 100 * t / tot, name[:110]))
