@@ -307,7 +307,7 @@ bool fvm_spmv_fusable(fvm_ctx* h);            // the tile / sliced-ELL kernels a
 int32_t fvm_spmv_fused_partials(fvm_ctx* h);  // entries of dotpart a kind-2 application writes (tiles + tail CTAs)
 int32_t fvm_apply_spmv_fused(fvm_ctx* h, double* x, double* out, bool add_b, bool scale, const SpmvFuse& f);
 // device scalars of the Krylov solvers / adaptive stepper (d_red + 8 * 2048)
-enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_SUM0, SC_SUM1, SC_SUM2, SC_N };
+enum { SC_RZ = 0, SC_PQ, SC_ALPHA, SC_BETA, SC_RR, SC_BNORM2, SC_RHO, SC_OMEGA, SC_TS, SC_TT, SC_RHV, SC_DONE, SC_ITER, SC_TOL2, SC_RESTART, SC_SUM0, SC_SUM1, SC_SUM2, SC_RZ2, SC_N };
 int32_t fvm_allreduce_sum(fvm_ctx* h, double* d_vals, int n);
 int32_t fvm_global_or(fvm_ctx* h, bool local, bool* global);
 #define FVM_NODE_GHOST 4

@@ -593,6 +593,66 @@ __global__ void __launch_bounds__(RED_THREADS) pcg_beta_fused_kernel(const doubl
         if (rr <= sc[SC_TOL2] || !(rr == rr)) sc[SC_DONE] = 1.0;
     }
 }
+// Small systems (few SpMV partials): the two 1-block kernels disappear as well -- EVERY block of the update kernel sums the
+// SpMV's partials itself (same fixed order in every block, a few KB out of L2) and forms alpha; every block of the
+// p-update sums the update kernel's partials and forms beta.  r.z ping-pongs between two scalar slots (`par`), so that
+// block 0 can publish the new value while other blocks still read the old one.  4 launches per iteration.
+__device__ __forceinline__ double block_sum_fixed(const double* __restrict__ v, const int count) {
+    __shared__ double sh[RED_THREADS / 32];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += RED_THREADS) s += __ldcg(v + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();  // sh may still be read by an earlier call
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int w = 0; w < RED_THREADS / 32; ++w) tot += sh[w];
+    return tot;
+}
+__global__ void __launch_bounds__(RED_THREADS)
+    pcg_update_merged_kernel(int64_t n, const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+                             const double* __restrict__ rowscale, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z,
+                             double* __restrict__ partial, double* sc, const double* __restrict__ dotpart, const int count, const int par) {
+    if (sc[SC_DONE] != 0.0) return;
+    const double pq = block_sum_fixed(dotpart, count);
+    const double alpha = sc[par ? SC_RZ2 : SC_RZ] / pq;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        sc[SC_PQ] = pq;
+        sc[SC_ALPHA] = alpha;
+    }
+    double v[2] = {0, 0};
+    GRID_STRIDE(i, n) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        const double zi = dinv[i] * ri;
+        r[i] = ri;
+        z[i] = zi;
+        const double ru = ri / rowscale[i];
+        v[0] += ri * zi;
+        v[1] += ru * ru;
+    }
+    block_reduce_store<2>(v, partial);
+}
+__global__ void __launch_bounds__(RED_THREADS)
+    pcg_p_merged_kernel(int64_t n, const double* __restrict__ z, double* __restrict__ p, const double* __restrict__ partial, double* sc,
+                        const int par) {
+    if (sc[SC_DONE] != 0.0) return;  // (set by block 0 of this very launch only when the iteration is over: p is dead then)
+    const double rz = block_sum_fixed(partial, RED_BLOCKS);
+    const double beta = rz / sc[par ? SC_RZ2 : SC_RZ];
+    if (blockIdx.x == 0) {
+        const double rr = block_sum_fixed(partial + RED_BLOCKS, RED_BLOCKS);
+        if (threadIdx.x == 0) {
+            sc[SC_BETA] = beta;
+            sc[par ? SC_RZ : SC_RZ2] = rz;
+            sc[SC_RR] = rr;
+            sc[SC_ITER] += 1.0;
+            if (rr <= sc[SC_TOL2] || !(rr == rr)) sc[SC_DONE] = 1.0;
+        }
+    }
+    GRID_STRIDE(i, n) p[i] = z[i] + beta * p[i];
+}
 __global__ void pcg_p_kernel(int64_t n, const double* z, double* p, const double* sc) {
     if (sc[SC_DONE] != 0.0) return;
     const double beta = sc[SC_BETA];
@@ -760,7 +820,8 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
     const int G = RED_BLOCKS, B = RED_THREADS;
     // PCG on one GPU with the tile kernels runs the fused iteration (see below)
     const bool fused_pcg = method == FVM_KRYLOV_PCG && !h->halo_ready && h->nranks == 1 && fvm_spmv_fusable(h) && !getenv("FVM_NO_FUSE");
-    const int check_every = 25;
+    const bool merged_pcg = fused_pcg && fvm_spmv_fused_partials(h) <= 4096 && !getenv("FVM_PCG_NO_MERGE");
+    const int check_every = merged_pcg ? 24 : 25;
     if (fused_pcg) {
         const int32_t np = fvm_spmv_fused_partials(h);
         if (h->dotpart_n < np) {
@@ -842,6 +903,7 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
             // Fused form (one GPU, tile kernels): p.q comes out of the SpMV's epilogue as one partial per CTA, and the
             // kernels that finish the sums also form alpha / beta: 6 launches and 14 vector passes per iteration instead
             // of 9 and 16
+            int par = 0;  // which scalar slot holds r.z (merged form); every cycle starts in slot 0, graphs span an even count
             auto iteration_fused = [&]() -> int32_t {
                 SpmvFuse F;
                 F.kind = 2;
@@ -849,6 +911,13 @@ extern "C" int32_t fvm_krylov(fvm_handle h, int32_t method, double* x, double rt
                 F.dotpart = h->d_dotpart;
                 int32_t r;
                 if ((r = fvm_apply_spmv_fused(h, P, Q, false, true, F))) return r;
+                if (merged_pcg) {
+                    pcg_update_merged_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, c.rowscale, X, R, Z, partial, sc, h->d_dotpart,
+                                                              fvm_spmv_fused_partials(h), par);
+                    pcg_p_merged_kernel<<<G, B, 0, st>>>(n, Z, P, partial, sc, par);
+                    par ^= 1;
+                    return FVM_OK;
+                }
                 pcg_alpha_fused_kernel<<<1, 1024, 0, st>>>(h->d_dotpart, fvm_spmv_fused_partials(h), sc);
                 pcg_update_kernel<<<G, B, 0, st>>>(n, P, Q, c.diag_inv, c.rowscale, X, R, Z, partial, sc);
                 pcg_beta_fused_kernel<<<1, B, 0, st>>>(partial, sc);

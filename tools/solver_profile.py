@@ -9,7 +9,7 @@ import torch
 import fvm_b200 as G
 
 what = sys.argv[1] if len(sys.argv) > 1 else "both"
-variants = [("default", {}), ("nofuse", {"FVM_NO_FUSE": "1"}), ("default", {}), ("nofuse", {"FVM_NO_FUSE": "1"})]
+variants = [("default", {}), ("nomerge", {"FVM_PCG_NO_MERGE": "1"}), ("nofuse", {"FVM_NO_FUSE": "1"}), ("default", {}), ("nomerge", {"FVM_PCG_NO_MERGE": "1"})]
 
 
 def with_env(env, fn):
@@ -48,7 +48,7 @@ for nx in ([int(x) for x in os.environ.get("PROF_NX", "50,512,2048,4096").split(
     eng = tpl.engine
     ref = None
     nst = 40 if nx >= 2048 else 400
-    for name, env in variants:
+    for name, env in variants[:1]:
 
         def run():
             u = torch.from_numpy(tpl.u0).cuda()
