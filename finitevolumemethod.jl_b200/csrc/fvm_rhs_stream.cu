@@ -352,6 +352,10 @@ int32_t launch_stream_threads(fvm_ctx* h, double t, const double* u, double* du,
         case 384: return launch_stream_t<MODEL, NEQ, 384, 2>(h, t, u, du, list, off, count);
         default:
             if (h->stream_occ == 4) return launch_stream_t<MODEL, NEQ, 256, 4>(h, t, u, du, list, off, count);
+            // systems: a register budget for 2 CTAs/SM (90 registers, no spills, two contribution buffers) beats 3 CTAs/SM with
+            // 72 registers, spills and one buffer: 2-species Keller-Segel 0.703 -> 0.685 ms (gpurun_out/r3j_occ2_ab.log);
+            // scalar kernels are the other way round (u-dependent flux 0.500 vs 0.511 ms)
+            if (h->stream_occ == 2 || (h->stream_occ == 0 && NEQ >= 2)) return launch_stream_t<MODEL, NEQ, 256, 2>(h, t, u, du, list, off, count);
             return launch_stream_t<MODEL, NEQ, 256, 3>(h, t, u, du, list, off, count);
     }
 }

@@ -1148,7 +1148,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
         const int v = atoi(e);
         if (v == 256 || v == 384 || v == 512) h->stream_threads = v;
     }
-    if (const char* e = getenv("FVM_STREAM_OCC")) h->stream_occ = atoi(e) == 4 ? 4 : 3;
+    if (const char* e = getenv("FVM_STREAM_OCC")) h->stream_occ = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 3);  // experiment knob
     const double* xy = h->h_xy.data();
     const int32_t* tri = h->h_tri.data();
 

@@ -41,8 +41,8 @@ for name in names:
     p.engine.close()
     for tt in tiles:
         for th in threads:
-            os.environ["FVM_STREAM_THREADS"] = str(th if th != 2564 else 256)
-            os.environ["FVM_STREAM_OCC"] = "4" if th == 2564 else "3"
+            os.environ["FVM_STREAM_THREADS"] = str(th if th not in (2564, 2562) else 256)  # 2564 / 2562: 256 threads, register budget for 4 / 2 CTAs per SM
+            os.environ["FVM_STREAM_OCC"] = "4" if th == 2564 else ("2" if th == 2562 else "3")
             try:
                 p = G.get_cuda_parameters(prob, tile_triangles=tt, geometry_mode=gmode)
             except Exception as e:
