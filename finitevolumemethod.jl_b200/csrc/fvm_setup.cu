@@ -16,6 +16,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <parallel/algorithm>
 #include <unordered_map>
@@ -26,6 +27,7 @@ static thread_local std::string g_create_err;
 
 // FVM_TIMING=1: wall-clock of the phases of fvm_finalize on stderr
 #include <chrono>
+#include <omp.h>
 struct PhaseTimer {
     bool on = getenv("FVM_TIMING") != nullptr;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
@@ -301,6 +303,58 @@ extern "C" int32_t fvm_set_source_table(fvm_handle h, const double* s_node) {
     return FVM_OK;
 }
 
+// Stable parallel LSD radix sort of (key, value) pairs by key, 11 bits per pass; passes whose digit is the same for every
+// key are skipped (Hilbert keys of a square domain use 32 of the 52 possible bits).  The result does not depend on the
+// number of threads: a stable sort has exactly one outcome.
+static void radix_sort_pairs(std::unique_ptr<uint64_t[]>& keys, std::unique_ptr<uint32_t[]>& vals, const int64_t n) {
+    if (n < 2) return;
+    uint64_t all_or = 0, all_and = ~(uint64_t)0;
+#pragma omp parallel for schedule(static) reduction(| : all_or) reduction(& : all_and)
+    for (int64_t i = 0; i < n; ++i) {
+        all_or |= keys[i];
+        all_and &= keys[i];
+    }
+    const uint64_t varying = all_or ^ all_and;
+    constexpr int BITS = 11, BINS = 1 << BITS;
+    std::unique_ptr<uint64_t[]> k2(new uint64_t[n]);  // uninitialised: first touched by the threads that fill them
+    std::unique_ptr<uint32_t[]> v2(new uint32_t[n]);
+    const int nt = omp_get_max_threads();
+    std::vector<int64_t> hist((size_t)nt * BINS);
+    for (int shift = 0; shift < 64; shift += BITS) {
+        if (((varying >> shift) & (BINS - 1)) == 0) continue;
+        std::fill(hist.begin(), hist.end(), 0);
+        const uint64_t* ks = keys.get();
+        const uint32_t* vs = vals.get();
+        uint64_t* kd = k2.get();
+        uint32_t* vd = v2.get();
+#pragma omp parallel num_threads(nt)
+        {
+            const int t = omp_get_thread_num();
+            const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+            int64_t* h = hist.data() + (size_t)t * BINS;
+            for (int64_t i = lo; i < hi; ++i) h[(ks[i] >> shift) & (BINS - 1)]++;
+#pragma omp barrier
+#pragma omp single
+            {
+                int64_t run = 0;
+                for (int d = 0; d < BINS; ++d)
+                    for (int q = 0; q < nt; ++q) {
+                        const int64_t c = hist[(size_t)q * BINS + d];
+                        hist[(size_t)q * BINS + d] = run;
+                        run += c;
+                    }
+            }
+            for (int64_t i = lo; i < hi; ++i) {
+                const int64_t at = h[(ks[i] >> shift) & (BINS - 1)]++;
+                kd[at] = ks[i];
+                vd[at] = vs[i];
+            }
+        }
+        keys.swap(k2);
+        vals.swap(v2);
+    }
+}
+
 // ---- Hilbert curve index of a 16-bit lattice point --------------------------------------
 static inline uint32_t hilbert_xy2d(uint32_t x, uint32_t y) {
     uint32_t d = 0;
@@ -344,6 +398,7 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     PhaseTimer tm;
     // ---- 1. Hilbert sort of triangles by centroid ------------------------------------
     double minx = xy[0], maxx = xy[0], miny = xy[1], maxy = xy[1];
+#pragma omp parallel for schedule(static) reduction(min : minx, miny) reduction(max : maxx, maxy)
     for (int64_t i = 0; i < N; ++i) {
         minx = std::min(minx, xy[2 * i]);
         maxx = std::max(maxx, xy[2 * i]);
@@ -361,7 +416,8 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     const int64_t n_blocks = e_short > 0 ? std::max<int64_t>(1, std::min<int64_t>(1 << 20, (int64_t)std::floor(e_long / e_short + 0.5))) : 1;
     const double bw = e_long / (double)n_blocks;
     const double s_long = bw > 0 ? 65535.0 / bw : 0.0, s_short = e_short > 0 ? 65535.0 / e_short : 0.0;
-    std::vector<std::pair<uint64_t, uint32_t>> keys(T);
+    std::unique_ptr<uint64_t[]> keys(new uint64_t[T]);
+    std::unique_ptr<uint32_t[]> order(new uint32_t[T]);
 #pragma omp parallel for schedule(static)
     for (int64_t t = 0; t < T; ++t) {
         const int32_t a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
@@ -371,13 +427,15 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
         const uint32_t il = (uint32_t)std::min(65535.0, std::max(0.0, (l - (double)blk * bw) * s_long));
         const uint32_t iw = (uint32_t)std::min(65535.0, std::max(0.0, w * s_short));
         // hilbert_xy2d starts at (0, 0) and ends at (65535, 0): its first argument is the direction the blocks advance in
-        keys[t] = {((uint64_t)blk << 32) | (uint64_t)hilbert_xy2d(il, iw), (uint32_t)t};
+        keys[t] = ((uint64_t)blk << 32) | (uint64_t)hilbert_xy2d(il, iw);
+        order[t] = (uint32_t)t;
     }
-    __gnu_parallel::sort(keys.begin(), keys.end());
+    radix_sort_pairs(keys, order, T);  // ties keep the caller's triangle order, like the (key, index) pair sort it replaces
     h->tri_old_of_new.resize(T);
 #pragma omp parallel for schedule(static)
-    for (int64_t t = 0; t < T; ++t) h->tri_old_of_new[t] = (int32_t)keys[t].second;
-    std::vector<std::pair<uint64_t, uint32_t>>().swap(keys);
+    for (int64_t t = 0; t < T; ++t) h->tri_old_of_new[t] = (int32_t)order[t];
+    keys.reset();
+    order.reset();
     const int32_t* told = h->tri_old_of_new.data();
     const int64_t n_tiles = (T + TT - 1) / TT;
     P.n_tiles = n_tiles;
@@ -759,6 +817,7 @@ static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, con
         std::vector<int16_t> colL, colR;  // [vertex][colour] -> edge using that colour there (or -1)
         std::vector<int32_t> eL, eR, path;
         std::vector<int8_t> ecol;
+        std::vector<uint16_t> usedL, usedR;
 #pragma omp for schedule(dynamic, 64)
         for (int64_t b = 0; b < n_tiles; ++b) {
             uint8_t* base = packs.data() + off[b];
@@ -829,19 +888,14 @@ static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, con
                     eL[e] = slot * nG + (lt >> 4);
                     eR[e] = 2 * (urow[l >> 5] + (q - iptr[l])) + ((l >> 4) & 1);
                 }
+            usedL.assign(nL, 0);  // bit c set: colour c is taken at that vertex (same information as colL / colR >= 0)
+            usedR.assign(std::max(nR, 1), 0);
             for (int32_t e = 0; e < nE; ++e) {
                 int16_t* cl = colL.data() + (size_t)eL[e] * 16;
                 int16_t* cr = colR.data() + (size_t)eR[e] * 16;
-                int ca = -1, cbb = -1, both = -1;
-                for (int c = 0; c < 16; ++c) {
-                    const bool fl = cl[c] < 0, fr = cr[c] < 0;
-                    if (fl && fr) {
-                        both = c;
-                        break;
-                    }
-                    if (fl && ca < 0) ca = c;
-                    if (fr && cbb < 0) cbb = c;
-                }
+                const uint32_t fl = (uint16_t)~usedL[eL[e]], fr = (uint16_t)~usedR[eR[e]];  // free colours (a vertex has <= 16 edges)
+                int both = (fl & fr) ? __builtin_ctz(fl & fr) : -1;
+                const int ca = fl ? __builtin_ctz(fl) : -1, cbb = fr ? __builtin_ctz(fr) : -1;
                 if (both < 0) {  // ca free on the left, cbb free on the right: flip the ca/cbb path that starts at the right end
                     path.clear();
                     int32_t cur = eR[e];
@@ -858,17 +912,23 @@ static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, con
                     for (int32_t e1 : path) {
                         colL[(size_t)eL[e1] * 16 + ecol[e1]] = -1;
                         colR[(size_t)eR[e1] * 16 + ecol[e1]] = -1;
+                        usedL[eL[e1]] &= (uint16_t)~(1u << ecol[e1]);
+                        usedR[eR[e1]] &= (uint16_t)~(1u << ecol[e1]);
                     }
                     for (int32_t e1 : path) {
                         ecol[e1] = (int8_t)(ecol[e1] == ca ? cbb : ca);
                         colL[(size_t)eL[e1] * 16 + ecol[e1]] = (int16_t)e1;
                         colR[(size_t)eR[e1] * 16 + ecol[e1]] = (int16_t)e1;
+                        usedL[eL[e1]] |= (uint16_t)(1u << ecol[e1]);
+                        usedR[eR[e1]] |= (uint16_t)(1u << ecol[e1]);
                     }
                     both = ca;
                 }
                 ecol[e] = (int8_t)both;
                 cl[both] = (int16_t)e;
                 cr[both] = (int16_t)e;
+                usedL[eL[e]] |= (uint16_t)(1u << both);
+                usedR[eR[e]] |= (uint16_t)(1u << both);
             }
             for (int32_t lt = 0; lt < H.ntri; ++lt)
                 tri_out[lt].w = (uint16_t)(ecol[3 * lt] | (ecol[3 * lt + 1] << 4) | (ecol[3 * lt + 2] << 8));
@@ -876,13 +936,8 @@ static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, con
                 for (int32_t r = urow[q]; r < urow[q + 1]; ++r)
                     for (int32_t half = 0; half < 2; ++half) {
                         // padded entries of this read group share a zero word in a bank pair no real entry of the group uses
-                        const int16_t* cr = colR.data() + (size_t)(2 * r + half) * 16;
-                        int freec = 0;
-                        for (int c = 0; c < 16; ++c)
-                            if (cr[c] < 0) {
-                                freec = c;
-                                break;
-                            }
+                        const uint32_t fr = (uint16_t)~usedR[2 * r + half];
+                        const int freec = fr ? __builtin_ctz(fr) : 0;
                         const int32_t j = r - urow[q];
                         for (int32_t i = 16 * half; i < 16 * half + 16; ++i) {
                             const int32_t l = 32 * q + i;
@@ -1057,7 +1112,9 @@ extern "C" int32_t fvm_plan_selftest(const double* xy, int64_t N, const int32_t*
         std::vector<uint8_t> packs;
         std::vector<int4> pdir;
         int32_t cap = 0;
+        PhaseTimer tmp;
         rc = build_tile_packs(h, P, TT, xyn.data(), kn.data(), nullptr, packs, pdir, cap);
+        tmp.lap("tile packs (selftest)");
         if (rc) return fvm_fail(nullptr, rc, h->err);
         for (int64_t b = 0; b < P.n_tiles; ++b) {
             const uint8_t* base = packs.data() + ((size_t)(uint32_t)pdir[2 * b].x << 4);
