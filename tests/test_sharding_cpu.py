@@ -1,6 +1,7 @@
 """N > 1 path on CPU (gloo, world_size 2): partitioners, rank-local meshes, halo plan and the
 exchange schedule; the sharded ORACLE right-hand side must equal the single-domain one on every
 owned node (only the summation order differs)."""
+import os
 import socket
 
 import numpy as np
@@ -109,3 +110,24 @@ def test_patch_mesh_reproduces_du_at_its_nodes():
     assert not dp[pl][~dg[nodes]].any()  # a sampled node keeps its complete triangle fan: it is interior to the patch
     part = fvm_eqs_general(patch.points, patch.triangles, u[verts], flux_params=(0.7,), dirichlet=dp)
     assert np.abs(part[pl] - full[nodes]).max() <= 1e-13 * np.abs(full).max()
+
+
+def test_graph_partitioner_large_path_is_thread_count_independent():
+    """Graphs above 131 072 nodes take the chunked parallel coarsening (fvm_partition.cu: coarsen_chunked); chunks are fixed
+    by the node count, not by the thread count, so 1 thread and all threads must give the same owner array -- every rank of
+    a sharded run computes the partition on its own slice of the cores and they must agree."""
+    import subprocess
+    import sys
+    code = ("import sys, zlib, numpy as np; sys.path.insert(0, %r); import fvm_b200 as G; "
+            "tri = G.triangulate_rectangle(0, 2, 0, 1, 520, 260, single_boundary=True); o = G.partition_graph(tri, 4); "
+            "c = np.bincount(o, minlength=4); print(zlib.crc32(o.tobytes()), c.min(), c.max(), G.edge_cut(tri, o), "
+            "G.edge_cut(tri, G.partition_rcb(tri.points, 4)))" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for nt in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=nt)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(r.stdout.split())
+    assert outs[0] == outs[1] == outs[2], outs
+    crc, cmin, cmax, cut, cut_rcb = map(int, outs[0])
+    assert cmax - cmin <= 1 and cut <= 1.3 * cut_rcb
