@@ -13,6 +13,8 @@
 
 #include <chrono>
 
+#include <cub/device/device_scan.cuh>
+
 #include "fvm_device.cuh"
 
 #define MAX_ROW 64
@@ -28,6 +30,33 @@ struct AsmEdge {          // one boundary edge for the template assembly (native
 };
 
 // ---- pattern ---------------------------------------------------------------------------------
+// node -> triangle incidence lists (code = triangle << 2 | slot), see fvm_build_pattern
+__global__ void n2t_count_kernel(int64_t n3, const int32_t* __restrict__ tri, int32_t* __restrict__ cnt) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n3) atomicAdd(cnt + tri[k], 1);
+}
+__global__ void n2t_fill_kernel(int64_t n3, const int32_t* __restrict__ tri, const int32_t* __restrict__ ptr, int32_t* __restrict__ fill,
+                                int32_t* __restrict__ items) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n3) return;
+    const int32_t g = tri[k];
+    items[ptr[g] + atomicAdd(fill + g, 1)] = (int32_t)((k / 3) << 2 | (k % 3));
+}
+__global__ void n2t_sort_kernel(int n, const int32_t* __restrict__ ptr, int32_t* __restrict__ items) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int lo = ptr[g], hi = ptr[g + 1];
+    for (int a = lo + 1; a < hi; ++a) {  // insertion sort: a node has ~6 incident triangles
+        const int32_t v = items[a];
+        int b = a - 1;
+        while (b >= lo && items[b] > v) {
+            items[b + 1] = items[b];
+            --b;
+        }
+        items[b + 1] = v;
+    }
+}
+
 __device__ __forceinline__ int row_neighbours(const int32_t* __restrict__ n2t_ptr, const int32_t* __restrict__ n2t,
                                               const int32_t* __restrict__ tri, int g, int32_t* out) {
     int cnt = 0;
@@ -612,21 +641,37 @@ int32_t fvm_build_pattern(fvm_ctx* h) {
     Csr& c = h->csr;
     if (c.pattern) return FVM_OK;
     const int64_t N = h->N, T = h->T;
-    const int32_t* tri = h->h_tri.data();
-    const int32_t* told = h->tri_old_of_new.data();
-    const int32_t* new_of_old = h->node_new_of_old.data();
-    std::vector<int32_t> ptr(N + 1, 0), items((size_t)3 * T);
-    for (int64_t nt = 0; nt < T; ++nt)
-        for (int r = 0; r < 3; ++r) ptr[new_of_old[tri[3 * (int64_t)told[nt] + r]] + 1]++;
-    for (int64_t g = 0; g < N; ++g) ptr[g + 1] += ptr[g];
-    {
-        std::vector<int32_t> fill(ptr.begin(), ptr.end() - 1);
-        for (int64_t nt = 0; nt < T; ++nt)
-            for (int r = 0; r < 3; ++r) items[fill[new_of_old[tri[3 * (int64_t)told[nt] + r]]]++] = (int32_t)(nt << 2 | r);
-    }
+    // node -> incident (triangle, slot) lists, built on the device from the native triangle table: count, exclusive scan,
+    // fill (integer atomics give each entry a position), then every node's few entries are sorted ascending -- the order
+    // the assembly sums in, so A does not depend on the scheduling of the fill (round 1 built these lists with serial
+    // host loops over 3T random accesses and uploaded 0.5 GB: ~1 s at 4096^2)
     int32_t rc;
-    if ((rc = fvm_dev_upload(h, &c.n2t_ptr, ptr))) return rc;
-    if ((rc = fvm_dev_upload(h, &c.n2t, items))) return rc;
+    if ((rc = fvm_dev_alloc(h, &c.n2t_ptr, (size_t)N + 1))) return rc;
+    if ((rc = fvm_dev_alloc(h, &c.n2t, (size_t)3 * T))) return rc;
+    {
+        int32_t* cnt = nullptr;
+        void* tmp = nullptr;
+        size_t tmp_bytes = 0;
+        FVM_CUDA(h, cudaMalloc((void**)&cnt, sizeof(int32_t) * ((size_t)N + 1)));
+        cudaError_t e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)N + 1), h->stream);
+        const unsigned gt = (unsigned)((3 * T + 255) / 256), gn = (unsigned)((N + 255) / 256);
+        if (e == cudaSuccess) {
+            n2t_count_kernel<<<gt, 256, 0, h->stream>>>(3 * T, h->d_tri_native, cnt);
+            e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, c.n2t_ptr, (int)(N + 1), h->stream);
+        }
+        if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+        if (e == cudaSuccess) e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, c.n2t_ptr, (int)(N + 1), h->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(cnt, 0, sizeof(int32_t) * ((size_t)N + 1), h->stream);
+        if (e == cudaSuccess) {
+            n2t_fill_kernel<<<gt, 256, 0, h->stream>>>(3 * T, h->d_tri_native, c.n2t_ptr, cnt, c.n2t);
+            n2t_sort_kernel<<<gn, 256, 0, h->stream>>>((int)N, c.n2t_ptr, c.n2t);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(cnt);
+        if (tmp) cudaFree(tmp);
+        FVM_CUDA(h, e);
+    }
     int32_t* rowlen = nullptr;
     FVM_CUDA(h, cudaMalloc((void**)&rowlen, sizeof(int32_t) * N));
     const unsigned grid = (unsigned)((N + 127) / 128);

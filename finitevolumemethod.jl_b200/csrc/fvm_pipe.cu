@@ -22,6 +22,10 @@
 
 #include "fvm_internal.h"
 
+#ifndef FVM_PIPE_ZC_DEFAULT
+#define FVM_PIPE_ZC_DEFAULT 0
+#endif
+
 namespace {
 
 struct PipePlan {
@@ -65,6 +69,61 @@ __global__ void band_gather_kernel(const int32_t* __restrict__ new_of_old, const
     const int64_t j = idx / neq;
     const int v = (int)(idx - j * neq);
     dst_caller[idx] = src_native[(int64_t)new_of_old[j] * neq + v];
+}
+
+// Zero-copy forms of the two kernels above: the caller's page-locked HOST vector is read / written through its device
+// alias, so a band crosses PCIe and changes numbering in ONE kernel -- no copy-engine launch per band (each
+// cudaMemcpyAsync + event costs the link ~15-20 us of idle time: 20 copies per call) and no staging pass through HBM.
+// A few persistent CTAs keep enough 8-byte loads in flight to fill the link (4 per thread before the first store).
+__global__ void __launch_bounds__(256) band_scatter_host_kernel(const int32_t* __restrict__ new_of_old, const double* __restrict__ src_host,
+                                                                double* __restrict__ dst_native, const int64_t lo, const int64_t hi, const int neq) {
+    const int64_t n = (hi - lo) * neq, base = lo * neq, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * stride < n) v[k] = __ldcs(src_host + base + i0 + k * stride);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t idx = base + i0 + k * stride;
+            if (idx < base + n) {
+                const int64_t j = idx / neq;
+                dst_native[(int64_t)new_of_old[j] * neq + (idx - j * neq)] = v[k];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) band_gather_host_kernel(const int32_t* __restrict__ new_of_old, const double* __restrict__ src_native,
+                                                               double* __restrict__ dst_host, const int64_t lo, const int64_t hi, const int neq) {
+    const int64_t n = (hi - lo) * neq, base = lo * neq, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t idx = base + i0 + k * stride;
+            if (idx < base + n) {
+                const int64_t j = idx / neq;
+                v[k] = src_native[(int64_t)new_of_old[j] * neq + (idx - j * neq)];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (i0 + k * stride < n) __stcs(dst_host + base + i0 + k * stride, v[k]);
+    }
+}
+
+// device alias of a page-locked host range (cudaHostAlloc / cudaHostRegister / fvm_host_register), or null
+const void* host_alias(const void* p, size_t bytes) {
+    cudaPointerAttributes a0, a1;
+    if (!p || bytes == 0 || cudaPointerGetAttributes(&a0, p) != cudaSuccess ||
+        cudaPointerGetAttributes(&a1, (const char*)p + bytes - 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost || !a0.devicePointer || !a1.devicePointer) return nullptr;
+    if ((const char*)a1.devicePointer - (const char*)a0.devicePointer != (ptrdiff_t)(bytes - 1)) return nullptr;
+    return a0.devicePointer;
 }
 
 }  // namespace
@@ -249,24 +308,42 @@ template <class StageFn>
 static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, double* out_host, StageFn stage) {
     const int K = P.K, neq = h->neq;
     cudaStream_t sc = h->stream;
+    // FVM_PIPE_TRACE=1: device timestamps of every band's copy-in, stage and copy-out on stderr (diagnostics only)
+    static const bool trace = getenv("FVM_PIPE_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tr;  // [0]: start, then K x (in, stage, out)
+    if (trace) {
+        tr.resize(1 + 3 * K);
+        for (cudaEvent_t& e : tr) cudaEventCreate(&e);
+    }
     // The copy streams carry nothing but copies, back to back, so that neither DMA engine ever waits for a
     // kernel: the scatter of band s and the gathers of the bands that stage s completes run on the compute
     // stream, which is idle most of the time (a stage is ~0.09 ms of kernels per ~0.3 ms of copy at 16.7M nodes).
+    // FVM_PIPE_ZC: bit 0 = copy-in by kernel, bit 1 = copy-out by kernel (page-locked buffers only)
+    const char* e_zc = getenv("FVM_PIPE_ZC");
+    const char* e_ctas = getenv("FVM_PIPE_ZC_CTAS");
+    const int zc_env = e_zc ? atoi(e_zc) : FVM_PIPE_ZC_DEFAULT;
+    const int zc_ctas = e_ctas ? std::max(1, atoi(e_ctas)) : 64;
+    const double* in_dev = (zc_env & 1) ? (const double*)host_alias(in_host, sizeof(double) * (size_t)h->N * neq) : nullptr;
+    double* out_dev = (zc_env & 2) ? (double*)host_alias(out_host, sizeof(double) * (size_t)h->N * neq) : nullptr;
     FVM_CUDA(h, cudaEventRecord(P.ev_start, sc));  // an earlier call's kernels precede the first copy-in
+    if (trace) cudaEventRecord(tr[0], sc);
     FVM_CUDA(h, cudaStreamWaitEvent(P.s_in, P.ev_start, 0));
     FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_start, 0));
     for (int b = 0; b < K; ++b) {
         const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
-        if (cnt > 0)
+        if (cnt > 0 && in_dev)
+            band_scatter_host_kernel<<<zc_ctas, 256, 0, P.s_in>>>(h->d_node_new_of_old, in_dev, h->d_u, lo, hi, neq);
+        else if (cnt > 0)
             FVM_CUDA(h, cudaMemcpyAsync(h->d_io + lo * neq, in_host + lo * neq, sizeof(double) * cnt, cudaMemcpyHostToDevice, P.s_in));
         FVM_CUDA(h, cudaEventRecord(P.ev_in[b], P.s_in));
+        if (trace) cudaEventRecord(tr[1 + 3 * b], P.s_in);
     }
     int32_t rc = FVM_OK;
     for (int s = 0; s < K && !rc; ++s) {
         FVM_CUDA(h, cudaStreamWaitEvent(sc, P.ev_in[s], 0));
         {
             const int64_t lo = P.band_lo[s], hi = P.band_lo[s + 1], cnt = (hi - lo) * neq;
-            if (cnt > 0)
+            if (cnt > 0 && !in_dev)
                 band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
         }
         if ((rc = stage(s))) break;
@@ -275,17 +352,21 @@ static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, doub
             if (P.out_stage[b] != s) continue;
             const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
             if (cnt == 0) continue;
-            band_gather_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_du, P.d_out, lo, hi, neq);
+            if (!out_dev) band_gather_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_du, P.d_out, lo, hi, neq);
             any = true;
         }
+        if (trace) cudaEventRecord(tr[2 + 3 * s], sc);
         if (!any) continue;
         FVM_CUDA(h, cudaEventRecord(P.ev_stage[s], sc));
         FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_stage[s], 0));
         for (int b = 0; b < K; ++b) {
             if (P.out_stage[b] != s) continue;
             const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
-            if (cnt > 0)
+            if (cnt > 0 && out_dev)
+                band_gather_host_kernel<<<zc_ctas, 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, out_dev, lo, hi, neq);
+            else if (cnt > 0)
                 FVM_CUDA(h, cudaMemcpyAsync(out_host + lo * neq, P.d_out + lo * neq, sizeof(double) * cnt, cudaMemcpyDeviceToHost, P.s_out));
+            if (trace && cnt > 0) cudaEventRecord(tr[3 + 3 * b], P.s_out);
         }
     }
     // leave the three streams joined whatever happened, so that the handle stays usable after an error
@@ -293,6 +374,19 @@ static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, doub
     cudaStreamWaitEvent(sc, P.ev_out, 0);
     cudaStreamWaitEvent(sc, P.ev_in[K - 1], 0);
     cudaError_t ce = cudaStreamSynchronize(sc);
+    if (trace) {
+        if (!rc && ce == cudaSuccess)
+            for (int b = 0; b < K; ++b) {
+                float ti = 0, ts = 0, to = 0;
+                cudaEventElapsedTime(&ti, tr[0], tr[1 + 3 * b]);
+                cudaEventElapsedTime(&ts, tr[0], tr[2 + 3 * b]);
+                cudaEventElapsedTime(&to, tr[0], tr[3 + 3 * b]);
+                fprintf(stderr, "[fvm_pipe] band %2d  nodes %9lld  copy-in done %7.3f  stage done %7.3f  copy-out done %7.3f ms  (final after stage %d)\n", b,
+                        (long long)(P.band_lo[b + 1] - P.band_lo[b]), ti, ts, to, P.out_stage[b]);
+            }
+        for (cudaEvent_t e : tr) cudaEventDestroy(e);
+        cudaGetLastError();
+    }
     if (rc) return rc;
     FVM_CUDA(h, ce);
     FVM_CUDA(h, cudaGetLastError());

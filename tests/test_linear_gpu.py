@@ -360,6 +360,14 @@ def test_operator_host_buffer_pipeline_is_bit_identical(case):
                 assert np.array_equal(tpl.mul(np.full_like(x, np.nan), x, add_b=False), y0)
             st = tpl.engine.stats()
             assert st["pipe_calls"] == 4 and st["pipe_bands"] == bands
+        x, y = xs[1].copy(), np.empty_like(xs[1])
+        with G.pinned(x, y):  # zero-copy bands on page-locked vectors
+            _pipeline_env(FVM_PIPE_MIN_NODES=0, FVM_PIPE_FORCE=1, FVM_PIPE_BANDS=4, FVM_PIPE_ZC=3)
+            tpl = build_template(c, "gpu", tile_triangles=128)
+            y[...] = np.nan
+            assert np.array_equal(tpl.mul(y, x), refs[1][0])
+            y[...] = np.nan
+            assert np.array_equal(tpl.mul(y, x, add_b=False), refs[1][1])
     finally:
         _pipeline_env()
 

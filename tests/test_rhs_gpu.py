@@ -386,7 +386,7 @@ def test_mesh_from_wire_container_gives_identical_rhs(tmp_path):
 
 def _pipeline_env(**kw):
     import os
-    keys = ("FVM_NO_PIPELINE", "FVM_PIPE_MIN_NODES", "FVM_PIPE_FORCE", "FVM_PIPE_BANDS")
+    keys = ("FVM_NO_PIPELINE", "FVM_PIPE_MIN_NODES", "FVM_PIPE_FORCE", "FVM_PIPE_BANDS", "FVM_PIPE_ZC", "FVM_PIPE_ZC_CTAS")
     for k in keys:
         os.environ.pop(k, None)
     for k, v in kw.items():
@@ -424,6 +424,20 @@ def test_host_buffer_pipeline_is_bit_identical(case):
             assert np.array_equal(dd.cpu().numpy(), ref)
             assert np.array_equal(G.fvm_eqs(np.full_like(c.u, np.nan), c.u, p, c.t), ref)
             assert p.engine.stats()["pipe_calls"] == 3
+        # page-locked caller arrays: the bands cross PCIe inside the renumbering kernels (zero-copy, FVM_PIPE_ZC bit 0 =
+        # copy-in, bit 1 = copy-out); every combination must give the same bits, also with very few CTAs
+        uz, dz = c.u.copy(), np.full_like(c.u, np.nan)
+        with G.pinned(uz, dz):
+            for zc, ctas in ((0, 64), (1, 64), (2, 3), (3, 1), (3, 64)):
+                _pipeline_env(FVM_PIPE_MIN_NODES=0, FVM_PIPE_FORCE=1, FVM_PIPE_BANDS=5, FVM_PIPE_ZC=zc, FVM_PIPE_ZC_CTAS=ctas)
+                p = G.get_cuda_parameters(c.gp, tile_triangles=64)
+                dz[...] = np.nan
+                assert np.array_equal(G.fvm_eqs(dz, uz, p, c.t), ref)
+                uz[...] = u2
+                dz[...] = np.nan
+                assert np.array_equal(G.fvm_eqs(dz, uz, p, c.t), ref2)  # the host wrote new values: the kernel must see them
+                uz[...] = c.u
+                assert p.engine.stats()["pipe_calls"] == 2
     finally:
         _pipeline_env()
 
