@@ -20,6 +20,8 @@
 // so the result is bit-identical to the unpipelined path.
 #include <algorithm>
 
+#include <omp.h>
+
 #include "fvm_internal.h"
 
 #ifndef FVM_PIPE_ZC_DEFAULT
@@ -36,7 +38,7 @@ struct PipePlan {
     std::vector<int32_t> tile_stage_ptr;  // [K+1] into d_tile_order
     std::vector<int32_t> ifc_stage_ptr;   // [K+1] into d_ifc_order
     std::vector<int32_t> edge_stage_ptr;  // [K+1] into d_edge_order (live boundary edges)
-    std::vector<int32_t> out_stage;       // [K]
+    std::vector<int64_t> out_lo;          // [K+1] stage s completes the caller indices out_lo[s] <= j < out_lo[s+1]
     int32_t* d_tile_order = nullptr;
     int32_t* d_ifc_order = nullptr;
     int32_t* d_edge_order = nullptr;
@@ -160,9 +162,13 @@ static int32_t build_plan(fvm_ctx* h, int K, int mode, void*& slot) {
     P->band_lo.assign(K + 1, 0);
     {
         const char* e = getenv("FVM_PIPE_TAPER");
-        const bool taper = K >= 6 && !(e && e[0] == '0');
-        std::vector<int64_t> w(K, 2);
-        if (taper) w[0] = w[1] = w[K - 2] = w[K - 1] = 1;
+        const int taper = K < 6 ? 0 : (e ? atoi(e) : 1);  // 0: uniform bands, 1: first / last two at half width, 2: quarter, half, ...
+        std::vector<int64_t> w(K, 4);
+        if (taper == 1) w[0] = w[1] = w[K - 2] = w[K - 1] = 2;
+        if (taper >= 2 && K >= 8) {
+            w[0] = w[1] = w[K - 2] = w[K - 1] = 1;
+            w[2] = w[K - 3] = 2;
+        }
         int64_t tot = 0, acc = 0;
         for (int b = 0; b < K; ++b) tot += w[b];
         for (int b = 0; b < K; ++b) {
@@ -251,37 +257,52 @@ static int32_t build_plan(fvm_ctx* h, int K, int mode, void*& slot) {
     sort_by_stage(tile_stage, P->tile_stage_ptr, tile_order);
     sort_by_stage(unit_stage, P->ifc_stage_ptr, ifc_order);
     sort_by_stage(edge_stage, P->edge_stage_ptr, edge_order);
-    // ---- stage after which an output band is final -------------------------------------------------------
-    P->out_stage.assign(K, 0);
+    // ---- output ranges -----------------------------------------------------------------------------------
+    // du[j] is final after stage fs(j) (its tile for an interior node, the last tile / edge feeding it for an interface
+    // node).  Stage s sends the caller indices [out_lo[s], out_lo[s+1]), where out_lo[s+1] is the longest PREFIX of the
+    // vector that is final after stage s: contiguous ranges whatever the numbering.  On a row-major lattice that prefix
+    // ends one tile height (~2 sqrt(TT/2) rows) before the end of input band s, so an output range leaves right after the
+    // stage of "its" input band (round 1 sent whole input bands, i.e. one stage -- a full band -- later, and the call ended
+    // with two bands of copy-out after the last copy-in instead of one: profiles/r02_e2e_timeline.txt).
     const int32_t* new_of_old = h->node_new_of_old.data();
-    for (int b = 0; b < K; ++b) {
-        int smax = 0;
-#pragma omp parallel for schedule(static) reduction(max : smax)
-        for (int64_t j = P->band_lo[b]; j < P->band_lo[b + 1]; ++j) {
-            const int32_t g = new_of_old[j];
-            int s;
-            if (g >= n_vertices) {
-                s = K - 1;  // points that are not vertices are zeroed in the last stage
-            } else {
-                const int32_t t = (int32_t)(std::upper_bound(h->h_tile_node0.begin(), h->h_tile_node0.end(), g) - h->h_tile_node0.begin()) - 1;
-                int32_t tt = t;  // tiles without own nodes share node0 with their successor: step back to the owner
-                while (tt > 0 && g >= h->h_tile_node0[tt] + h->h_tile_nown[tt]) --tt;
-                const int32_t l = g - h->h_tile_node0[tt];
-                if (l < h->h_tile_nint[tt]) {
-                    s = tile_stage[tt];
+    std::vector<int64_t> first_of_stage(K, N);  // smallest caller index whose result is final only after stage f
+    {
+        const int nth = omp_get_max_threads();
+        std::vector<int64_t> loc((size_t)nth * K, N);
+#pragma omp parallel
+        {
+            int64_t* mine = loc.data() + (size_t)omp_get_thread_num() * K;
+#pragma omp for schedule(static)
+            for (int64_t j = 0; j < N; ++j) {
+                const int32_t g = new_of_old[j];
+                int s;
+                if (g >= n_vertices) {
+                    s = K - 1;  // points that are not vertices are zeroed in the last stage
                 } else {
-                    const int32_t i = (int32_t)(std::lower_bound(h->h_ifc_node.begin(), h->h_ifc_node.end(), g) - h->h_ifc_node.begin());
-                    s = ifc_stage[i];
+                    const int32_t t = (int32_t)(std::upper_bound(h->h_tile_node0.begin(), h->h_tile_node0.end(), g) - h->h_tile_node0.begin()) - 1;
+                    int32_t tt = t;  // tiles without own nodes share node0 with their successor: step back to the owner
+                    while (tt > 0 && g >= h->h_tile_node0[tt] + h->h_tile_nown[tt]) --tt;
+                    const int32_t l = g - h->h_tile_node0[tt];
+                    if (l < h->h_tile_nint[tt]) {
+                        s = tile_stage[tt];
+                    } else {
+                        const int32_t i = (int32_t)(std::lower_bound(h->h_ifc_node.begin(), h->h_ifc_node.end(), g) - h->h_ifc_node.begin());
+                        s = ifc_stage[i];
+                    }
                 }
+                if (j < mine[s]) mine[s] = j;
             }
-            smax = std::max(smax, s);
         }
-        P->out_stage[b] = smax;
+        for (int th = 0; th < nth; ++th)
+            for (int f = 0; f < K; ++f) first_of_stage[f] = std::min(first_of_stage[f], loc[(size_t)th * K + f]);
     }
+    P->out_lo.assign(K + 1, 0);
+    P->out_lo[K] = N;
+    for (int s = K - 2; s >= 0; --s) P->out_lo[s + 1] = std::min(P->out_lo[s + 2], first_of_stage[s + 1]);
     // worth it only if a good part of the output leaves before the last stage
     int early = 0;
-    for (int b = 0; b < K; ++b) early += P->out_stage[b] < K - 1;
-    P->useful = early * 2 >= K;
+    for (int s = 0; s + 1 < K; ++s) early += P->out_lo[s + 1] > P->out_lo[s];
+    P->useful = 2 * P->out_lo[K - 1] >= N;
     int32_t rc;
     if ((rc = fvm_dev_upload(h, &P->d_tile_order, tile_order))) return rc;
     if ((rc = fvm_dev_upload(h, &P->d_ifc_order, ifc_order))) return rc;
@@ -347,27 +368,17 @@ static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, doub
                 band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
         }
         if ((rc = stage(s))) break;
-        bool any = false;
-        for (int b = 0; b < K; ++b) {
-            if (P.out_stage[b] != s) continue;
-            const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
-            if (cnt == 0) continue;
-            if (!out_dev) band_gather_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_du, P.d_out, lo, hi, neq);
-            any = true;
-        }
+        const int64_t olo = P.out_lo[s], ohi = P.out_lo[s + 1], ocnt = (ohi - olo) * neq;
         if (trace) cudaEventRecord(tr[2 + 3 * s], sc);
-        if (!any) continue;
+        if (ocnt <= 0) continue;
+        if (!out_dev) band_gather_kernel<<<(unsigned)((ocnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_du, P.d_out, olo, ohi, neq);
         FVM_CUDA(h, cudaEventRecord(P.ev_stage[s], sc));
         FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_stage[s], 0));
-        for (int b = 0; b < K; ++b) {
-            if (P.out_stage[b] != s) continue;
-            const int64_t lo = P.band_lo[b], hi = P.band_lo[b + 1], cnt = (hi - lo) * neq;
-            if (cnt > 0 && out_dev)
-                band_gather_host_kernel<<<zc_ctas, 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, out_dev, lo, hi, neq);
-            else if (cnt > 0)
-                FVM_CUDA(h, cudaMemcpyAsync(out_host + lo * neq, P.d_out + lo * neq, sizeof(double) * cnt, cudaMemcpyDeviceToHost, P.s_out));
-            if (trace && cnt > 0) cudaEventRecord(tr[3 + 3 * b], P.s_out);
-        }
+        if (out_dev)
+            band_gather_host_kernel<<<zc_ctas, 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, out_dev, olo, ohi, neq);
+        else
+            FVM_CUDA(h, cudaMemcpyAsync(out_host + olo * neq, P.d_out + olo * neq, sizeof(double) * ocnt, cudaMemcpyDeviceToHost, P.s_out));
+        if (trace) cudaEventRecord(tr[3 + 3 * s], P.s_out);
     }
     // leave the three streams joined whatever happened, so that the handle stays usable after an error
     cudaEventRecord(P.ev_out, P.s_out);
@@ -381,8 +392,8 @@ static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, doub
                 cudaEventElapsedTime(&ti, tr[0], tr[1 + 3 * b]);
                 cudaEventElapsedTime(&ts, tr[0], tr[2 + 3 * b]);
                 cudaEventElapsedTime(&to, tr[0], tr[3 + 3 * b]);
-                fprintf(stderr, "[fvm_pipe] band %2d  nodes %9lld  copy-in done %7.3f  stage done %7.3f  copy-out done %7.3f ms  (final after stage %d)\n", b,
-                        (long long)(P.band_lo[b + 1] - P.band_lo[b]), ti, ts, to, P.out_stage[b]);
+                fprintf(stderr, "[fvm_pipe] stage %2d  nodes in %9lld  copy-in done %7.3f  kernels done %7.3f   nodes out %9lld  copy-out done %7.3f ms\n", b,
+                        (long long)(P.band_lo[b + 1] - P.band_lo[b]), ti, ts, (long long)(P.out_lo[b + 1] - P.out_lo[b]), to);
             }
         for (cudaEvent_t e : tr) cudaEventDestroy(e);
         cudaGetLastError();
