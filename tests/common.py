@@ -192,3 +192,41 @@ def annulus_mesh(nr, nt, r_in=0.2, r_out=1.0):
     area2 = (q[:, 0] - p[:, 0]) * (s[:, 1] - p[:, 1]) - (q[:, 1] - p[:, 1]) * (s[:, 0] - p[:, 0])
     tris[area2 < 0] = tris[area2 < 0][:, [0, 2, 1]]
     return G.Triangulation(pts, tris)
+
+
+def disk_mesh(nr, radius=1.0):
+    """Disk of the 'reaction-diffusion equation with a time-dependent Dirichlet boundary condition on a disk' tutorial:
+    centre node, ring k = 1..nr with 6k nodes, Delaunay-triangulated (the domain is convex); one boundary loop."""
+    from scipy.spatial import Delaunay
+    pts = [(0.0, 0.0)]
+    for k in range(1, nr + 1):
+        th = 2 * np.pi * (np.arange(6 * k) + 0.5 * (k % 2)) / (6 * k)
+        pts += list(zip(radius * k / nr * np.cos(th), radius * k / nr * np.sin(th)))
+    pts = np.asarray(pts)
+    tris = Delaunay(pts).simplices.astype(np.int32)
+    p, q, r = pts[tris[:, 0]], pts[tris[:, 1]], pts[tris[:, 2]]
+    area2 = (q[:, 0] - p[:, 0]) * (r[:, 1] - p[:, 1]) - (q[:, 1] - p[:, 1]) * (r[:, 0] - p[:, 0])
+    tris[area2 < 0] = tris[area2 < 0][:, [0, 2, 1]]
+    return G.Triangulation(pts, tris[np.abs(area2) > 1e-12])
+
+
+def wedge_mesh(nr, alpha=np.pi / 4):
+    """Circular wedge 0 <= r <= 1, 0 <= theta <= alpha of the 'diffusion equation in a wedge with mixed boundary
+    conditions' tutorial: apex node, ring k = 1..nr with k+1 nodes; three boundary sections in the tutorial's order
+    (bottom edge, arc, upper edge), consecutive sections sharing their end node."""
+    ring0 = [0]
+    pts = [(0.0, 0.0)]
+    rings = [ring0]
+    for k in range(1, nr + 1):
+        th = alpha * np.arange(k + 1) / k
+        rings.append(list(range(len(pts), len(pts) + k + 1)))
+        pts += list(zip(k / nr * np.cos(th), k / nr * np.sin(th)))
+    tris = []
+    for k in range(nr):
+        a, b = rings[k], rings[k + 1]
+        for j in range(k):
+            tris.append((a[j], b[j], b[j + 1]))
+            tris.append((a[j], b[j + 1], a[j + 1]))
+        tris.append((a[k], b[k], b[k + 1]))
+    sections = [[r[0] for r in rings], rings[nr], [r[-1] for r in rings[::-1]]]
+    return G.Triangulation(np.asarray(pts), np.asarray(tris, dtype=np.int32), boundary_sections=sections)

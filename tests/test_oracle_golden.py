@@ -592,3 +592,59 @@ def test_porous_medium_barenblatt_solution():
     assert np.abs(u - ref).max() <= 0.03 * ref.max()  # the free boundary is resolved to O(h)
     assert abs(u @ mesh.cv_volumes - M) <= 2e-3 * M  # mass M is conserved (zero flux through the support)
     assert (ref > 0).sum() > 500 and ref[0] == 0.0
+
+
+def _wedge_series(r, t, terms=40):
+    """Exact solution of the wedge tutorial for f = 1 - r (diffusion_equation_in_a_wedge_with_mixed_boundary_conditions.jl
+    :112-150): f does not depend on theta, so only the order-0 terms of the tutorial's double series survive:
+    u = sum_m [2 I_m / J1(z_m)^2] exp(-z_m^2 t) J0(z_m r),  I_m = int_0^1 (1-s) s J0(z_m s) ds,  J0(z_m) = 0."""
+    from scipy.integrate import quad
+    from scipy.special import j0, j1, jn_zeros
+    z = jn_zeros(0, terms)
+    c = [2 * quad(lambda s: (1 - s) * s * j0(zm * s), 0, 1)[0] / j1(zm) ** 2 for zm in z]
+    return sum(cm * np.exp(-zm * zm * t) * j0(zm * r) for cm, zm in zip(c, z))
+
+
+def test_wedge_mixed_conditions_bessel_series():
+    """docs/src/literate_tutorials/diffusion_equation_in_a_wedge_with_mixed_boundary_conditions.jl:20-45 (alpha = pi/4,
+    zero-flux Neumann on the two straight edges, Dirichlet u = 0 on the arc, f = 1 - r, D = 1, t = 0.1) against the
+    tutorial's exact series (:133-150): pins three boundary sections of different kinds on a curved domain, the
+    homogeneous Neumann edges and the Dirichlet callback."""
+    from tests.common import to_oracle_tri, wedge_mesh
+    tri = to_oracle_tri(wedge_mesh(24))
+    mesh = O.FVMGeometry(tri)
+    r = np.hypot(tri.points[:, 0], tri.points[:, 1])
+    zero = lambda x, y, t, u, p: 0.0 * x
+    BCs = O.BoundaryConditions(mesh, (zero, zero, zero), (O.Neumann, O.Dirichlet, O.Neumann))
+    prob = O.FVMProblem(mesh, BCs, diffusion_function=lambda x, y, t, u, p: 1.0 + 0.0 * u, initial_condition=1 - r, final_time=0.1)
+    u = O.tsit5_fixed(lambda d, v, t: O.fvm_eqs_vec(d, v, prob, t), prob.initial_condition, 0.0, 0.1, 2e-4,
+                      callback=lambda v, t: (O.update_dirichlet_nodes(v, t, prob), True)[1])
+    exact = _wedge_series(r, 0.1)
+    assert np.abs(u - exact).max() <= 4e-3 * exact.max()  # measured 1.9e-3 at 24 rings (1.1e-3 at 32)
+    assert np.abs(u[r > 1 - 1e-12]).max() == 0.0  # the arc stays at its Dirichlet value
+    # the template assembles the same semi-discrete operator (diffusion_equation.jl:69-101): A u + b == fvm_eqs!(u)
+    tpl = O.DiffusionEquation(mesh, BCs, diffusion_function=lambda x, y, p: 1.0, initial_condition=1 - r, final_time=0.1)
+    free = r < 1 - 1e-12
+    du = O.fvm_eqs_vec(np.zeros_like(u), u, prob, 0.05)
+    assert np.abs((tpl.A @ u + tpl.b - du)[free]).max() <= 1e-11 * np.abs(du).max()
+
+
+def test_disk_dudt_boundary_exact_solution():
+    """docs/src/literate_tutorials/reaction_diffusion_equation_with_a_time_dependent_dirichlet_boundary_condition_on_a_disk.jl
+    :20-45: u_t = div(u grad u) + u(1-u) on the unit disk with du/dt = u on the boundary has the exact solution
+    u = exp(t) sqrt(I0(sqrt(2) r)) (:62-65 of the tutorial's test block).  Pins Dudt boundary nodes (source_contributions.jl
+    :10-12), the u-dependent diffusion and the nonlinear source on an unstructured mesh."""
+    from scipy.special import i0
+    from tests.common import disk_mesh, to_oracle_tri
+    tri = to_oracle_tri(disk_mesh(16))
+    mesh = O.FVMGeometry(tri)
+    r = np.hypot(tri.points[:, 0], tri.points[:, 1])
+    ic = np.sqrt(i0(np.sqrt(2) * r))
+    BCs = O.BoundaryConditions(mesh, lambda x, y, t, u, p: u, O.Dudt)
+    prob = O.FVMProblem(mesh, BCs, diffusion_function=lambda x, y, t, u, p: u, source_function=lambda x, y, t, u, p: u * (1 - u),
+                        initial_condition=ic, final_time=0.1)
+    u = O.tsit5_fixed(lambda d, v, t: O.fvm_eqs_vec(d, v, prob, t), ic, 0.0, 0.1, 5e-4)
+    exact = math.exp(0.1) * ic
+    assert np.abs(u - exact).max() <= 2e-4 * exact.max()  # measured 5.7e-5
+    bnd = r > 1 - 1e-9
+    assert bnd.sum() == 96 and np.abs(u[bnd] - exact[bnd]).max() <= 1e-12 * exact.max()  # du/dt = u integrated to Tsit5 accuracy

@@ -69,3 +69,47 @@ def test_porous_medium_barenblatt():
     ref = exact(x, y, 2.0)
     assert np.abs(sol.u - ref).max() <= 0.03 * ref.max()
     assert abs(sol.u @ pair.omesh.cv_volumes - M) <= 2e-3 * M
+
+
+def test_wedge_mixed_conditions_bessel_series():
+    """docs/src/literate_tutorials/diffusion_equation_in_a_wedge_with_mixed_boundary_conditions.jl:20-45: zero-flux Neumann
+    edges, Dirichlet arc, f = 1 - r.  The device Tsit5 on fvm_eqs! with the Dirichlet callback against the oracle's
+    integrator (1e-10), and both the FVMProblem and the DiffusionEquation template (device operator Tsit5) against the
+    tutorial's exact Bessel series (discretisation level; the oracle itself is pinned to it on the CPU)."""
+    from tests.common import wedge_mesh
+    from tests.test_oracle_golden import _wedge_series
+    pair = Pair(wedge_mesh(24))
+    r = np.hypot(pair.gtri.points[:, 0], pair.gtri.points[:, 1])
+    specs, types = (G.Const(0.0),) * 3, (G.Neumann, G.Dirichlet, G.Neumann)
+    gp, op = pair.problem(specs, types, G.ConstantDiffusion(1.0), ic=1 - r, final_time=0.1)
+    sol = G.solve(gp, G.Tsit5(2e-4), tile_triangles=128)
+    uref = O.tsit5_fixed(lambda d, v, t: O.fvm_eqs_vec(d, v, op, t), 1 - r, 0.0, 0.1, 2e-4,
+                         callback=lambda v, t: (O.update_dirichlet_nodes(v, t, op), True)[1])
+    assert rel_err(sol.u, uref) <= RTOL_TSIT5
+    exact = _wedge_series(r, 0.1)
+    assert np.abs(sol.u - exact).max() <= 4e-3 * exact.max()
+    tpl = G.DiffusionEquation(pair.gmesh, G.BoundaryConditions(pair.gmesh, specs, types), diffusion_function=1.0,
+                              initial_condition=1 - r, final_time=0.1, tile_triangles=128)
+    tsol = G.solve(tpl, G.Tsit5(2e-4))
+    assert len(tsol.u) == len(r) + 1 and tsol.u[-1] == 1.0  # the augmented state [u; 1] (diffusion_equation.jl:82-94)
+    assert np.abs(tsol.u[:-1] - exact).max() <= 4e-3 * exact.max()
+    assert rel_err(tsol.u[:-1], sol.u) <= 1e-9  # same semi-discrete system, integrated with and without the callback
+
+
+def test_disk_dudt_boundary_exact_solution():
+    """docs/src/literate_tutorials/reaction_diffusion_equation_with_a_time_dependent_dirichlet_boundary_condition_on_a_disk.jl
+    :20-45: u_t = div(u grad u) + u(1-u), du/dt = u on the boundary, exact u = exp(t) sqrt(I0(sqrt(2) r)): Dudt nodes,
+    u-dependent diffusion and a nonlinear source on an unstructured mesh, device Tsit5 vs the oracle's integrator and vs
+    the exact solution."""
+    from scipy.special import i0
+    from tests.common import disk_mesh
+    pair = Pair(disk_mesh(16))
+    r = np.hypot(pair.gtri.points[:, 0], pair.gtri.points[:, 1])
+    ic = np.sqrt(i0(np.sqrt(2) * r))
+    gp, op = pair.problem(G.AffineU(0.0, 1.0), G.Dudt, G.PowerDiffusion(1.0, 2.0), source=G.LogisticSource(1.0), ic=ic, final_time=0.1)
+    du = G.fvm_eqs(np.zeros_like(ic), ic, G.get_cuda_parameters(gp, tile_triangles=128), 0.0)
+    assert rel_err(du, O.fvm_eqs_vec(np.zeros_like(ic), ic, op, 0.0)) <= 1e-12
+    sol = G.solve(gp, G.Tsit5(5e-4), tile_triangles=128)
+    uref = O.tsit5_fixed(lambda d, v, t: O.fvm_eqs_vec(d, v, op, t), ic, 0.0, 0.1, 5e-4)
+    assert rel_err(sol.u, uref) <= RTOL_TSIT5
+    assert np.abs(sol.u - math.exp(0.1) * ic).max() <= 2e-4 * math.exp(0.1) * ic.max()
