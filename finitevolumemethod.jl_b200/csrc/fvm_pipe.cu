@@ -39,6 +39,7 @@ struct PipePlan {
     std::vector<int32_t> ifc_stage_ptr;   // [K+1] into d_ifc_order
     std::vector<int32_t> edge_stage_ptr;  // [K+1] into d_edge_order (live boundary edges)
     std::vector<int64_t> out_lo;          // [K+1] stage s completes the caller indices out_lo[s] <= j < out_lo[s+1]
+    int64_t head = 0;                     // ... and the last stage also [0, head)  (out_lo[0] == head)
     int32_t* d_tile_order = nullptr;
     int32_t* d_ifc_order = nullptr;
     int32_t* d_edge_order = nullptr;
@@ -264,8 +265,39 @@ static int32_t build_plan(fvm_ctx* h, int K, int mode, void*& slot) {
     // ends one tile height (~2 sqrt(TT/2) rows) before the end of input band s, so an output range leaves right after the
     // stage of "its" input band (round 1 sent whole input bands, i.e. one stage -- a full band -- later, and the call ended
     // with two bands of copy-out after the last copy-in instead of one: profiles/r02_e2e_timeline.txt).
+    // A sharded strip also has a HEAD that is final only after the last stage (the rows next to the lower neighbour wait for
+    // the halo exchange): whatever of the first input band ends that late is sent as a second range of the last stage and
+    // the prefix rule applies behind it.
     const int32_t* new_of_old = h->node_new_of_old.data();
-    std::vector<int64_t> first_of_stage(K, N);  // smallest caller index whose result is final only after stage f
+    std::vector<uint8_t> fs(N);
+#pragma omp parallel for schedule(static)
+    for (int64_t j = 0; j < N; ++j) {
+        const int32_t g = new_of_old[j];
+        int s;
+        if (g >= n_vertices) {
+            s = K - 1;  // points that are not vertices are zeroed in the last stage
+        } else {
+            const int32_t t = (int32_t)(std::upper_bound(h->h_tile_node0.begin(), h->h_tile_node0.end(), g) - h->h_tile_node0.begin()) - 1;
+            int32_t tt = t;  // tiles without own nodes share node0 with their successor: step back to the owner
+            while (tt > 0 && g >= h->h_tile_node0[tt] + h->h_tile_nown[tt]) --tt;
+            const int32_t l = g - h->h_tile_node0[tt];
+            if (l < h->h_tile_nint[tt]) {
+                s = tile_stage[tt];
+            } else {
+                const int32_t i = (int32_t)(std::lower_bound(h->h_ifc_node.begin(), h->h_ifc_node.end(), g) - h->h_ifc_node.begin());
+                s = ifc_stage[i];
+            }
+        }
+        fs[j] = (uint8_t)s;
+    }
+    int64_t head = 0;
+    if (K > 1 && fs[0] == K - 1)  // (a vector whose first entry is early has no late head)
+        for (int64_t j = P->band_lo[1] - 1; j >= 0; --j)
+            if (fs[j] == K - 1) {
+                head = j + 1;
+                break;
+            }
+    std::vector<int64_t> first_of_stage(K, N);  // smallest caller index >= head whose result is final only after stage f
     {
         const int nth = omp_get_max_threads();
         std::vector<int64_t> loc((size_t)nth * K, N);
@@ -273,36 +305,20 @@ static int32_t build_plan(fvm_ctx* h, int K, int mode, void*& slot) {
         {
             int64_t* mine = loc.data() + (size_t)omp_get_thread_num() * K;
 #pragma omp for schedule(static)
-            for (int64_t j = 0; j < N; ++j) {
-                const int32_t g = new_of_old[j];
-                int s;
-                if (g >= n_vertices) {
-                    s = K - 1;  // points that are not vertices are zeroed in the last stage
-                } else {
-                    const int32_t t = (int32_t)(std::upper_bound(h->h_tile_node0.begin(), h->h_tile_node0.end(), g) - h->h_tile_node0.begin()) - 1;
-                    int32_t tt = t;  // tiles without own nodes share node0 with their successor: step back to the owner
-                    while (tt > 0 && g >= h->h_tile_node0[tt] + h->h_tile_nown[tt]) --tt;
-                    const int32_t l = g - h->h_tile_node0[tt];
-                    if (l < h->h_tile_nint[tt]) {
-                        s = tile_stage[tt];
-                    } else {
-                        const int32_t i = (int32_t)(std::lower_bound(h->h_ifc_node.begin(), h->h_ifc_node.end(), g) - h->h_ifc_node.begin());
-                        s = ifc_stage[i];
-                    }
-                }
-                if (j < mine[s]) mine[s] = j;
-            }
+            for (int64_t j = head; j < N; ++j)
+                if (j < mine[fs[j]]) mine[fs[j]] = j;
         }
         for (int th = 0; th < nth; ++th)
             for (int f = 0; f < K; ++f) first_of_stage[f] = std::min(first_of_stage[f], loc[(size_t)th * K + f]);
     }
-    P->out_lo.assign(K + 1, 0);
+    P->out_lo.assign(K + 1, head);
     P->out_lo[K] = N;
-    for (int s = K - 2; s >= 0; --s) P->out_lo[s + 1] = std::min(P->out_lo[s + 2], first_of_stage[s + 1]);
+    for (int s = K - 2; s >= 0; --s) P->out_lo[s + 1] = std::max(head, std::min(P->out_lo[s + 2], first_of_stage[s + 1]));
+    P->head = head;
     // worth it only if a good part of the output leaves before the last stage
     int early = 0;
     for (int s = 0; s + 1 < K; ++s) early += P->out_lo[s + 1] > P->out_lo[s];
-    P->useful = 2 * P->out_lo[K - 1] >= N;
+    P->useful = 2 * (P->out_lo[K - 1] - head) >= N;
     int32_t rc;
     if ((rc = fvm_dev_upload(h, &P->d_tile_order, tile_order))) return rc;
     if ((rc = fvm_dev_upload(h, &P->d_ifc_order, ifc_order))) return rc;
@@ -368,16 +384,22 @@ static int32_t run_pipeline(fvm_ctx* h, PipePlan& P, const double* in_host, doub
                 band_scatter_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_io, h->d_u, lo, hi, neq);
         }
         if ((rc = stage(s))) break;
-        const int64_t olo = P.out_lo[s], ohi = P.out_lo[s + 1], ocnt = (ohi - olo) * neq;
         if (trace) cudaEventRecord(tr[2 + 3 * s], sc);
-        if (ocnt <= 0) continue;
-        if (!out_dev) band_gather_kernel<<<(unsigned)((ocnt + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_du, P.d_out, olo, ohi, neq);
+        const int64_t rng[2][2] = {{P.out_lo[s], P.out_lo[s + 1]}, {0, s == K - 1 ? P.head : 0}};
+        if (rng[0][1] <= rng[0][0] && rng[1][1] <= rng[1][0]) continue;
+        if (!out_dev)
+            for (const auto& r : rng)
+                if (r[1] > r[0])
+                    band_gather_kernel<<<(unsigned)(((r[1] - r[0]) * neq + 255) / 256), 256, 0, sc>>>(h->d_node_new_of_old, h->d_du, P.d_out, r[0], r[1], neq);
         FVM_CUDA(h, cudaEventRecord(P.ev_stage[s], sc));
         FVM_CUDA(h, cudaStreamWaitEvent(P.s_out, P.ev_stage[s], 0));
-        if (out_dev)
-            band_gather_host_kernel<<<zc_ctas, 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, out_dev, olo, ohi, neq);
-        else
-            FVM_CUDA(h, cudaMemcpyAsync(out_host + olo * neq, P.d_out + olo * neq, sizeof(double) * ocnt, cudaMemcpyDeviceToHost, P.s_out));
+        for (const auto& r : rng) {
+            if (r[1] <= r[0]) continue;
+            if (out_dev)
+                band_gather_host_kernel<<<zc_ctas, 256, 0, P.s_out>>>(h->d_node_new_of_old, h->d_du, out_dev, r[0], r[1], neq);
+            else
+                FVM_CUDA(h, cudaMemcpyAsync(out_host + r[0] * neq, P.d_out + r[0] * neq, sizeof(double) * (r[1] - r[0]) * neq, cudaMemcpyDeviceToHost, P.s_out));
+        }
         if (trace) cudaEventRecord(tr[3 + 3 * s], P.s_out);
     }
     // leave the three streams joined whatever happened, so that the handle stays usable after an error
