@@ -217,7 +217,7 @@ struct fvm_ctx {
     int32_t pack_cap = 0;         // largest pack (bytes)
     int64_t pack_bytes_total = 0;
     bool packs_ready = false;
-    int32_t stream_threads = 256;  // consumer threads per CTA of the streaming kernel
+    int32_t stream_threads = 0;    // consumer threads per CTA of the streaming kernel (0: chosen per flux model, FVM_STREAM_THREADS)
     int32_t stream_occ = 0;        // resident CTAs per SM its register budget is planned for (256-thread variant); 0: 3, systems 2
     std::map<const void*, int32_t> occ_cache;  // kernel -> resident CTAs per SM at the configured shared memory
     int32_t sm_count = 148;

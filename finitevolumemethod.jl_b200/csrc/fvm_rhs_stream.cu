@@ -234,7 +234,9 @@ __global__ void __launch_bounds__(NCONS + SK_PROD, OCC)
         const unsigned char* cbytes = reinterpret_cast<const unsigned char*>(cb);
         const bool simple = (h1.y & 1) && sp.model == FVM_SRC_ZERO;
 #pragma unroll 1
-        for (int q = warp; q < nunit; q += NCONS / 32) {
+        // (the units left over after the last full round go to a different pair of warps every tile: with two contribution
+        // buffers a warp that finishes early starts the next tile's triangle pass, so the imbalance averages out)
+        for (int q = (warp + i) % (NCONS / 32); q < nunit; q += NCONS / 32) {
             const int r0 = urow[q], r1 = urow[q + 1];
             const uint16_t* lp = lst + r0 * 32 + lane;
             double acc[NEQ];
@@ -334,6 +336,12 @@ int32_t launch_stream_t(fvm_ctx* h, double t, const double* u, double* du, const
         occ = (one || nb2 < 1) ? nb1 : nb2;
     }
     a.nbuf = configured == plane_smem + stage_smem ? 1 : 2;
+    if (getenv("FVM_STREAM_VERBOSE")) {
+        static int said = 0;
+        if (said++ < 4)
+            fprintf(stderr, "[fvm_stream] model %d neq %d: %d consumer threads, %d-triangle tiles, %d contribution buffer(s), %d B shared memory, %d CTAs/SM\n",
+                    MODEL, NEQ, NCONS, h->dm.tile_tris, a.nbuf, configured, occ);
+    }
     const int32_t smem = configured;
     h->smem_rhs = smem;
     const int grid = std::min(count, h->sm_count * occ);
@@ -347,9 +355,22 @@ int32_t launch_stream_t(fvm_ctx* h, double t, const double* u, double* du, const
 
 template <int MODEL, int NEQ>
 int32_t launch_stream_threads(fvm_ctx* h, double t, const double* u, double* du, const int32_t* list, int off, int count) {
-    switch (h->stream_threads) {
+    // Thread / tile balance (gpurun_out/s3f..s3i_sweep*.log, 4096^2): with T triangles per tile and W consumer warps the
+    // triangle pass takes ceil(T / 32W) iterations and the node pass ceil(units / W) rounds of ~T/64 + 2 units.  The round-2
+    // default (T = 512, W = 8) fills 10 of 16 node-pass slots; T = 768 = 3 x 256 fills three whole triangle iterations and 14 of
+    // 16 slots and, with ONE contribution buffer, still fits 3 CTAs per SM: const-D 0.371 -> 0.347 ms per RHS (kernel 0.330 ->
+    // 0.310), u-dependent flux 0.548 -> 0.536.  Smaller CTAs with the same balance come close (T = 576, W = 6, 4 CTAs: 0.355 /
+    // 0.311) but leave more interface nodes; W = 7 (T = 512, 4 CTAs, 60 registers) 0.362; systems stay at T = 512 (0.756 vs 0.755).
+    int threads = h->stream_threads;
+    if (threads == 0) threads = 256;
+    switch (threads) {
         case 512: return launch_stream_t<MODEL, NEQ, 512, 2>(h, t, u, du, list, off, count);
         case 384: return launch_stream_t<MODEL, NEQ, 384, 2>(h, t, u, du, list, off, count);
+        case 224:  // 7 consumer warps + the producer = 256 threads: 4 CTAs/SM at 60-64 registers
+            if constexpr (NEQ == 1) return launch_stream_t<MODEL, NEQ, 224, 4>(h, t, u, du, list, off, count);
+            return launch_stream_t<MODEL, NEQ, 256, 2>(h, t, u, du, list, off, count);
+        case 192:  // 6 consumer warps: 4 CTAs/SM with the full register budget (systems: 3)
+            return launch_stream_t<MODEL, NEQ, 192, (NEQ >= 2 ? 3 : 4)>(h, t, u, du, list, off, count);
         default:
             if (h->stream_occ == 4) return launch_stream_t<MODEL, NEQ, 256, 4>(h, t, u, du, list, off, count);
             // systems: a register budget for 2 CTAs/SM (90 registers, no spills, two contribution buffers) beats 3 CTAs/SM with

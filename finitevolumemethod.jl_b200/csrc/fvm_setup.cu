@@ -1191,9 +1191,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     // register-limited to 3 CTAs/SM and like big tiles; the reduced stream wants 8 small CTAs per SM
     const bool full_flux = h->flux.model == FVM_FLUX_DIFF_POWER || h->flux.model == FVM_FLUX_ADVDIFF || h->flux.model == FVM_FLUX_KELLER_SEGEL;
     // (systems: 768 measured best for the 2-species Keller-Segel kernel: 1.20 ms vs 1.45 ms at 1024)
-    // recompute mode (streaming kernel, fvm_rhs_stream.cu): two stages + two contribution buffers per CTA want small tiles
+    // recompute mode (streaming kernel, fvm_rhs_stream.cu): 768 = three full triangle iterations of its 256 consumer threads
+    // and 14 of 16 node-pass slots, 3 CTAs/SM with one contribution buffer (see launch_stream_threads); systems: 512
     int TT = tile_triangles > 0 ? tile_triangles
-                                : (geometry_mode == 1 ? 512 : (neq >= 2 ? 768 : (!full_flux ? 512 : 1024)));
+                                : (geometry_mode == 1 ? (neq >= 2 ? 512 : 768) : (neq >= 2 ? 768 : (!full_flux ? 512 : 1024)));
     if (tile_triangles <= 0)
         if (const char* e = getenv("FVM_TILE_TRIANGLES")) TT = atoi(e);
     FVM_REQUIRE(h, TT >= 64 && TT <= 4096 && TT % 64 == 0, "fvm_finalize: tile_triangles must be a multiple of 64 in 64..4096");
@@ -1203,7 +1204,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     h->geometry_mode = geometry_mode;
     if (const char* e = getenv("FVM_STREAM_THREADS")) {
         const int v = atoi(e);
-        if (v == 256 || v == 384 || v == 512) h->stream_threads = v;
+        if (v == 192 || v == 224 || v == 256 || v == 384 || v == 512) h->stream_threads = v;
     }
     if (const char* e = getenv("FVM_STREAM_OCC")) h->stream_occ = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 3);  // experiment knob
     const double* xy = h->h_xy.data();
