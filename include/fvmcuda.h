@@ -152,7 +152,11 @@ int32_t fvm_from_native(fvm_handle h, const double* v_native_dev, double* v_call
  * third stream while later bands are still arriving (PCIe is full duplex).  Bit-identical to the plain
  * schedule.  Page-lock the buffers once with fvm_host_register to get the full rate (a Julia Vector or NumPy
  * array is pageable); unregister before freeing them.  Sharded handles do their halo
- * exchange at the head of the last stage.  Environment: FVM_NO_PIPELINE=1, FVM_PIPE_BANDS=K, FVM_PIPE_TAPER=0. */
+ * exchange at the head of the last stage.  A stage sends back the longest prefix of the output that is final after
+ * it (not whole input bands).  Environment: FVM_NO_PIPELINE=1, FVM_PIPE_BANDS=K, FVM_PIPE_TAPER=0|1|2 (uniform bands /
+ * first and last two at half width / quarter, quarter, half), FVM_PIPE_TRACE=1 (per-band device timeline on stderr),
+ * FVM_PIPE_ZC=1|2|3 (page-locked buffers only: copy-in / copy-out / both through zero-copy kernels instead of the copy
+ * engines; measured slower on B200, off by default). */
 int32_t fvm_host_register(void* host_ptr, int64_t nbytes);
 int32_t fvm_host_unregister(void* host_ptr);
 /* the *_native calls are asynchronous on the handle's stream */
