@@ -248,8 +248,26 @@ int32_t fvm_dev_alloc(fvm_ctx* h, Tp** p, size_t count) {
     *p = (Tp*)q;
     return FVM_OK;
 }
-template <class Tp>
-int32_t fvm_dev_upload(fvm_ctx* h, Tp** p, const std::vector<Tp>& v) {
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the big host staging buffers of
+// fvm_finalize (tile packs: 1 GB at 4096^2) are first touched by the OpenMP threads that fill them instead of being
+// zero-filled and page-faulted by one thread
+template <class T>
+struct fvm_noinit_alloc : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = fvm_noinit_alloc<U>;
+    };
+    template <class U, class... A>
+    void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+        else ::new ((void*)p) U(static_cast<A&&>(a)...);
+    }
+};
+template <class T>
+using fvm_rawvec = std::vector<T, fvm_noinit_alloc<T>>;
+
+template <class Tp, class Al>
+int32_t fvm_dev_upload(fvm_ctx* h, Tp** p, const std::vector<Tp, Al>& v) {
     int32_t rc = fvm_dev_alloc(h, p, v.size());
     if (rc) return rc;
     if (!v.empty())

@@ -383,9 +383,11 @@ struct HostPlan {
     int64_t n_tiles = 0, tpad = 0, n_partial = 0;
     int32_t n_vertices = 0, n_ifc = 0, max_nloc = 0;
     std::vector<int32_t> tile_node0, tile_nint, tile_nown, tile_nloc, tile_ext0, tile_loc0, tile_pp0;
-    std::vector<ushort4> tri_loc;
-    std::vector<int32_t> tri_native, ext_ids, ifc_node, ifc_pptr, ppos, live_edges;
-    std::vector<uint16_t> inc_ptr, inc;
+    fvm_rawvec<ushort4> tri_loc;  // (the three T-sized tables are first touched by the tile-parallel passes)
+    fvm_rawvec<int32_t> tri_native;
+    std::vector<int32_t> ext_ids, ifc_node, ifc_pptr, ppos, live_edges;
+    std::vector<uint16_t> inc_ptr;
+    fvm_rawvec<uint16_t> inc;
     std::vector<BndEdge> bnd;
     std::vector<double> dbnd_live;
 };
@@ -570,19 +572,22 @@ static int32_t plan_host(fvm_ctx* h, const int TT, HostPlan& P) {
     // ---- 4. tile-local indices, gather lists, interface bookkeeping -----------------------
     const int64_t tpad = n_tiles * TT;
     P.tpad = tpad;
-    std::vector<ushort4>& tri_loc = P.tri_loc;
-    tri_loc.assign(tpad, make_ushort4(0, 0, 0, 0));
-    std::vector<int32_t>& tri_native = P.tri_native;  // native node ids per native triangle (geometry kernel input)
-    tri_native.assign(3 * T, 0);
+    fvm_rawvec<ushort4>& tri_loc = P.tri_loc;
+    tri_loc.resize(tpad);  // every real triangle is written below; the padding of the last tile is zeroed here
+    for (int64_t nt = T; nt < tpad; ++nt) tri_loc[nt] = make_ushort4(0, 0, 0, 0);
+    fvm_rawvec<int32_t>& tri_native = P.tri_native;  // native node ids per native triangle (geometry kernel input)
+    tri_native.resize(3 * T);
     std::vector<int32_t>&tile_ext0 = P.tile_ext0, &tile_loc0 = P.tile_loc0, &tile_pp0 = P.tile_pp0;
     tile_ext0.assign(n_tiles + 1, 0);
     tile_loc0.assign(n_tiles + 1, 0);
     tile_pp0.assign(n_tiles + 1, 0);
     std::vector<int32_t>& ext_ids = P.ext_ids;
     ext_ids.clear();
-    std::vector<uint16_t>&inc_ptr = P.inc_ptr, &inc = P.inc;
+    std::vector<uint16_t>& inc_ptr = P.inc_ptr;
+    fvm_rawvec<uint16_t>& inc = P.inc;
     inc_ptr.clear();
-    inc.assign((size_t)3 * tpad, 0);
+    inc.resize((size_t)3 * tpad);  // 3 entries per real triangle are written below
+    for (size_t k = (size_t)3 * TT * (n_tiles - 1) + (size_t)3 * (T - (n_tiles - 1) * TT); k < (size_t)3 * tpad; ++k) inc[k] = 0;
     std::vector<int32_t> ifc_of_new(N, -1);  // compact interface index by native id
     std::vector<int32_t>& ifc_node = P.ifc_node;
     ifc_node.clear();
@@ -776,7 +781,7 @@ static inline int32_t unit_rows(const uint16_t* iptr, int32_t nloc, int32_t q) {
 }
 
 static int32_t build_tile_packs(fvm_ctx* h, const HostPlan& P, const int TT, const double* xyn, const uint8_t* kn,
-                                const double* dtab_native /* [3][tpad] or null */, std::vector<uint8_t>& packs,
+                                const double* dtab_native /* [3][tpad] or null */, fvm_rawvec<uint8_t>& packs,
                                 std::vector<int4>& dir, int32_t& pack_cap) {
     const int64_t n_tiles = P.n_tiles, N = h->N, T = h->T;
     const int neq = h->neq;
@@ -1109,7 +1114,7 @@ extern "C" int32_t fvm_plan_selftest(const double* xy, int64_t N, const int32_t*
             xyn[2 * g] = xy[2 * (int64_t)h->node_old_of_new[g]];
             xyn[2 * g + 1] = xy[2 * (int64_t)h->node_old_of_new[g] + 1];
         }
-        std::vector<uint8_t> packs;
+        fvm_rawvec<uint8_t> packs;  // every byte is written by build_tile_packs (memset + fields, tile by tile)
         std::vector<int4> pdir;
         int32_t cap = 0;
         PhaseTimer tmp;
@@ -1220,9 +1225,11 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     const int32_t* told = h->tri_old_of_new.data();
     std::vector<int32_t>&tile_node0 = P.tile_node0, &tile_nint = P.tile_nint, &tile_nown = P.tile_nown, &tile_nloc = P.tile_nloc;
     std::vector<int32_t>&tile_ext0 = P.tile_ext0, &tile_loc0 = P.tile_loc0, &tile_pp0 = P.tile_pp0;
-    std::vector<ushort4>& tri_loc = P.tri_loc;
-    std::vector<int32_t>&tri_native = P.tri_native, &ext_ids = P.ext_ids, &ifc_node = P.ifc_node, &ifc_pptr = P.ifc_pptr, &ppos = P.ppos;
-    std::vector<uint16_t>&inc_ptr = P.inc_ptr, &inc = P.inc;
+    fvm_rawvec<ushort4>& tri_loc = P.tri_loc;
+    fvm_rawvec<int32_t>& tri_native = P.tri_native;
+    std::vector<int32_t>&ext_ids = P.ext_ids, &ifc_node = P.ifc_node, &ifc_pptr = P.ifc_pptr, &ppos = P.ppos;
+    std::vector<uint16_t>& inc_ptr = P.inc_ptr;
+    fvm_rawvec<uint16_t>& inc = P.inc;
     std::vector<BndEdge>& bnd = P.bnd;
     std::vector<double>& dbnd_live = P.dbnd_live;
     // ---- 6. upload --------------------------------------------------------------------------
@@ -1279,10 +1286,10 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     m.n_partial = n_partial;
     if ((rc = fvm_dev_alloc(h, &m.partial, (size_t)n_partial * neq))) return rc;
     // per-node arrays in native order
-    std::vector<double> xyn(2 * N);
-    std::vector<uint8_t> kn((size_t)neq * N);
+    fvm_rawvec<double> xyn(2 * N);  // (filled completely by the parallel loop below)
+    fvm_rawvec<uint8_t> kn((size_t)neq * N);
     {
-        std::vector<int32_t> fn((size_t)neq * N);
+        fvm_rawvec<int32_t> fn((size_t)neq * N);
         std::vector<int32_t> dir;
 #pragma omp parallel for schedule(static)
         for (int64_t g = 0; g < N; ++g) {
@@ -1325,7 +1332,7 @@ extern "C" int32_t fvm_finalize(fvm_handle h, int32_t tile_triangles, int32_t ge
     // tile packs of the streaming recompute kernel (geometry_mode 1; big template tiles keep the plain tile kernel)
     cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
     if (geometry_mode == 1 && TT <= FVM_STREAM_MAX_TT && !getenv("FVM_NO_STREAM")) {
-        std::vector<uint8_t> packs;
+        fvm_rawvec<uint8_t> packs;  // every byte is written by build_tile_packs (memset + fields, tile by tile)
         std::vector<int4> pdir;
         if ((rc = build_tile_packs(h, P, TT, xyn.data(), kn.data(), dt.empty() ? nullptr : dt.data(), packs, pdir, h->pack_cap))) return rc;
         if ((rc = fvm_dev_upload(h, &h->d_packs, packs))) return rc;
