@@ -648,3 +648,32 @@ def test_disk_dudt_boundary_exact_solution():
     assert np.abs(u - exact).max() <= 2e-4 * exact.max()  # measured 5.7e-5
     bnd = r > 1 - 1e-9
     assert bnd.sum() == 96 and np.abs(u[bnd] - exact[bnd]).max() <= 1e-12 * exact.max()  # du/dt = u integrated to Tsit5 accuracy
+
+
+def test_control_volume_polygon_areas_unstructured():
+    """test/geometry.jl:16-20: `geo.cv_volumes[i]` equals the area of the control-volume polygon around vertex i (triangle
+    centroids joined to edge midpoints).  Restated independently of geometry.jl:117-130 (which uses cross products of
+    centroid-to-vertex and midpoint-to-midpoint vectors): shoelace area of the quadrilateral vertex -> midpoint of the next
+    edge -> centroid -> midpoint of the previous edge in every incident triangle, on an unstructured Delaunay mesh with
+    points that are not vertices (volume 0, fix_missing_vertices)."""
+    from tests.common import delaunay_mesh, to_oracle_tri
+    tri = to_oracle_tri(delaunay_mesh(400, 11, extra_points=3))
+    mesh = O.FVMGeometry(tri)
+    P, Tr = tri.points, tri.triangles
+
+    def shoelace(poly):
+        x, y = np.asarray(poly).T
+        return 0.5 * abs(np.dot(x, np.roll(y, -1)) - np.dot(y, np.roll(x, -1)))
+
+    vol = np.zeros(len(P))
+    for T in Tr.tolist():
+        c = P[T].mean(axis=0)
+        for r in range(3):
+            v, nxt, prv = T[r], T[(r + 1) % 3], T[(r + 2) % 3]
+            vol[v] += shoelace([P[v], (P[v] + P[nxt]) / 2, c, (P[v] + P[prv]) / 2])
+    assert np.allclose(mesh.cv_volumes, vol, rtol=1e-10, atol=0.0)  # the shoelace sums cancel in absolute coordinates: 1.5e-12 measured
+    assert np.all(mesh.cv_volumes[-3:] == 0.0) and np.all(mesh.cv_volumes[:-3] > 0.0)
+    # the control volumes tile the domain: their total is the total triangle area
+    p, q, r = P[Tr[:, 0]], P[Tr[:, 1]], P[Tr[:, 2]]
+    area = 0.5 * ((q[:, 0] - p[:, 0]) * (r[:, 1] - p[:, 1]) - (q[:, 1] - p[:, 1]) * (r[:, 0] - p[:, 0]))
+    assert math.isclose(mesh.cv_volumes.sum(), area.sum(), rel_tol=1e-12)
