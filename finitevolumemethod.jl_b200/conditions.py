@@ -26,6 +26,12 @@ class BoundaryConditions:
         self.condition_types = tuple(condition_types)
         self.parameters = parameters  # kept for signature parity; registry specs carry their parameters
 
+    def __repr__(self):  # Base.show, conditions.jl:173-180
+        n = len(self.functions)
+        if n > 1:
+            return "BoundaryConditions with %d boundary conditions with types (%s)" % (n, ", ".join(self.condition_types))
+        return "BoundaryConditions with %d boundary condition with type %s" % (n, self.condition_types[0])
+
 
 class InternalConditions:
     """conditions.jl:223-230,253-269: dirichlet_nodes / dudt_nodes map node -> function index."""
@@ -37,6 +43,9 @@ class InternalConditions:
         self.dirichlet_nodes = dict(dirichlet_nodes or {})
         self.dudt_nodes = dict(dudt_nodes or {})
         self.parameters = parameters
+
+    def __repr__(self):  # Base.show, conditions.jl:231-235
+        return "InternalConditions with %d Dirichlet nodes and %d Dudt nodes" % (len(self.dirichlet_nodes), len(self.dudt_nodes))
 
 
 class Conditions:
@@ -85,6 +94,11 @@ class Conditions:
         self.node_fidx[is_dudt] = dudt_f[is_dudt]
         self.node_kind[is_dir] = NODE_DIRICHLET  # Dirichlet takes precedence
         self.node_fidx[is_dir] = dir_f[is_dir]
+
+    def __repr__(self):  # Base.show, conditions.jl:325-335
+        return "Conditions with\n   %d Neumann edges\n   %d Constrained edges\n   %d Dirichlet nodes\n   %d Dudt nodes" % (
+            int((self.edge_kind == EDGE_NEUMANN).sum()), int((self.edge_kind == EDGE_CONSTRAINED).sum()),
+            int((self.dirichlet_fidx >= 0).sum()), int((self.dudt_fidx >= 0).sum()))
 
     # the reference's predicates (conditions.jl:342-484)
     def is_dirichlet_node(self, i):

@@ -21,6 +21,13 @@ class FVMGeometry:
         self.triangulation = tri
         self._geom = None
 
+    def __repr__(self):  # Base.show, geometry.jl:50-55
+        tri = self.triangulation
+        t = tri.triangles.astype(np.int64)
+        e = np.sort(np.concatenate([t[:, [0, 1]], t[:, [1, 2]], t[:, [2, 0]]]), axis=1)
+        ne = len(np.unique(e[:, 0] * tri.num_points + e[:, 1]))
+        return "FVMGeometry with %d control volumes, %d triangles, and %d edges" % (int(tri.solid_vertex_mask().sum()), tri.num_triangles, ne)
+
     def _fetch(self):
         if self._geom is None:
             tri = self.triangulation
@@ -203,6 +210,12 @@ class SteadyFVMProblem:
     def __init__(self, prob):
         self.problem = prob
         self.neqs = prob.neqs
+
+    def __repr__(self):  # Base.show, problem.jl:182-190
+        nv = int(self.problem.mesh.triangulation.solid_vertex_mask().sum())
+        if self.neqs:
+            return "SteadyFVMProblem with %d nodes and %d equations" % (nv, self.neqs)
+        return "SteadyFVMProblem with %d nodes" % nv
 
 
 # ---------------------------------------------------------------------------------------------

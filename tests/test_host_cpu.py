@@ -125,6 +125,35 @@ def test_constructor_errors_mirror_the_reference():
     assert "FVMProblem with 25 nodes" in repr(p1)
 
 
+def test_show_strings_mirror_the_reference():
+    """The text/plain `show` methods the reference's own tests compare verbatim: test/conditions.jl:39-46 (BoundaryConditions,
+    InternalConditions, Conditions), test/problem.jl:18-19,80-81,97-98 (FVMProblem, SteadyFVMProblem, FVMSystem), and
+    geometry.jl:50-55 (FVMGeometry: solid vertices, triangles, edges)."""
+    tri = G.triangulate_rectangle(0, 1, 0, 1, 5, 4, single_boundary=False)
+    mesh = G.FVMGeometry(tri)
+    assert repr(mesh) == "FVMGeometry with 20 control volumes, 24 triangles, and 43 edges"  # E = N + T - 1
+    types = (G.Neumann, G.Dirichlet, G.Dudt, G.Constrained)
+    BCs = G.BoundaryConditions(mesh, (G.Const(0.0),) * 4, types)
+    assert repr(BCs) == "BoundaryConditions with 4 boundary conditions with types (Neumann, Dirichlet, Dudt, Constrained)"
+    one = G.FVMGeometry(G.triangulate_rectangle(0, 1, 0, 1, 5, 4, single_boundary=True))
+    assert repr(G.BoundaryConditions(one, G.Const(0.0), G.Dirichlet)) == "BoundaryConditions with 1 boundary condition with type Dirichlet"
+    ICs = G.InternalConditions((G.Const(1.0),), dirichlet_nodes={6: 0, 7: 0}, dudt_nodes={11: 0})
+    assert repr(ICs) == "InternalConditions with 2 Dirichlet nodes and 1 Dudt nodes"
+    conds = G.Conditions(mesh, BCs, ICs)
+    # bottom: 4 Neumann edges; right: Dirichlet on its 4 nodes; top: Dudt on its 5 nodes, one of which (the top right
+    # corner) is also a Dirichlet node and is counted in both Dicts like merge_conditions! does; left: 3 Constrained edges
+    assert repr(conds) == "Conditions with\n   4 Neumann edges\n   3 Constrained edges\n   6 Dirichlet nodes\n   6 Dudt nodes"
+    prob = G.FVMProblem(one, G.BoundaryConditions(one, G.Const(0.0), G.Dirichlet), diffusion_function=1.0, initial_condition=np.zeros(20),
+                        initial_time=0.5, final_time=2.0)
+    assert repr(prob) == "FVMProblem with 20 nodes and time span (0.5, 2.0)"
+    assert repr(G.SteadyFVMProblem(prob)) == "SteadyFVMProblem with 20 nodes"
+    q = G.FVMProblem(one, G.BoundaryConditions(one, G.Const(0.0), G.Dirichlet), flux_function=G.ConstantDiffusion(1.0), initial_condition=np.zeros(20),
+                     final_time=2.0)
+    system = G.FVMSystem(q, q, q)
+    assert repr(system) == "FVMSystem with 3 equations and time span (0.0, 2.0)"
+    assert repr(G.SteadyFVMProblem(system)) == "SteadyFVMProblem with 20 nodes and 3 equations"
+
+
 def test_template_argument_errors_mirror_the_reference():
     """poissons_equation.jl:69-70, mean_exit_time.jl:66-69: ArgumentError before any device work."""
     pair = Pair(G.triangulate_rectangle(0, 1, 0, 1, 5, 5, single_boundary=False))
