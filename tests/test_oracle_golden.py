@@ -677,3 +677,68 @@ def test_control_volume_polygon_areas_unstructured():
     p, q, r = P[Tr[:, 0]], P[Tr[:, 1]], P[Tr[:, 2]]
     area = 0.5 * ((q[:, 0] - p[:, 0]) * (r[:, 1] - p[:, 1]) - (q[:, 1] - p[:, 1]) * (r[:, 0] - p[:, 0]))
     assert math.isclose(mesh.cv_volumes.sum(), area.sum(), rel_tol=1e-12)
+
+
+def test_compute_flux_and_pl_interpolate_restated():
+    """test/test_functions.jl:659-750 (test_compute_flux): on every boundary edge (i, j) and every interior edge,
+    compute_flux(prob, i, j, u, t) (problem.jl:458-487) equals q(midpoint) . n with n = (e_y, -e_x)/|e| the normal to the
+    RIGHT of i -> j, where alpha, beta, gamma come from an independent 3x3 solve on the triangle that holds the edge (the
+    triangle left of i -> j for a boundary edge, left of j -> i for an interior one); the system form returns one value per
+    species and its first species equals the scalar problem's value.  pl_interpolate (utils.jl:23-27) reproduces the nodal
+    values at the vertices and is affine inside the triangle."""
+    tri = O.triangulate_rectangle(0.0, 1.0, 0.0, 1.5, 6, 5, single_boundary=False)
+    mesh = O.FVMGeometry(tri)
+    zero = lambda x, y, t, u, p: 0.0 * x
+    BCs = O.BoundaryConditions(mesh, (zero,) * 4, (O.Neumann, O.Dirichlet, O.Dudt, O.Neumann))
+    P, Tr = tri.points, tri.triangles
+    rng = np.random.default_rng(12)
+    u = rng.random(len(P))
+    qfun = lambda x, y, t, a, b, g, p: (-a * x + t * g, x + t - b * (a * x + b * y + g) * p[1])  # test_functions.jl:287-293 style
+    prob = O.FVMProblem(mesh, BCs, flux_function=qfun, flux_parameters=(0.5, 1.3), initial_condition=u, final_time=5.0)
+    q1 = lambda x, y, t, a, b, g, p: qfun(x, y, t, a[0], b[0], g[0], p)
+    q2 = lambda x, y, t, a, b, g, p: (-a[1] * b[0], g[1] - x * b[1])
+    sys_ = O.FVMSystem(O.FVMProblem(mesh, BCs, flux_function=q1, flux_parameters=(0.5, 1.3), initial_condition=u, final_time=5.0),
+                       O.FVMProblem(mesh, BCs, flux_function=q2, initial_condition=u, final_time=5.0))
+    U = np.stack([u, rng.random(len(P))], axis=1)
+    left_of = {}  # directed edge -> third vertex of the triangle on its left
+    for a, b, c in Tr.tolist():
+        left_of[(a, b)], left_of[(b, c)], left_of[(c, a)] = c, a, b
+
+    def abg(vals, verts):
+        M = np.array([[P[v, 0], P[v, 1], 1.0] for v in verts])
+        return np.linalg.solve(M, vals[list(verts)])
+
+    n_bnd = n_int = 0
+    for (i, j), k in left_of.items():
+        boundary = (j, i) not in left_of
+        if boundary:
+            verts = (i, j, k)  # get_adjacent(tri, i, j)
+            n_bnd += 1
+        else:
+            verts = (j, i, left_of[(j, i)])  # get_adjacent(tri, j, i): the triangle on the other side
+            n_int += 1
+        p, q = P[i], P[j]
+        ex, ey = (q - p) / np.linalg.norm(q - p)
+        nx, ny = ey, -ex
+        assert (q[0] - p[0]) * (ny) - (q[1] - p[1]) * (nx) < 0  # midpoint + n lies to the right of p -> q
+        mx, my = (p + q) / 2
+        a, b, g = abg(u, verts)
+        qv = qfun(mx, my, 2.5, a, b, g, (0.5, 1.3))
+        got = O.compute_flux(prob, i, j, u, 2.5)
+        assert math.isclose(got, qv[0] * nx + qv[1] * ny, rel_tol=1e-10, abs_tol=1e-12)
+        A = [abg(U[:, v], verts) for v in range(2)]
+        al, be, ga = [A[0][0], A[1][0]], [A[0][1], A[1][1]], [A[0][2], A[1][2]]
+        want = [np.dot(f(mx, my, 2.5, al, be, ga, (0.5, 1.3)), (nx, ny)) for f in (q1, q2)]
+        gs = O.compute_flux(sys_, i, j, U, 2.5)
+        assert np.allclose(gs, want, rtol=1e-10, atol=1e-12) and math.isclose(gs[0], got, rel_tol=1e-10, abs_tol=1e-12)
+    assert n_bnd == 2 * (5 + 4) and n_int == 2 * (len(Tr) * 3 - n_bnd) // 2
+    for T in Tr.tolist():
+        for v in T:
+            assert math.isclose(O.pl_interpolate(prob, T, u, P[v, 0], P[v, 1]), u[v], rel_tol=1e-11, abs_tol=1e-12)
+        w = rng.dirichlet((1, 1, 1))
+        x, y = w @ P[T]
+        assert math.isclose(O.pl_interpolate(prob, T, u, x, y), w @ u[T], rel_tol=1e-10, abs_tol=1e-12)
+        Ts = (T[1], T[2], T[0])  # any rotation of the stored key finds the same triangle (_safe_get_triangle_props, utils.jl:1-14)
+        assert math.isclose(O.pl_interpolate(prob, Ts, u, x, y), w @ u[T], rel_tol=1e-10, abs_tol=1e-12)
+        vals = O.pl_interpolate(sys_, T, U, x, y)
+        assert np.allclose(vals, w @ U[T], rtol=1e-10, atol=1e-12)
