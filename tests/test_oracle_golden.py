@@ -742,3 +742,28 @@ def test_compute_flux_and_pl_interpolate_restated():
         assert math.isclose(O.pl_interpolate(prob, Ts, u, x, y), w @ u[T], rel_tol=1e-10, abs_tol=1e-12)
         vals = O.pl_interpolate(sys_, T, U, x, y)
         assert np.allclose(vals, w @ U[T], rtol=1e-10, atol=1e-12)
+
+
+def test_jacobian_sparsity_pattern_restated():
+    """test/test_functions.jl:749-794 (test_jacobian_sparsity): the pattern is A[i,i] = 1 and A[i,j] = 1 for every
+    non-ghost neighbour j of i (scalar); for an N-species system the unknowns are interleaved node-major
+    (idx = (node-1) N + species, :768-779) and every (species, species) pair of a connected node pair is set.  The
+    neighbour relation is restated here straight from the triangles, on an unstructured mesh."""
+    from tests.common import delaunay_mesh, to_oracle_tri
+    tri = to_oracle_tri(delaunay_mesh(150, 4))
+    n = tri.num_points
+    adj = np.zeros((n, n), dtype=bool)
+    for a, b, c in tri.triangles.tolist():
+        for i, j in ((a, b), (b, c), (c, a)):
+            adj[i, j] = adj[j, i] = True
+    np.fill_diagonal(adj, True)
+    r, c = O.jacobian_sparsity(tri)
+    got = np.zeros((n, n), dtype=bool)
+    got[r, c] = True
+    assert np.array_equal(got, adj) and len(r) == adj.sum()  # no duplicates
+    for N in (2, 3):
+        R, C = O.jacobian_sparsity(tri, N)
+        want = np.kron(adj, np.ones((N, N), dtype=bool))  # node-major interleaving: block (i, j) is all ones
+        got = np.zeros((n * N, n * N), dtype=bool)
+        got[R, C] = True
+        assert np.array_equal(got, want) and len(R) == want.sum()
