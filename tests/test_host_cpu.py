@@ -237,3 +237,36 @@ def test_header_is_plain_c_and_the_c_example_runs(tmp_path):
     else:
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
     assert not os.path.exists(str(tmp_path / "readme_mesh.fvmw")) or r.returncode != 2
+
+
+def test_sass_is_sm100a_without_fp64_atomics_and_with_bulk_copies():
+    """What the design claims about the generated code, checked on the objects the library is linked from: every cubin is
+    sm_100a; no kernel on the path contains an atomic or a reduction (the scatter is a fixed-order gather) -- the only
+    ones in the library are the integer counters of the one-off incidence-list build (fvm_linear) and the halo epoch
+    counters (fvm_shard), never fp64; the streaming RHS kernel moves its tile packs with bulk async copies completing on
+    mbarriers (UBLKCP / SYNCS) and gathers external values with cp.async (LDGSTS)."""
+    import re
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    from fvm_b200 import _lib as L
+    L.lib()  # builds the objects if they are missing
+    libdir = os.path.join(ROOT, "finitevolumemethod.jl_b200", "lib")
+    if not os.path.exists(os.path.join(libdir, "fvm_rhs_stream.o")):
+        pytest.skip("object files are not in the tree (library built elsewhere)")
+    atom = re.compile(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?(ATOM|ATOMG|ATOMS|RED)\b(\S*)", re.M)
+    counts = {}
+    for name in sorted(f for f in os.listdir(libdir) if f.endswith(".o")):
+        sass = subprocess.run([exe, "-sass", os.path.join(libdir, name)], capture_output=True, text=True, check=True).stdout
+        archs = set(re.findall(r"arch = (sm_\w+)", sass))
+        assert archs <= {"sm_100a"}, (name, archs)
+        hits = atom.findall(sass)
+        assert not any("F64" in suffix or "64.F" in suffix for _, suffix in hits), (name, hits)
+        counts[name] = len(hits)
+        if name == "fvm_rhs_stream.o":
+            assert "UBLKCP" in sass and "SYNCS.ARRIVE.TRANS64" in sass and "LDGSTS" in sass
+    assert {k for k, v in counts.items() if v} <= {"fvm_linear.o", "fvm_shard.o"}, counts
+    for name in ("fvm_rhs.o", "fvm_rhs_stream.o", "fvm_solvers.o", "fvm_jacobian.o", "fvm_pipe.o"):
+        assert counts[name] == 0
